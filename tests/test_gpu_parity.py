@@ -1,0 +1,229 @@
+"""GPU parity tests: the CUDA library (through its C ABI) against the CPU oracle on the same
+seeded inputs.  Integer / index / byte work and the whole of phase 1 must be BIT-EXACT;
+delta-Cp time histories are held to 1e-5 relative (fp32) as defined in chain.cp_errors."""
+import numpy as np
+import pytest
+
+from chain import Case, cp_errors, run_gpu, run_oracle, same_bits
+
+pytestmark = pytest.mark.gpu
+
+CP_TOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative (fp32) on per-node Cp time histories"
+
+
+# ------------------------------------------------------------------ stand-alone operators
+def test_unpack12_matches_oracle(up, orc, gpu):
+    rng = np.random.default_rng(0)
+    for npix in (1024 * 1024, 1280 * 800, 6, 8 * 37 + 2):
+        pix = rng.integers(0, 4096, npix).astype(np.uint16)
+        packed = orc.pack_12bit(pix)
+        got = up.op_unpack(packed, up.PIX_PACKED12, npix)
+        assert np.array_equal(got, orc.unpack_12bit(packed))
+        assert np.array_equal(got, pix)
+
+
+def test_unpack10_with_and_without_lut(up, orc, gpu):
+    rng = np.random.default_rng(1)
+    npix = 64 * 48
+    pix = rng.integers(0, 1024, npix).astype(np.uint16)
+    packed = orc.pack_10bit(pix)
+    lut = (np.arange(1024, dtype=np.uint32) * 4 + 1).astype(np.uint16)
+    assert np.array_equal(up.op_unpack(packed, up.PIX_PACKED10, npix), orc.unpack_10bit(packed))
+    assert np.array_equal(up.op_unpack(packed, up.PIX_PACKED10, npix, lut), orc.unpack_10bit(packed, lut))
+    assert np.array_equal(up.op_unpack(packed, up.PIX_PACKED10, npix), pix)
+
+
+def _hot_cases(rng, h, w):
+    base = rng.integers(100, 3000, (h, w)).astype(np.uint16)
+    cases = []
+    for pts in ([], [(5, 5)], [(0, 0)], [(h - 1, w - 1)], [(0, 7), (h - 1, 3), (4, 0), (9, w - 1)],
+                [(3, 3), (3, 4)],                      # adjacent hot pixels: the second sees the first's fix
+                [(1, 1), (2, 2), (3, 3), (4, 4), (5, 5)],           # exactly max_hot
+                [(1, 1), (2, 2), (3, 3), (4, 4), (5, 5), (6, 6)],   # too many: untouched
+                ):
+        img = base.copy()
+        for (r, c) in pts:
+            img[r, c] = 4095
+        cases.append(img)
+    img = base.copy()
+    img[10, 10] = 4064          # at the threshold
+    img[9, 10] = img[11, 10] = img[10, 9] = img[10, 11] = 3800   # drop < 512: kept
+    cases.append(img)
+    img = base.copy()
+    img[20, 20] = 4063          # just below: not hot
+    cases.append(img)
+    return np.stack(cases)
+
+
+def test_fix_hot_pixels_matches_oracle(up, orc, gpu):
+    rng = np.random.default_rng(2)
+    frames = _hot_cases(rng, 32, 40)
+    got, n_hot = up.op_fix_hot_pixels(frames)
+    for f in range(frames.shape[0]):
+        ref, n = orc.fix_hot_pixels(frames[f])
+        assert np.array_equal(got[f], ref), f"frame {f}"
+        assert n_hot[f] == n
+
+
+@pytest.mark.parametrize("interp", [0, 1])
+def test_warp_affine_matches_oracle_and_golden(up, orc, gpu, interp):
+    import os
+    from conftest import GOLDEN
+    rng = np.random.default_rng(3)
+    h, w = 97, 130
+    nf = 12
+    frames = rng.integers(0, 4096, (nf, h, w)).astype(np.uint16)
+    m = np.zeros((nf, 2, 3), np.float32)
+    m[:, 0, 0] = m[:, 1, 1] = 1
+    scale = np.array([5e-4, 5e-2, 0.3])[np.arange(nf) % 3]
+    m[:, :, :2] += (rng.normal(0, 1, (nf, 2, 2)) * scale[:, None, None]).astype(np.float32)
+    m[:, :, 2] = (rng.normal(0, 1, (nf, 2)) * np.array([1, 5, 60])[np.arange(nf) % 3][:, None]).astype(np.float32)
+    got = up.op_warp_affine(frames, m.reshape(nf, 6), interp)
+    for f in range(nf):
+        assert np.array_equal(got[f], orc.warp_affine(frames[f], m[f], interp)), f"frame {f}"
+    # the committed cv2.warpAffine golden vectors (tests/golden/make_golden.py)
+    g = np.load(os.path.join(GOLDEN, "warp_golden.npz"))
+    got = up.op_warp_affine(g["src"], g["m6"], interp)
+    assert np.array_equal(got, g["linear" if interp == 1 else "nearest"])
+
+
+def test_project_frames_matches_oracle(up, orc, gpu):
+    import upsp_b200
+    rng = np.random.default_rng(4)
+    h, w, n = 64, 80, 5000
+    frames = rng.uniform(0, 4095, (5, h, w)).astype(np.float32)
+    for csr in (upsp_b200.synth.make_projection(n, h, w, "random", weights=True),
+                upsp_b200.synth.make_multi_nnz_projection(n, h, w, 9)):
+        got = up.op_project_frames(*csr, frames)
+        for f in range(frames.shape[0]):
+            assert same_bits(got[f], orc.project_frame(*csr, frames[f]))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 5), (64, 64), (100, 257), (333, 64), (129, 1000)])
+def test_transpose_exact(up, orc, gpu, shape):
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=shape).astype(np.float32)
+    assert np.array_equal(up.op_transpose(a), a.T)
+
+
+def test_detrend_reference_unit_test_recipe(up, orc, gpu):
+    """cpp/test/test_filtering.cpp:19-85: degree-6 data reproduced to 1e-4 abs (F=25, 13 pts)."""
+    F, npts = 25, 13
+    x = (np.arange(F, dtype=np.float32) / np.float32(F))
+    y = np.zeros((npts, F), np.float32)
+    for p in range(npts):
+        for c in range(7):
+            y[p] += (np.power(x.astype(np.float64), c) * np.float32(2.5 / (c + 1) + p / (c + 1))).astype(np.float32)
+    fit = up.op_polyfit_detrend(y, 6)
+    assert np.abs(fit - y).max() < 1e-4
+    for p in range(npts):
+        ofit, _ = orc.transpoly_fit(y[p], 6)
+        assert np.abs(fit[p] - ofit).max() < 1e-4
+
+
+@pytest.mark.parametrize("F", [25, 1000, 20000, 70001])
+def test_detrend_long_series_vs_oracle(up, orc, gpu, F):
+    """ratio-like series (1 + drift + noise): GPU fit vs the float-QR oracle fit and vs the
+    float64 least-squares fit; F=70001 exercises the not-in-shared-memory path."""
+    rng = np.random.default_rng(6)
+    t = np.arange(F) / F
+    y = (1.0 + 0.02 * np.sin(2 * np.pi * t) + 0.01 * t + rng.normal(0, 4e-3, (3, F))).astype(np.float32)
+    fit = up.op_polyfit_detrend(y, 6)
+    A = np.stack([(np.arange(F, dtype=np.float32) / np.float32(F)).astype(np.float64) ** c for c in range(7)], 1)
+    for p in range(3):
+        exact = A @ np.linalg.lstsq(A, y[p].astype(np.float64), rcond=None)[0]
+        assert np.abs(fit[p] - exact).max() < 2.5e-7          # ~2 ulp of 1.0
+        if F <= 20000:
+            ofit, _ = orc.transpoly_fit(y[p], 6)
+            assert np.abs(fit[p] - ofit).max() < 1e-5
+
+
+# ------------------------------------------------------------------ the whole chain
+def _check_chain(case, ref, got, patched_exact=True):
+    assert same_bits(got["intensity"], ref["intensity"]), "frame-major intensity not bit-exact"
+    assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
+    assert same_bits(got["coverage"], ref["coverage"])
+    assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact"
+    assert same_bits(got["gain"], ref["gain"])
+    skipped = ref["coverage"] == 0
+    assert np.all(got["ptrans"][skipped] == 0) and np.all(np.isnan(got["rms2"][skipped]))
+    e_op, e_cp = cp_errors(case, ref, got)
+    assert e_op.max() <= CP_TOL, f"delta-Cp error {e_op.max():.3e} (relative to operands) > {CP_TOL}"
+    v = ~skipped
+    scale = np.abs(ref["rms2"][v]).max()
+    assert np.abs(got["rms2"][v] - ref["rms2"][v]).max() <= 1e-5 * scale
+    assert np.abs(got["avg2"][v] - ref["avg2"][v]).max() <= 1e-5 * scale
+    return e_op.max(), e_cp.max()
+
+
+def test_chain_config1_plain(up, orc, gpu):
+    """config 1: one camera, registration none, patcher none, u16 frames, 128 frames."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=128, n_nodes=5000)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got)
+    assert got["launches"] > 0
+
+
+def test_chain_packed12_small_batches_and_ring(up, orc, gpu):
+    """12-bit packed input, batch of 5 frames, 16-slot input ring (streaming mode)."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=50, n_nodes=2000, fmt="p12", seed=3)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case, batch_frames=5, frame_capacity=16)
+    _check_chain(case, ref, got)
+
+
+def test_chain_registration_patches_overlap(up, orc, gpu):
+    """warp (given matrices) + polynomial patcher (incl. dependent clusters and a clipped
+    target) + P3D overlap remap; linear and nearest interpolation."""
+    import upsp_b200
+    for interp in (1, 0):
+        case = Case(upsp_b200.synth, n_frames=40, n_nodes=6000, registration=True, interp=interp,
+                    patches=True, overlap=True, overlap_pair=True, kind="random", seed=7)
+        ref = run_oracle(orc, case)
+        got = run_gpu(up, orc, case, alias=False)
+        _check_chain(case, ref, got)
+
+
+def test_chain_multi_camera_weights(up, orc, gpu):
+    """3 cameras, weighted entries, nodes seen by 0..3 cameras."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_cams=3, n_frames=33, n_nodes=4000, registration=True, patches=True, seed=11)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got)
+
+
+def test_chain_general_csr(up, orc, gpu):
+    """rows with up to 4 entries (cfg-5 variant) take the general CSR kernel."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_cams=2, n_frames=20, n_nodes=3000, multi_nnz=4, seed=13)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got)
+
+
+def test_chain_ragged_sizes(up, orc, gpu):
+    """odd frame size (not a multiple of 8), F and N not multiples of the tile sizes."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=37, n_nodes=1003, height=51, width=67, registration=True,
+                patches=True, seed=17)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got)
+
+
+def test_error_behaviour(up, gpu):
+    g = up.PspGpu(1, 10, 4)
+    with pytest.raises(up.UpspGpuError):
+        g.process_frames()            # no camera / projection yet
+    g.set_camera(0, 8, 8)
+    with pytest.raises(up.UpspGpuError):
+        g.set_projection(0, np.arange(11, dtype=np.int32), np.full(10, 64, np.int32), np.ones(10, np.float32))
+    with pytest.raises(up.UpspGpuError):
+        g.transpose()
+    with pytest.raises(up.UpspGpuError):
+        g.phase2([0] * 6, 1.0, 1.0, np.zeros(10), np.zeros(10))
+    g.close()

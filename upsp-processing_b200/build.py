@@ -1,0 +1,55 @@
+"""Build recipe for libupsp_gpu.so (sm_100a only, in-tree).
+
+    python upsp-processing_b200/build.py            # build if stale
+    python upsp-processing_b200/build.py --force
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libupsp_gpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "-Xptxas=-v",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
+    "-shared", "-cudart", "static",
+]
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp"))] + [
+        os.path.join(HERE, "..", "include", "upsp_gpu.h")]
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [NVCC] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "upsp_gpu.cu")]
+    env = dict(os.environ)
+    # nvcc's host compiler must be the system gcc (the image's $CC wrapper lacks libgomp specs)
+    cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed building libupsp_gpu.so")
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,1367 @@
+// upsp_gpu.cu -- C ABI (include/upsp_gpu.h) over the sm_100a kernels.
+// Context lifecycle, device memory layout, batching, stream/event plumbing, multi-GPU
+// wiring.  No CPU fallback anywhere: every compute entry point launches CUDA kernels.
+#include "../../include/upsp_gpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "host_qr.hpp"
+#include "kernels_frame.cuh"
+#include "kernels_phase2.cuh"
+#include "kernels_project.cuh"
+#include "kernels_transpose.cuh"
+
+using namespace upsp;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess)                                                            \
+      return fail(e_ == cudaErrorMemoryAllocation ? UPSP_ERR_NOMEM : UPSP_ERR_CUDA,   \
+                  "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define REQUIRE(cond, code, ...) \
+  do {                           \
+    if (!(cond)) return fail(code, __VA_ARGS__); \
+  } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// apportion() cpp/exec/psp_process.cpp:611-624
+static void apportion(int value, int bins, std::vector<int>& start, std::vector<int>& extent) {
+  start.assign(bins, 0);
+  extent.assign(bins, 0);
+  long block = value / bins, rem = value - block * bins, next = 0;
+  for (int b = 0; b < bins; ++b) {
+    start[b] = (int)next;
+    extent[b] = (int)(block + (b < rem));
+    next += extent[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct Camera {
+  int W = 0, H = 0;
+  size_t npix = 0;
+  // caller's CSR (kept on the host until finalize folds remap + patch codes into it)
+  std::vector<int> rowptr, col;
+  std::vector<float> val;
+  bool has_proj = false;
+  // input store (device-resident slots) and per-batch working buffers
+  int format = -1;
+  size_t frame_bytes = 0;
+  uint8_t* d_in = nullptr;
+  uint16_t* d_work = nullptr;
+  uint16_t* d_warp = nullptr;
+  int* d_hot_cnt = nullptr;
+  int* d_hot_pos = nullptr;
+  // registration
+  float* d_m6 = nullptr;      // [F_local][6]
+  float* d_rho = nullptr;     // [F_local]
+  int* d_iters = nullptr;     // [F_local]
+  int* d_tab = nullptr;       // [batch][2W+2H]
+  uint8_t* d_skip = nullptr;  // [batch]
+  uint16_t* d_ref16 = nullptr;
+  bool has_ref = false, has_m6 = false;
+  // patches
+  bool has_patches = false;
+  PatchGeom geom{};
+  std::vector<void*> patch_allocs;
+  std::vector<std::vector<int>> levels;  // cluster ids per dependency level
+  int* d_cl_list = nullptr;              // concatenated level lists
+  std::vector<int> level_off;
+  int total_bounds = 0, total_internal = 0;
+  float* d_scratch = nullptr;
+  float* d_pv = nullptr;
+  std::unordered_map<int, int> pix2slot;  // interior pixel -> slot of the LAST active cluster
+  // projection tables
+  int* d_code = nullptr;
+  float* d_val = nullptr;
+  int* d_rowptr = nullptr;
+};
+
+struct upsp_gpu_ctx {
+  upsp_gpu_config cfg{};
+  int F = 0, N = 0, R = 1, rank = 0;
+  std::vector<int> f_start, f_count, n_start, n_count;
+  int F_local = 0, N_local = 0, f0 = 0, n0 = 0;
+  int capacity = 0, batch = 32;
+  int registration = UPSP_REG_NONE, interp = UPSP_INTERP_LINEAR, patcher = UPSP_PATCH_NONE;
+  int hot_fix = 1;
+  std::vector<Camera> cams;
+  std::vector<int> remap;  // src_index or empty
+  bool finalized = false, ell1 = true;
+  uint16_t* d_lut = nullptr;
+
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
+  float stage_ms[4] = {0, 0, 0, 0};
+  long long launches = 0;
+
+  // big buffers
+  float* d_intensity = nullptr;  // [F_local][N]
+  char* d_shared = nullptr;      // one allocation (IPC-exportable): [itrans | sum | sumsq]
+  float* d_itrans = nullptr;     // [N_local][F]
+  double* d_sum = nullptr;       // [N]
+  double* d_sumsq = nullptr;     // [N]
+  float* d_ptrans = nullptr;     // [N_local][F] (may alias d_intensity)
+  bool ptrans_owned = false;
+  float *d_avg = nullptr, *d_rms = nullptr, *d_cov = nullptr;  // [N]
+  float *d_steady = nullptr, *d_temp = nullptr;                // [N]
+  double *d_rms2 = nullptr, *d_avg2 = nullptr, *d_gain2 = nullptr;     // [N_local]
+  float *d_rms2f = nullptr, *d_avg2f = nullptr, *d_gain2f = nullptr;   // [N_local]
+  size_t shared_bytes = 0, off_sum = 0, off_sumsq = 0;
+
+  // peers: base of every rank's shared allocation as seen from this device
+  char* peer_base[UPSP_MAX_RANKS] = {nullptr};
+  bool peer_is_ipc[UPSP_MAX_RANKS] = {false};
+  bool peers_ready = false;
+  int exchange = UPSP_XCHG_PEER;
+  bool phase1_done = false, transposed = false, phase2_done = false;
+  int frames_processed = 0;
+};
+
+static int set_dev(const upsp_gpu_ctx* c) {
+  CU(cudaSetDevice(c->cfg.device));
+  return UPSP_OK;
+}
+#define ENTER(ctx)                                               \
+  REQUIRE((ctx) != nullptr, UPSP_ERR_INVALID, "null context");   \
+  {                                                              \
+    int rc_ = set_dev(ctx);                                      \
+    if (rc_) return rc_;                                         \
+  }
+#define KCHECK(ctx)            \
+  do {                         \
+    (ctx)->launches++;         \
+    CU(cudaGetLastError());    \
+  } while (0)
+
+template <typename T>
+static int dmalloc(T** p, size_t count) {
+  CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+  return UPSP_OK;
+}
+template <typename T>
+static int upload(T** p, const T* h, size_t count) {
+  int rc = dmalloc(p, count);
+  if (rc) return rc;
+  if (count) CU(cudaMemcpy(*p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  return UPSP_OK;
+}
+#define TRY(x)            \
+  do {                    \
+    int rc__ = (x);       \
+    if (rc__) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" const char* upsp_gpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int upsp_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
+  REQUIRE(cfg && out, UPSP_ERR_INVALID, "null argument");
+  REQUIRE(cfg->n_cams >= 1 && cfg->n_cams <= UPSP_MAX_CAMS, UPSP_ERR_INVALID,
+          "n_cams must be in [1,%d]", UPSP_MAX_CAMS);
+  REQUIRE(cfg->n_nodes > 0 && cfg->n_frames_total > 0, UPSP_ERR_INVALID, "empty problem");
+  REQUIRE(cfg->n_ranks >= 1 && cfg->n_ranks <= UPSP_MAX_RANKS && cfg->rank >= 0 &&
+              cfg->rank < cfg->n_ranks,
+          UPSP_ERR_INVALID, "bad rank %d / %d", cfg->rank, cfg->n_ranks);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  REQUIRE(e == cudaSuccess && ndev > 0, UPSP_ERR_CUDA,
+          "no usable CUDA device (%s); libupsp_gpu has no CPU fallback",
+          e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+  REQUIRE(cfg->device >= 0 && cfg->device < ndev, UPSP_ERR_INVALID, "device %d of %d",
+          cfg->device, ndev);
+  auto* c = new upsp_gpu_ctx();
+  c->cfg = *cfg;
+  c->F = cfg->n_frames_total;
+  c->N = cfg->n_nodes;
+  c->R = cfg->n_ranks;
+  c->rank = cfg->rank;
+  apportion(c->F, c->R, c->f_start, c->f_count);
+  apportion(c->N, c->R, c->n_start, c->n_count);
+  c->F_local = c->f_count[c->rank];
+  c->f0 = c->f_start[c->rank];
+  c->N_local = c->n_count[c->rank];
+  c->n0 = c->n_start[c->rank];
+  c->capacity = cfg->frame_capacity > 0 ? std::min(cfg->frame_capacity, std::max(c->F_local, 1))
+                                        : std::max(c->F_local, 1);
+  c->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 32;
+  c->batch = std::min(c->batch, c->capacity);
+  c->cams.resize(cfg->n_cams);
+  *out = c;
+  int rc = [&]() -> int {
+    CU(cudaSetDevice(cfg->device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_proc, cudaEventDisableTiming));
+    CU(cudaEventCreate(&c->ev_a));
+    CU(cudaEventCreate(&c->ev_b));
+    CU(cudaEventCreate(&c->ev_pa));
+    CU(cudaEventCreate(&c->ev_pb));
+    const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
+    const bool alias = cfg->pressure_aliases_intensity != 0;
+    TRY(dmalloc(&c->d_intensity, alias ? std::max(fn, nf) : fn));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    c->off_sum = al(nf * sizeof(float));
+    c->off_sumsq = c->off_sum + al((size_t)c->N * sizeof(double));
+    c->shared_bytes = c->off_sumsq + al((size_t)c->N * sizeof(double));
+    TRY(dmalloc(&c->d_shared, c->shared_bytes));
+    c->d_itrans = reinterpret_cast<float*>(c->d_shared);
+    c->d_sum = reinterpret_cast<double*>(c->d_shared + c->off_sum);
+    c->d_sumsq = reinterpret_cast<double*>(c->d_shared + c->off_sumsq);
+    CU(cudaMemsetAsync(c->d_sum, 0, (size_t)c->N * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->d_sumsq, 0, (size_t)c->N * sizeof(double), c->stream));
+    if (alias) {
+      c->d_ptrans = c->d_intensity;
+    } else {
+      TRY(dmalloc(&c->d_ptrans, nf));
+      c->ptrans_owned = true;
+    }
+    TRY(dmalloc(&c->d_avg, c->N));
+    TRY(dmalloc(&c->d_rms, c->N));
+    TRY(dmalloc(&c->d_cov, c->N));
+    TRY(dmalloc(&c->d_steady, c->N));
+    TRY(dmalloc(&c->d_temp, c->N));
+    TRY(dmalloc(&c->d_rms2, c->N_local));
+    TRY(dmalloc(&c->d_avg2, c->N_local));
+    TRY(dmalloc(&c->d_gain2, c->N_local));
+    TRY(dmalloc(&c->d_rms2f, c->N_local));
+    TRY(dmalloc(&c->d_avg2f, c->N_local));
+    TRY(dmalloc(&c->d_gain2f, c->N_local));
+    c->peer_base[c->rank] = c->d_shared;
+    if (c->R == 1) c->peers_ready = true;
+    CU(cudaStreamSynchronize(c->stream));
+    return UPSP_OK;
+  }();
+  if (rc) {
+    std::string keep = g_err;
+    upsp_gpu_destroy(c);
+    g_err = keep;
+    *out = nullptr;
+  }
+  return rc;
+}
+
+static void free_camera(Camera& cam) {
+  cudaFree(cam.d_in);
+  cudaFree(cam.d_work);
+  cudaFree(cam.d_warp);
+  cudaFree(cam.d_hot_cnt);
+  cudaFree(cam.d_hot_pos);
+  cudaFree(cam.d_m6);
+  cudaFree(cam.d_rho);
+  cudaFree(cam.d_iters);
+  cudaFree(cam.d_tab);
+  cudaFree(cam.d_skip);
+  cudaFree(cam.d_ref16);
+  for (void* p : cam.patch_allocs) cudaFree(p);
+  cudaFree(cam.d_cl_list);
+  cudaFree(cam.d_scratch);
+  cudaFree(cam.d_pv);
+  cudaFree(cam.d_code);
+  cudaFree(cam.d_val);
+  cudaFree(cam.d_rowptr);
+}
+
+extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
+  if (!c) return UPSP_OK;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int r = 0; r < c->R; ++r)
+    if (r != c->rank && c->peer_base[r] && c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  for (auto& cam : c->cams) free_camera(cam);
+  cudaFree(c->d_lut);
+  cudaFree(c->d_intensity);
+  cudaFree(c->d_shared);
+  if (c->ptrans_owned) cudaFree(c->d_ptrans);
+  cudaFree(c->d_avg);
+  cudaFree(c->d_rms);
+  cudaFree(c->d_cov);
+  cudaFree(c->d_steady);
+  cudaFree(c->d_temp);
+  cudaFree(c->d_rms2);
+  cudaFree(c->d_avg2);
+  cudaFree(c->d_gain2);
+  cudaFree(c->d_rms2f);
+  cudaFree(c->d_avg2f);
+  cudaFree(c->d_gain2f);
+  if (c->ev_push) cudaEventDestroy(c->ev_push);
+  if (c->ev_proc) cudaEventDestroy(c->ev_proc);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_pa) cudaEventDestroy(c->ev_pa);
+  if (c->ev_pb) cudaEventDestroy(c->ev_pb);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_get_slices(const upsp_gpu_ctx* c, int* ff, int* nf, int* fn, int* nn) {
+  REQUIRE(c, UPSP_ERR_INVALID, "null context");
+  if (ff) *ff = c->f0;
+  if (nf) *nf = c->F_local;
+  if (fn) *fn = c->n0;
+  if (nn) *nn = c->N_local;
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// setup
+// ------------------------------------------------------------------------------------------
+#define CAM_CHECK(c, cam) \
+  REQUIRE((cam) >= 0 && (cam) < (int)(c)->cams.size(), UPSP_ERR_INVALID, "camera %d out of range", cam)
+#define NOT_FINAL(c) \
+  REQUIRE(!(c)->finalized, UPSP_ERR_STATE, "setup calls are not allowed after the first process_frames")
+
+extern "C" int upsp_gpu_set_camera(upsp_gpu_ctx* c, int cam, int width, int height) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  NOT_FINAL(c);
+  REQUIRE(width > 0 && height > 0, UPSP_ERR_INVALID, "bad frame size %dx%d", width, height);
+  c->cams[cam].W = width;
+  c->cams[cam].H = height;
+  c->cams[cam].npix = (size_t)width * height;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_projection(upsp_gpu_ctx* c, int cam, const int32_t* rowptr,
+                                       const int32_t* col, const float* val) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  NOT_FINAL(c);
+  Camera& k = c->cams[cam];
+  REQUIRE(k.npix > 0, UPSP_ERR_STATE, "set_camera(%d) first", cam);
+  REQUIRE(rowptr, UPSP_ERR_INVALID, "null rowptr");
+  REQUIRE(rowptr[0] == 0, UPSP_ERR_INVALID, "rowptr[0] != 0");
+  for (int i = 0; i < c->N; ++i)
+    REQUIRE(rowptr[i + 1] >= rowptr[i], UPSP_ERR_INVALID, "rowptr not monotone at row %d", i);
+  const int nnz = rowptr[c->N];
+  REQUIRE(nnz == 0 || (col && val), UPSP_ERR_INVALID, "null col/val");
+  for (int i = 0; i < nnz; ++i)
+    REQUIRE(col[i] >= 0 && (size_t)col[i] < k.npix, UPSP_ERR_INVALID,
+            "column %d of entry %d outside the %dx%d frame", col[i], i, k.W, k.H);
+  k.rowptr.assign(rowptr, rowptr + c->N + 1);
+  k.col.assign(col, col + nnz);
+  k.val.assign(val, val + nnz);
+  k.has_proj = true;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_overlap_remap(upsp_gpu_ctx* c, const int32_t* src) {
+  ENTER(c);
+  NOT_FINAL(c);
+  if (!src) {
+    c->remap.clear();
+    return UPSP_OK;
+  }
+  for (int i = 0; i < c->N; ++i)
+    REQUIRE(src[i] >= 0 && src[i] < c->N, UPSP_ERR_INVALID, "src_index[%d]=%d out of range", i, src[i]);
+  c->remap.assign(src, src + c->N);
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_options(upsp_gpu_ctx* c, int registration, int interp, int patcher,
+                                    int hot_pixel_fix) {
+  ENTER(c);
+  NOT_FINAL(c);
+  REQUIRE(registration >= UPSP_REG_NONE && registration <= UPSP_REG_GIVEN, UPSP_ERR_INVALID,
+          "registration %d", registration);
+  REQUIRE(registration != UPSP_REG_PIXEL, UPSP_ERR_INVALID,
+          "registration=pixel (on-device ECC solve) is not built yet; solve on the host and "
+          "use UPSP_REG_GIVEN");
+  REQUIRE(interp == UPSP_INTERP_NEAREST || interp == UPSP_INTERP_LINEAR, UPSP_ERR_INVALID,
+          "interp %d", interp);
+  REQUIRE(patcher == UPSP_PATCH_NONE || patcher == UPSP_PATCH_POLYNOMIAL, UPSP_ERR_INVALID,
+          "patcher %d", patcher);
+  c->registration = registration;
+  c->interp = interp;
+  c->patcher = patcher;
+  c->hot_fix = hot_pixel_fix != 0;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_unpack_lut(upsp_gpu_ctx* c, const uint16_t* lut) {
+  ENTER(c);
+  cudaFree(c->d_lut);
+  c->d_lut = nullptr;
+  if (lut) TRY(upload(&c->d_lut, lut, 1024));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_reference_frame(upsp_gpu_ctx* c, int cam, const uint16_t* frame) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  Camera& k = c->cams[cam];
+  REQUIRE(k.npix > 0, UPSP_ERR_STATE, "set_camera(%d) first", cam);
+  REQUIRE(frame, UPSP_ERR_INVALID, "null frame");
+  cudaFree(k.d_ref16);
+  k.d_ref16 = nullptr;
+  TRY(upload(&k.d_ref16, frame, k.npix));
+  k.has_ref = true;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_warp_matrices(upsp_gpu_ctx* c, int cam, int off, int count,
+                                          const float* m6) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID,
+          "frames [%d,%d) outside the local slice of %d", off, off + count, c->F_local);
+  REQUIRE(m6 || count == 0, UPSP_ERR_INVALID, "null matrices");
+  Camera& k = c->cams[cam];
+  if (!k.d_m6) {
+    TRY(dmalloc(&k.d_m6, (size_t)std::max(c->F_local, 1) * 6));
+    std::vector<float> id((size_t)std::max(c->F_local, 1) * 6, 0.0f);
+    for (int f = 0; f < c->F_local; ++f) id[(size_t)f * 6 + 0] = id[(size_t)f * 6 + 4] = 1.0f;
+    CU(cudaMemcpy(k.d_m6, id.data(), id.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if (count)
+    CU(cudaMemcpyAsync(k.d_m6 + (size_t)off * 6, m6, (size_t)count * 6 * sizeof(float),
+                       cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  k.has_m6 = true;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_patches(upsp_gpu_ctx* c, int cam, int ncl, const int32_t* boff,
+                                    const uint32_t* bx, const uint32_t* by, const int32_t* ioff,
+                                    const uint32_t* ix, const uint32_t* iy) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  NOT_FINAL(c);
+  Camera& k = c->cams[cam];
+  REQUIRE(k.npix > 0, UPSP_ERR_STATE, "set_camera(%d) first", cam);
+  REQUIRE(!k.has_patches, UPSP_ERR_STATE, "patches of camera %d already set", cam);
+  REQUIRE(ncl >= 0, UPSP_ERR_INVALID, "n_clusters %d", ncl);
+  if (ncl == 0) return UPSP_OK;
+  REQUIRE(boff && ioff, UPSP_ERR_INVALID, "null offsets");
+  const int nbt = boff[ncl], nit = ioff[ncl];
+  REQUIRE(boff[0] == 0 && ioff[0] == 0, UPSP_ERR_INVALID, "offsets must start at 0");
+  for (int i = 0; i < nbt; ++i)
+    REQUIRE((int)bx[i] < k.W && (int)by[i] < k.H, UPSP_ERR_INVALID, "boundary pixel outside frame");
+  for (int i = 0; i < nit; ++i)
+    REQUIRE((int)ix[i] < k.W && (int)iy[i] < k.H, UPSP_ERR_INVALID, "interior pixel outside frame");
+
+  std::vector<int> bsrc(nbt), nzp(ncl), perm((size_t)ncl * 10, 0), islot_pix(nit), level(ncl, 0);
+  std::vector<float> qr_e((size_t)10 * nbt, 0.0f), qr_te((size_t)10 * nbt, 0.0f),
+      hcoef((size_t)ncl * 10, 0.0f), ipow((size_t)6 * nit);
+  std::unordered_map<int, std::pair<int, int>> owner;  // pixel -> (cluster, slot) of earlier active clusters
+  int max_level = 0;
+  for (int cl = 0; cl < ncl; ++cl) {
+    const int o = boff[cl], nb = boff[cl + 1] - o;
+    REQUIRE(nb >= 0 && ioff[cl + 1] >= ioff[cl], UPSP_ERR_INVALID, "offsets not monotone");
+    nzp[cl] = -1;                    // inactive: fewer than (3+2)(3+1)/2 = 10 boundary px
+    if (nb < 10) continue;           // patches.ipp:112-115
+    std::vector<float> A((size_t)nb * 10);
+    for (int i = 0; i < nb; ++i) {
+      const int pix = (int)by[o + i] * k.W + (int)bx[o + i];
+      auto it = owner.find(pix);
+      if (it != owner.end()) {
+        bsrc[o + i] = -1 - it->second.second;
+        level[cl] = std::max(level[cl], level[it->second.first] + 1);
+      } else {
+        bsrc[o + i] = pix;
+      }
+      int cnt = 0;  // patches.ipp:183-195: A(ind,count) = (T)pow(y,i) * (T)pow(x,j)
+      for (int a = 0; a <= 3; ++a)
+        for (int b = 0; b <= 3; ++b)
+          if (a + b <= 3) {
+            A[(size_t)cnt * nb + i] =
+                (float)std::pow((double)by[o + i], a) * (float)std::pow((double)bx[o + i], b);
+            ++cnt;
+          }
+    }
+    ColPivQR f = colpiv_householder_qr(std::move(A), nb, 10);
+    nzp[cl] = f.nonzero_pivots;
+    for (int q = 0; q < 10; ++q) {
+      hcoef[(size_t)cl * 10 + q] = f.hcoef[q];
+      perm[(size_t)cl * 10 + q] = f.perm[q];
+      for (int i = 0; i < nb; ++i) {
+        const float e = f.qr[(size_t)q * nb + i];
+        qr_e[(size_t)10 * o + (size_t)q * nb + i] = e;
+        qr_te[(size_t)10 * o + (size_t)q * nb + i] = f.hcoef[q] * e;
+      }
+    }
+    max_level = std::max(max_level, level[cl]);
+    for (int j = ioff[cl]; j < ioff[cl + 1]; ++j) {
+      const int pix = (int)iy[j] * k.W + (int)ix[j];
+      owner[pix] = {cl, j};
+      k.pix2slot[pix] = j;
+    }
+  }
+  for (int j = 0; j < nit; ++j) {
+    islot_pix[j] = (int)iy[j] * k.W + (int)ix[j];
+    for (int p = 1; p <= 3; ++p) {
+      ipow[(size_t)6 * j + p - 1] = (float)std::pow((double)ix[j], p);
+      ipow[(size_t)6 * j + 2 + p] = (float)std::pow((double)iy[j], p);
+    }
+  }
+  k.levels.assign(max_level + 1, {});
+  for (int cl = 0; cl < ncl; ++cl)
+    if (nzp[cl] >= 0) k.levels[level[cl]].push_back(cl);
+  std::vector<int> cl_list;
+  k.level_off.assign(1, 0);
+  for (auto& l : k.levels) {
+    cl_list.insert(cl_list.end(), l.begin(), l.end());
+    k.level_off.push_back((int)cl_list.size());
+  }
+  auto up = [&](auto** dptr, const auto& h) -> int {
+    typedef typename std::remove_reference<decltype(h[0])>::type T;
+    typename std::remove_const<T>::type* d = nullptr;
+    TRY(upload(&d, h.data(), h.size()));
+    *dptr = d;
+    k.patch_allocs.push_back((void*)d);
+    return UPSP_OK;
+  };
+  std::vector<int> boff_v(boff, boff + ncl + 1), ioff_v(ioff, ioff + ncl + 1);
+  PatchGeom& g = k.geom;
+  g.n_clusters = ncl;
+  TRY(up(&g.bounds_off, boff_v));
+  TRY(up(&g.bsrc, bsrc));
+  TRY(up(&g.qr_e, qr_e));
+  TRY(up(&g.qr_te, qr_te));
+  TRY(up(&g.hcoef, hcoef));
+  TRY(up(&g.perm, perm));
+  TRY(up(&g.nzp, nzp));
+  TRY(up(&g.internal_off, ioff_v));
+  TRY(up(&g.ipow, ipow));
+  TRY(up(&g.islot_pix, islot_pix));
+  TRY(upload(&k.d_cl_list, cl_list.data(), cl_list.size()));
+  k.total_bounds = nbt;
+  k.total_internal = nit;
+  k.has_patches = true;
+  return UPSP_OK;
+}
+
+// Fold remap + patched-pixel codes into device tables; allocate per-batch working buffers.
+static int finalize(upsp_gpu_ctx* c) {
+  if (c->finalized) return UPSP_OK;
+  const int N = c->N;
+  for (size_t i = 0; i < c->cams.size(); ++i) {
+    REQUIRE(c->cams[i].npix > 0, UPSP_ERR_STATE, "camera %zu has no frame size", i);
+    REQUIRE(c->cams[i].has_proj, UPSP_ERR_STATE, "camera %zu has no projection matrix", i);
+  }
+  const bool use_patch = c->patcher == UPSP_PATCH_POLYNOMIAL;
+  // is every remapped row <= 1 entry in every camera?
+  c->ell1 = true;
+  for (auto& k : c->cams)
+    for (int n = 0; n < N && c->ell1; ++n)
+      if (k.rowptr[n + 1] - k.rowptr[n] > 1) c->ell1 = false;
+  std::vector<float> cov(N, 0.0f);
+  for (size_t ci = 0; ci < c->cams.size(); ++ci) {
+    Camera& k = c->cams[ci];
+    auto code_of = [&](int col) -> int {
+      if (use_patch && k.has_patches) {
+        auto it = k.pix2slot.find(col);
+        if (it != k.pix2slot.end()) return -2 - it->second;
+      }
+      return col;
+    };
+    std::vector<int> code, rp;
+    std::vector<float> val;
+    if (c->ell1) {
+      code.assign(N, -1);
+      val.assign(N, 0.0f);
+      for (int n = 0; n < N; ++n) {
+        const int s = c->remap.empty() ? n : c->remap[n];
+        if (k.rowptr[s + 1] > k.rowptr[s]) {
+          code[n] = code_of(k.col[k.rowptr[s]]);
+          val[n] = k.val[k.rowptr[s]];
+        }
+      }
+    } else {
+      rp.assign(N + 1, 0);
+      for (int n = 0; n < N; ++n) {
+        const int s = c->remap.empty() ? n : c->remap[n];
+        rp[n + 1] = rp[n] + (k.rowptr[s + 1] - k.rowptr[s]);
+      }
+      code.resize(rp[N]);
+      val.resize(rp[N]);
+      for (int n = 0; n < N; ++n) {
+        const int s = c->remap.empty() ? n : c->remap[n];
+        for (int j = 0; j < k.rowptr[s + 1] - k.rowptr[s]; ++j) {
+          code[rp[n] + j] = code_of(k.col[k.rowptr[s] + j]);
+          val[rp[n] + j] = k.val[k.rowptr[s] + j];
+        }
+      }
+      TRY(upload(&k.d_rowptr, rp.data(), rp.size()));
+    }
+    TRY(upload(&k.d_code, code.data(), code.size()));
+    TRY(upload(&k.d_val, val.data(), val.size()));
+    // coverage = sum_c project(ones) (psp_process.cpp:1953-1966), then adjust_solution (:1974)
+    for (int n = 0; n < N; ++n) {
+      const int s = c->remap.empty() ? n : c->remap[n];
+      float t = 0.0f;
+      for (int j = k.rowptr[s]; j < k.rowptr[s + 1]; ++j) t += k.val[j] * 1.0f;
+      t = 0.0f + t;
+      cov[n] = ci == 0 ? t : cov[n] + t;
+    }
+    // working buffers
+    TRY(dmalloc(&k.d_work, (size_t)c->batch * k.npix));
+    TRY(dmalloc(&k.d_hot_cnt, (size_t)c->batch));
+    TRY(dmalloc(&k.d_hot_pos, (size_t)c->batch * UPSP_HOT_STORE));
+    if (c->registration != UPSP_REG_NONE) {
+      TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
+      TRY(dmalloc(&k.d_tab, (size_t)c->batch * (2 * k.W + 2 * k.H)));
+      if (c->registration == UPSP_REG_GIVEN)
+        REQUIRE(k.has_m6, UPSP_ERR_STATE, "registration=given but camera %zu has no warp matrices", ci);
+    }
+    if (use_patch && k.has_patches) {
+      TRY(dmalloc(&k.d_scratch, (size_t)k.total_bounds * c->batch));
+      TRY(dmalloc(&k.d_pv, (size_t)std::max(k.total_internal, 1) * c->batch));
+    }
+  }
+  CU(cudaMemcpy(c->d_cov, cov.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  c->finalized = true;
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1
+// ------------------------------------------------------------------------------------------
+static size_t frame_bytes_of(int format, size_t npix) {
+  switch (format) {
+    case UPSP_PIX_U16: return npix * 2;
+    case UPSP_PIX_PACKED12: return npix * 12 / 8;
+    case UPSP_PIX_PACKED10: return npix * 10 / 8;
+  }
+  return 0;
+}
+
+extern "C" int upsp_gpu_push_frames(upsp_gpu_ctx* c, int cam, const void* host, int format,
+                                    int off, int count) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  Camera& k = c->cams[cam];
+  REQUIRE(k.npix > 0, UPSP_ERR_STATE, "set_camera(%d) first", cam);
+  REQUIRE(format >= UPSP_PIX_U16 && format <= UPSP_PIX_PACKED10, UPSP_ERR_INVALID, "format %d", format);
+  REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID,
+          "frames [%d,%d) outside the local slice of %d", off, off + count, c->F_local);
+  REQUIRE(count <= c->capacity, UPSP_ERR_INVALID, "%d frames exceed the %d input slots", count, c->capacity);
+  REQUIRE(host || count == 0, UPSP_ERR_INVALID, "null frames");
+  if (format == UPSP_PIX_PACKED12)
+    REQUIRE(k.npix % 2 == 0, UPSP_ERR_INVALID, "12-bit packing needs an even pixel count");
+  if (format == UPSP_PIX_PACKED10)
+    REQUIRE(k.npix % 4 == 0, UPSP_ERR_INVALID, "10-bit packing needs a pixel count divisible by 4");
+  if (k.format < 0) {
+    k.format = format;
+    k.frame_bytes = frame_bytes_of(format, k.npix);
+    TRY(dmalloc(&k.d_in, (size_t)c->capacity * k.frame_bytes));
+  }
+  REQUIRE(k.format == format, UPSP_ERR_INVALID, "camera %d was fed format %d before", cam, k.format);
+  // slots being overwritten must have been consumed
+  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_proc, 0));
+  int done = 0;
+  while (done < count) {
+    const int slot = (off + done) % c->capacity;
+    const int run = std::min(count - done, c->capacity - slot);
+    CU(cudaMemcpyAsync(k.d_in + (size_t)slot * k.frame_bytes,
+                       (const uint8_t*)host + (size_t)done * k.frame_bytes,
+                       (size_t)run * k.frame_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    done += run;
+  }
+  CU(cudaEventRecord(c->ev_push, c->copy_stream));
+  return UPSP_OK;
+}
+
+template <int U>
+static void launch_project_ell1(upsp_gpu_ctx* c, const ProjArgs& a) {
+  const unsigned g = cdiv(a.n_nodes, 256);
+  switch (a.n_cams) {
+    case 1: k_project_ell1<1, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 2: k_project_ell1<2, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 3: k_project_ell1<3, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 4: k_project_ell1<4, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 5: k_project_ell1<5, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 6: k_project_ell1<6, U><<<g, 256, 0, c->stream>>>(a); break;
+    case 7: k_project_ell1<7, U><<<g, 256, 0, c->stream>>>(a); break;
+    default: k_project_ell1<8, U><<<g, 256, 0, c->stream>>>(a); break;
+  }
+}
+
+// one batch: local frames [off, off+nb)
+static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
+  ProjArgs pa{};
+  pa.n_cams = (int)c->cams.size();
+  pa.n_nodes = c->N;
+  pa.nframes = nb;
+  pa.bstride = c->batch;
+  pa.out = c->d_intensity + (size_t)off * c->N;
+  pa.sum = c->d_sum;
+  pa.sumsq = c->d_sumsq;
+  const int slot = off % c->capacity;
+  REQUIRE(slot + nb <= c->capacity, UPSP_ERR_STATE, "batch wraps the input ring");
+  for (size_t ci = 0; ci < c->cams.size(); ++ci) {
+    Camera& k = c->cams[ci];
+    REQUIRE(k.format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
+    const int thresh = c->hot_fix ? UPSP_HOT_THRESH : 0x7fffffff;
+    CU(cudaMemsetAsync(k.d_hot_cnt, 0, (size_t)nb * sizeof(int), c->stream));
+    const uint8_t* in = k.d_in + (size_t)slot * k.frame_bytes;
+    if (k.format == UPSP_PIX_PACKED12) {
+      k_unpack12_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
+          in, k.frame_bytes, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
+    } else if (k.format == UPSP_PIX_PACKED10) {
+      k_unpack10_scan<<<dim3(cdiv(cdiv(k.npix, 4), 256), nb), 256, 0, c->stream>>>(
+          in, k.frame_bytes, k.d_work, k.npix, c->d_lut, thresh, k.d_hot_cnt, k.d_hot_pos);
+    } else {
+      k_copy16_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
+          (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
+    }
+    KCHECK(c);
+    if (c->hot_fix) {
+      k_fix_hot<<<cdiv(nb, 32), 32, 0, c->stream>>>(k.d_work, k.npix, k.H, k.W, nb, k.d_hot_cnt,
+                                                   k.d_hot_pos, UPSP_HOT_MIN_CHANGE, UPSP_HOT_MAX);
+      KCHECK(c);
+    }
+    const uint16_t* cur = k.d_work;
+    if (c->registration != UPSP_REG_NONE) {
+      // global frame 0 is never registered (psp_process.cpp:1777)
+      const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
+      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), nb), 256, 0, c->stream>>>(
+          k.d_m6 + (size_t)off * 6, nb, k.W, k.H, c->interp, k.d_tab);
+      KCHECK(c);
+      k_warp_affine_u16<<<dim3(cdiv(k.W, 128), cdiv(k.H, 4), nb), dim3(64, 4), 0, c->stream>>>(
+          k.d_work, k.d_warp, k.W, k.H, k.d_tab, c->interp, skip_frame);
+      KCHECK(c);
+      cur = k.d_warp;
+    }
+    const bool patch = c->patcher == UPSP_PATCH_POLYNOMIAL && k.has_patches;
+    if (patch) {
+      for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
+        const int ncl = k.level_off[l + 1] - k.level_off[l];
+        if (!ncl) continue;
+        k_patch<<<dim3(ncl, cdiv(nb, 32)), 32, 0, c->stream>>>(
+            k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
+        KCHECK(c);
+      }
+    }
+    pa.cam[ci].frames = cur;
+    pa.cam[ci].npix = k.npix;
+    pa.cam[ci].pv = patch ? k.d_pv : nullptr;
+    pa.cam[ci].code = k.d_code;
+    pa.cam[ci].val = k.d_val;
+    pa.cam[ci].rowptr = k.d_rowptr;
+  }
+  if (c->ell1)
+    launch_project_ell1<4>(c, pa);
+  else
+    k_project_csr<4><<<cdiv(c->N, 256), 256, 0, c->stream>>>(pa);
+  KCHECK(c);
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
+  ENTER(c);
+  REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID,
+          "frames [%d,%d) outside the local slice of %d", off, off + count, c->F_local);
+  TRY(finalize(c));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_push, 0));
+  CU(cudaEventRecord(c->ev_pa, c->stream));
+  int done = 0;
+  while (done < count) {
+    const int o = off + done;
+    int nb = std::min(c->batch, count - done);
+    nb = std::min(nb, c->capacity - (o % c->capacity));
+    TRY(process_batch(c, o, nb));
+    done += nb;
+  }
+  CU(cudaEventRecord(c->ev_pb, c->stream));
+  CU(cudaEventRecord(c->ev_proc, c->stream));
+  c->frames_processed += count;
+  c->stage_ms[0] = -1.0f;  // resolved lazily in stage_ms (needs a sync)
+  return UPSP_OK;
+}
+
+// sum over ranks in rank order: identical bits on every rank
+__global__ void k_allreduce_peer(double* const* bases_sum, double* const* bases_sq, int n_ranks,
+                                 int n, double* out_sum, double* out_sq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < n_ranks; ++r) {
+    s += bases_sum[r][i];
+    q += bases_sq[r][i];
+  }
+  out_sum[i] = s;
+  out_sq[i] = q;
+}
+
+extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
+  ENTER(c);
+  REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
+  CU(cudaEventRecord(c->ev_a, c->stream));
+  const double *sum = c->d_sum, *sq = c->d_sumsq;
+  double *tsum = nullptr, *tsq = nullptr;
+  double** d_ptrs = nullptr;
+  if (c->R > 1) {
+    REQUIRE(c->peers_ready, UPSP_ERR_STATE,
+            "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
+    std::vector<double*> ptrs(2 * c->R);
+    for (int r = 0; r < c->R; ++r) {
+      ptrs[r] = reinterpret_cast<double*>(c->peer_base[r] + c->off_sum);
+      ptrs[c->R + r] = reinterpret_cast<double*>(c->peer_base[r] + c->off_sumsq);
+    }
+    TRY(upload(&d_ptrs, ptrs.data(), ptrs.size()));
+    TRY(dmalloc(&tsum, c->N));
+    TRY(dmalloc(&tsq, c->N));
+    k_allreduce_peer<<<cdiv(c->N, 256), 256, 0, c->stream>>>(d_ptrs, d_ptrs + c->R, c->R, c->N, tsum, tsq);
+    KCHECK(c);
+    sum = tsum;
+    sq = tsq;
+  }
+  k_phase1_finals<<<cdiv(c->N, 256), 256, 0, c->stream>>>(sum, sq, c->N, (unsigned)c->F, c->d_avg, c->d_rms);
+  KCHECK(c);
+  CU(cudaEventRecord(c->ev_b, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&c->stage_ms[1], c->ev_a, c->ev_b));
+  cudaFree(tsum);
+  cudaFree(tsq);
+  cudaFree(d_ptrs);
+  c->phase1_done = true;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_transpose(upsp_gpu_ctx* c) {
+  ENTER(c);
+  REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
+  REQUIRE(c->exchange == UPSP_XCHG_PEER, UPSP_ERR_STATE, "only UPSP_XCHG_PEER is built");
+  if (c->R > 1)
+    REQUIRE(c->peers_ready, UPSP_ERR_STATE,
+            "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
+  XposeArgs a{};
+  a.src = c->d_intensity;
+  a.rows = c->F_local;
+  a.cols = c->N;
+  a.n_ranks = c->R;
+  a.f_total = c->F;
+  a.col0 = c->f0;
+  for (int r = 0; r < c->R; ++r) {
+    a.dst[r] = reinterpret_cast<float*>(c->peer_base[r]);
+    a.node_start[r] = c->n_start[r];
+  }
+  a.node_start[c->R] = c->N;
+  CU(cudaEventRecord(c->ev_a, c->stream));
+  if (c->F_local > 0) {
+    k_transpose_a2a<<<dim3(cdiv(c->N, XT), cdiv(c->F_local, XT)), 256, 0, c->stream>>>(a);
+    KCHECK(c);
+  }
+  CU(cudaEventRecord(c->ev_b, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&c->stage_ms[2], c->ev_a, c->ev_b));
+  c->transposed = true;
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2
+// ------------------------------------------------------------------------------------------
+// inverse Gram matrix of T_k(x_f), x_f as the device computes it, in long double
+static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
+  std::vector<long double> G((size_t)nc * nc, 0.0L);
+  std::vector<long double> T(nc);
+  for (int f = 0; f < F; ++f) {
+    const float xf = fmaf((float)f, xa, xb);
+    const long double x = (long double)xf;
+    T[0] = 1.0L;
+    if (nc > 1) T[1] = x;
+    for (int k = 2; k < nc; ++k) T[k] = 2.0L * x * T[k - 1] - T[k - 2];
+    for (int i = 0; i < nc; ++i)
+      for (int j = 0; j < nc; ++j) G[(size_t)i * nc + j] += T[i] * T[j];
+  }
+  // Gauss-Jordan with partial pivoting
+  std::vector<long double> I((size_t)nc * nc, 0.0L);
+  for (int i = 0; i < nc; ++i) I[(size_t)i * nc + i] = 1.0L;
+  for (int col = 0; col < nc; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < nc; ++r)
+      if (fabsl(G[(size_t)r * nc + col]) > fabsl(G[(size_t)piv * nc + col])) piv = r;
+    if (G[(size_t)piv * nc + col] == 0.0L) continue;  // F < nc: rank deficient, leave zero rows
+    if (piv != col)
+      for (int j = 0; j < nc; ++j) {
+        std::swap(G[(size_t)piv * nc + j], G[(size_t)col * nc + j]);
+        std::swap(I[(size_t)piv * nc + j], I[(size_t)col * nc + j]);
+      }
+    const long double d = G[(size_t)col * nc + col];
+    for (int j = 0; j < nc; ++j) {
+      G[(size_t)col * nc + j] /= d;
+      I[(size_t)col * nc + j] /= d;
+    }
+    for (int r = 0; r < nc; ++r) {
+      if (r == col) continue;
+      const long double m = G[(size_t)r * nc + col];
+      if (m == 0.0L) continue;
+      for (int j = 0; j < nc; ++j) {
+        G[(size_t)r * nc + j] -= m * G[(size_t)col * nc + j];
+        I[(size_t)r * nc + j] -= m * I[(size_t)col * nc + j];
+      }
+    }
+  }
+  for (int i = 0; i < nc * nc; ++i) ginv[i] = (double)I[i];
+}
+
+template <int NC>
+static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
+  constexpr int NT = 256;
+  const size_t row_bytes = (size_t)a.F * sizeof(float);
+  const size_t smem_max = 227 * 1024 - 2048;
+  if (a.n_local == 0) return UPSP_OK;
+  if (row_bytes <= smem_max) {
+    CU(cudaFuncSetAttribute(k_phase2<NC, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)smem_max));
+    k_phase2<NC, true, NT><<<a.n_local, NT, row_bytes, st>>>(a);
+  } else {
+    k_phase2<NC, false, NT><<<a.n_local, NT, 0, st>>>(a);
+  }
+  (void)c;
+  ++*launches;
+  CU(cudaGetLastError());
+  return UPSP_OK;
+}
+
+static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
+  switch (a.ncoef) {
+    case 1: return launch_phase2<1>(c, a, st, launches);
+    case 2: return launch_phase2<2>(c, a, st, launches);
+    case 3: return launch_phase2<3>(c, a, st, launches);
+    case 4: return launch_phase2<4>(c, a, st, launches);
+    case 5: return launch_phase2<5>(c, a, st, launches);
+    case 6: return launch_phase2<6>(c, a, st, launches);
+    case 7: return launch_phase2<7>(c, a, st, launches);
+    case 8: return launch_phase2<8>(c, a, st, launches);
+    case 9: return launch_phase2<9>(c, a, st, launches);
+  }
+  return fail(UPSP_ERR_INVALID, "detrend degree %d not in [0,%d]", a.ncoef - 1, UPSP_MAX_COEF - 1);
+}
+
+static void fill_basis(Phase2Args& a, int F, int degree) {
+  a.F = F;
+  a.ncoef = degree + 1;
+  a.xa = 2.0f / (float)F;
+  a.xb = (1.0f - (float)F) / (float)F;
+  cheb_ginv(F, a.ncoef, a.xa, a.xb, a.ginv);
+}
+
+extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, const float* steady,
+                               const float* model_temp) {
+  ENTER(c);
+  REQUIRE(p && steady && model_temp, UPSP_ERR_INVALID, "null argument");
+  REQUIRE(c->phase1_done && c->transposed, UPSP_ERR_STATE,
+          "phase2 needs finish_phase1 and transpose first");
+  REQUIRE(p->degree >= 0 && p->degree < UPSP_MAX_COEF, UPSP_ERR_INVALID, "degree %d", p->degree);
+  CU(cudaMemcpyAsync(c->d_steady, steady, (size_t)c->N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_temp, model_temp, (size_t)c->N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  Phase2Args a{};
+  a.itrans = c->d_itrans;
+  a.ptrans = c->d_ptrans;
+  a.n_local = c->N_local;
+  a.node0 = c->n0;
+  a.avg = c->d_avg;
+  a.coverage = c->d_cov;
+  a.steady = c->d_steady;
+  a.temp = c->d_temp;
+  memcpy(a.cal, p->paint_cal, sizeof a.cal);
+  a.qbar = p->qbar;
+  a.ps = p->ps;
+  fill_basis(a, c->F, p->degree);
+  a.rms = c->d_rms2;
+  a.avgp = c->d_avg2;
+  a.gain = c->d_gain2;
+  a.fit_out = nullptr;
+  CU(cudaEventRecord(c->ev_a, c->stream));
+  TRY(dispatch_phase2(c, a, c->stream, &c->launches));
+  if (c->N_local) {
+    k_phase2_finals<<<cdiv(c->N_local, 256), 256, 0, c->stream>>>(
+        c->d_rms2, c->d_avg2, c->d_gain2, c->N_local, (unsigned)c->F, c->d_rms2f, c->d_avg2f, c->d_gain2f);
+    KCHECK(c);
+  }
+  CU(cudaEventRecord(c->ev_b, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&c->stage_ms[3], c->ev_a, c->ev_b));
+  c->phase2_done = true;
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------
+extern "C" int upsp_gpu_sync(upsp_gpu_ctx* c) {
+  ENTER(c);
+  CU(cudaStreamSynchronize(c->copy_stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return UPSP_OK;
+}
+
+static int d2h(upsp_gpu_ctx* c, void* host, const void* dev, size_t bytes) {
+  CU(cudaStreamSynchronize(c->stream));
+  if (bytes) CU(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_read_intensity(upsp_gpu_ctx* c, int off, int n, float* host) {
+  ENTER(c);
+  REQUIRE(off >= 0 && n >= 0 && off + n <= c->F_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
+  REQUIRE(!(c->phase2_done && !c->ptrans_owned), UPSP_ERR_STATE,
+          "frame-major intensity was overwritten by pressure_transpose (pressure_aliases_intensity)");
+  return d2h(c, host, c->d_intensity + (size_t)off * c->N, (size_t)n * c->N * sizeof(float));
+}
+
+extern "C" int upsp_gpu_read_intensity_transpose(upsp_gpu_ctx* c, int off, int n, float* host) {
+  ENTER(c);
+  REQUIRE(off >= 0 && n >= 0 && off + n <= c->N_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
+  REQUIRE(c->transposed, UPSP_ERR_STATE, "transpose first");
+  return d2h(c, host, c->d_itrans + (size_t)off * c->F, (size_t)n * c->F * sizeof(float));
+}
+
+extern "C" int upsp_gpu_read_pressure_transpose(upsp_gpu_ctx* c, int off, int n, float* host) {
+  ENTER(c);
+  REQUIRE(off >= 0 && n >= 0 && off + n <= c->N_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
+  REQUIRE(c->phase2_done, UPSP_ERR_STATE, "phase2 first");
+  return d2h(c, host, c->d_ptrans + (size_t)off * c->F, (size_t)n * c->F * sizeof(float));
+}
+
+extern "C" int upsp_gpu_read_phase1_stats(upsp_gpu_ctx* c, float* avg, float* rms, float* cov) {
+  ENTER(c);
+  REQUIRE(c->phase1_done, UPSP_ERR_STATE, "finish_phase1 first");
+  if (avg) TRY(d2h(c, avg, c->d_avg, (size_t)c->N * sizeof(float)));
+  if (rms) TRY(d2h(c, rms, c->d_rms, (size_t)c->N * sizeof(float)));
+  if (cov) TRY(d2h(c, cov, c->d_cov, (size_t)c->N * sizeof(float)));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_read_phase2_stats(upsp_gpu_ctx* c, float* rms, float* avg, float* gain) {
+  ENTER(c);
+  REQUIRE(c->phase2_done, UPSP_ERR_STATE, "phase2 first");
+  if (rms) TRY(d2h(c, rms, c->d_rms2f, (size_t)c->N_local * sizeof(float)));
+  if (avg) TRY(d2h(c, avg, c->d_avg2f, (size_t)c->N_local * sizeof(float)));
+  if (gain) TRY(d2h(c, gain, c->d_gain2f, (size_t)c->N_local * sizeof(float)));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_read_warp_matrices(upsp_gpu_ctx* c, int cam, int off, int count, float* m6,
+                                           float* rho, int* iters) {
+  ENTER(c);
+  CAM_CHECK(c, cam);
+  Camera& k = c->cams[cam];
+  REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID, "bad range");
+  REQUIRE(k.d_m6, UPSP_ERR_STATE, "camera %d has no warp matrices", cam);
+  if (m6) TRY(d2h(c, m6, k.d_m6 + (size_t)off * 6, (size_t)count * 6 * sizeof(float)));
+  if (rho) {
+    REQUIRE(k.d_rho, UPSP_ERR_STATE, "no ECC results");
+    TRY(d2h(c, rho, k.d_rho + off, (size_t)count * sizeof(float)));
+  }
+  if (iters) {
+    REQUIRE(k.d_iters, UPSP_ERR_STATE, "no ECC results");
+    TRY(d2h(c, iters, k.d_iters + off, (size_t)count * sizeof(int)));
+  }
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_stage_ms(upsp_gpu_ctx* c, int stage, float* ms) {
+  ENTER(c);
+  REQUIRE(stage >= 0 && stage < 4 && ms, UPSP_ERR_INVALID, "stage %d", stage);
+  if (stage == 0 && c->stage_ms[0] < 0.0f) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->stage_ms[0], c->ev_pa, c->ev_pb));
+  }
+  *ms = c->stage_ms[stage];
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_reset_timers(upsp_gpu_ctx* c) {
+  ENTER(c);
+  for (float& m : c->stage_ms) m = 0.0f;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_launch_count(const upsp_gpu_ctx* c, long long* n) {
+  REQUIRE(c && n, UPSP_ERR_INVALID, "null argument");
+  *n = c->launches;
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU wiring
+// ------------------------------------------------------------------------------------------
+extern "C" int upsp_gpu_ipc_export(upsp_gpu_ctx* c, void* handle) {
+  ENTER(c);
+  REQUIRE(handle, UPSP_ERR_INVALID, "null handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == UPSP_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, c->d_shared);
+  REQUIRE(e == cudaSuccess, UPSP_ERR_COMM, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  memcpy(handle, &h, sizeof h);
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_ipc_import(upsp_gpu_ctx* c, const void* handles) {
+  ENTER(c);
+  REQUIRE(handles, UPSP_ERR_INVALID, "null handles");
+  for (int r = 0; r < c->R; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * UPSP_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    REQUIRE(e == cudaSuccess, UPSP_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+    c->peer_base[r] = (char*)p;
+    c->peer_is_ipc[r] = true;
+  }
+  c->peers_ready = true;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_connect_local(upsp_gpu_ctx** ctxs, int n) {
+  REQUIRE(ctxs && n >= 1, UPSP_ERR_INVALID, "bad argument");
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(ctxs[i] && ctxs[i]->R == n && ctxs[i]->rank == i, UPSP_ERR_INVALID,
+            "context %d must be rank %d of %d", i, i, n);
+  }
+  for (int i = 0; i < n; ++i) {
+    CU(cudaSetDevice(ctxs[i]->cfg.device));
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      if (ctxs[i]->cfg.device != ctxs[j]->cfg.device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ctxs[i]->cfg.device, ctxs[j]->cfg.device));
+        REQUIRE(can, UPSP_ERR_COMM, "device %d cannot access device %d", ctxs[i]->cfg.device,
+                ctxs[j]->cfg.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->cfg.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else REQUIRE(e == cudaSuccess, UPSP_ERR_COMM, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      }
+      ctxs[i]->peer_base[j] = ctxs[j]->d_shared;
+    }
+    ctxs[i]->peers_ready = true;
+  }
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_exchange(upsp_gpu_ctx* c, int exchange) {
+  ENTER(c);
+  REQUIRE(exchange == UPSP_XCHG_PEER, UPSP_ERR_INVALID,
+          "exchange %d: only UPSP_XCHG_PEER (fused transpose + peer stores) is built", exchange);
+  c->exchange = exchange;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_nccl_unique_id(void* id) {
+  (void)id;
+  return fail(UPSP_ERR_COMM, "NCCL exchange is not built in this round; use UPSP_XCHG_PEER");
+}
+extern "C" int upsp_gpu_nccl_init(upsp_gpu_ctx* c, const void* id) {
+  (void)c;
+  (void)id;
+  return fail(UPSP_ERR_COMM, "NCCL exchange is not built in this round; use UPSP_XCHG_PEER");
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone operators
+// ------------------------------------------------------------------------------------------
+struct DevScope {
+  int dev;
+  std::vector<void*> bufs;
+  explicit DevScope(int d) : dev(d) {}
+  ~DevScope() {
+    for (void* p : bufs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    int rc = dmalloc(p, n);
+    if (!rc) bufs.push_back((void*)*p);
+    return rc;
+  }
+  template <typename T>
+  int put(T** p, const T* h, size_t n) {
+    TRY(alloc(p, n));
+    if (n) CU(cudaMemcpy(*p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return UPSP_OK;
+  }
+};
+#define OP_ENTER(device)                                                                \
+  {                                                                                     \
+    int nd_ = upsp_gpu_device_count();                                                  \
+    REQUIRE(nd_ > 0, UPSP_ERR_CUDA, "no usable CUDA device; libupsp_gpu has no CPU fallback"); \
+    REQUIRE((device) >= 0 && (device) < nd_, UPSP_ERR_INVALID, "device %d of %d", device, nd_); \
+    CU(cudaSetDevice(device));                                                          \
+  }                                                                                     \
+  DevScope S(device)
+
+extern "C" int upsp_op_unpack(int device, const uint8_t* packed, int format, size_t npix,
+                              const uint16_t* lut, uint16_t* out) {
+  OP_ENTER(device);
+  REQUIRE(packed && out && npix > 0, UPSP_ERR_INVALID, "null/empty argument");
+  REQUIRE(format == UPSP_PIX_PACKED12 || format == UPSP_PIX_PACKED10, UPSP_ERR_INVALID, "format %d", format);
+  REQUIRE(npix % (format == UPSP_PIX_PACKED12 ? 2 : 4) == 0, UPSP_ERR_INVALID, "pixel count %zu", npix);
+  const size_t nbytes = frame_bytes_of(format, npix);
+  uint8_t* d_in;
+  uint16_t *d_out, *d_lut = nullptr;
+  int *d_cnt, *d_pos;
+  TRY(S.put(&d_in, packed, nbytes));
+  TRY(S.alloc(&d_out, npix));
+  TRY(S.alloc(&d_cnt, 1));
+  TRY(S.alloc(&d_pos, UPSP_HOT_STORE));
+  if (lut) TRY(S.put(&d_lut, lut, 1024));
+  CU(cudaMemset(d_cnt, 0, sizeof(int)));
+  if (format == UPSP_PIX_PACKED12)
+    k_unpack12_scan<<<dim3(cdiv(cdiv(npix, 8), 256), 1), 256>>>(d_in, nbytes, d_out, npix, 0x7fffffff, d_cnt, d_pos);
+  else
+    k_unpack10_scan<<<dim3(cdiv(cdiv(npix, 4), 256), 1), 256>>>(d_in, nbytes, d_out, npix, d_lut, 0x7fffffff, d_cnt, d_pos);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d_out, npix * 2, cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_fix_hot_pixels(int device, uint16_t* frames, int nf, int rows, int cols, int* n_hot) {
+  OP_ENTER(device);
+  REQUIRE(frames && nf > 0 && rows > 0 && cols > 0, UPSP_ERR_INVALID, "null/empty argument");
+  const size_t npix = (size_t)rows * cols;
+  uint16_t *d_in, *d_out;
+  int *d_cnt, *d_pos;
+  TRY(S.put(&d_in, frames, npix * nf));
+  TRY(S.alloc(&d_out, npix * nf));
+  TRY(S.alloc(&d_cnt, nf));
+  TRY(S.alloc(&d_pos, (size_t)nf * UPSP_HOT_STORE));
+  CU(cudaMemset(d_cnt, 0, sizeof(int) * nf));
+  k_copy16_scan<<<dim3(cdiv(cdiv(npix, 8), 256), nf), 256>>>(d_in, npix, d_out, npix, UPSP_HOT_THRESH, d_cnt, d_pos);
+  CU(cudaGetLastError());
+  k_fix_hot<<<cdiv(nf, 32), 32>>>(d_out, npix, rows, cols, nf, d_cnt, d_pos, UPSP_HOT_MIN_CHANGE, UPSP_HOT_MAX);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(frames, d_out, npix * nf * 2, cudaMemcpyDeviceToHost));
+  if (n_hot) {
+    std::vector<int> cnt(nf);
+    CU(cudaMemcpy(cnt.data(), d_cnt, sizeof(int) * nf, cudaMemcpyDeviceToHost));
+    for (int f = 0; f < nf; ++f) n_hot[f] = cnt[f] > UPSP_HOT_MAX ? -1 : cnt[f];
+  }
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_warp_affine(int device, const uint16_t* src, int nf, int W, int H,
+                                   const float* m6, int interp, uint16_t* dst) {
+  OP_ENTER(device);
+  REQUIRE(src && dst && m6 && nf > 0 && W > 0 && H > 0, UPSP_ERR_INVALID, "null/empty argument");
+  REQUIRE(interp == 0 || interp == 1, UPSP_ERR_INVALID, "interp %d", interp);
+  const size_t npix = (size_t)W * H;
+  uint16_t *d_src, *d_dst;
+  float* d_m;
+  int* d_tab;
+  TRY(S.put(&d_src, src, npix * nf));
+  TRY(S.alloc(&d_dst, npix * nf));
+  TRY(S.put(&d_m, m6, (size_t)nf * 6));
+  TRY(S.alloc(&d_tab, (size_t)nf * (2 * W + 2 * H)));
+  k_warp_tables<<<dim3(cdiv(std::max(W, H), 256), nf), 256>>>(d_m, nf, W, H, interp, d_tab);
+  CU(cudaGetLastError());
+  k_warp_affine_u16<<<dim3(cdiv(W, 128), cdiv(H, 4), nf), dim3(64, 4)>>>(d_src, d_dst, W, H, d_tab, interp, -1);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dst, d_dst, npix * nf * 2, cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_project_frames(int device, const int32_t* rowptr, const int32_t* col,
+                                      const float* val, int n_rows, const float* frames, int nf,
+                                      size_t npix, float* out) {
+  OP_ENTER(device);
+  REQUIRE(rowptr && frames && out && n_rows > 0 && nf > 0 && npix > 0, UPSP_ERR_INVALID, "null/empty argument");
+  const int nnz = rowptr[n_rows];
+  for (int i = 0; i < nnz; ++i)
+    REQUIRE(col[i] >= 0 && (size_t)col[i] < npix, UPSP_ERR_INVALID, "column %d outside the frame", col[i]);
+  int *d_rp, *d_col;
+  float *d_val, *d_fr, *d_out;
+  TRY(S.put(&d_rp, rowptr, (size_t)n_rows + 1));
+  TRY(S.put(&d_col, col, (size_t)nnz));
+  TRY(S.put(&d_val, val, (size_t)nnz));
+  TRY(S.put(&d_fr, frames, npix * nf));
+  TRY(S.alloc(&d_out, (size_t)n_rows * nf));
+  k_project_f32<<<dim3(cdiv(n_rows, 256), nf), 256>>>(d_rp, d_col, d_val, n_rows, d_fr, npix, d_out);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d_out, (size_t)n_rows * nf * sizeof(float), cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_transpose(int device, const float* src, int x_extent, int y_extent, float* dst) {
+  OP_ENTER(device);
+  REQUIRE(src && dst && x_extent > 0 && y_extent > 0, UPSP_ERR_INVALID, "null/empty argument");
+  float *d_src, *d_dst;
+  const size_t n = (size_t)x_extent * y_extent;
+  TRY(S.put(&d_src, src, n));
+  TRY(S.alloc(&d_dst, n));
+  XposeArgs a{};
+  a.src = d_src;
+  a.rows = y_extent;
+  a.cols = x_extent;
+  a.n_ranks = 1;
+  a.f_total = y_extent;
+  a.col0 = 0;
+  a.dst[0] = d_dst;
+  a.node_start[0] = 0;
+  a.node_start[1] = x_extent;
+  k_transpose_a2a<<<dim3(cdiv(x_extent, XT), cdiv(y_extent, XT)), 256>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dst, d_dst, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_polyfit_detrend(int device, const float* data, int n_pts, int n_frames,
+                                       int degree, float* fit) {
+  OP_ENTER(device);
+  REQUIRE(data && fit && n_pts > 0 && n_frames > 0, UPSP_ERR_INVALID, "null/empty argument");
+  REQUIRE(degree >= 0 && degree < UPSP_MAX_COEF, UPSP_ERR_INVALID, "degree %d", degree);
+  float *d_data, *d_fit;
+  const size_t n = (size_t)n_pts * n_frames;
+  TRY(S.put(&d_data, data, n));
+  TRY(S.alloc(&d_fit, n));
+  Phase2Args a{};
+  a.itrans = d_data;
+  a.ptrans = d_fit;
+  a.fit_out = d_fit;
+  a.n_local = n_pts;
+  fill_basis(a, n_frames, degree);
+  long long l = 0;
+  TRY(dispatch_phase2(nullptr, a, 0, &l));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(fit, d_fit, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}

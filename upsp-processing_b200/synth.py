@@ -1,0 +1,164 @@
+"""Synthetic workloads for tests and bench: 12-bit cine-like frames, a
+one-nearest-pixel-per-node projection matrix, fiducial patch clusters, P3D-style seam
+overlaps, tunnel conditions.  Pure numpy; seeded; no reference code involved."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def make_frames(n_frames, height, width, seed=0, hot_frames=0.25, jitter=True, noise=8.0):
+    """u16 [F,H,W]: 1800 + 600 sin(x/37) cos(y/53) + 300 gauss blob + N(0,noise), slow drift
+    over the run (so the detrend has something to remove), optional sub-pixel affine jitter
+    per frame, <= 5 injected hot pixels (4095) in a fraction of the frames.
+    Returns (frames, true_shift[F,2])."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width].astype(np.float32)
+    cx, cy = 0.55 * width, 0.45 * height
+    frames = np.empty((n_frames, height, width), np.uint16)
+    shifts = np.zeros((n_frames, 2), np.float32)
+    for f in range(n_frames):
+        dx, dy = (rng.uniform(-1, 1, 2) if (jitter and f > 0) else (0.0, 0.0))
+        shifts[f] = (dx, dy)
+        xs, ys = x + dx, y + dy
+        t = f / max(n_frames, 1)
+        base = (1800.0 + 600.0 * np.sin(xs / 37.0) * np.cos(ys / 53.0)
+                + 300.0 * np.exp(-(((xs - cx) / (0.2 * width)) ** 2 + ((ys - cy) / (0.2 * height)) ** 2)))
+        base *= (1.0 + 0.03 * np.sin(2.0 * np.pi * t) + 0.02 * t)
+        img = base + rng.normal(0.0, noise, base.shape)
+        frames[f] = np.clip(np.rint(img), 0, 4095).astype(np.uint16)
+        if rng.random() < hot_frames:
+            k = int(rng.integers(1, 6))
+            frames[f].reshape(-1)[rng.integers(0, height * width, k)] = 4095
+    return frames, shifts
+
+
+def make_projection(n_nodes, height, width, kind="surface", seed=1, skipped_frac=0.02,
+                    weights=False):
+    """CSR (rowptr, col, val) with <= 1 entry per row, col = y*W+x, val = 1 (or a camera
+    weight in (0,1]).  kind="surface": node order follows image raster order with local
+    scatter (mesh-like locality, ~1 node per pixel neighbourhood); kind="random": uniformly
+    random pixels (worst-case gather)."""
+    rng = np.random.default_rng(seed)
+    npix = height * width
+    seen = rng.random(n_nodes) >= skipped_frac
+    if kind == "random":
+        cols = rng.integers(0, npix, n_nodes)
+    else:
+        base = np.sort(rng.integers(0, npix, n_nodes))
+        dx = rng.integers(-3, 4, n_nodes)
+        dy = rng.integers(-3, 4, n_nodes)
+        yy = np.clip(base // width + dy, 0, height - 1)
+        xx = np.clip(base % width + dx, 0, width - 1)
+        cols = yy * width + xx
+    rowptr = np.zeros(n_nodes + 1, np.int32)
+    rowptr[1:] = np.cumsum(seen)
+    col = cols[seen].astype(np.int32)
+    val = (rng.uniform(0.2, 1.0, col.size).astype(np.float32) if weights
+           else np.ones(col.size, np.float32))
+    return rowptr, col, val
+
+
+def make_multi_nnz_projection(n_nodes, height, width, nnz_per_row=4, seed=2):
+    """cfg-5 variant: several weighted pixels per node (filter-folded stencil)."""
+    rng = np.random.default_rng(seed)
+    npix = height * width
+    counts = rng.integers(0, nnz_per_row + 1, n_nodes)
+    rowptr = np.zeros(n_nodes + 1, np.int32)
+    rowptr[1:] = np.cumsum(counts)
+    nnz = int(rowptr[-1])
+    centre = np.repeat(rng.integers(0, npix, n_nodes), counts)
+    col = np.clip(centre + rng.integers(-2, 3, nnz) + width * rng.integers(-2, 3, nnz), 0, npix - 1)
+    val = rng.uniform(0.05, 0.6, nnz).astype(np.float32)
+    return rowptr, col.astype(np.int32), val
+
+
+def make_patches(height, width, n_targets=12, seed=3, bound_pts=2, buffer=1, half=3,
+                 overlap_pair=False):
+    """Single-target clusters laid out like get_target_boundary (cpp/lib/patches.ipp:290-327):
+    interior = the target's bounding box, boundary = a `bound_pts`-thick frame `buffer` pixels
+    outside it, both enumerated x-outer / y-inner and clipped to the frame.
+    overlap_pair adds a cluster whose boundary frame crosses an earlier cluster's interior
+    (exercises the in-order dependency between clusters).
+    Returns (bounds, internal): lists over clusters of (x[], y[])."""
+    rng = np.random.default_rng(seed)
+    centres = []
+    tries = 0
+    margin = half + bound_pts + buffer + 2
+    while len(centres) < n_targets and tries < 10000:
+        tries += 1
+        c = (int(rng.integers(margin, width - margin)), int(rng.integers(margin, height - margin)))
+        if all(abs(c[0] - o[0]) > 4 * margin or abs(c[1] - o[1]) > 4 * margin for o in centres):
+            centres.append(c)
+    if overlap_pair and centres:
+        c0 = centres[0]
+        centres.append((min(c0[0] + half + buffer + 2, width - 2), c0[1]))
+    # one target hugging the frame edge (clipping path)
+    centres.append((1, height // 2))
+    bounds, internal = [], []
+    for (cx, cy) in centres:
+        x0, x1, y0, y1 = cx - half, cx + half, cy - half, cy + half
+        ix, iy, bx, by = [], [], [], []
+        for x in range(x0, x1 + 1):
+            for y in range(y0, y1 + 1):
+                if 0 <= x < width and 0 <= y < height:
+                    ix.append(x)
+                    iy.append(y)
+        o = bound_pts + buffer
+        for x in range(x0 - o, x1 + o + 1):
+            for y in range(y0 - o, y1 + o + 1):
+                if (x < x0 - buffer or x > x1 + buffer or y < y0 - buffer or y > y1 + buffer):
+                    if 0 <= x < width and 0 <= y < height:
+                        bx.append(x)
+                        by.append(y)
+        bounds.append((np.array(bx, np.uint32), np.array(by, np.uint32)))
+        internal.append((np.array(ix, np.uint32), np.array(iy, np.uint32)))
+    return bounds, internal
+
+
+def flatten_patches(bounds, internal):
+    """-> (bounds_off, bx, by, internal_off, ix, iy) as upsp_gpu_set_patches wants them."""
+    n = len(bounds)
+    bo = np.zeros(n + 1, np.int32)
+    io = np.zeros(n + 1, np.int32)
+    for i in range(n):
+        bo[i + 1] = bo[i] + len(bounds[i][0])
+        io[i + 1] = io[i] + len(internal[i][0])
+    cat = lambda l, k: (np.concatenate([a[k] for a in l]).astype(np.uint32) if n else np.zeros(0, np.uint32))
+    return bo, cat(bounds, 0), cat(bounds, 1), io, cat(internal, 0), cat(internal, 1)
+
+
+def make_overlap(n_nodes, n_groups=50, seed=4):
+    """P3D seam overlap groups: {curr: [alt, ...]} as P3DModel_::overlap_pts_ holds them
+    (symmetric, pairwise)."""
+    rng = np.random.default_rng(seed)
+    ov = {}
+    for _ in range(n_groups):
+        k = int(rng.integers(2, 4))
+        grp = [int(v) for v in rng.choice(n_nodes, k, replace=False)]
+        for a in grp:
+            ov.setdefault(a, [])
+            for b in grp:
+                if b != a and b not in ov[a]:
+                    ov[a].append(b)
+    return ov
+
+
+def make_warps(n_frames, seed=5, trans=1.0, lin=5e-4):
+    """Per-frame inverse affine maps near identity: translation within +-trans px, linear part
+    within +-lin of identity.  f32 [F,6] row-major 2x3."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((n_frames, 2, 3), np.float32)
+    m[:, 0, 0] = m[:, 1, 1] = 1.0
+    m[:, :, :2] += rng.uniform(-lin, lin, (n_frames, 2, 2)).astype(np.float32)
+    m[:, :, 2] = rng.uniform(-trans, trans, (n_frames, 2)).astype(np.float32)
+    return m.reshape(n_frames, 6)
+
+
+def tunnel_conditions(n_nodes, seed=6):
+    """paint cal (a..f), qbar, ps, steady-state Cp [N], model temperature [N] (degF)."""
+    rng = np.random.default_rng(seed)
+    cal = np.array([0.62, -1.3e-3, 2.1e-6, 2.4e-4, 3.0e-7, -1.1e-9], np.float32)
+    qbar, ps = np.float32(251.3), np.float32(1456.8)
+    steady = rng.uniform(-1.2, 0.9, n_nodes).astype(np.float32)
+    temp = (68.0 + rng.normal(0, 1.5, n_nodes)).astype(np.float32)
+    return cal, qbar, ps, steady, temp
