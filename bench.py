@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- cine -> surface delta-Cp throughput of the psp_process frame chain on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one whole psp_process job of BASELINE.json's configs[1] per GPU: 1 camera,
+1024x1024 12-bit packed frames, 20 000 frames per GPU onto a 500 000-node grid
+(weak scaling: F_total = 20 000 x N GPUs, nodes fixed): decode, hot-pixel fix, affine warp
+(registration result supplied; the ECC solve is not part of either arm), fiducial patch,
+projection, sum/sum-sq, frame-major -> node-major transpose (all-to-all when N > 1), detrend +
+gain + delta-Cp.  One JSON line on stdout (rank 0).
+
+  value   : frames/s with the packed frames already resident in HBM (device time, CUDA events
+            on the library's stream, max over ranks)
+  e2e     : frames/s through the C ABI with HOST buffers: pinned-host packed frames H2D every
+            step, intensity_transpose + pressure_transpose D2H every step
+  roofline: dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline: the CPU oracle (C port of the reference's algorithm, all host threads) on a
+            bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(height=1024, width=1024, frames_per_gpu=20000, nodes=500_000, cams=1, targets=32,
+           distinct_frames=128, degree=6)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def build_workload(args, synth):
+    H, W, N = args.height, args.width, args.nodes
+    t0 = time.time()
+    frames = synth.make_frames_fast(args.distinct, H, W, seed=1)
+    packed = synth.pack_12bit(frames.reshape(args.distinct, -1))
+    csr = synth.make_projection(N, H, W, kind=args.csr, seed=1)
+    bounds, internal = synth.make_patches(H, W, n_targets=args.targets, seed=3)
+    patches = synth.flatten_patches(bounds, internal)
+    cal, qbar, ps, steady, temp = synth.tunnel_conditions(N)
+    log(f"[bench] workload built in {time.time() - t0:.1f}s: {args.distinct} distinct frames {H}x{W}, "
+        f"N={N}, nnz={csr[1].size}, clusters={len(bounds)}")
+    return dict(frames=frames, packed=packed, csr=csr, patches=patches, cal=cal, qbar=qbar, ps=ps,
+                steady=steady, temp=temp)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        hi = [x for x in sm if x >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    """torch.distributed is plumbing only: handle exchange + barriers."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        return rank, world, local, dist
+    if n_gpus > 1:
+        log("[bench] --gpus > 1 needs torchrun (one process per GPU); running rank 0 of 1")
+    return 0, 1, 0, None
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def allmax(dist, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def configure(up, wl, args, rank, world, local, capacity, dist):
+    F_total = args.frames * world
+    g = up.PspGpu(1, args.nodes, F_total, device=local, rank=rank, n_ranks=world,
+                  frame_capacity=capacity, batch_frames=args.batch)
+    g.set_camera(0, args.width, args.height)
+    g.set_projection(0, *wl["csr"])
+    reg = up.REG_GIVEN if args.registration == "given" else up.REG_NONE
+    g.set_options(registration=reg, interp=up.INTERP_LINEAR,
+                  patcher=up.PATCH_POLYNOMIAL if args.targets else up.PATCH_NONE)
+    if args.targets:
+        g.set_patches(0, *wl["patches"])
+    if reg == up.REG_GIVEN:
+        from upsp_b200 import synth
+        g.set_warp_matrices(0, 0, synth.make_warps(g.n_frames, seed=5 + rank))
+    if world > 1:
+        import torch
+        h = torch.frombuffer(bytearray(g.ipc_export()), dtype=torch.uint8).clone()
+        allh = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(allh, h)
+        g.ipc_import(b"".join(bytes(x.numpy().tobytes()) for x in allh))
+    return g
+
+
+def run_step_resident(g, wl, args, dist):
+    g.reset_run()
+    g.process_frames(0, g.n_frames)
+    if dist is not None:
+        g.sync()
+        barrier(dist)            # MPI_Barrier before the reduce (psp_process.cpp:1859)
+    g.finish_phase1()
+    g.transpose()
+    if dist is not None:
+        barrier(dist)            # psp_process.cpp:2034-2035
+    g.phase2(wl["cal"], wl["qbar"], wl["ps"], wl["steady"], wl["temp"], args.degree)
+
+
+def bench_b200(args):
+    import upsp_b200 as up
+    from upsp_b200 import synth
+    up.build.build()
+    rank, world, local, dist = dist_setup(args.gpus)
+    if up.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible (there is no CPU fallback)")
+    wl = build_workload(args, synth)
+    P = args.height * args.width
+    N = args.nodes
+    F_local = args.frames
+    F_total = F_local * world
+
+    # ---------------- device-resident arm
+    g = configure(up, wl, args, rank, world, local, 0, dist)
+    D = args.distinct
+    for o in range(0, g.n_frames, D):
+        n = min(D, g.n_frames - o)
+        g.push_frames(0, wl["packed"][:n], up.PIX_PACKED12, o, n)
+    g.sync()
+    for _ in range(args.warmup):
+        run_step_resident(g, wl, args, dist)
+    g.sync()
+    barrier(dist)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = g.launch_count()
+    stage = np.zeros(4)
+    g.timer_start()
+    t_wall = time.time()
+    for _ in range(args.steps):
+        run_step_resident(g, wl, args, dist)
+        stage += [g.stage_ms(i) for i in range(4)]
+    ms_dev = g.timer_stop()
+    g.sync()
+    barrier(dist)
+    wall_ms = (time.time() - t_wall) * 1e3
+    clocks = sampler.stop() if sampler else None
+    launches = g.launch_count() - l0
+    ms_dev = allmax(dist, ms_dev)
+    stage /= args.steps
+    stage = np.array([allmax(dist, float(s)) for s in stage])
+    value = F_total * args.steps / (ms_dev * 1e-3)
+    g.close()
+    del g
+
+    # ---------------- end-to-end arm (host buffers through the C ABI)
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = bench_e2e(up, wl, args, rank, world, local, dist)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # dominant stage kernel and its algorithmic bytes per launch (DESIGN.md "algorithmic bytes")
+    names = ["process_frames(K0-K5)", "finish_phase1", "k_transpose_a2a", "k_phase2"]
+    alg = [(1.5 * P + 4.0 * N) * F_local, 24.0 * N, 8.0 * N * F_local, 8.0 * (N / world) * F_total]
+    dom = int(np.argmax(stage))
+    achieved = alg[dom] / (stage[dom] * 1e-3) / 1e9
+    chain_bytes = (1.5 * P + 20.0 * N) * F_local
+    chain_gbs = chain_bytes / (ms_dev / args.steps * 1e-3) / 1e9
+    out = {
+        "metric": "frames/sec cine->surface Cp", "value": round(value, 1), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (u16 pixels, f64 accumulators)", "data": "synthetic",
+        "config": {"workload": f"configs[1]: 1 camera {args.height}x{args.width} 12-bit packed, "
+                               f"{F_local} frames/GPU onto {N}-node grid",
+                   "frames_total": F_total, "nodes": N, "registration": args.registration,
+                   "patch_clusters": args.targets + 1 if args.targets else 0, "csr": args.csr,
+                   "detrend_degree": args.degree, "batch_frames": args.batch,
+                   "l2": "inputs (31 GB packed frames, 40 GB intensity) far exceed the 126 MB L2"},
+        "stage_ms": {n: round(float(s), 3) for n, s in zip(names, stage)},
+        "chain": {"algorithmic_bytes_per_frame": 1.5 * P + 20.0 * N, "achieved_gbs": round(chain_gbs, 1),
+                  "frac_of_peak": round(chain_gbs / peak, 4)},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg[dom]},
+        "gpu_launches": int(launches), "wall_ms_per_step": round(wall_ms / args.steps, 3),
+        "clocks": clocks, "e2e": e2e,
+    }
+    if args.cpu_seconds > 0:
+        out["cpu_baseline"] = cpu_baseline(args, wl, budget_s=args.cpu_seconds)
+    print(json.dumps(out), flush=True)
+
+
+def bench_e2e(up, wl, args, rank, world, local, dist):
+    """Same job, host buffers: every step pushes all packed frames from pinned host memory
+    (H2D overlapped with processing through the library's copy stream) and reads
+    intensity_transpose and pressure_transpose back to pinned host memory."""
+    import torch
+    N, F_local = args.nodes, args.frames
+    F_total = F_local * world
+    chunk = args.distinct
+    g = configure(up, wl, args, rank, world, local, 2 * chunk, dist)
+    fb = wl["packed"].shape[1]
+    pin_in = torch.empty((chunk, fb), dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[:] = wl["packed"][:chunk]
+    rows = max(1, min(g.n_local_nodes, (256 << 20) // (F_total * 4)))     # 256 MB D2H staging
+    pin_out = torch.empty((rows, F_total), dtype=torch.float32, pin_memory=True)
+
+    def step():
+        g.reset_run()
+        for o in range(0, g.n_frames, chunk):
+            n = min(chunk, g.n_frames - o)
+            g.push_frames(0, pin_in.data_ptr(), up.PIX_PACKED12, o, n)
+            g.process_frames(o, n)
+        if dist is not None:
+            g.sync()
+            barrier(dist)
+        g.finish_phase1()
+        g.transpose()
+        if dist is not None:
+            barrier(dist)
+        for o in range(0, g.n_local_nodes, rows):
+            g.read_raw("intensity_transpose", o, min(rows, g.n_local_nodes - o), pin_out.data_ptr())
+        g.phase2(wl["cal"], wl["qbar"], wl["ps"], wl["steady"], wl["temp"], args.degree)
+        for o in range(0, g.n_local_nodes, rows):
+            g.read_raw("pressure_transpose", o, min(rows, g.n_local_nodes - o), pin_out.data_ptr())
+
+    step()                                   # warm-up
+    g.sync()
+    barrier(dist)
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step()
+    g.sync()
+    barrier(dist)
+    dt = allmax(dist, time.perf_counter() - t0)
+    g.close()
+    return {"value": round(F_total * args.e2e_steps / dt, 1), "unit": "frames/s",
+            "h2d_bytes_per_step": int(fb) * F_local * world,
+            "d2h_bytes_per_step": 2 * 4 * N * F_total, "steps": args.e2e_steps,
+            "ms_per_step": round(dt / args.e2e_steps * 1e3, 1),
+            "note": "H2D of packed 12-bit frames from pinned host memory + D2H of intensity_transpose "
+                    "and pressure_transpose (the two flat files the reference writes) inside the timed region"}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_job(orc, wl, args, n_frames):
+    """The reference's algorithm (CPU oracle port, OpenMP over frames / nodes like the
+    reference) on the first n_frames frames of the same workload.  Returns seconds per stage."""
+    from upsp_b200 import synth
+    frames = wl["frames"]
+    idx = np.arange(n_frames) % frames.shape[0]
+    fr = frames[idx]
+    bo, bx, by, io, ix, iy = wl["patches"]
+    pobj = None
+    if args.targets:
+        pobj = orc.Patches.__new__(orc.Patches)
+        pobj.n, pobj.bounds_off, pobj.internal_off = bo.size - 1, bo, io
+        pobj.bx, pobj.by, pobj.ix, pobj.iy = bx, by, ix, iy
+    warp = [synth.make_warps(n_frames, seed=5)] if args.registration == "given" else None
+    t0 = time.perf_counter()
+    inten, s, q = orc.phase1([fr], [wl["csr"]], warp=warp, interp=1, patches=[pobj] if pobj else None)
+    avg, rms = orc.phase1_finals(s, q, n_frames)
+    cov = orc.coverage([wl["csr"]])
+    t1 = time.perf_counter()
+    itr = orc.global_transpose([inten], args.nodes, n_frames)[0]
+    t2 = time.perf_counter()
+    orc.phase2(itr, avg, cov, wl["steady"], wl["temp"], wl["cal"], wl["qbar"], wl["ps"], args.degree)
+    t3 = time.perf_counter()
+    return t1 - t0, t2 - t1, t3 - t2
+
+
+def cpu_baseline(args, wl, budget_s=20.0):
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.num_threads()
+    # probe with a few frames, then size the sample to ~budget_s of CPU work
+    p = cpu_job(orc, wl, args, 2 * threads)
+    per_frame = sum(p) / (2 * threads)
+    n = int(max(4 * threads, min(2048, budget_s / max(per_frame, 1e-6))))
+    a, b, c = cpu_job(orc, wl, args, n)
+    return {"value": round(n / (a + b + c), 2), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{n} frames of the same workload (same frame size, grid, patches, warp); "
+                      f"process-frames {a:.2f}s, transpose {b:.2f}s, phase2 {c:.2f}s",
+            "note": "C port of the reference's algorithm (oracle/upsp_oracle.c), OpenMP over frames and "
+                    "nodes as the reference; the reference's own C++ cannot be compiled here (DESIGN.md)"}
+
+
+def bench_reference(args):
+    """--impl reference: the reference's CPU algorithm on the host cores (oracle port; the
+    reference itself needs OpenCV C++/Eigen/MPI/HDF5, none of which exist in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import upsp_b200  # noqa: F401  (synthetic workload generator only)
+    from upsp_b200 import synth
+    from oracle import oracle as orc
+    orc.build()
+    wl = build_workload(args, synth)
+    threads = orc.num_threads()
+    n = args.ref_frames if args.ref_frames > 0 else 8 * threads
+    for _ in range(args.warmup):
+        cpu_job(orc, wl, args, max(threads, n // 4))
+    t0 = time.perf_counter()
+    parts = np.zeros(3)
+    for _ in range(args.steps):
+        parts += cpu_job(orc, wl, args, n)
+    dt = time.perf_counter() - t0
+    v = round(n * args.steps / dt, 2)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = (f"each step = {n} frames of configs[1] ({args.height}x{args.width}, N={args.nodes}); "
+              f"process-frames {parts[0] / args.steps:.2f}s transpose {parts[1] / args.steps:.2f}s "
+              f"phase2 {parts[2] / args.steps:.2f}s per step")
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/sec cine->surface Cp", "value": v, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (u16 pixels, f64 accumulators)", "data": "synthetic",
+        "config": {"workload": f"configs[1]: 1 camera {args.height}x{args.width} 12-bit, "
+                               f"{args.frames} frames/GPU onto {args.nodes}-node grid",
+                   "registration": args.registration, "patch_clusters": args.targets + 1 if args.targets else 0,
+                   "csr": args.csr, "detrend_degree": args.degree},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=CFG["frames_per_gpu"], help="frames per GPU")
+    ap.add_argument("--nodes", type=int, default=CFG["nodes"])
+    ap.add_argument("--height", type=int, default=CFG["height"])
+    ap.add_argument("--width", type=int, default=CFG["width"])
+    ap.add_argument("--targets", type=int, default=CFG["targets"])
+    ap.add_argument("--distinct", type=int, default=CFG["distinct_frames"])
+    ap.add_argument("--degree", type=int, default=CFG["degree"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--csr", default="surface", choices=["surface", "random"])
+    ap.add_argument("--registration", default="given", choices=["given", "none"])
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget (0 = skip)")
+    ap.add_argument("--ref-frames", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,6 +164,13 @@ UPSP_API int upsp_gpu_read_warp_matrices(upsp_gpu_ctx* ctx, int cam, int local_o
  * 0 process_frames (accumulated since create/reset), 1 finish_phase1, 2 transpose, 3 phase2 */
 UPSP_API int upsp_gpu_stage_ms(upsp_gpu_ctx* ctx, int stage, float* ms);
 UPSP_API int upsp_gpu_reset_timers(upsp_gpu_ctx* ctx);
+/* bracket an arbitrary sequence of calls with CUDA events on the context's stream
+ * (the stream every kernel of this context is launched on) */
+UPSP_API int upsp_gpu_timer_start(upsp_gpu_ctx* ctx);
+UPSP_API int upsp_gpu_timer_stop(upsp_gpu_ctx* ctx, float* ms);
+/* start a new run on the same context (same setup, same device buffers): zeroes the
+ * sum / sum-sq accumulators and the phase flags; pushed frames stay resident */
+UPSP_API int upsp_gpu_reset_run(upsp_gpu_ctx* ctx);
 /* number of kernels this context has launched since create */
 UPSP_API int upsp_gpu_launch_count(const upsp_gpu_ctx* ctx, long long* n);
 

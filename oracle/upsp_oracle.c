@@ -126,24 +126,38 @@ ORC_API void orc_warp_affine_u16(const uint16_t* src, int sw, int sh, const floa
                                  int interp, uint16_t* dst, int dw, int dh) {
   double M[6];
   for (int i = 0; i < 6; ++i) M[i] = (double)Mf[i];
+  /* per-column tables, exactly WarpAffineInvoker's adelta / bdelta */
+  int* adelta = (int*)malloc(sizeof(int) * 2 * (size_t)dw);
+  int* bdelta = adelta + dw;
+  for (int x = 0; x < dw; ++x) {
+    adelta[x] = orc_cvround(M[0] * x * 1024.0);
+    bdelta[x] = orc_cvround(M[3] * x * 1024.0);
+  }
+  const int round_delta = interp == 0 ? 512 : 16;
   for (int y = 0; y < dh; ++y) {
+    const int X0 = orc_cvround((M[1] * y + M[2]) * 1024.0) + round_delta;
+    const int Y0 = orc_cvround((M[4] * y + M[5]) * 1024.0) + round_delta;
+    uint16_t* drow = dst + (size_t)y * dw;
     for (int x = 0; x < dw; ++x) {
-      int X, Y;
+      int X = X0 + adelta[x], Y = Y0 + bdelta[x];
       if (interp == 0) {
-        warp_coords(M, x, y, 512, &X, &Y);
         int sx = X >> 10, sy = Y >> 10;
-        dst[(size_t)y * dw + x] =
-            (sx >= 0 && sx < sw && sy >= 0 && sy < sh) ? src[(size_t)sy * sw + sx] : 0;
+        drow[x] = (sx >= 0 && sx < sw && sy >= 0 && sy < sh) ? src[(size_t)sy * sw + sx] : 0;
       } else {
-        warp_coords(M, x, y, 16, &X, &Y);
         X >>= 5;
         Y >>= 5;
         int sx = X >> 5, sy = Y >> 5;
         float fx = (float)(X & 31) / 32.0f, fy = (float)(Y & 31) / 32.0f;
         float w0 = (1.0f - fy) * (1.0f - fx), w1 = (1.0f - fy) * fx;
         float w2 = fy * (1.0f - fx), w3 = fy * fx;
+        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+          const uint16_t* s0 = src + (size_t)sy * sw + sx;
+          float sum = (float)s0[0] * w0 + (float)s0[1] * w1 + (float)s0[sw] * w2 + (float)s0[sw + 1] * w3;
+          drow[x] = sat_u16(sum);
+          continue;
+        }
         if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
-          dst[(size_t)y * dw + x] = 0;
+          drow[x] = 0;
           continue;
         }
         int x0 = sx >= 0 && sx < sw, x1 = sx + 1 >= 0 && sx + 1 < sw;
@@ -153,10 +167,11 @@ ORC_API void orc_warp_affine_u16(const uint16_t* src, int sw, int sh, const floa
         float v2 = (x0 && y1) ? (float)src[(size_t)(sy + 1) * sw + sx] : 0.0f;
         float v3 = (x1 && y1) ? (float)src[(size_t)(sy + 1) * sw + sx + 1] : 0.0f;
         float sum = v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
-        dst[(size_t)y * dw + x] = sat_u16(sum);
+        drow[x] = sat_u16(sum);
       }
     }
   }
+  free(adelta);
 }
 
 /* f32 flavour (used by the ECC restatement: cv::findTransformECC warps the   */

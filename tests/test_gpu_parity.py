@@ -150,9 +150,10 @@ def _check_chain(case, ref, got, patched_exact=True):
     e_op, e_cp = cp_errors(case, ref, got)
     assert e_op.max() <= CP_TOL, f"delta-Cp error {e_op.max():.3e} (relative to operands) > {CP_TOL}"
     v = ~skipped
-    scale = np.abs(ref["rms2"][v]).max()
-    assert np.abs(got["rms2"][v] - ref["rms2"][v]).max() <= 1e-5 * scale
-    assert np.abs(got["avg2"][v] - ref["avg2"][v]).max() <= 1e-5 * scale
+    # statistics of delta-Cp: same criterion -- 1e-5 of the operand scale K_n * |r| (r ~ 1)
+    K = np.abs(ref["gain"][v]).astype(np.float64) * 144.0 / float(case.qbar)
+    assert (np.abs(got["rms2"][v] - ref["rms2"][v]) / K).max() <= CP_TOL
+    assert (np.abs(got["avg2"][v] - ref["avg2"][v]) / K).max() <= CP_TOL
     return e_op.max(), e_cp.max()
 
 

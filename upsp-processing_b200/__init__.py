@@ -231,6 +231,17 @@ class PspGpu:
         _chk(lib().upsp_gpu_stage_ms(self._h, stage, C.byref(ms)))
         return ms.value
 
+    def timer_start(self):
+        _chk(lib().upsp_gpu_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _chk(lib().upsp_gpu_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def reset_run(self):
+        _chk(lib().upsp_gpu_reset_run(self._h))
+
     def launch_count(self) -> int:
         n = C.c_longlong()
         _chk(lib().upsp_gpu_launch_count(self._h, C.byref(n)))

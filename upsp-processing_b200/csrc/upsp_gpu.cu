@@ -126,6 +126,10 @@ struct upsp_gpu_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
+  struct ProcRec { int off, count; cudaEvent_t ev; };
+  std::vector<ProcRec> proc_recs;                // recent process_frames calls (input-ring reuse)
+  size_t proc_next = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   long long launches = 0;
 
@@ -240,6 +244,13 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     CU(cudaEventCreate(&c->ev_b));
     CU(cudaEventCreate(&c->ev_pa));
     CU(cudaEventCreate(&c->ev_pb));
+    CU(cudaEventCreate(&c->ev_t0));
+    CU(cudaEventCreate(&c->ev_t1));
+    c->proc_recs.resize(16);
+    for (auto& r : c->proc_recs) {
+      r.off = r.count = 0;
+      CU(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    }
     const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
     const bool alias = cfg->pressure_aliases_intensity != 0;
     TRY(dmalloc(&c->d_intensity, alias ? std::max(fn, nf) : fn));
@@ -333,6 +344,9 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_pa) cudaEventDestroy(c->ev_pa);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  for (auto& r : c->proc_recs) if (r.ev) cudaEventDestroy(r.ev);
   if (c->ev_pb) cudaEventDestroy(c->ev_pb);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -693,8 +707,15 @@ extern "C" int upsp_gpu_push_frames(upsp_gpu_ctx* c, int cam, const void* host, 
     TRY(dmalloc(&k.d_in, (size_t)c->capacity * k.frame_bytes));
   }
   REQUIRE(k.format == format, UPSP_ERR_INVALID, "camera %d was fed format %d before", cam, k.format);
-  // slots being overwritten must have been consumed
-  CU(cudaStreamWaitEvent(c->copy_stream, c->ev_proc, 0));
+  // slots being overwritten must have been consumed: wait for the process_frames calls
+  // whose frames (an earlier lap of the ring) live in the slots of [off, off+count)
+  for (auto& r : c->proc_recs) {
+    if (r.count == 0) continue;
+    const long lo = (long)off - c->capacity, hi = (long)off + count - c->capacity;  // previous lap
+    const bool overlap_prev = r.off < hi && r.off + r.count > lo;
+    const bool older = r.off + r.count <= lo;  // even older laps: also done by stream order, cheap to wait
+    if (overlap_prev || older) CU(cudaStreamWaitEvent(c->copy_stream, r.ev, 0));
+  }
   int done = 0;
   while (done < count) {
     const int slot = (off + done) % c->capacity;
@@ -811,6 +832,12 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
   }
   CU(cudaEventRecord(c->ev_pb, c->stream));
   CU(cudaEventRecord(c->ev_proc, c->stream));
+  {
+    auto& r = c->proc_recs[c->proc_next++ % c->proc_recs.size()];
+    r.off = off;
+    r.count = count;
+    CU(cudaEventRecord(r.ev, c->stream));
+  }
   c->frames_processed += count;
   c->stage_ms[0] = -1.0f;  // resolved lazily in stage_ms (needs a sync)
   return UPSP_OK;
@@ -1114,6 +1141,30 @@ extern "C" int upsp_gpu_stage_ms(upsp_gpu_ctx* c, int stage, float* ms) {
 extern "C" int upsp_gpu_reset_timers(upsp_gpu_ctx* c) {
   ENTER(c);
   for (float& m : c->stage_ms) m = 0.0f;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_timer_start(upsp_gpu_ctx* c) {
+  ENTER(c);
+  CU(cudaEventRecord(c->ev_t0, c->stream));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_timer_stop(upsp_gpu_ctx* c, float* ms) {
+  ENTER(c);
+  REQUIRE(ms, UPSP_ERR_INVALID, "null argument");
+  CU(cudaEventRecord(c->ev_t1, c->stream));
+  CU(cudaEventSynchronize(c->ev_t1));
+  CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_reset_run(upsp_gpu_ctx* c) {
+  ENTER(c);
+  CU(cudaMemsetAsync(c->d_sum, 0, (size_t)c->N * sizeof(double), c->stream));
+  CU(cudaMemsetAsync(c->d_sumsq, 0, (size_t)c->N * sizeof(double), c->stream));
+  c->phase1_done = c->transposed = c->phase2_done = false;
+  c->frames_processed = 0;
   return UPSP_OK;
 }
 

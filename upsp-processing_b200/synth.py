@@ -162,3 +162,33 @@ def tunnel_conditions(n_nodes, seed=6):
     steady = rng.uniform(-1.2, 0.9, n_nodes).astype(np.float32)
     temp = (68.0 + rng.normal(0, 1.5, n_nodes)).astype(np.float32)
     return cal, qbar, ps, steady, temp
+
+
+def pack_12bit(pix):
+    """MSB-first 12-bit packing of an even number of pixels (the .mraw / packed .cine layout
+    that unpack_12bit, cpp/lib/PSPVideo.cpp:134-150, decodes).  pix: u16 [..., npix]."""
+    pix = np.asarray(pix, np.uint16)
+    a, b = pix[..., 0::2], pix[..., 1::2]
+    buf = np.empty(pix.shape[:-1] + (pix.shape[-1] * 3 // 2,), np.uint8)
+    buf[..., 0::3] = a >> 4
+    buf[..., 1::3] = ((a & 0x0F) << 4) | (b >> 8)
+    buf[..., 2::3] = b & 0xFF
+    return buf
+
+
+def make_frames_fast(n_frames, height, width, seed=0, noise=8.0, hot_frames=0.25):
+    """Bench-sized variant of make_frames: one base field, per-frame drift + integer noise."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width].astype(np.float32)
+    base = (1800.0 + 600.0 * np.sin(x / 37.0) * np.cos(y / 53.0)
+            + 300.0 * np.exp(-(((x - 0.55 * width) / (0.2 * width)) ** 2
+                               + ((y - 0.45 * height) / (0.2 * height)) ** 2))).astype(np.float32)
+    frames = np.empty((n_frames, height, width), np.uint16)
+    for f in range(n_frames):
+        t = f / max(n_frames, 1)
+        img = base * np.float32(1.0 + 0.03 * np.sin(2.0 * np.pi * t)) \
+            + rng.standard_normal(base.shape, dtype=np.float32) * np.float32(noise)
+        frames[f] = np.clip(np.rint(img), 0, 4095).astype(np.uint16)
+        if rng.random() < hot_frames:
+            frames[f].reshape(-1)[rng.integers(0, height * width, int(rng.integers(1, 6)))] = 4095
+    return frames
