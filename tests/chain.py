@@ -135,6 +135,14 @@ def same_bits(a, b):
     return bool(np.all((a == b) | (nan_a & nan_b)))
 
 
+def degenerate_nodes(ref):
+    """Covered nodes whose intensity history holds a zero / non-finite sample (e.g. a node whose
+    pixel is warped in from outside the frame: BORDER_CONSTANT 0).  avg / 0 = inf poisons the
+    reference's whole row (NaN after the QR solve); there is nothing to compare but NaN-ness."""
+    it = ref["itrans"]
+    return (ref["coverage"] != 0) & ~np.all(np.isfinite(it) & (it != 0), axis=1)
+
+
 def cp_errors(case: Case, ref, got):
     """Per-node error of the delta-Cp time histories.
     Returns (err_operand, err_cp):
@@ -142,7 +150,7 @@ def cp_errors(case: Case, ref, got):
                        cancelling subtraction (r - fit), K_n = |gain|*144/qbar;  this is the
                        1e-5 (fp32) criterion of BASELINE.json, see DESIGN.md "tolerances".
       err_cp[n]      = max_f |dCp| / max_f |Cp_ref|      -- relative to the signal itself."""
-    valid = ref["coverage"] != 0
+    valid = (ref["coverage"] != 0) & ~degenerate_nodes(ref)
     d = np.abs(got["ptrans"][valid] - ref["ptrans"][valid]).max(axis=1)
     K = np.abs(ref["gain"][valid]).astype(np.float64) * 144.0 / float(case.qbar)
     r = ref["avg"][valid, None] / ref["itrans"][valid]

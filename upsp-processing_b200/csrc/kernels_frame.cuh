@@ -133,14 +133,8 @@ k_copy16_scan(const uint16_t* __restrict__ in, size_t in_stride_px, uint16_t* __
 // applied serially in raster order (a later fix sees an earlier one).  One thread per frame.
 // hot_cnt is left holding the count (> max_hot means "too many, frame untouched").
 // ---------------------------------------------------------------------------------------
-__global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
-                          int nframes, const int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
-                          int min_change, int max_hot) {
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= nframes) return;
-  int n = hot_cnt[f];
-  if (n <= 0 || n > max_hot) return;
-  int* pos = hot_pos + f * UPSP_HOT_STORE;
+__device__ __forceinline__ void fix_hot_frame(uint16_t* __restrict__ img, int rows, int cols,
+                                              int n, int* __restrict__ pos, int min_change) {
   int loc[UPSP_HOT_STORE];
   for (int i = 0; i < n; ++i) loc[i] = pos[i];
   for (int i = 1; i < n; ++i) {  // insertion sort -> raster order
@@ -151,7 +145,6 @@ __global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, 
     }
     loc[j + 1] = v;
   }
-  uint16_t* img = frames + (size_t)f * npix;
   for (int h = 0; h < n; ++h) {
     int row = loc[h] / cols, col = loc[h] % cols;
     int vals[4], nv = 0;
@@ -171,6 +164,47 @@ __global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, 
     int new_val = vals[nv / 2];
     if (old_val - new_val > min_change) img[(size_t)row * cols + col] = (uint16_t)new_val;
     pos[h] = loc[h];
+  }
+}
+
+__global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
+                          int nframes, const int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
+                          int min_change, int max_hot) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  int n = hot_cnt[f];
+  if (n <= 0 || n > max_hot) return;
+  fix_hot_frame(frames + (size_t)f * npix, rows, cols, n, hot_pos + f * UPSP_HOT_STORE, min_change);
+}
+
+// One block per frame: thread 0 applies the (<= 5) hot-pixel fixes while the whole block builds
+// the frame's warp tables (when m6 != nullptr).  Replaces two tiny launches per batch.
+__global__ void __launch_bounds__(256)
+k_frame_prep(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
+             const int* __restrict__ hot_cnt, int* __restrict__ hot_pos, int min_change, int max_hot,
+             const float* __restrict__ m6, int interp, int* __restrict__ tab) {
+  const int f = blockIdx.x;
+  if (threadIdx.x == 0 && max_hot > 0) {
+    int n = hot_cnt[f];
+    if (n > 0 && n <= max_hot)
+      fix_hot_frame(frames + (size_t)f * npix, rows, cols, n, hot_pos + f * UPSP_HOT_STORE, min_change);
+  }
+  if (m6 == nullptr) return;
+  const int W = cols, H = rows;
+  const float* M = m6 + (size_t)f * 6;
+  int* t = tab + (size_t)f * (2 * W + 2 * H);
+  const int round_delta = interp == 0 ? 512 : 16;
+  const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
+  for (int i = threadIdx.x; i < max(W, H); i += blockDim.x) {
+    const double v = (double)i;
+    if (i < W) {
+      t[i] = __double2int_rn(__dmul_rn(__dmul_rn(m0, v), 1024.0));
+      t[W + i] = __double2int_rn(__dmul_rn(__dmul_rn(m3, v), 1024.0));
+    }
+    if (i < H) {
+      t[2 * W + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, v), m2), 1024.0)) + round_delta;
+      t[2 * W + H + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, v), m5), 1024.0)) + round_delta;
+    }
   }
 }
 
@@ -270,6 +304,113 @@ k_warp_affine_u16(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, 
   }
 }
 
+// 8 output pixels per thread (one 16-byte store).  Near-identity maps (the registration case:
+// sub-pixel jitter) put the 8 pixels' taps in one contiguous 9-pixel run of two source rows;
+// that run is fetched with three 8-byte loads per row instead of 32 two-byte loads.  Any other
+// map (large rotation / scale, image border) takes the per-pixel path with identical
+// arithmetic.  block = 128 threads = 1024 px of one row; grid (ceil(W/1024), H, frames).
+__device__ __forceinline__ void window9(const uint16_t* __restrict__ p /*8B aligned*/, int off,
+                                        uint32_t (&px)[9]) {
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+  const uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  uint32_t w[7] = {a.x, a.y, b.x, b.y, c.x, c.y, 0u};
+  const int wo = off >> 1, hs = (off & 1) * 16;
+  uint32_t u[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const uint32_t lo = wo ? w[i + 1] : w[i], hi = wo ? w[i + 2] : w[i + 1];
+    u[i] = __funnelshift_r(lo, hi, hs);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) px[k] = (u[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+}
+
+__global__ void __launch_bounds__(128)
+k_warp_affine8_u16(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
+                   const int* __restrict__ tab, int interp, int skip_frame) {
+  const int f = blockIdx.z;
+  const int x = (blockIdx.x * 128 + threadIdx.x) * 8;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const size_t P = (size_t)W * H;
+  const uint16_t* s = src + (size_t)f * P;
+  uint16_t* d = dst + (size_t)f * P + (size_t)y * W + x;
+  const bool full = (x + 8 <= W) && ((W & 7) == 0);
+  if (f == skip_frame) {  // global frame 0 is never registered (psp_process.cpp:1777)
+    if (full) {
+      *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s + (size_t)y * W + x));
+    } else {
+      for (int k = 0; k < 8 && x + k < W; ++k) d[k] = s[(size_t)y * W + x + k];
+    }
+    return;
+  }
+  const int* t = tab + (size_t)f * (2 * W + 2 * H);
+  const int X0 = __ldg(t + 2 * W + y), Y0 = __ldg(t + 2 * W + H + y);
+  int X[8], Y[8];
+  if (full && ((W & 3) == 0)) {
+    const int4 a0 = __ldg(reinterpret_cast<const int4*>(t + x)), a1 = __ldg(reinterpret_cast<const int4*>(t + x + 4));
+    const int4 b0 = __ldg(reinterpret_cast<const int4*>(t + W + x)), b1 = __ldg(reinterpret_cast<const int4*>(t + W + x + 4));
+    X[0] = X0 + a0.x; X[1] = X0 + a0.y; X[2] = X0 + a0.z; X[3] = X0 + a0.w;
+    X[4] = X0 + a1.x; X[5] = X0 + a1.y; X[6] = X0 + a1.z; X[7] = X0 + a1.w;
+    Y[0] = Y0 + b0.x; Y[1] = Y0 + b0.y; Y[2] = Y0 + b0.z; Y[3] = Y0 + b0.w;
+    Y[4] = Y0 + b1.x; Y[5] = Y0 + b1.y; Y[6] = Y0 + b1.z; Y[7] = Y0 + b1.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int xx = min(x + k, W - 1);
+      X[k] = X0 + __ldg(t + xx);
+      Y[k] = Y0 + __ldg(t + W + xx);
+    }
+  }
+  uint32_t o[8];
+  bool done = false;
+  if (interp == 1 && full) {
+    const int sx0 = X[0] >> 10, sy0 = Y[0] >> 10;
+    bool run = sx0 >= 0 && sx0 + 9 <= W && sy0 >= 0 && sy0 + 1 < H;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) run = run && ((X[k] >> 10) == sx0 + k) && ((Y[k] >> 10) == sy0);
+    const size_t a = (size_t)sy0 * W + sx0;
+    const size_t a4 = a & ~(size_t)3;
+    run = run && ((W & 3) == 0) && (a4 + W + 12 <= P);
+    if (run) {
+      uint32_t r0[9], r1[9];
+      window9(s + a4, (int)(a - a4), r0);
+      window9(s + a4 + W, (int)(a - a4), r1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int Xs = X[k] >> 5, Ys = Y[k] >> 5;
+        const float fx = (float)(Xs & 31) * 0.03125f, fy = (float)(Ys & 31) * 0.03125f;
+        const float w0 = __fmul_rn(1.0f - fy, 1.0f - fx), w1 = __fmul_rn(1.0f - fy, fx);
+        const float w2 = __fmul_rn(fy, 1.0f - fx), w3 = __fmul_rn(fy, fx);
+        float v = __fadd_rn(__fmul_rn((float)r0[k], w0), __fmul_rn((float)r0[k + 1], w1));
+        v = __fadd_rn(v, __fmul_rn((float)r1[k], w2));
+        v = __fadd_rn(v, __fmul_rn((float)r1[k + 1], w3));
+        o[k] = sat_u16_rn(v);
+      }
+      done = true;
+    }
+  }
+  if (!done) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = 0;
+      if (x + k >= W) continue;
+      if (interp == 0) {
+        const int sx = X[k] >> 10, sy = Y[k] >> 10;
+        o[k] = (sx >= 0 && sx < W && sy >= 0 && sy < H) ? (uint32_t)__ldg(s + (size_t)sy * W + sx) : 0u;
+      } else {
+        o[k] = sat_u16_rn(warp_sample_linear<uint16_t>(s, W, H, X[k], Y[k]));
+      }
+    }
+  }
+  if (full) {
+    *reinterpret_cast<uint4*>(d) = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16),
+                                              o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+  } else {
+    for (int k = 0; k < 8 && x + k < W; ++k) d[k] = (uint16_t)o[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K3b: PatchClusters<float>::operator() (cpp/lib/patches.ipp:98-164).
 // The cubic 2-D Vandermonde A depends only on cluster geometry, so its float
@@ -297,63 +438,106 @@ struct PatchGeom {            // device pointers, one per camera
   const int* order;           // clusters sorted by dependency level
 };
 
+// One warp per (cluster, 32 frames).  SMEM: the cluster's reflectors (E, tau*E) are staged in
+// shared memory once (coalesced) and the per-lane work vector c lives there too ([nb][32]
+// floats), so the strictly sequential dot-product chains run at shared-memory latency;
+// otherwise (huge clusters) both stay in global memory.
+template <bool SMEM>
 __global__ void __launch_bounds__(32)
 k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict__ frames,
         size_t npix, int nframes, int bstride, float* __restrict__ scratch,
         float* __restrict__ pv) {
+  extern __shared__ float psh[];
   const int cl = cl_list[blockIdx.x];
-  const int b = blockIdx.y * 32 + threadIdx.x;
-  if (b >= nframes) return;
+  const int lane = threadIdx.x;
+  const int b = blockIdx.y * 32 + lane;
+  const bool live = b < nframes;
   const int nz = g.nzp[cl];
-  if (nz == 0) return;
+  if (nz < 0) return;
   const int off = g.bounds_off[cl], nb = g.bounds_off[cl + 1] - off;
+  const float* Eg = g.qr_e + (size_t)10 * off;
+  const float* TEg = g.qr_te + (size_t)10 * off;
+  const float* E = Eg;
+  const float* TE = TEg;
+  float* c;
+  int cs;
+  if (SMEM) {
+    float* Es = psh;               // [10*nb]
+    float* TEs = psh + 10 * nb;    // [10*nb]
+    for (int i = lane; i < 10 * nb; i += 32) {
+      Es[i] = __ldg(Eg + i);
+      TEs[i] = __ldg(TEg + i);
+    }
+    E = Es;
+    TE = TEs;
+    c = psh + 20 * nb + lane;      // [nb][32]
+    cs = 32;
+    __syncwarp();
+  } else {
+    c = scratch + (size_t)off * bstride + (live ? b : 0);
+    cs = bstride;
+  }
+  if (!live) return;
   const uint16_t* img = frames + (size_t)b * npix;
-  float* c = scratch + (size_t)off * bstride + b;  // c[i] at c[i*bstride]
   for (int i = 0; i < nb; ++i) {
     int s = __ldg(g.bsrc + off + i);
-    c[(size_t)i * bstride] = s >= 0 ? (float)img[s] : pv[(size_t)(-1 - s) * bstride + b];
+    c[(size_t)i * cs] = s >= 0 ? (float)img[s] : pv[(size_t)(-1 - s) * bstride + b];
   }
-  const float* E = g.qr_e + (size_t)10 * off;
-  const float* TE = g.qr_te + (size_t)10 * off;
   const float* hc = g.hcoef + cl * 10;
   for (int k = 0; k < nz; ++k) {
     const int n = nb - k;
     const float tau = hc[k];
     if (n == 1) {
-      c[(size_t)k * bstride] = __fmul_rn(c[(size_t)k * bstride], __fsub_rn(1.0f, tau));
+      c[(size_t)k * cs] = __fmul_rn(c[(size_t)k * cs], __fsub_rn(1.0f, tau));
     } else if (tau != 0.0f) {
       const float* e = E + (size_t)k * nb + k + 1;
       const float* te = TE + (size_t)k * nb + k + 1;
+      const float* ck = c + (size_t)(k + 1) * cs;
       float s = 0.0f;
-      for (int i = 0; i < n - 1; ++i)
-        s = __fadd_rn(s, __fmul_rn(__ldg(e + i), c[(size_t)(k + 1 + i) * bstride]));
-      const float t = __fadd_rn(s, c[(size_t)k * bstride]);
-      c[(size_t)k * bstride] = __fsub_rn(c[(size_t)k * bstride], __fmul_rn(tau, t));
-      for (int i = 0; i < n - 1; ++i) {
-        float* ci = c + (size_t)(k + 1 + i) * bstride;
-        *ci = __fsub_rn(*ci, __fmul_rn(t, __ldg(te + i)));
+      int i = 0;
+      for (; i + 4 <= n - 1; i += 4) {   // products are independent; the adds stay in order
+        const float p0 = __fmul_rn(e[i], ck[(size_t)i * cs]);
+        const float p1 = __fmul_rn(e[i + 1], ck[(size_t)(i + 1) * cs]);
+        const float p2 = __fmul_rn(e[i + 2], ck[(size_t)(i + 2) * cs]);
+        const float p3 = __fmul_rn(e[i + 3], ck[(size_t)(i + 3) * cs]);
+        s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, p0), p1), p2), p3);
+      }
+      for (; i < n - 1; ++i) s = __fadd_rn(s, __fmul_rn(e[i], ck[(size_t)i * cs]));
+      const float t = __fadd_rn(s, c[(size_t)k * cs]);
+      c[(size_t)k * cs] = __fsub_rn(c[(size_t)k * cs], __fmul_rn(tau, t));
+#pragma unroll 4
+      for (int j = 0; j < n - 1; ++j) {
+        float* ci = c + (size_t)(k + 1 + j) * cs;
+        *ci = __fsub_rn(*ci, __fmul_rn(t, te[j]));
       }
     }
   }
   float x[10], poly[10];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) x[i] = i < nz ? c[(size_t)i * bstride] : 0.0f;
-  for (int i = nz - 1; i >= 0; --i) {
-    x[i] = __fdiv_rn(x[i], __ldg(E + (size_t)i * nb + i));
-    for (int j = 0; j < i; ++j) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], __ldg(E + (size_t)i * nb + j)));
+  for (int i = 0; i < 10; ++i) x[i] = i < nz ? c[(size_t)i * cs] : 0.0f;
+#pragma unroll
+  for (int i = 9; i >= 0; --i) {
+    if (i < nz) {
+      x[i] = __fdiv_rn(x[i], E[(size_t)i * nb + i]);
+#pragma unroll
+      for (int j = 0; j < 10; ++j)
+        if (j < i) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], E[(size_t)i * nb + j]));
+    }
   }
   const int* pm = g.perm + cl * 10;
 #pragma unroll
   for (int i = 0; i < 10; ++i) poly[i] = 0.0f;
+#pragma unroll
   for (int i = 0; i < 10; ++i) {
-    float v = i < nz ? x[i] : 0.0f;
-    int pi = pm[i];
+    const float v = i < nz ? x[i] : 0.0f;
+    const int pi = pm[i];
 #pragma unroll
     for (int q = 0; q < 10; ++q)
       if (q == pi) poly[q] = v;
   }
   // polyval2D: z = sum_c poly[c] * y^i * x^j, order [1,x,x2,x3,y,xy,x2y,y2,xy2,y3]
   const int ioff = g.internal_off[cl], ni = g.internal_off[cl + 1] - ioff;
+#pragma unroll 2
   for (int i = 0; i < ni; ++i) {
     const float* pw = g.ipow + (size_t)6 * (ioff + i);
     const float xp[4] = {1.0f, __ldg(pw), __ldg(pw + 1), __ldg(pw + 2)};

@@ -100,7 +100,7 @@ struct Camera {
   std::vector<std::vector<int>> levels;  // cluster ids per dependency level
   int* d_cl_list = nullptr;              // concatenated level lists
   std::vector<int> level_off;
-  int total_bounds = 0, total_internal = 0;
+  int total_bounds = 0, total_internal = 0, max_bounds = 0;
   float* d_scratch = nullptr;
   float* d_pv = nullptr;
   std::unordered_map<int, int> pix2slot;  // interior pixel -> slot of the LAST active cluster
@@ -541,6 +541,7 @@ extern "C" int upsp_gpu_set_patches(upsp_gpu_ctx* c, int cam, int ncl, const int
       }
     }
     max_level = std::max(max_level, level[cl]);
+    k.max_bounds = std::max(k.max_bounds, nb);
     for (int j = ioff[cl]; j < ioff[cl + 1]; ++j) {
       const int pix = (int)iy[j] * k.W + (int)ix[j];
       owner[pix] = {cl, j};
@@ -773,19 +774,18 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
           (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
     }
     KCHECK(c);
-    if (c->hot_fix) {
-      k_fix_hot<<<cdiv(nb, 32), 32, 0, c->stream>>>(k.d_work, k.npix, k.H, k.W, nb, k.d_hot_cnt,
-                                                   k.d_hot_pos, UPSP_HOT_MIN_CHANGE, UPSP_HOT_MAX);
+    const bool reg = c->registration != UPSP_REG_NONE;
+    if (c->hot_fix || reg) {
+      k_frame_prep<<<nb, 256, 0, c->stream>>>(k.d_work, k.npix, k.H, k.W, k.d_hot_cnt, k.d_hot_pos,
+                                               UPSP_HOT_MIN_CHANGE, c->hot_fix ? UPSP_HOT_MAX : 0,
+                                               reg ? k.d_m6 + (size_t)off * 6 : nullptr, c->interp, k.d_tab);
       KCHECK(c);
     }
     const uint16_t* cur = k.d_work;
-    if (c->registration != UPSP_REG_NONE) {
+    if (reg) {
       // global frame 0 is never registered (psp_process.cpp:1777)
       const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
-      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), nb), 256, 0, c->stream>>>(
-          k.d_m6 + (size_t)off * 6, nb, k.W, k.H, c->interp, k.d_tab);
-      KCHECK(c);
-      k_warp_affine_u16<<<dim3(cdiv(k.W, 128), cdiv(k.H, 4), nb), dim3(64, 4), 0, c->stream>>>(
+      k_warp_affine8_u16<<<dim3(cdiv(k.W, 1024), k.H, nb), 128, 0, c->stream>>>(
           k.d_work, k.d_warp, k.W, k.H, k.d_tab, c->interp, skip_frame);
       KCHECK(c);
       cur = k.d_warp;
@@ -795,8 +795,16 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
         const int ncl = k.level_off[l + 1] - k.level_off[l];
         if (!ncl) continue;
-        k_patch<<<dim3(ncl, cdiv(nb, 32)), 32, 0, c->stream>>>(
-            k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
+        const size_t sm = (size_t)k.max_bounds * (32 + 20) * sizeof(float);
+        if (sm <= 96 * 1024) {
+          if (sm > 48 * 1024)
+            CU(cudaFuncSetAttribute(k_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          k_patch<true><<<dim3(ncl, cdiv(nb, 32)), 32, sm, c->stream>>>(
+              k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
+        } else {
+          k_patch<false><<<dim3(ncl, cdiv(nb, 32)), 32, 0, c->stream>>>(
+              k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
+        }
         KCHECK(c);
       }
     }
@@ -972,7 +980,7 @@ static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
 
 template <int NC>
 static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
-  constexpr int NT = 256;
+  constexpr int NT = 512;
   const size_t row_bytes = (size_t)a.F * sizeof(float);
   const size_t smem_max = 227 * 1024 - 2048;
   if (a.n_local == 0) return UPSP_OK;
@@ -1345,7 +1353,7 @@ extern "C" int upsp_op_warp_affine(int device, const uint16_t* src, int nf, int 
   TRY(S.alloc(&d_tab, (size_t)nf * (2 * W + 2 * H)));
   k_warp_tables<<<dim3(cdiv(std::max(W, H), 256), nf), 256>>>(d_m, nf, W, H, interp, d_tab);
   CU(cudaGetLastError());
-  k_warp_affine_u16<<<dim3(cdiv(W, 128), cdiv(H, 4), nf), dim3(64, 4)>>>(d_src, d_dst, W, H, d_tab, interp, -1);
+  k_warp_affine8_u16<<<dim3(cdiv(W, 1024), H, nf), 128>>>(d_src, d_dst, W, H, d_tab, interp, -1);
   CU(cudaGetLastError());
   CU(cudaMemcpy(dst, d_dst, npix * nf * 2, cudaMemcpyDeviceToHost));
   return UPSP_OK;
