@@ -157,3 +157,15 @@ def cp_errors(case: Case, ref, got):
     err_operand = d / (K * np.abs(r).max(axis=1))
     err_cp = d / np.abs(ref["ptrans"][valid]).max(axis=1)
     return err_operand, err_cp
+
+
+def monomial_mass(orc, ref):
+    """sum_c |coef_c| of the reference's degree-6 monomial fit per valid node, divided by
+    max|r|.  The reference's design matrix A[f,c] = (float)pow(f/F, c) is only defined to float
+    precision, so fitted values are only defined to ~eps32 * sum_c|coef_c| (each column entry
+    carries a relative rounding error of up to 6e-8 that is multiplied by its coefficient);
+    rows with outliers have large alternating coefficients."""
+    valid = (ref["coverage"] != 0) & ~degenerate_nodes(ref)
+    r = (ref["avg"][valid, None] / ref["itrans"][valid]).astype(np.float32)
+    mass = np.array([np.abs(orc.transpoly_fit(row, 6)[1]).sum() for row in r])
+    return mass / np.abs(r).max(axis=1)

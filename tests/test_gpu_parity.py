@@ -4,7 +4,7 @@ delta-Cp time histories are held to 1e-5 relative (fp32) as defined in chain.cp_
 import numpy as np
 import pytest
 
-from chain import Case, cp_errors, degenerate_nodes, run_gpu, run_oracle, same_bits
+from chain import Case, cp_errors, degenerate_nodes, monomial_mass, run_gpu, run_oracle, same_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -144,7 +144,8 @@ def _check_chain(case, ref, got, orc, strict=False):
     """Phase 1, transpose, gain: bit-exact.  delta-Cp: the detrend is the one stage the GPU does
     not compute in the reference's float operation order (DESIGN.md "tolerances"), so
       (a) vs the float64 least-squares model of the reference chain: <= 1e-6 of the operand
-          scale K_n*max|r| on every node;
+          scale K_n*max|r| on every node, plus 8 eps32 * sum|monomial coef| (the precision to
+          which the reference's float design matrix defines the fit, chain.monomial_mass);
       (b) vs the float-QR oracle (the reference's arithmetic): <= 1e-5 plus that oracle's own
           distance from the float64 model on the node (its float rounding noise, which reaches
           ~1e-4 on short series with outliers -- no implementation that does not replay Eigen's
@@ -161,7 +162,8 @@ def _check_chain(case, ref, got, orc, strict=False):
     assert not np.isfinite(ref["ptrans"][deg]).any() and not np.isfinite(got["ptrans"][deg]).any()
     exact = run_oracle(orc, case, exact_fit=True)
     e_exact, _ = cp_errors(case, exact, got)
-    assert e_exact.max() <= EXACT_TOL, f"delta-Cp vs float64 model: {e_exact.max():.3e} > {EXACT_TOL}"
+    cond = 8 * np.finfo(np.float32).eps * monomial_mass(orc, ref)
+    assert np.all(e_exact <= EXACT_TOL + cond), f"delta-Cp vs float64 model: {(e_exact - cond).max():.3e} > {EXACT_TOL}"
     e_op, e_cp = cp_errors(case, ref, got)
     noise, _ = cp_errors(case, ref, exact)       # the float-QR oracle's own rounding noise
     assert np.all(e_op <= CP_TOL + noise), f"delta-Cp vs float-QR oracle: {(e_op - noise).max():.3e} > {CP_TOL}"
@@ -171,7 +173,7 @@ def _check_chain(case, ref, got, orc, strict=False):
     # statistics of delta-Cp: same criterion, against the float64 model and the float-QR oracle
     K = np.abs(ref["gain"][v]).astype(np.float64) * 144.0 / float(case.qbar)
     for key in ("rms2", "avg2"):
-        assert (np.abs(got[key][v] - exact[key][v]) / K).max() <= EXACT_TOL
+        assert np.all(np.abs(got[key][v] - exact[key][v]) / K <= EXACT_TOL + cond)
         nz = np.abs(ref[key][v] - exact[key][v]) / K
         assert np.all(np.abs(got[key][v] - ref[key][v]) / K <= CP_TOL + nz)
     return e_op.max(), e_cp.max()

@@ -38,6 +38,17 @@ __device__ __forceinline__ void st_stream_f4(void* p, const float4& v) {
                              __float_as_uint(v.w)));
 }
 
+// Conversions without the (quarter-rate) I2F / F2I pipe: exact for the stated ranges.
+__device__ __forceinline__ float u2f_exact(uint32_t v) {        // v < 2^23
+  return __fadd_rn(__uint_as_float(0x4B000000u | v), -8388608.0f);
+}
+__device__ __forceinline__ float frac32_exact(uint32_t v) {     // v in [0,32) -> v/32
+  return __fadd_rn(__uint_as_float(0x48800000u | v), -262144.0f);
+}
+__device__ __forceinline__ int f2i_rn_small(float v) {           // |v| < 2^22, round half to even
+  return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -243,25 +243,25 @@ __device__ __forceinline__ float warp_sample_linear(const LoadT* __restrict__ sr
   X >>= 5;
   Y >>= 5;
   const int sx = X >> 5, sy = Y >> 5;
-  const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;
+  const float fx = frac32_exact(X & 31), fy = frac32_exact(Y & 31);
   if (sx >= W || sx + 1 < 0 || sy >= H || sy + 1 < 0) return 0.0f;
   const float w0 = __fmul_rn(1.0f - fy, 1.0f - fx), w1 = __fmul_rn(1.0f - fy, fx);
   const float w2 = __fmul_rn(fy, 1.0f - fx), w3 = __fmul_rn(fy, fx);
   const bool x0 = sx >= 0, x1 = sx + 1 < W, y0 = sy >= 0, y1 = sy + 1 < H;
   const LoadT* r0 = src + (size_t)(y0 ? sy : 0) * W;
   const LoadT* r1 = src + (size_t)(y1 ? sy + 1 : 0) * W;
-  float v0 = (x0 && y0) ? (float)__ldg(r0 + sx) : 0.0f;
-  float v1 = (x1 && y0) ? (float)__ldg(r0 + sx + 1) : 0.0f;
-  float v2 = (x0 && y1) ? (float)__ldg(r1 + sx) : 0.0f;
-  float v3 = (x1 && y1) ? (float)__ldg(r1 + sx + 1) : 0.0f;
+  float v0 = (x0 && y0) ? u2f_exact(__ldg(r0 + sx)) : 0.0f;
+  float v1 = (x1 && y0) ? u2f_exact(__ldg(r0 + sx + 1)) : 0.0f;
+  float v2 = (x0 && y1) ? u2f_exact(__ldg(r1 + sx)) : 0.0f;
+  float v3 = (x1 && y1) ? u2f_exact(__ldg(r1 + sx + 1)) : 0.0f;
   float s = __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
   s = __fadd_rn(s, __fmul_rn(v2, w2));
   s = __fadd_rn(s, __fmul_rn(v3, w3));
   return s;
 }
 
-__device__ __forceinline__ uint32_t sat_u16_rn(float v) {
-  int iv = __float2int_rn(v);
+__device__ __forceinline__ uint32_t sat_u16_rn(float v) {   // v in [0, 65536): taps are u16, weights sum to 1
+  int iv = f2i_rn_small(v);
   return (uint32_t)min(max(iv, 0), 65535);
 }
 
@@ -379,12 +379,12 @@ k_warp_affine8_u16(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int Xs = X[k] >> 5, Ys = Y[k] >> 5;
-        const float fx = (float)(Xs & 31) * 0.03125f, fy = (float)(Ys & 31) * 0.03125f;
+        const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
         const float w0 = __fmul_rn(1.0f - fy, 1.0f - fx), w1 = __fmul_rn(1.0f - fy, fx);
         const float w2 = __fmul_rn(fy, 1.0f - fx), w3 = __fmul_rn(fy, fx);
-        float v = __fadd_rn(__fmul_rn((float)r0[k], w0), __fmul_rn((float)r0[k + 1], w1));
-        v = __fadd_rn(v, __fmul_rn((float)r1[k], w2));
-        v = __fadd_rn(v, __fmul_rn((float)r1[k + 1], w3));
+        float v = __fadd_rn(__fmul_rn(u2f_exact(r0[k]), w0), __fmul_rn(u2f_exact(r0[k + 1]), w1));
+        v = __fadd_rn(v, __fmul_rn(u2f_exact(r1[k]), w2));
+        v = __fadd_rn(v, __fmul_rn(u2f_exact(r1[k + 1]), w3));
         o[k] = sat_u16_rn(v);
       }
       done = true;

@@ -34,7 +34,7 @@ struct ProjArgs {
 };
 
 __device__ __forceinline__ float fetch_px(const ProjCam& c, int code, int b, int bstride) {
-  return code >= 0 ? (float)__ldg(c.frames + (size_t)b * c.npix + code)
+  return code >= 0 ? u2f_exact(__ldg(c.frames + (size_t)b * c.npix + code))
                    : __ldg(c.pv + (size_t)(-2 - code) * bstride + b);
 }
 

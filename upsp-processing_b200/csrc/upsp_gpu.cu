@@ -975,7 +975,20 @@ static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
       }
     }
   }
-  for (int i = 0; i < nc * nc; ++i) ginv[i] = (double)I[i];
+  // fold in the Chebyshev -> power basis change: T_k(x) = sum_j C[k][j] x^j, so the power-basis
+  // coefficients of the fit are p = C^T (Ginv m)
+  std::vector<long double> Cm((size_t)nc * nc, 0.0L);
+  Cm[0] = 1.0L;
+  if (nc > 1) Cm[(size_t)1 * nc + 1] = 1.0L;
+  for (int k = 2; k < nc; ++k)
+    for (int j = 0; j < nc; ++j)
+      Cm[(size_t)k * nc + j] = (j > 0 ? 2.0L * Cm[(size_t)(k - 1) * nc + j - 1] : 0.0L) - Cm[(size_t)(k - 2) * nc + j];
+  for (int j = 0; j < nc; ++j)
+    for (int i = 0; i < nc; ++i) {
+      long double t = 0.0L;
+      for (int k = 0; k < nc; ++k) t += Cm[(size_t)k * nc + j] * I[(size_t)k * nc + i];
+      ginv[(size_t)j * nc + i] = (double)t;
+    }
 }
 
 template <int NC>
