@@ -995,8 +995,10 @@ template <int NC>
 static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
   constexpr int NT = 512;
   const size_t row_bytes = (size_t)a.F * sizeof(float);
-  const size_t smem_max = 227 * 1024 - 2048;
   if (a.n_local == 0) return UPSP_OK;
+  cudaFuncAttributes fa;
+  CU(cudaFuncGetAttributes(&fa, k_phase2<NC, true, NT>));
+  const size_t smem_max = 227 * 1024 - fa.sharedSizeBytes - 1024;  // opt-in limit minus static part
   if (row_bytes <= smem_max) {
     CU(cudaFuncSetAttribute(k_phase2<NC, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem_max));
