@@ -233,7 +233,7 @@ def bench_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # dominant stage kernel and its algorithmic bytes per launch (DESIGN.md "algorithmic bytes")
-    names = ["process_frames(K0-K5)", "finish_phase1", "k_transpose_a2a", "k_phase2"]
+    names = ["process_frames(decode+prep+patch+k_project_fused)", "finish_phase1", "k_transpose_a2a", "k_phase2"]
     alg = [(1.5 * P + 4.0 * N) * F_local, 24.0 * N, 8.0 * N * F_local, 8.0 * (N / world) * F_total]
     dom = int(np.argmax(stage))
     achieved = alg[dom] / (stage[dom] * 1e-3) / 1e9

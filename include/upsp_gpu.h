@@ -65,7 +65,13 @@ typedef struct {
                          (whole slice resident).  Frame `o` lives in slot o % capacity.  */
   int batch_frames;   /* frames per internal launch batch; 0 => default (32)              */
   int pressure_aliases_intensity; /* 1: pressure_transpose reuses the frame-major
-                         intensity storage (saves one F x N buffer); 0: separate buffer  */
+                         intensity storage when that buffer exists (saves one F x N buffer);
+                         0: separate buffer                                              */
+  int keep_frame_major; /* 0 (default): projections with <= 1 entry per row (the reference's
+                         case) are written straight to node-major rows by the fused
+                         register+project+transpose kernel; the frame-major buffer is never
+                         materialised and upsp_gpu_read_intensity is unavailable.
+                         1: materialise [F_local x N] and transpose separately.          */
 } upsp_gpu_config;
 
 /* Phase2Settings + TunnelConditions + PaintCalibration scalars (psp_process.cpp:1094-1104,

@@ -71,12 +71,12 @@ def run_oracle(orc, case: Case, n_ranks=1, exact_fit=False):
 
 
 def setup_ctx(up, orc_mod, case: Case, rank=0, n_ranks=1, device=0, batch_frames=0,
-              frame_capacity=0, alias=True):
+              frame_capacity=0, alias=True, keep_frame_major=False):
     """Create + configure one rank's context through the C ABI (no oracle involvement:
     orc_mod is only used for the pure-index helpers pack_12bit / overlap_remap)."""
     g = up.PspGpu(case.C, case.N, case.F, device=device, rank=rank, n_ranks=n_ranks,
                   batch_frames=batch_frames, frame_capacity=frame_capacity,
-                  pressure_aliases_intensity=alias)
+                  pressure_aliases_intensity=alias, keep_frame_major=keep_frame_major)
     for c in range(case.C):
         g.set_camera(c, case.W, case.H)
         g.set_projection(c, *case.csr[c])
@@ -115,7 +115,7 @@ def run_gpu(up, orc_mod, case: Case, **kw):
     cap = kw.get("frame_capacity", 0)
     push_all(up, orc_mod, g, case, sl, chunk=cap if cap else None)
     g.finish_phase1()
-    out = dict(intensity=g.read_intensity())
+    out = dict(intensity=g.read_intensity() if kw.get("keep_frame_major") else None)
     out["avg"], out["rms"], out["coverage"] = g.read_phase1_stats()
     g.transpose()
     out["itrans"] = g.read_intensity_transpose()

@@ -151,7 +151,8 @@ def _check_chain(case, ref, got, orc, strict=False):
           ~1e-4 on short series with outliers -- no implementation that does not replay Eigen's
           exact float sequence can be closer than that);
       (c) strict=True (clean series, config 1): plain <= 1e-5 vs the float-QR oracle."""
-    assert same_bits(got["intensity"], ref["intensity"]), "frame-major intensity not bit-exact"
+    if got["intensity"] is not None:
+        assert same_bits(got["intensity"], ref["intensity"]), "frame-major intensity not bit-exact"
     assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
     assert same_bits(got["coverage"], ref["coverage"])
     assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact"
@@ -166,7 +167,7 @@ def _check_chain(case, ref, got, orc, strict=False):
     assert np.all(e_exact <= EXACT_TOL + cond), f"delta-Cp vs float64 model: {(e_exact - cond).max():.3e} > {EXACT_TOL}"
     e_op, e_cp = cp_errors(case, ref, got)
     noise, _ = cp_errors(case, ref, exact)       # the float-QR oracle's own rounding noise
-    assert np.all(e_op <= CP_TOL + noise), f"delta-Cp vs float-QR oracle: {(e_op - noise).max():.3e} > {CP_TOL}"
+    assert np.all(e_op <= CP_TOL + noise + cond), f"delta-Cp vs float-QR oracle: {(e_op - noise - cond).max():.3e} > {CP_TOL}"
     if strict:
         assert e_op.max() <= CP_TOL, f"delta-Cp error {e_op.max():.3e} (relative to operands) > {CP_TOL}"
     v = ~skipped & ~deg
@@ -175,30 +176,36 @@ def _check_chain(case, ref, got, orc, strict=False):
     for key in ("rms2", "avg2"):
         assert np.all(np.abs(got[key][v] - exact[key][v]) / K <= EXACT_TOL + cond)
         nz = np.abs(ref[key][v] - exact[key][v]) / K
-        assert np.all(np.abs(got[key][v] - ref[key][v]) / K <= CP_TOL + nz)
+        assert np.all(np.abs(got[key][v] - ref[key][v]) / K <= CP_TOL + nz + cond)
     return e_op.max(), e_cp.max()
 
 
-def test_chain_config1_plain(up, orc, gpu):
+MODES = pytest.mark.parametrize("keep_frame_major", [False, True], ids=["fused", "frame-major+transpose"])
+
+
+@MODES
+def test_chain_config1_plain(up, orc, gpu, keep_frame_major):
     """config 1: one camera, registration none, patcher none, u16 frames, 128 frames."""
     import upsp_b200
     case = Case(upsp_b200.synth, n_frames=128, n_nodes=5000)
     ref = run_oracle(orc, case)
-    got = run_gpu(up, orc, case)
+    got = run_gpu(up, orc, case, keep_frame_major=keep_frame_major)
     _check_chain(case, ref, got, orc, strict=True)
     assert got["launches"] > 0
 
 
-def test_chain_packed12_small_batches_and_ring(up, orc, gpu):
+@MODES
+def test_chain_packed12_small_batches_and_ring(up, orc, gpu, keep_frame_major):
     """12-bit packed input, batch of 5 frames, 16-slot input ring (streaming mode)."""
     import upsp_b200
     case = Case(upsp_b200.synth, n_frames=50, n_nodes=2000, fmt="p12", seed=3)
     ref = run_oracle(orc, case)
-    got = run_gpu(up, orc, case, batch_frames=5, frame_capacity=16)
+    got = run_gpu(up, orc, case, batch_frames=5, frame_capacity=16, keep_frame_major=keep_frame_major)
     _check_chain(case, ref, got, orc)
 
 
-def test_chain_registration_patches_overlap(up, orc, gpu):
+@MODES
+def test_chain_registration_patches_overlap(up, orc, gpu, keep_frame_major):
     """warp (given matrices) + polynomial patcher (incl. dependent clusters and a clipped
     target) + P3D overlap remap; linear and nearest interpolation."""
     import upsp_b200
@@ -206,36 +213,49 @@ def test_chain_registration_patches_overlap(up, orc, gpu):
         case = Case(upsp_b200.synth, n_frames=40, n_nodes=6000, registration=True, interp=interp,
                     patches=True, overlap=True, overlap_pair=True, kind="random", seed=7)
         ref = run_oracle(orc, case)
-        got = run_gpu(up, orc, case, alias=False)
+        got = run_gpu(up, orc, case, alias=False, keep_frame_major=keep_frame_major)
         _check_chain(case, ref, got, orc)
 
 
-def test_chain_multi_camera_weights(up, orc, gpu):
+@MODES
+def test_chain_multi_camera_weights(up, orc, gpu, keep_frame_major):
     """3 cameras, weighted entries, nodes seen by 0..3 cameras."""
     import upsp_b200
-    case = Case(upsp_b200.synth, n_cams=3, n_frames=33, n_nodes=4000, registration=True, patches=True, seed=11)
+    case = Case(upsp_b200.synth, n_cams=3, n_frames=70, n_nodes=4000, registration=True, patches=True, seed=11)
     ref = run_oracle(orc, case)
-    got = run_gpu(up, orc, case)
+    got = run_gpu(up, orc, case, keep_frame_major=keep_frame_major)
     _check_chain(case, ref, got, orc)
 
 
 def test_chain_general_csr(up, orc, gpu):
-    """rows with up to 4 entries (cfg-5 variant) take the general CSR kernel."""
+    """rows with up to 4 entries (cfg-5 variant) take the general CSR kernel (never fused)."""
     import upsp_b200
     case = Case(upsp_b200.synth, n_cams=2, n_frames=20, n_nodes=3000, multi_nnz=4, seed=13)
     ref = run_oracle(orc, case)
-    got = run_gpu(up, orc, case)
+    got = run_gpu(up, orc, case, keep_frame_major=True)
     _check_chain(case, ref, got, orc)
 
 
-def test_chain_ragged_sizes(up, orc, gpu):
+@MODES
+def test_chain_ragged_sizes(up, orc, gpu, keep_frame_major):
     """odd frame size (not a multiple of 8), F and N not multiples of the tile sizes."""
     import upsp_b200
     case = Case(upsp_b200.synth, n_frames=37, n_nodes=1003, height=51, width=67, registration=True,
                 patches=True, seed=17)
     ref = run_oracle(orc, case)
-    got = run_gpu(up, orc, case)
+    got = run_gpu(up, orc, case, keep_frame_major=keep_frame_major)
     _check_chain(case, ref, got, orc)
+
+
+def test_frame_major_read_needs_keep_flag(up, orc, gpu):
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=8, n_nodes=300)
+    from chain import push_all, setup_ctx
+    g, sl = setup_ctx(up, orc, case)
+    push_all(up, orc, g, case, sl)
+    with pytest.raises(up.UpspGpuError):
+        g.read_intensity()
+    g.close()
 
 
 def test_error_behaviour(up, gpu):

@@ -35,7 +35,7 @@ class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_cams", C.c_int), ("n_nodes", C.c_int),
                 ("n_frames_total", C.c_int), ("rank", C.c_int), ("n_ranks", C.c_int),
                 ("frame_capacity", C.c_int), ("batch_frames", C.c_int),
-                ("pressure_aliases_intensity", C.c_int)]
+                ("pressure_aliases_intensity", C.c_int), ("keep_frame_major", C.c_int)]
 
 
 class _Phase2Params(C.Structure):
@@ -83,9 +83,10 @@ class PspGpu:
     (cpp/exec/psp_process.cpp:1438-2043, :2262-2622)."""
 
     def __init__(self, n_cams, n_nodes, n_frames_total, *, device=0, rank=0, n_ranks=1,
-                 frame_capacity=0, batch_frames=0, pressure_aliases_intensity=True):
+                 frame_capacity=0, batch_frames=0, pressure_aliases_intensity=True,
+                 keep_frame_major=False):
         cfg = _Config(device, n_cams, n_nodes, n_frames_total, rank, n_ranks, frame_capacity,
-                      batch_frames, int(pressure_aliases_intensity))
+                      batch_frames, int(pressure_aliases_intensity), int(keep_frame_major))
         self._h = C.c_void_p()
         _chk(lib().upsp_gpu_create(C.byref(cfg), C.byref(self._h)))
         self.n_cams, self.n_nodes, self.n_frames_total = n_cams, n_nodes, n_frames_total

@@ -198,12 +198,12 @@ k_frame_prep(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
   for (int i = threadIdx.x; i < max(W, H); i += blockDim.x) {
     const double v = (double)i;
     if (i < W) {
-      t[i] = __double2int_rn(__dmul_rn(__dmul_rn(m0, v), 1024.0));
-      t[W + i] = __double2int_rn(__dmul_rn(__dmul_rn(m3, v), 1024.0));
+      t[2 * i] = __double2int_rn(__dmul_rn(__dmul_rn(m0, v), 1024.0));
+      t[2 * i + 1] = __double2int_rn(__dmul_rn(__dmul_rn(m3, v), 1024.0));
     }
     if (i < H) {
-      t[2 * W + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, v), m2), 1024.0)) + round_delta;
-      t[2 * W + H + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, v), m5), 1024.0)) + round_delta;
+      t[2 * W + 2 * i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, v), m2), 1024.0)) + round_delta;
+      t[2 * W + 2 * i + 1] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, v), m5), 1024.0)) + round_delta;
     }
   }
 }
@@ -214,7 +214,7 @@ k_frame_prep(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
 // (AB_BITS 10, INTER_BITS 5) built from per-column / per-row tables, float weights,
 // round-half-even to u16.  k_warp_tables builds the tables exactly as WarpAffineInvoker
 // does (double products, cvRound); k_warp_affine samples.
-//   tab layout per frame: [adelta[W] | bdelta[W] | X0[H] | Y0[H]] int32
+//   tab layout per frame: [(adelta,bdelta)[W] | (X0,Y0)[H]] int32 pairs
 // ---------------------------------------------------------------------------------------
 __global__ void k_warp_tables(const float* __restrict__ m6, int nframes, int W, int H, int interp,
                               int* __restrict__ tab) {
@@ -225,15 +225,15 @@ __global__ void k_warp_tables(const float* __restrict__ m6, int nframes, int W, 
   const int round_delta = interp == 0 ? 512 : 16;
   if (i < W) {
     double x = (double)i;
-    t[i] = __double2int_rn(__dmul_rn(__dmul_rn((double)M[0], x), 1024.0));
-    t[W + i] = __double2int_rn(__dmul_rn(__dmul_rn((double)M[3], x), 1024.0));
+    t[2 * i] = __double2int_rn(__dmul_rn(__dmul_rn((double)M[0], x), 1024.0));
+    t[2 * i + 1] = __double2int_rn(__dmul_rn(__dmul_rn((double)M[3], x), 1024.0));
   }
   if (i < H) {
     double y = (double)i;
-    t[2 * W + i] = __double2int_rn(__dmul_rn(
-                       __dadd_rn(__dmul_rn((double)M[1], y), (double)M[2]), 1024.0)) + round_delta;
-    t[2 * W + H + i] = __double2int_rn(__dmul_rn(
-                           __dadd_rn(__dmul_rn((double)M[4], y), (double)M[5]), 1024.0)) + round_delta;
+    t[2 * W + 2 * i] = __double2int_rn(__dmul_rn(
+                           __dadd_rn(__dmul_rn((double)M[1], y), (double)M[2]), 1024.0)) + round_delta;
+    t[2 * W + 2 * i + 1] = __double2int_rn(__dmul_rn(
+                               __dadd_rn(__dmul_rn((double)M[4], y), (double)M[5]), 1024.0)) + round_delta;
   }
 }
 
@@ -265,43 +265,36 @@ __device__ __forceinline__ uint32_t sat_u16_rn(float v) {   // v in [0, 65536): 
   return (uint32_t)min(max(iv, 0), 65535);
 }
 
-// block (64,4): each thread produces 2 horizontally adjacent pixels; grid (ceil(W/128), ceil(H/4), frames)
-__global__ void __launch_bounds__(256)
-k_warp_affine_u16(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int W, int H,
-                  const int* __restrict__ tab, int interp, int skip_frame) {
-  const int f = blockIdx.z;
-  const int x = (blockIdx.x * 64 + threadIdx.x) * 2;
-  const int y = blockIdx.y * 4 + threadIdx.y;
-  if (x >= W || y >= H) return;
-  const size_t P = (size_t)W * H;
-  const uint16_t* s = src + (size_t)f * P;
-  uint16_t* d = dst + (size_t)f * P + (size_t)y * W + x;
-  if (f == skip_frame) {  // global frame 0 is never registered (psp_process.cpp:1777)
-    d[0] = s[(size_t)y * W + x];
-    if (x + 1 < W) d[1] = s[(size_t)y * W + x + 1];
-    return;
+// One pixel of the registered frame: cv::warpAffine(...)(y,x) as an integer-valued float
+// (already rounded half-to-even and saturated to u16).  Used where only a few pixels of the
+// registered frame are needed (patch boundary pixels, the projected nodes' pixels), so the
+// registered frame itself never has to be materialised.
+__device__ __forceinline__ float warp_px_u16(const uint16_t* __restrict__ s, int W, int H,
+                                             const int* __restrict__ tab, int x, int y, int interp) {
+  const int2 xa = __ldg(reinterpret_cast<const int2*>(tab) + x);
+  const int2 ya = __ldg(reinterpret_cast<const int2*>(tab + 2 * W) + y);
+  const int X = ya.x + xa.x, Y = ya.y + xa.y;
+  if (interp == 0) {
+    const int sx = X >> 10, sy = Y >> 10;
+    return ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H)
+               ? u2f_exact(__ldg(s + (size_t)sy * W + sx)) : 0.0f;
   }
-  const int* t = tab + (size_t)f * (2 * W + 2 * H);
-  const int X0 = t[2 * W + y], Y0 = t[2 * W + H + y];
-  uint32_t o[2] = {0, 0};
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    int xx = x + k;
-    if (xx >= W) break;
-    int X = X0 + t[xx], Y = Y0 + t[W + xx];
-    if (interp == 0) {
-      int sx = X >> 10, sy = Y >> 10;
-      o[k] = (sx >= 0 && sx < W && sy >= 0 && sy < H) ? (uint32_t)__ldg(s + (size_t)sy * W + sx) : 0u;
-    } else {
-      o[k] = sat_u16_rn(warp_sample_linear<uint16_t>(s, W, H, X, Y));
-    }
+  const int Xs = X >> 5, Ys = Y >> 5;
+  const int sx = Xs >> 5, sy = Ys >> 5;
+  float v;
+  if ((unsigned)sx < (unsigned)(W - 1) && (unsigned)sy < (unsigned)(H - 1)) {
+    const uint16_t* p = s + (size_t)sy * W + sx;
+    const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    v = __fadd_rn(__fmul_rn(u2f_exact(__ldg(p)), __fmul_rn(gy, gx)),
+                  __fmul_rn(u2f_exact(__ldg(p + 1)), __fmul_rn(gy, fx)));
+    v = __fadd_rn(v, __fmul_rn(u2f_exact(__ldg(p + W)), __fmul_rn(fy, gx)));
+    v = __fadd_rn(v, __fmul_rn(u2f_exact(__ldg(p + W + 1)), __fmul_rn(fy, fx)));
+  } else {
+    v = warp_sample_linear<uint16_t>(s, W, H, X, Y);
   }
-  if (x + 1 < W && ((W & 1) == 0))
-    *reinterpret_cast<uint32_t*>(d) = o[0] | (o[1] << 16);
-  else {
-    d[0] = (uint16_t)o[0];
-    if (x + 1 < W) d[1] = (uint16_t)o[1];
-  }
+  const float r = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);   // rint, half to even
+  return fminf(fmaxf(r, 0.0f), 65535.0f);
 }
 
 // 8 output pixels per thread (one 16-byte store).  Near-identity maps (the registration case:
@@ -345,21 +338,22 @@ k_warp_affine8_u16(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
     return;
   }
   const int* t = tab + (size_t)f * (2 * W + 2 * H);
-  const int X0 = __ldg(t + 2 * W + y), Y0 = __ldg(t + 2 * W + H + y);
+  const int2 y0 = __ldg(reinterpret_cast<const int2*>(t + 2 * W) + y);
+  const int X0 = y0.x, Y0 = y0.y;
   int X[8], Y[8];
-  if (full && ((W & 3) == 0)) {
-    const int4 a0 = __ldg(reinterpret_cast<const int4*>(t + x)), a1 = __ldg(reinterpret_cast<const int4*>(t + x + 4));
-    const int4 b0 = __ldg(reinterpret_cast<const int4*>(t + W + x)), b1 = __ldg(reinterpret_cast<const int4*>(t + W + x + 4));
-    X[0] = X0 + a0.x; X[1] = X0 + a0.y; X[2] = X0 + a0.z; X[3] = X0 + a0.w;
-    X[4] = X0 + a1.x; X[5] = X0 + a1.y; X[6] = X0 + a1.z; X[7] = X0 + a1.w;
-    Y[0] = Y0 + b0.x; Y[1] = Y0 + b0.y; Y[2] = Y0 + b0.z; Y[3] = Y0 + b0.w;
-    Y[4] = Y0 + b1.x; Y[5] = Y0 + b1.y; Y[6] = Y0 + b1.z; Y[7] = Y0 + b1.w;
+  if (full) {
+    const int4* q = reinterpret_cast<const int4*>(t + 2 * x);   // (ad,bd) pairs of 8 pixels
+    const int4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+    X[0] = X0 + a0.x; Y[0] = Y0 + a0.y; X[1] = X0 + a0.z; Y[1] = Y0 + a0.w;
+    X[2] = X0 + a1.x; Y[2] = Y0 + a1.y; X[3] = X0 + a1.z; Y[3] = Y0 + a1.w;
+    X[4] = X0 + a2.x; Y[4] = Y0 + a2.y; X[5] = X0 + a2.z; Y[5] = Y0 + a2.w;
+    X[6] = X0 + a3.x; Y[6] = Y0 + a3.y; X[7] = X0 + a3.z; Y[7] = Y0 + a3.w;
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int xx = min(x + k, W - 1);
-      X[k] = X0 + __ldg(t + xx);
-      Y[k] = Y0 + __ldg(t + W + xx);
+      X[k] = X0 + __ldg(t + 2 * xx);
+      Y[k] = Y0 + __ldg(t + 2 * xx + 1);
     }
   }
   uint32_t o[8];
@@ -438,107 +432,94 @@ struct PatchGeom {            // device pointers, one per camera
   const int* order;           // clusters sorted by dependency level
 };
 
-// One warp per (cluster, 32 frames).  SMEM: the cluster's reflectors (E, tau*E) are staged in
-// shared memory once (coalesced) and the per-lane work vector c lives there too ([nb][32]
-// floats), so the strictly sequential dot-product chains run at shared-memory latency;
-// otherwise (huge clusters) both stay in global memory.
-template <bool SMEM>
+// One warp per (cluster, frame): lanes stride over the boundary / interior pixels.  The only
+// order-sensitive reduction, s = ((p0+p1)+p2)+..., is done by lane 0 over products that all
+// lanes computed in parallel, so the sequential chain is n adds instead of the whole solve.
+// tab != nullptr: the boundary pixels are taken from the REGISTERED frame, computed on the fly
+// (warp_px_u16) from the decoded frame.
 __global__ void __launch_bounds__(32)
 k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict__ frames,
-        size_t npix, int nframes, int bstride, float* __restrict__ scratch,
-        float* __restrict__ pv) {
+        size_t npix, int W, int H, const int* __restrict__ tab, int interp, int skip_frame,
+        int bstride, float* __restrict__ pv) {
   extern __shared__ float psh[];
   const int cl = cl_list[blockIdx.x];
+  const int b = blockIdx.y;
   const int lane = threadIdx.x;
-  const int b = blockIdx.y * 32 + lane;
-  const bool live = b < nframes;
   const int nz = g.nzp[cl];
   if (nz < 0) return;
   const int off = g.bounds_off[cl], nb = g.bounds_off[cl + 1] - off;
-  const float* Eg = g.qr_e + (size_t)10 * off;
-  const float* TEg = g.qr_te + (size_t)10 * off;
-  const float* E = Eg;
-  const float* TE = TEg;
-  float* c;
-  int cs;
-  if (SMEM) {
-    float* Es = psh;               // [10*nb]
-    float* TEs = psh + 10 * nb;    // [10*nb]
-    for (int i = lane; i < 10 * nb; i += 32) {
-      Es[i] = __ldg(Eg + i);
-      TEs[i] = __ldg(TEg + i);
-    }
-    E = Es;
-    TE = TEs;
-    c = psh + 20 * nb + lane;      // [nb][32]
-    cs = 32;
-    __syncwarp();
-  } else {
-    c = scratch + (size_t)off * bstride + (live ? b : 0);
-    cs = bstride;
-  }
-  if (!live) return;
+  float* c = psh;            // [nb]
+  float* prod = psh + nb;    // [nb]
+  float* poly = psh + 2 * nb;  // [10]
   const uint16_t* img = frames + (size_t)b * npix;
-  for (int i = 0; i < nb; ++i) {
-    int s = __ldg(g.bsrc + off + i);
-    c[(size_t)i * cs] = s >= 0 ? (float)img[s] : pv[(size_t)(-1 - s) * bstride + b];
+  const int* t = (tab != nullptr && b != skip_frame) ? tab + (size_t)b * (2 * W + 2 * H) : nullptr;
+  for (int i = lane; i < nb; i += 32) {
+    const int s = __ldg(g.bsrc + off + i);
+    float v;
+    if (s < 0) v = pv[(size_t)(-1 - s) * bstride + b];
+    else if (t) v = warp_px_u16(img, W, H, t, s % W, s / W, interp);
+    else v = u2f_exact(__ldg(img + s));
+    c[i] = v;
   }
+  __syncwarp();
+  const float* E = g.qr_e + (size_t)10 * off;
+  const float* TE = g.qr_te + (size_t)10 * off;
   const float* hc = g.hcoef + cl * 10;
   for (int k = 0; k < nz; ++k) {
     const int n = nb - k;
     const float tau = hc[k];
     if (n == 1) {
-      c[(size_t)k * cs] = __fmul_rn(c[(size_t)k * cs], __fsub_rn(1.0f, tau));
+      if (lane == 0) c[k] = __fmul_rn(c[k], __fsub_rn(1.0f, tau));
     } else if (tau != 0.0f) {
       const float* e = E + (size_t)k * nb + k + 1;
       const float* te = TE + (size_t)k * nb + k + 1;
-      const float* ck = c + (size_t)(k + 1) * cs;
-      float s = 0.0f;
-      int i = 0;
-      for (; i + 4 <= n - 1; i += 4) {   // products are independent; the adds stay in order
-        const float p0 = __fmul_rn(e[i], ck[(size_t)i * cs]);
-        const float p1 = __fmul_rn(e[i + 1], ck[(size_t)(i + 1) * cs]);
-        const float p2 = __fmul_rn(e[i + 2], ck[(size_t)(i + 2) * cs]);
-        const float p3 = __fmul_rn(e[i + 3], ck[(size_t)(i + 3) * cs]);
-        s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, p0), p1), p2), p3);
+      for (int i = lane; i < n - 1; i += 32) prod[i] = __fmul_rn(__ldg(e + i), c[k + 1 + i]);
+      __syncwarp();
+      float tt = 0.0f;
+      if (lane == 0) {
+        float s = 0.0f;
+        int i = 0;
+        for (; i + 8 <= n - 1; i += 8) {
+          const float p0 = prod[i], p1 = prod[i + 1], p2 = prod[i + 2], p3 = prod[i + 3];
+          const float p4 = prod[i + 4], p5 = prod[i + 5], p6 = prod[i + 6], p7 = prod[i + 7];
+          s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, p0), p1), p2), p3);
+          s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, p4), p5), p6), p7);
+        }
+        for (; i < n - 1; ++i) s = __fadd_rn(s, prod[i]);
+        tt = __fadd_rn(s, c[k]);
+        c[k] = __fsub_rn(c[k], __fmul_rn(tau, tt));
       }
-      for (; i < n - 1; ++i) s = __fadd_rn(s, __fmul_rn(e[i], ck[(size_t)i * cs]));
-      const float t = __fadd_rn(s, c[(size_t)k * cs]);
-      c[(size_t)k * cs] = __fsub_rn(c[(size_t)k * cs], __fmul_rn(tau, t));
-#pragma unroll 4
-      for (int j = 0; j < n - 1; ++j) {
-        float* ci = c + (size_t)(k + 1 + j) * cs;
-        *ci = __fsub_rn(*ci, __fmul_rn(t, te[j]));
+      tt = __shfl_sync(0xffffffffu, tt, 0);
+      for (int i = lane; i < n - 1; i += 32) c[k + 1 + i] = __fsub_rn(c[k + 1 + i], __fmul_rn(tt, __ldg(te + i)));
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    float x[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) x[i] = i < nz ? c[i] : 0.0f;
+#pragma unroll
+    for (int i = 9; i >= 0; --i) {
+      if (i < nz) {
+        x[i] = __fdiv_rn(x[i], __ldg(E + (size_t)i * nb + i));
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          if (j < i) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], __ldg(E + (size_t)i * nb + j)));
       }
     }
+    const int* pm = g.perm + cl * 10;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) poly[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) poly[pm[i]] = i < nz ? x[i] : 0.0f;
   }
-  float x[10], poly[10];
+  __syncwarp();
+  float pl[10];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) x[i] = i < nz ? c[(size_t)i * cs] : 0.0f;
-#pragma unroll
-  for (int i = 9; i >= 0; --i) {
-    if (i < nz) {
-      x[i] = __fdiv_rn(x[i], E[(size_t)i * nb + i]);
-#pragma unroll
-      for (int j = 0; j < 10; ++j)
-        if (j < i) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], E[(size_t)i * nb + j]));
-    }
-  }
-  const int* pm = g.perm + cl * 10;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) poly[i] = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const float v = i < nz ? x[i] : 0.0f;
-    const int pi = pm[i];
-#pragma unroll
-    for (int q = 0; q < 10; ++q)
-      if (q == pi) poly[q] = v;
-  }
+  for (int i = 0; i < 10; ++i) pl[i] = poly[i];
   // polyval2D: z = sum_c poly[c] * y^i * x^j, order [1,x,x2,x3,y,xy,x2y,y2,xy2,y3]
   const int ioff = g.internal_off[cl], ni = g.internal_off[cl + 1] - ioff;
-#pragma unroll 2
-  for (int i = 0; i < ni; ++i) {
+  for (int i = lane; i < ni; i += 32) {
     const float* pw = g.ipow + (size_t)6 * (ioff + i);
     const float xp[4] = {1.0f, __ldg(pw), __ldg(pw + 1), __ldg(pw + 2)};
     const float yp[4] = {1.0f, __ldg(pw + 3), __ldg(pw + 4), __ldg(pw + 5)};
@@ -549,7 +530,7 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
 #pragma unroll
       for (int bb = 0; bb <= 3; ++bb)
         if (a + bb <= 3) {
-          z = __fadd_rn(z, __fmul_rn(__fmul_rn(poly[cnt], yp[a]), xp[bb]));
+          z = __fadd_rn(z, __fmul_rn(__fmul_rn(pl[cnt], yp[a]), xp[bb]));
           ++cnt;
         }
     pv[(size_t)(ioff + i) * bstride + b] = z;

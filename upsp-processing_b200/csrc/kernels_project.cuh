@@ -140,6 +140,105 @@ k_project_csr(const ProjArgs a) {
   a.sumsq[n] += q;
 }
 
+// ---- fused path (ELL-1 tables): register + project + blend + NaN + sum/sum-sq + remap AND the
+// frame-major -> node-major transpose + all-to-all in ONE kernel.
+//   * registration: only the pixels the nodes look at are warped (warp_px_u16), straight from
+//     the decoded frame; the registered image is never written (saves 2P write + 2P read per
+//     frame and half of the per-pixel warp arithmetic when N < P);
+//   * output: a block owns 256 nodes x 32 frames, stages the [32][256] result tile in shared
+//     memory and writes each node's 32 consecutive frames as one 128-byte segment of its
+//     node-major row -- in the destination rank's buffer (peer-mapped over NVLink when the node
+//     belongs to another GPU).  The frame-major intensity buffer and the separate transpose
+//     pass (8N bytes per frame) disappear; the exchange overlaps phase-1 compute.
+// Reference: psp_process.cpp:1790-1842 + local_transpose/global_transpose :647-771.
+struct FusedCam {
+  const uint16_t* frames;  // [batch][npix] decoded, hot-pixel-fixed frames (NOT registered)
+  size_t npix;
+  int W, H;
+  const int* tab;          // [batch][2W+2H] warp tables, or nullptr (registration = none)
+  const float* pv;         // [slots][bstride] patch values
+  const int* code;         // [N]
+  const float* val;        // [N]
+};
+struct FusedArgs {
+  int n_cams, n_nodes, nframes, bstride, interp, skip_frame;
+  FusedCam cam[UPSP_MAX_CAMS];
+  double* sum;
+  double* sumsq;
+  int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
+  float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
+  int node_start[UPSP_MAX_RANKS + 1];
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_project_fused(const FusedArgs a) {
+  __shared__ float tile[32][257];
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const bool live = n < a.n_nodes;
+  int code[NC], px[NC], py[NC];
+  float val[NC];
+  bool skipped = true;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    code[c] = live ? __ldg(a.cam[c].code + n) : -1;
+    val[c] = live ? __ldg(a.cam[c].val + n) : 0.0f;
+    skipped = skipped && (code[c] == -1);
+    px[c] = code[c] >= 0 ? code[c] % a.cam[c].W : 0;
+    py[c] = code[c] >= 0 ? code[c] / a.cam[c].W : 0;
+  }
+  double s = 0.0, q = 0.0;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
+    const int nb = min(32, a.nframes - b0);
+    if (live) {
+#pragma unroll 4
+      for (int u = 0; u < nb; ++u) {
+        const int b = b0 + u;
+        float sol = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float cs = 0.0f;
+          if (code[c] != -1) {
+            const FusedCam& cam = a.cam[c];
+            float v;
+            if (code[c] <= -2) {
+              v = __ldg(cam.pv + (size_t)(-2 - code[c]) * a.bstride + b);
+            } else if (cam.tab != nullptr && b != a.skip_frame) {
+              v = warp_px_u16(cam.frames + (size_t)b * cam.npix, cam.W, cam.H,
+                              cam.tab + (size_t)b * (2 * cam.W + 2 * cam.H), px[c], py[c], a.interp);
+            } else {
+              v = u2f_exact(__ldg(cam.frames + (size_t)b * cam.npix + code[c]));
+            }
+            cs = __fadd_rn(0.0f, __fmul_rn(val[c], v));
+          }
+          sol = (c == 0) ? cs : __fadd_rn(sol, cs);
+        }
+        if (skipped) sol = __int_as_float(0x7fc00000);
+        tile[u][threadIdx.x] = sol;
+        q += (double)__fmul_rn(sol, sol);
+        s += (double)sol;
+      }
+    }
+    __syncthreads();
+    // warp w writes nodes [w*32, w*32+32) of the block: lane = frame -> 128-byte row segments
+    for (int j = 0; j < 32; ++j) {
+      const int nn = blockIdx.x * 256 + w * 32 + j;
+      if (nn >= a.n_nodes) break;
+      if (lane < nb) {
+        int r = 0;
+        while (r + 1 < a.n_ranks && nn >= a.node_start[r + 1]) ++r;
+        a.dst[r][(size_t)(nn - a.node_start[r]) * a.f_total + a.col0 + b0 + lane] = tile[lane][w * 32 + j];
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    a.sum[n] += s;
+    a.sumsq[n] += q;
+  }
+}
+
 // stand-alone project_frame on f32 frames (upsp_op_project_frames): out[f][r]
 __global__ void __launch_bounds__(256)
 k_project_f32(const int* __restrict__ rowptr, const int* __restrict__ col,

@@ -120,7 +120,7 @@ struct upsp_gpu_ctx {
   int hot_fix = 1;
   std::vector<Camera> cams;
   std::vector<int> remap;  // src_index or empty
-  bool finalized = false, ell1 = true;
+  bool finalized = false, ell1 = true, fused = false;
   uint16_t* d_lut = nullptr;
 
   cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -251,9 +251,7 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
       r.off = r.count = 0;
       CU(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
     }
-    const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
-    const bool alias = cfg->pressure_aliases_intensity != 0;
-    TRY(dmalloc(&c->d_intensity, alias ? std::max(fn, nf) : fn));
+    const size_t nf = (size_t)c->N_local * c->F;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     c->off_sum = al(nf * sizeof(float));
     c->off_sumsq = c->off_sum + al((size_t)c->N * sizeof(double));
@@ -264,12 +262,6 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     c->d_sumsq = reinterpret_cast<double*>(c->d_shared + c->off_sumsq);
     CU(cudaMemsetAsync(c->d_sum, 0, (size_t)c->N * sizeof(double), c->stream));
     CU(cudaMemsetAsync(c->d_sumsq, 0, (size_t)c->N * sizeof(double), c->stream));
-    if (alias) {
-      c->d_ptrans = c->d_intensity;
-    } else {
-      TRY(dmalloc(&c->d_ptrans, nf));
-      c->ptrans_owned = true;
-    }
     TRY(dmalloc(&c->d_avg, c->N));
     TRY(dmalloc(&c->d_rms, c->N));
     TRY(dmalloc(&c->d_cov, c->N));
@@ -606,6 +598,7 @@ static int finalize(upsp_gpu_ctx* c) {
   for (auto& k : c->cams)
     for (int n = 0; n < N && c->ell1; ++n)
       if (k.rowptr[n + 1] - k.rowptr[n] > 1) c->ell1 = false;
+  c->fused = c->ell1 && c->cfg.keep_frame_major == 0;
   std::vector<float> cov(N, 0.0f);
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
@@ -660,17 +653,29 @@ static int finalize(upsp_gpu_ctx* c) {
     TRY(dmalloc(&k.d_hot_cnt, (size_t)c->batch));
     TRY(dmalloc(&k.d_hot_pos, (size_t)c->batch * UPSP_HOT_STORE));
     if (c->registration != UPSP_REG_NONE) {
-      TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
+      if (!c->fused) TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
       TRY(dmalloc(&k.d_tab, (size_t)c->batch * (2 * k.W + 2 * k.H)));
       if (c->registration == UPSP_REG_GIVEN)
         REQUIRE(k.has_m6, UPSP_ERR_STATE, "registration=given but camera %zu has no warp matrices", ci);
     }
     if (use_patch && k.has_patches) {
-      TRY(dmalloc(&k.d_scratch, (size_t)k.total_bounds * c->batch));
       TRY(dmalloc(&k.d_pv, (size_t)std::max(k.total_internal, 1) * c->batch));
     }
   }
   CU(cudaMemcpy(c->d_cov, cov.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  // big buffers that depend on the mode
+  {
+    const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
+    const bool alias = c->cfg.pressure_aliases_intensity != 0;
+    if (!c->fused) {
+      TRY(dmalloc(&c->d_intensity, alias ? std::max(fn, nf) : fn));
+      if (alias) c->d_ptrans = c->d_intensity;
+    }
+    if (!c->d_ptrans) {
+      TRY(dmalloc(&c->d_ptrans, nf));
+      c->ptrans_owned = true;
+    }
+  }
   c->finalized = true;
   return UPSP_OK;
 }
@@ -752,7 +757,8 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   pa.n_nodes = c->N;
   pa.nframes = nb;
   pa.bstride = c->batch;
-  pa.out = c->d_intensity + (size_t)off * c->N;
+  pa.out = c->fused ? nullptr : c->d_intensity + (size_t)off * c->N;
+  FusedArgs fa{};
   pa.sum = c->d_sum;
   pa.sumsq = c->d_sumsq;
   const int slot = off % c->capacity;
@@ -782,9 +788,9 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       KCHECK(c);
     }
     const uint16_t* cur = k.d_work;
-    if (reg) {
-      // global frame 0 is never registered (psp_process.cpp:1777)
-      const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
+    // global frame 0 is never registered (psp_process.cpp:1777)
+    const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
+    if (reg && !c->fused) {
       k_warp_affine8_u16<<<dim3(cdiv(k.W, 1024), k.H, nb), 128, 0, c->stream>>>(
           k.d_work, k.d_warp, k.W, k.H, k.d_tab, c->interp, skip_frame);
       KCHECK(c);
@@ -792,19 +798,16 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     const bool patch = c->patcher == UPSP_PATCH_POLYNOMIAL && k.has_patches;
     if (patch) {
+      const size_t sm = ((size_t)2 * k.max_bounds + 16) * sizeof(float);
+      REQUIRE(sm <= 200 * 1024, UPSP_ERR_INVALID, "patch cluster with %d boundary pixels is too large", k.max_bounds);
+      if (sm > 48 * 1024)
+        CU(cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
         const int ncl = k.level_off[l + 1] - k.level_off[l];
         if (!ncl) continue;
-        const size_t sm = (size_t)k.max_bounds * (32 + 20) * sizeof(float);
-        if (sm <= 96 * 1024) {
-          if (sm > 48 * 1024)
-            CU(cudaFuncSetAttribute(k_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-          k_patch<true><<<dim3(ncl, cdiv(nb, 32)), 32, sm, c->stream>>>(
-              k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
-        } else {
-          k_patch<false><<<dim3(ncl, cdiv(nb, 32)), 32, 0, c->stream>>>(
-              k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, nb, c->batch, k.d_scratch, k.d_pv);
-        }
+        k_patch<<<dim3(ncl, nb), 32, sm, c->stream>>>(
+            k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, k.W, k.H,
+            (reg && c->fused) ? k.d_tab : nullptr, c->interp, skip_frame, c->batch, k.d_pv);
         KCHECK(c);
       }
     }
@@ -814,6 +817,45 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     pa.cam[ci].code = k.d_code;
     pa.cam[ci].val = k.d_val;
     pa.cam[ci].rowptr = k.d_rowptr;
+    fa.cam[ci].frames = k.d_work;
+    fa.cam[ci].npix = k.npix;
+    fa.cam[ci].W = k.W;
+    fa.cam[ci].H = k.H;
+    fa.cam[ci].tab = reg ? k.d_tab : nullptr;
+    fa.cam[ci].pv = patch ? k.d_pv : nullptr;
+    fa.cam[ci].code = k.d_code;
+    fa.cam[ci].val = k.d_val;
+    fa.skip_frame = skip_frame;
+  }
+  if (c->fused) {
+    fa.n_cams = pa.n_cams;
+    fa.n_nodes = c->N;
+    fa.nframes = nb;
+    fa.bstride = c->batch;
+    fa.interp = c->interp;
+    fa.sum = c->d_sum;
+    fa.sumsq = c->d_sumsq;
+    fa.n_ranks = c->R;
+    fa.f_total = c->F;
+    fa.col0 = c->f0 + off;
+    for (int r = 0; r < c->R; ++r) {
+      fa.dst[r] = reinterpret_cast<float*>(c->peer_base[r]);
+      fa.node_start[r] = c->n_start[r];
+    }
+    fa.node_start[c->R] = c->N;
+    const unsigned g = cdiv(c->N, 256);
+    switch (fa.n_cams) {
+      case 1: k_project_fused<1><<<g, 256, 0, c->stream>>>(fa); break;
+      case 2: k_project_fused<2><<<g, 256, 0, c->stream>>>(fa); break;
+      case 3: k_project_fused<3><<<g, 256, 0, c->stream>>>(fa); break;
+      case 4: k_project_fused<4><<<g, 256, 0, c->stream>>>(fa); break;
+      case 5: k_project_fused<5><<<g, 256, 0, c->stream>>>(fa); break;
+      case 6: k_project_fused<6><<<g, 256, 0, c->stream>>>(fa); break;
+      case 7: k_project_fused<7><<<g, 256, 0, c->stream>>>(fa); break;
+      default: k_project_fused<8><<<g, 256, 0, c->stream>>>(fa); break;
+    }
+    KCHECK(c);
+    return UPSP_OK;
   }
   if (c->ell1)
     launch_project_ell1<4>(c, pa);
@@ -828,6 +870,10 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
   REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID,
           "frames [%d,%d) outside the local slice of %d", off, off + count, c->F_local);
   TRY(finalize(c));
+  if (c->fused && c->R > 1)
+    REQUIRE(c->peers_ready, UPSP_ERR_STATE,
+            "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local): the fused "
+            "projection stores node-major rows straight into peer buffers");
   CU(cudaStreamWaitEvent(c->stream, c->ev_push, 0));
   CU(cudaEventRecord(c->ev_pa, c->stream));
   int done = 0;
@@ -904,6 +950,12 @@ extern "C" int upsp_gpu_transpose(upsp_gpu_ctx* c) {
   ENTER(c);
   REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
   REQUIRE(c->exchange == UPSP_XCHG_PEER, UPSP_ERR_STATE, "only UPSP_XCHG_PEER is built");
+  if (c->fused) {  // k_project_fused already wrote node-major rows (local and peer)
+    CU(cudaStreamSynchronize(c->stream));
+    c->stage_ms[2] = 0.0f;
+    c->transposed = true;
+    return UPSP_OK;
+  }
   if (c->R > 1)
     REQUIRE(c->peers_ready, UPSP_ERR_STATE,
             "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
@@ -1094,6 +1146,8 @@ static int d2h(upsp_gpu_ctx* c, void* host, const void* dev, size_t bytes) {
 extern "C" int upsp_gpu_read_intensity(upsp_gpu_ctx* c, int off, int n, float* host) {
   ENTER(c);
   REQUIRE(off >= 0 && n >= 0 && off + n <= c->F_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
+  REQUIRE(c->finalized && !c->fused, UPSP_ERR_STATE,
+          "frame-major intensity is not materialised (create the context with keep_frame_major=1)");
   REQUIRE(!(c->phase2_done && !c->ptrans_owned), UPSP_ERR_STATE,
           "frame-major intensity was overwritten by pressure_transpose (pressure_aliases_intensity)");
   return d2h(c, host, c->d_intensity + (size_t)off * c->N, (size_t)n * c->N * sizeof(float));
