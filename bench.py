@@ -198,6 +198,7 @@ def bench_b200(args):
     g.sync()
     barrier(dist)
     sampler = ClockSampler(local) if rank == 0 else None
+    g.set_kernel_sampling(8)          # CUDA events around every 8th batch's kernels (+ phase 2)
     l0 = g.launch_count()
     stage = np.zeros(4)
     g.timer_start()
@@ -205,6 +206,8 @@ def bench_b200(args):
     for _ in range(args.steps):
         run_step_resident(g, wl, args, dist)
         stage += [g.stage_ms(i) for i in range(4)]
+        if _ == args.steps - 1:
+            kms = [g.kernel_ms(k) for k in range(7)]     # of the last timed step
     ms_dev = g.timer_stop()
     g.sync()
     barrier(dist)
@@ -232,11 +235,24 @@ def bench_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant stage kernel and its algorithmic bytes per launch (DESIGN.md "algorithmic bytes")
-    names = ["process_frames(decode+prep+patch+k_project_fused)", "finish_phase1", "k_transpose_a2a", "k_phase2"]
-    alg = [(1.5 * P + 4.0 * N) * F_local, 24.0 * N, 8.0 * N * F_local, 8.0 * (N / world) * F_total]
-    dom = int(np.argmax(stage))
-    achieved = alg[dom] / (stage[dom] * 1e-3) / 1e9
+    # per-kernel launches of one step, CUDA-event mean duration (sampled inside the timed region),
+    # algorithmic bytes per launch
+    B = args.batch if args.batch > 0 else 32
+    nbatch = -(-F_local // B)
+    knames = ["k_unpack12_scan", "k_frame_prep", "k_warp_affine8_u16", "k_patch", "k_project_fused",
+              "k_transpose_a2a", "k_phase2"]
+    kalg = [B * 3.5 * P, 0.0, B * 4.0 * P, 0.0, B * (2.0 * P + 4.0 * N), 8.0 * N * F_local,
+            8.0 * (N / world) * F_total]
+    klaunch = [nbatch, nbatch, nbatch, nbatch, nbatch, 1, 1]
+    kernels = {}
+    for nm, (ms, ns), ab, nl in zip(knames, kms, kalg, klaunch):
+        if ns:
+            kernels[nm] = {"mean_ms": round(ms, 4), "launches_per_step": nl, "ms_per_step": round(ms * nl, 3),
+                           "alg_bytes_per_launch": ab, "gbs": round(ab / (ms * 1e-3) / 1e9, 1) if ab else None,
+                           "sampled": ns}
+    dom = max((k for k in kernels if kernels[k]["alg_bytes_per_launch"]), key=lambda k: kernels[k]["ms_per_step"])
+    achieved = kernels[dom]["gbs"]
+    names = ["process_frames", "finish_phase1", "transpose", "phase2"]
     chain_bytes = (1.5 * P + 20.0 * N) * F_local
     chain_gbs = chain_bytes / (ms_dev / args.steps * 1e-3) / 1e9
     out = {
@@ -252,11 +268,15 @@ def bench_b200(args):
                    "l2": "inputs (31 GB packed frames, 40 GB intensity) far exceed the 126 MB L2"},
         "stage_ms": {n: round(float(s), 3) for n, s in zip(names, stage)},
         "chain": {"algorithmic_bytes_per_frame": 1.5 * P + 20.0 * N, "achieved_gbs": round(chain_gbs, 1),
-                  "frac_of_peak": round(chain_gbs / peak, 4)},
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
+                  "frac_of_peak": round(chain_gbs / peak, 4),
+                  "note": "SURVEY 8d formula (frame read + 4N row write + 8N transpose + 8N phase 2); the fused "
+                          "projection writes node-major rows directly, so the implementation moves 8N less"},
+        "kernels": kernels,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg[dom]},
+                     "algorithmic_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
+                     "launch_ms": kernels[dom]["mean_ms"], "share_of_step": round(kernels[dom]["ms_per_step"] / (ms_dev / args.steps), 3)},
         "gpu_launches": int(launches), "wall_ms_per_step": round(wall_ms / args.steps, 3),
         "clocks": clocks, "e2e": e2e,
     }

@@ -174,6 +174,13 @@ UPSP_API int upsp_gpu_reset_timers(upsp_gpu_ctx* ctx);
  * (the stream every kernel of this context is launched on) */
 UPSP_API int upsp_gpu_timer_start(upsp_gpu_ctx* ctx);
 UPSP_API int upsp_gpu_timer_stop(upsp_gpu_ctx* ctx, float* ms);
+/* Per-kernel device times: every `sample_every`-th internal batch (and every transpose /
+ * phase-2 launch) is bracketed with CUDA events on the launching stream.  kernel_class:
+ * 0 decode(+scan), 1 frame prep, 2 warp (unfused mode), 3 patch, 4 projection (fused: +transpose
+ * +exchange), 5 transpose, 6 phase 2.  Returns the mean launch duration and the number of
+ * sampled launches since the last upsp_gpu_reset_run / create. */
+UPSP_API int upsp_gpu_set_kernel_sampling(upsp_gpu_ctx* ctx, int sample_every);
+UPSP_API int upsp_gpu_kernel_ms(upsp_gpu_ctx* ctx, int kernel_class, float* mean_ms, int* n_sampled);
 /* start a new run on the same context (same setup, same device buffers): zeroes the
  * sum / sum-sq accumulators and the phase flags; pushed frames stay resident */
 UPSP_API int upsp_gpu_reset_run(upsp_gpu_ctx* ctx);

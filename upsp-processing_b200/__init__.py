@@ -240,6 +240,14 @@ class PspGpu:
         _chk(lib().upsp_gpu_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def set_kernel_sampling(self, every):
+        _chk(lib().upsp_gpu_set_kernel_sampling(self._h, int(every)))
+
+    def kernel_ms(self, kernel_class):
+        ms, n = C.c_float(), C.c_int()
+        _chk(lib().upsp_gpu_kernel_ms(self._h, kernel_class, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def reset_run(self):
         _chk(lib().upsp_gpu_reset_run(self._h))
 

@@ -130,6 +130,12 @@ struct upsp_gpu_ctx {
   struct ProcRec { int off, count; cudaEvent_t ev; };
   std::vector<ProcRec> proc_recs;                // recent process_frames calls (input-ring reuse)
   size_t proc_next = 0;
+  // sampled per-kernel timing
+  int sample_every = 0;
+  long batch_counter = 0;
+  std::vector<cudaEvent_t> kev;   // event pairs
+  std::vector<int> kcls;
+  size_t kn = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   long long launches = 0;
 
@@ -171,6 +177,31 @@ static int set_dev(const upsp_gpu_ctx* c) {
     (ctx)->launches++;         \
     CU(cudaGetLastError());    \
   } while (0)
+
+// sampled kernel timing: KBEGIN/KEND bracket one launch with events when `on`
+static int kprof_begin(upsp_gpu_ctx* c, bool on, int cls) {
+  if (!on) return UPSP_OK;
+  if (2 * c->kn + 2 > c->kev.size()) {
+    if (c->kev.size() >= 16384) return UPSP_OK;  // pool exhausted: stop sampling
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->kev.push_back(e);
+    }
+    c->kcls.push_back(cls);
+  }
+  c->kcls[c->kn] = cls;
+  CU(cudaEventRecord(c->kev[2 * c->kn], c->stream));
+  return UPSP_OK;
+}
+static int kprof_end(upsp_gpu_ctx* c, bool on) {
+  if (!on || 2 * c->kn + 2 > c->kev.size()) return UPSP_OK;
+  CU(cudaEventRecord(c->kev[2 * c->kn + 1], c->stream));
+  c->kn++;
+  return UPSP_OK;
+}
+#define KBEGIN(cls) TRY(kprof_begin(c, prof, cls))
+#define KEND() TRY(kprof_end(c, prof))
 
 template <typename T>
 static int dmalloc(T** p, size_t count) {
@@ -339,6 +370,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   for (auto& r : c->proc_recs) if (r.ev) cudaEventDestroy(r.ev);
+  for (auto e : c->kev) cudaEventDestroy(e);
   if (c->ev_pb) cudaEventDestroy(c->ev_pb);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -763,12 +795,14 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   pa.sumsq = c->d_sumsq;
   const int slot = off % c->capacity;
   REQUIRE(slot + nb <= c->capacity, UPSP_ERR_STATE, "batch wraps the input ring");
+  const bool prof = c->sample_every > 0 && (c->batch_counter++ % c->sample_every) == 0;
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
     REQUIRE(k.format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
     const int thresh = c->hot_fix ? UPSP_HOT_THRESH : 0x7fffffff;
     CU(cudaMemsetAsync(k.d_hot_cnt, 0, (size_t)nb * sizeof(int), c->stream));
     const uint8_t* in = k.d_in + (size_t)slot * k.frame_bytes;
+    KBEGIN(0);
     if (k.format == UPSP_PIX_PACKED12) {
       k_unpack12_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
           in, k.frame_bytes, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
@@ -780,20 +814,25 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
           (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
     }
     KCHECK(c);
+    KEND();
     const bool reg = c->registration != UPSP_REG_NONE;
     if (c->hot_fix || reg) {
+      KBEGIN(1);
       k_frame_prep<<<nb, 256, 0, c->stream>>>(k.d_work, k.npix, k.H, k.W, k.d_hot_cnt, k.d_hot_pos,
                                                UPSP_HOT_MIN_CHANGE, c->hot_fix ? UPSP_HOT_MAX : 0,
                                                reg ? k.d_m6 + (size_t)off * 6 : nullptr, c->interp, k.d_tab);
       KCHECK(c);
+      KEND();
     }
     const uint16_t* cur = k.d_work;
     // global frame 0 is never registered (psp_process.cpp:1777)
     const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
     if (reg && !c->fused) {
+      KBEGIN(2);
       k_warp_affine8_u16<<<dim3(cdiv(k.W, 1024), k.H, nb), 128, 0, c->stream>>>(
           k.d_work, k.d_warp, k.W, k.H, k.d_tab, c->interp, skip_frame);
       KCHECK(c);
+      KEND();
       cur = k.d_warp;
     }
     const bool patch = c->patcher == UPSP_PATCH_POLYNOMIAL && k.has_patches;
@@ -802,6 +841,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       REQUIRE(sm <= 200 * 1024, UPSP_ERR_INVALID, "patch cluster with %d boundary pixels is too large", k.max_bounds);
       if (sm > 48 * 1024)
         CU(cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      KBEGIN(3);
       for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
         const int ncl = k.level_off[l + 1] - k.level_off[l];
         if (!ncl) continue;
@@ -810,6 +850,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
             (reg && c->fused) ? k.d_tab : nullptr, c->interp, skip_frame, c->batch, k.d_pv);
         KCHECK(c);
       }
+      KEND();
     }
     pa.cam[ci].frames = cur;
     pa.cam[ci].npix = k.npix;
@@ -844,6 +885,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     fa.node_start[c->R] = c->N;
     const unsigned g = cdiv(c->N, 256);
+    KBEGIN(4);
     switch (fa.n_cams) {
       case 1: k_project_fused<1><<<g, 256, 0, c->stream>>>(fa); break;
       case 2: k_project_fused<2><<<g, 256, 0, c->stream>>>(fa); break;
@@ -855,13 +897,16 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       default: k_project_fused<8><<<g, 256, 0, c->stream>>>(fa); break;
     }
     KCHECK(c);
+    KEND();
     return UPSP_OK;
   }
+  KBEGIN(4);
   if (c->ell1)
     launch_project_ell1<4>(c, pa);
   else
     k_project_csr<4><<<cdiv(c->N, 256), 256, 0, c->stream>>>(pa);
   KCHECK(c);
+  KEND();
   return UPSP_OK;
 }
 
@@ -972,9 +1017,12 @@ extern "C" int upsp_gpu_transpose(upsp_gpu_ctx* c) {
   }
   a.node_start[c->R] = c->N;
   CU(cudaEventRecord(c->ev_a, c->stream));
+  const bool prof = c->sample_every > 0;
   if (c->F_local > 0) {
+    KBEGIN(5);
     k_transpose_a2a<<<dim3(cdiv(c->N, XT), cdiv(c->F_local, XT)), 256, 0, c->stream>>>(a);
     KCHECK(c);
+    KEND();
   }
   CU(cudaEventRecord(c->ev_b, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1114,7 +1162,10 @@ extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, con
   a.gain = c->d_gain2;
   a.fit_out = nullptr;
   CU(cudaEventRecord(c->ev_a, c->stream));
+  const bool prof = c->sample_every > 0;
+  KBEGIN(6);
   TRY(dispatch_phase2(c, a, c->stream, &c->launches));
+  KEND();
   if (c->N_local) {
     k_phase2_finals<<<cdiv(c->N_local, 256), 256, 0, c->stream>>>(
         c->d_rms2, c->d_avg2, c->d_gain2, c->N_local, (unsigned)c->F, c->d_rms2f, c->d_avg2f, c->d_gain2f);
@@ -1242,6 +1293,33 @@ extern "C" int upsp_gpu_reset_run(upsp_gpu_ctx* c) {
   CU(cudaMemsetAsync(c->d_sumsq, 0, (size_t)c->N * sizeof(double), c->stream));
   c->phase1_done = c->transposed = c->phase2_done = false;
   c->frames_processed = 0;
+  c->kn = 0;
+  c->batch_counter = 0;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_kernel_sampling(upsp_gpu_ctx* c, int every) {
+  ENTER(c);
+  REQUIRE(every >= 0, UPSP_ERR_INVALID, "sample_every %d", every);
+  c->sample_every = every;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_kernel_ms(upsp_gpu_ctx* c, int cls, float* mean_ms, int* n_sampled) {
+  ENTER(c);
+  REQUIRE(mean_ms && n_sampled && cls >= 0 && cls <= 6, UPSP_ERR_INVALID, "bad argument");
+  CU(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i < c->kn; ++i) {
+    if (c->kcls[i] != cls) continue;
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, c->kev[2 * i], c->kev[2 * i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *mean_ms = n ? (float)(tot / n) : 0.0f;
+  *n_sampled = n;
   return UPSP_OK;
 }
 
