@@ -20,16 +20,70 @@ __device__ __forceinline__ void note_hot(uint32_t v, size_t pix, int thresh, int
   }
 }
 
+__device__ __forceinline__ void fix_hot_frame(uint16_t* __restrict__ img, int rows, int cols,
+                                              int n, int* __restrict__ pos, int min_change) {
+  int loc[UPSP_HOT_STORE];
+  for (int i = 0; i < n; ++i) loc[i] = pos[i];
+  for (int i = 1; i < n; ++i) {  // insertion sort -> raster order
+    int v = loc[i], j = i - 1;
+    while (j >= 0 && loc[j] > v) {
+      loc[j + 1] = loc[j];
+      --j;
+    }
+    loc[j + 1] = v;
+  }
+  for (int h = 0; h < n; ++h) {
+    int row = loc[h] / cols, col = loc[h] % cols;
+    int vals[4], nv = 0;
+    if (row > 0) vals[nv++] = img[(size_t)(row - 1) * cols + col];
+    if (col > 0) vals[nv++] = img[(size_t)row * cols + col - 1];
+    if (row < rows - 1) vals[nv++] = img[(size_t)(row + 1) * cols + col];
+    if (col < cols - 1) vals[nv++] = img[(size_t)row * cols + col + 1];
+    for (int i = 1; i < nv; ++i) {
+      int v = vals[i], j = i - 1;
+      while (j >= 0 && vals[j] > v) {
+        vals[j + 1] = vals[j];
+        --j;
+      }
+      vals[j + 1] = v;
+    }
+    int old_val = img[(size_t)row * cols + col];
+    int new_val = vals[nv / 2];
+    if (old_val - new_val > min_change) img[(size_t)row * cols + col] = (uint16_t)new_val;
+    pos[h] = loc[h];
+  }
+}
+
+// Folded K1b: the block that finishes a frame last (ticket counter) applies that frame's
+// (<= 5) hot-pixel fixes, so no separate launch is needed.  done == nullptr disables it.
+__device__ __forceinline__ void hot_fix_tail(uint16_t* __restrict__ frame, int rows, int cols,
+                                             int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
+                                             int* __restrict__ done, int f, int max_hot) {
+  if (done == nullptr) return;
+  __shared__ int s_last;
+  __threadfence();          // this block's pixels + hot-pixel notes are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done + f, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const int n = *((volatile int*)(hot_cnt + f));
+    if (n > 0 && n <= max_hot)
+      fix_hot_frame(frame, rows, cols, n, hot_pos + f * UPSP_HOT_STORE, UPSP_HOT_MIN_CHANGE);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_unpack12_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __restrict__ out,
-                size_t npix, int thresh, int* __restrict__ hot_cnt, int* __restrict__ hot_pos) {
+                size_t npix, int thresh, int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
+                int* __restrict__ done, int rows, int cols) {
   const int f = blockIdx.y;
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 px
   const size_t p0 = g * 8;
-  if (p0 >= npix) return;
   const uint8_t* src = in + (size_t)f * in_stride;
   uint16_t* dst = out + (size_t)f * npix;
-  if (p0 + 8 <= npix && ((in_stride | (size_t)(uintptr_t)in) & 3) == 0) {
+  if (p0 >= npix) {
+  } else if (p0 + 8 <= npix && ((in_stride | (size_t)(uintptr_t)in) & 3) == 0) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(src + g * 12);
     uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
     // bytes b0..b11, MSB-first 12-bit fields: px0=b0<<4|b1>>4, px1=(b1&15)<<8|b2, ...
@@ -68,6 +122,7 @@ k_unpack12_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __re
       }
     }
   }
+  hot_fix_tail(dst, rows, cols, hot_cnt, hot_pos, done, f, UPSP_HOT_MAX);
 }
 
 // 10-bit packed (5 bytes -> 4 px) with the optional 10->12-bit table
@@ -75,37 +130,41 @@ k_unpack12_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __re
 __global__ void __launch_bounds__(256)
 k_unpack10_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __restrict__ out,
                 size_t npix, const uint16_t* __restrict__ lut, int thresh,
-                int* __restrict__ hot_cnt, int* __restrict__ hot_pos) {
+                int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
+                int* __restrict__ done, int rows, int cols) {
   const int f = blockIdx.y;
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t p0 = g * 4;
-  if (p0 >= npix) return;
-  const uint8_t* s = in + (size_t)f * in_stride + g * 5;
-  uint32_t p = s[0], q = s[1], r = s[2], t = s[3], u = s[4];
-  uint32_t px[4] = {(p << 2) | (q >> 6), ((q & 0x3F) << 4) | (r >> 4),
-                    ((r & 0x0F) << 6) | (t >> 2), ((t & 0x03) << 8) | u};
   uint16_t* dst = out + (size_t)f * npix;
+  if (p0 < npix) {
+    const uint8_t* s = in + (size_t)f * in_stride + g * 5;
+    uint32_t p = s[0], q = s[1], r = s[2], t = s[3], u = s[4];
+    uint32_t px[4] = {(p << 2) | (q >> 6), ((q & 0x3F) << 4) | (r >> 4),
+                      ((r & 0x0F) << 6) | (t >> 2), ((t & 0x03) << 8) | u};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (p0 + k < npix) {
-      uint32_t v = lut ? (uint32_t)__ldg(lut + px[k]) : px[k];
-      dst[p0 + k] = (uint16_t)v;
-      note_hot(v, p0 + k, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
+    for (int k = 0; k < 4; ++k) {
+      if (p0 + k < npix) {
+        uint32_t v = lut ? (uint32_t)__ldg(lut + px[k]) : px[k];
+        dst[p0 + k] = (uint16_t)v;
+        note_hot(v, p0 + k, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
+      }
     }
   }
+  hot_fix_tail(dst, rows, cols, hot_cnt, hot_pos, done, f, UPSP_HOT_MAX);
 }
 
 // u16 container: copy into the working buffer (the reference's `copyTo(img)`,
 // psp_process.cpp:1773) + scan.  One thread = 8 px.
 __global__ void __launch_bounds__(256)
 k_copy16_scan(const uint16_t* __restrict__ in, size_t in_stride_px, uint16_t* __restrict__ out,
-              size_t npix, int thresh, int* __restrict__ hot_cnt, int* __restrict__ hot_pos) {
+              size_t npix, int thresh, int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
+              int* __restrict__ done, int rows, int cols) {
   const int f = blockIdx.y;
   const size_t p0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (p0 >= npix) return;
   const uint16_t* src = in + (size_t)f * in_stride_px;
   uint16_t* dst = out + (size_t)f * npix;
-  if (p0 + 8 <= npix && ((npix | in_stride_px) & 7) == 0) {
+  if (p0 >= npix) {
+  } else if (p0 + 8 <= npix && ((npix | in_stride_px) & 7) == 0) {
     uint4 v = ld_stream_u4(src + p0);
     *reinterpret_cast<uint4*>(dst + p0) = v;
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -126,6 +185,7 @@ k_copy16_scan(const uint16_t* __restrict__ in, size_t in_stride_px, uint16_t* __
       note_hot(v, p, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
     }
   }
+  hot_fix_tail(dst, rows, cols, hot_cnt, hot_pos, done, f, UPSP_HOT_MAX);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -133,40 +193,6 @@ k_copy16_scan(const uint16_t* __restrict__ in, size_t in_stride_px, uint16_t* __
 // applied serially in raster order (a later fix sees an earlier one).  One thread per frame.
 // hot_cnt is left holding the count (> max_hot means "too many, frame untouched").
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void fix_hot_frame(uint16_t* __restrict__ img, int rows, int cols,
-                                              int n, int* __restrict__ pos, int min_change) {
-  int loc[UPSP_HOT_STORE];
-  for (int i = 0; i < n; ++i) loc[i] = pos[i];
-  for (int i = 1; i < n; ++i) {  // insertion sort -> raster order
-    int v = loc[i], j = i - 1;
-    while (j >= 0 && loc[j] > v) {
-      loc[j + 1] = loc[j];
-      --j;
-    }
-    loc[j + 1] = v;
-  }
-  for (int h = 0; h < n; ++h) {
-    int row = loc[h] / cols, col = loc[h] % cols;
-    int vals[4], nv = 0;
-    if (row > 0) vals[nv++] = img[(size_t)(row - 1) * cols + col];
-    if (col > 0) vals[nv++] = img[(size_t)row * cols + col - 1];
-    if (row < rows - 1) vals[nv++] = img[(size_t)(row + 1) * cols + col];
-    if (col < cols - 1) vals[nv++] = img[(size_t)row * cols + col + 1];
-    for (int i = 1; i < nv; ++i) {
-      int v = vals[i], j = i - 1;
-      while (j >= 0 && vals[j] > v) {
-        vals[j + 1] = vals[j];
-        --j;
-      }
-      vals[j + 1] = v;
-    }
-    int old_val = img[(size_t)row * cols + col];
-    int new_val = vals[nv / 2];
-    if (old_val - new_val > min_change) img[(size_t)row * cols + col] = (uint16_t)new_val;
-    pos[h] = loc[h];
-  }
-}
-
 __global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
                           int nframes, const int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
                           int min_change, int max_hot) {
@@ -175,37 +201,6 @@ __global__ void k_fix_hot(uint16_t* __restrict__ frames, size_t npix, int rows, 
   int n = hot_cnt[f];
   if (n <= 0 || n > max_hot) return;
   fix_hot_frame(frames + (size_t)f * npix, rows, cols, n, hot_pos + f * UPSP_HOT_STORE, min_change);
-}
-
-// One block per frame: thread 0 applies the (<= 5) hot-pixel fixes while the whole block builds
-// the frame's warp tables (when m6 != nullptr).  Replaces two tiny launches per batch.
-__global__ void __launch_bounds__(256)
-k_frame_prep(uint16_t* __restrict__ frames, size_t npix, int rows, int cols,
-             const int* __restrict__ hot_cnt, int* __restrict__ hot_pos, int min_change, int max_hot,
-             const float* __restrict__ m6, int interp, int* __restrict__ tab) {
-  const int f = blockIdx.x;
-  if (threadIdx.x == 0 && max_hot > 0) {
-    int n = hot_cnt[f];
-    if (n > 0 && n <= max_hot)
-      fix_hot_frame(frames + (size_t)f * npix, rows, cols, n, hot_pos + f * UPSP_HOT_STORE, min_change);
-  }
-  if (m6 == nullptr) return;
-  const int W = cols, H = rows;
-  const float* M = m6 + (size_t)f * 6;
-  int* t = tab + (size_t)f * (2 * W + 2 * H);
-  const int round_delta = interp == 0 ? 512 : 16;
-  const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
-  for (int i = threadIdx.x; i < max(W, H); i += blockDim.x) {
-    const double v = (double)i;
-    if (i < W) {
-      t[2 * i] = __double2int_rn(__dmul_rn(__dmul_rn(m0, v), 1024.0));
-      t[2 * i + 1] = __double2int_rn(__dmul_rn(__dmul_rn(m3, v), 1024.0));
-    }
-    if (i < H) {
-      t[2 * W + 2 * i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, v), m2), 1024.0)) + round_delta;
-      t[2 * W + 2 * i + 1] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, v), m5), 1024.0)) + round_delta;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -432,25 +427,36 @@ struct PatchGeom {            // device pointers, one per camera
   const int* order;           // clusters sorted by dependency level
 };
 
-// One warp per (cluster, frame): lanes stride over the boundary / interior pixels.  The only
-// order-sensitive reduction, s = ((p0+p1)+p2)+..., is done by lane 0 over products that all
-// lanes computed in parallel, so the sequential chain is n adds instead of the whole solve.
-// tab != nullptr: the boundary pixels are taken from the REGISTERED frame, computed on the fly
-// (warp_px_u16) from the decoded frame.
-__global__ void __launch_bounds__(32)
+// One warp per (cluster, frame): lanes stride over the boundary / interior pixels; a block
+// holds PATCH_WARPS frames of the same cluster and stages the cluster's reflectors (E, tau*E)
+// in shared memory once.  The only order-sensitive reduction, s = ((p0+p1)+p2)+..., is done by
+// lane 0 over products that all lanes computed in parallel, so the sequential chain is n adds
+// instead of the whole solve.  tab != nullptr: the boundary pixels are taken from the REGISTERED
+// frame, computed on the fly (warp_px_u16) from the decoded frame.
+constexpr int PATCH_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * PATCH_WARPS)
 k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict__ frames,
         size_t npix, int W, int H, const int* __restrict__ tab, int interp, int skip_frame,
-        int bstride, float* __restrict__ pv) {
+        int nframes, int bstride, float* __restrict__ pv) {
   extern __shared__ float psh[];
   const int cl = cl_list[blockIdx.x];
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y * PATCH_WARPS + wid;
   const int nz = g.nzp[cl];
   if (nz < 0) return;
   const int off = g.bounds_off[cl], nb = g.bounds_off[cl + 1] - off;
-  float* c = psh;            // [nb]
-  float* prod = psh + nb;    // [nb]
-  float* poly = psh + 2 * nb;  // [10]
+  float* E = psh;                 // [10*nb]
+  float* TE = psh + 10 * nb;      // [10*nb]
+  for (int i = threadIdx.x; i < 10 * nb; i += blockDim.x) {
+    E[i] = __ldg(g.qr_e + (size_t)10 * off + i);
+    TE[i] = __ldg(g.qr_te + (size_t)10 * off + i);
+  }
+  __syncthreads();
+  if (b >= nframes) return;
+  float* c = psh + 20 * nb + wid * (2 * nb + 16);   // [nb]
+  float* prod = c + nb;                              // [nb]
+  float* poly = c + 2 * nb;                          // [10]
   const uint16_t* img = frames + (size_t)b * npix;
   const int* t = (tab != nullptr && b != skip_frame) ? tab + (size_t)b * (2 * W + 2 * H) : nullptr;
   for (int i = lane; i < nb; i += 32) {
@@ -462,8 +468,6 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
     c[i] = v;
   }
   __syncwarp();
-  const float* E = g.qr_e + (size_t)10 * off;
-  const float* TE = g.qr_te + (size_t)10 * off;
   const float* hc = g.hcoef + cl * 10;
   for (int k = 0; k < nz; ++k) {
     const int n = nb - k;
@@ -473,7 +477,7 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
     } else if (tau != 0.0f) {
       const float* e = E + (size_t)k * nb + k + 1;
       const float* te = TE + (size_t)k * nb + k + 1;
-      for (int i = lane; i < n - 1; i += 32) prod[i] = __fmul_rn(__ldg(e + i), c[k + 1 + i]);
+      for (int i = lane; i < n - 1; i += 32) prod[i] = __fmul_rn(e[i], c[k + 1 + i]);
       __syncwarp();
       float tt = 0.0f;
       if (lane == 0) {
@@ -490,7 +494,7 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
         c[k] = __fsub_rn(c[k], __fmul_rn(tau, tt));
       }
       tt = __shfl_sync(0xffffffffu, tt, 0);
-      for (int i = lane; i < n - 1; i += 32) c[k + 1 + i] = __fsub_rn(c[k + 1 + i], __fmul_rn(tt, __ldg(te + i)));
+      for (int i = lane; i < n - 1; i += 32) c[k + 1 + i] = __fsub_rn(c[k + 1 + i], __fmul_rn(tt, te[i]));
     }
     __syncwarp();
   }
@@ -501,10 +505,10 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
 #pragma unroll
     for (int i = 9; i >= 0; --i) {
       if (i < nz) {
-        x[i] = __fdiv_rn(x[i], __ldg(E + (size_t)i * nb + i));
+        x[i] = __fdiv_rn(x[i], E[(size_t)i * nb + i]);
 #pragma unroll
         for (int j = 0; j < 10; ++j)
-          if (j < i) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], __ldg(E + (size_t)i * nb + j)));
+          if (j < i) x[j] = __fsub_rn(x[j], __fmul_rn(x[i], E[(size_t)i * nb + j]));
       }
     }
     const int* pm = g.perm + cl * 10;

@@ -170,13 +170,25 @@ struct FusedArgs {
   int node_start[UPSP_MAX_RANKS + 1];
 };
 
-template <int NC>
+// border / nearest-neighbour pixels: rare, kept out of the hot loop's code
+__device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W, int H, int X, int Y,
+                                           int interp) {
+  if (interp == 0) {
+    const int sx = X >> 10, sy = Y >> 10;
+    return ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H) ? (float)s[(size_t)sy * W + sx] : 0.0f;
+  }
+  const float v = warp_sample_linear<uint16_t>(s, W, H, X, Y);
+  const float r = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);
+  return fminf(fmaxf(r, 0.0f), 65535.0f);
+}
+
+template <int NC, bool REG>
 __global__ void __launch_bounds__(256)
 k_project_fused(const FusedArgs a) {
   __shared__ float tile[32][257];
   const int n = blockIdx.x * 256 + threadIdx.x;
   const bool live = n < a.n_nodes;
-  int code[NC], px[NC], py[NC];
+  int code[NC], tx[NC], ty[NC];
   float val[NC];
   bool skipped = true;
 #pragma unroll
@@ -184,8 +196,10 @@ k_project_fused(const FusedArgs a) {
     code[c] = live ? __ldg(a.cam[c].code + n) : -1;
     val[c] = live ? __ldg(a.cam[c].val + n) : 0.0f;
     skipped = skipped && (code[c] == -1);
-    px[c] = code[c] >= 0 ? code[c] % a.cam[c].W : 0;
-    py[c] = code[c] >= 0 ? code[c] / a.cam[c].W : 0;
+    const int W = a.cam[c].W;
+    const int px = code[c] >= 0 ? code[c] % W : 0, py = code[c] >= 0 ? code[c] / W : 0;
+    tx[c] = px;              // int2 index of (adelta,bdelta)[px] inside a frame's table
+    ty[c] = W + py;          // int2 index of (X0,Y0)[py]
   }
   double s = 0.0, q = 0.0;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,18 +213,38 @@ k_project_fused(const FusedArgs a) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           float cs = 0.0f;
-          if (code[c] != -1) {
-            const FusedCam& cam = a.cam[c];
+          const FusedCam& cam = a.cam[c];
+          if (code[c] >= 0) {
             float v;
-            if (code[c] <= -2) {
-              v = __ldg(cam.pv + (size_t)(-2 - code[c]) * a.bstride + b);
-            } else if (cam.tab != nullptr && b != a.skip_frame) {
-              v = warp_px_u16(cam.frames + (size_t)b * cam.npix, cam.W, cam.H,
-                              cam.tab + (size_t)b * (2 * cam.W + 2 * cam.H), px[c], py[c], a.interp);
+            const unsigned fbase = (unsigned)b * (unsigned)cam.npix;   // batch-local pixel index (< 2^31)
+            if (REG && b != a.skip_frame) {
+              const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (unsigned)b * (unsigned)(cam.W + cam.H);
+              const int2 xa = __ldg(tb + tx[c]);
+              const int2 ya = __ldg(tb + ty[c]);
+              const int X = ya.x + xa.x, Y = ya.y + xa.y;
+              const int Xs = X >> 5, Ys = Y >> 5;
+              const int sx = X >> 10, sy = Y >> 10;
+              if (a.interp == 1 && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1)) {
+                const uint16_t* p = cam.frames + (fbase + (unsigned)(sy * cam.W + sx));
+                const uint16_t* p2 = p + cam.W;
+                const float t00 = (float)__ldg(p), t01 = (float)__ldg(p + 1);
+                const float t10 = (float)__ldg(p2), t11 = (float)__ldg(p2 + 1);
+                const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
+                const float gx = 1.0f - fx, gy = 1.0f - fy;
+                v = __fadd_rn(__fmul_rn(t00, __fmul_rn(gy, gx)), __fmul_rn(t01, __fmul_rn(gy, fx)));
+                v = __fadd_rn(v, __fmul_rn(t10, __fmul_rn(fy, gx)));
+                v = __fadd_rn(v, __fmul_rn(t11, __fmul_rn(fy, fx)));
+                v = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);   // rint (half to even)
+                v = fminf(v, 65535.0f);                                    // v >= 0 by construction
+              } else {
+                v = warp_px_slow(cam.frames + fbase, cam.W, cam.H, X, Y, a.interp);
+              }
             } else {
-              v = u2f_exact(__ldg(cam.frames + (size_t)b * cam.npix + code[c]));
+              v = (float)__ldg(cam.frames + (fbase + (unsigned)code[c]));
             }
             cs = __fadd_rn(0.0f, __fmul_rn(val[c], v));
+          } else if (code[c] <= -2) {
+            cs = __fadd_rn(0.0f, __fmul_rn(val[c], __ldg(cam.pv + (size_t)(-2 - code[c]) * a.bstride + b)));
           }
           sol = (c == 0) ? cs : __fadd_rn(sol, cs);
         }
@@ -222,13 +256,24 @@ k_project_fused(const FusedArgs a) {
     }
     __syncthreads();
     // warp w writes nodes [w*32, w*32+32) of the block: lane = frame -> 128-byte row segments
-    for (int j = 0; j < 32; ++j) {
-      const int nn = blockIdx.x * 256 + w * 32 + j;
-      if (nn >= a.n_nodes) break;
-      if (lane < nb) {
-        int r = 0;
-        while (r + 1 < a.n_ranks && nn >= a.node_start[r + 1]) ++r;
-        a.dst[r][(size_t)(nn - a.node_start[r]) * a.f_total + a.col0 + b0 + lane] = tile[lane][w * 32 + j];
+    {
+      const int n0 = blockIdx.x * 256 + w * 32;
+      const int n1 = min(n0 + 32, a.n_nodes);
+      int r = 0;
+      while (r + 1 < a.n_ranks && n0 >= a.node_start[r + 1]) ++r;
+      const size_t col = (size_t)a.col0 + b0 + lane;
+      float* p = a.dst[r] + (size_t)(n0 - a.node_start[r]) * a.f_total + col;
+      int next = a.node_start[r + 1];
+      for (int nn = n0; nn < n1; ++nn) {
+        if (nn >= next) {   // the warp's node run crosses into the next rank's slice
+          do {
+            ++r;
+            next = a.node_start[r + 1];
+          } while (nn >= next);
+          p = a.dst[r] + (size_t)(nn - a.node_start[r]) * a.f_total + col;
+        }
+        if (lane < nb) *p = tile[lane][nn - blockIdx.x * 256];
+        p += a.f_total;
       }
     }
     __syncthreads();

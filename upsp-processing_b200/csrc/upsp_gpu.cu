@@ -89,7 +89,7 @@ struct Camera {
   float* d_m6 = nullptr;      // [F_local][6]
   float* d_rho = nullptr;     // [F_local]
   int* d_iters = nullptr;     // [F_local]
-  int* d_tab = nullptr;       // [batch][2W+2H]
+  int* d_tab = nullptr;       // [F_local][2W+2H] warp tables of every local frame
   uint8_t* d_skip = nullptr;  // [batch]
   uint16_t* d_ref16 = nullptr;
   bool has_ref = false, has_m6 = false;
@@ -682,11 +682,11 @@ static int finalize(upsp_gpu_ctx* c) {
     }
     // working buffers
     TRY(dmalloc(&k.d_work, (size_t)c->batch * k.npix));
-    TRY(dmalloc(&k.d_hot_cnt, (size_t)c->batch));
+    TRY(dmalloc(&k.d_hot_cnt, (size_t)2 * c->batch));   // [hot counts | finished-block tickets]
     TRY(dmalloc(&k.d_hot_pos, (size_t)c->batch * UPSP_HOT_STORE));
     if (c->registration != UPSP_REG_NONE) {
       if (!c->fused) TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
-      TRY(dmalloc(&k.d_tab, (size_t)c->batch * (2 * k.W + 2 * k.H)));
+      TRY(dmalloc(&k.d_tab, (size_t)std::max(c->F_local, 1) * (2 * k.W + 2 * k.H)));
       if (c->registration == UPSP_REG_GIVEN)
         REQUIRE(k.has_m6, UPSP_ERR_STATE, "registration=given but camera %zu has no warp matrices", ci);
     }
@@ -800,44 +800,38 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     Camera& k = c->cams[ci];
     REQUIRE(k.format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
     const int thresh = c->hot_fix ? UPSP_HOT_THRESH : 0x7fffffff;
-    CU(cudaMemsetAsync(k.d_hot_cnt, 0, (size_t)nb * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(k.d_hot_cnt, 0, (size_t)2 * c->batch * sizeof(int), c->stream));
+    int* done = c->hot_fix ? k.d_hot_cnt + c->batch : nullptr;
     const uint8_t* in = k.d_in + (size_t)slot * k.frame_bytes;
     KBEGIN(0);
     if (k.format == UPSP_PIX_PACKED12) {
       k_unpack12_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
-          in, k.frame_bytes, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
+          in, k.frame_bytes, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
     } else if (k.format == UPSP_PIX_PACKED10) {
       k_unpack10_scan<<<dim3(cdiv(cdiv(k.npix, 4), 256), nb), 256, 0, c->stream>>>(
-          in, k.frame_bytes, k.d_work, k.npix, c->d_lut, thresh, k.d_hot_cnt, k.d_hot_pos);
+          in, k.frame_bytes, k.d_work, k.npix, c->d_lut, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
     } else {
       k_copy16_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
-          (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos);
+          (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
     }
     KCHECK(c);
     KEND();
     const bool reg = c->registration != UPSP_REG_NONE;
-    if (c->hot_fix || reg) {
-      KBEGIN(1);
-      k_frame_prep<<<nb, 256, 0, c->stream>>>(k.d_work, k.npix, k.H, k.W, k.d_hot_cnt, k.d_hot_pos,
-                                               UPSP_HOT_MIN_CHANGE, c->hot_fix ? UPSP_HOT_MAX : 0,
-                                               reg ? k.d_m6 + (size_t)off * 6 : nullptr, c->interp, k.d_tab);
-      KCHECK(c);
-      KEND();
-    }
+    const int* tabs = reg ? k.d_tab + (size_t)off * (2 * k.W + 2 * k.H) : nullptr;   // this batch's tables
     const uint16_t* cur = k.d_work;
     // global frame 0 is never registered (psp_process.cpp:1777)
     const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
     if (reg && !c->fused) {
       KBEGIN(2);
       k_warp_affine8_u16<<<dim3(cdiv(k.W, 1024), k.H, nb), 128, 0, c->stream>>>(
-          k.d_work, k.d_warp, k.W, k.H, k.d_tab, c->interp, skip_frame);
+          k.d_work, k.d_warp, k.W, k.H, tabs, c->interp, skip_frame);
       KCHECK(c);
       KEND();
       cur = k.d_warp;
     }
     const bool patch = c->patcher == UPSP_PATCH_POLYNOMIAL && k.has_patches;
     if (patch) {
-      const size_t sm = ((size_t)2 * k.max_bounds + 16) * sizeof(float);
+      const size_t sm = ((size_t)20 * k.max_bounds + PATCH_WARPS * ((size_t)2 * k.max_bounds + 16)) * sizeof(float);
       REQUIRE(sm <= 200 * 1024, UPSP_ERR_INVALID, "patch cluster with %d boundary pixels is too large", k.max_bounds);
       if (sm > 48 * 1024)
         CU(cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -845,9 +839,9 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
         const int ncl = k.level_off[l + 1] - k.level_off[l];
         if (!ncl) continue;
-        k_patch<<<dim3(ncl, nb), 32, sm, c->stream>>>(
+        k_patch<<<dim3(ncl, cdiv(nb, PATCH_WARPS)), 32 * PATCH_WARPS, sm, c->stream>>>(
             k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, k.W, k.H,
-            (reg && c->fused) ? k.d_tab : nullptr, c->interp, skip_frame, c->batch, k.d_pv);
+            (reg && c->fused) ? tabs : nullptr, c->interp, skip_frame, nb, c->batch, k.d_pv);
         KCHECK(c);
       }
       KEND();
@@ -862,7 +856,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.cam[ci].npix = k.npix;
     fa.cam[ci].W = k.W;
     fa.cam[ci].H = k.H;
-    fa.cam[ci].tab = reg ? k.d_tab : nullptr;
+    fa.cam[ci].tab = tabs;
     fa.cam[ci].pv = patch ? k.d_pv : nullptr;
     fa.cam[ci].code = k.d_code;
     fa.cam[ci].val = k.d_val;
@@ -886,16 +880,21 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.node_start[c->R] = c->N;
     const unsigned g = cdiv(c->N, 256);
     KBEGIN(4);
+    const bool regk = c->registration != UPSP_REG_NONE;
+#define FUSED_LAUNCH(NCAM)                                              \
+  if (regk) k_project_fused<NCAM, true><<<g, 256, 0, c->stream>>>(fa);  \
+  else k_project_fused<NCAM, false><<<g, 256, 0, c->stream>>>(fa)
     switch (fa.n_cams) {
-      case 1: k_project_fused<1><<<g, 256, 0, c->stream>>>(fa); break;
-      case 2: k_project_fused<2><<<g, 256, 0, c->stream>>>(fa); break;
-      case 3: k_project_fused<3><<<g, 256, 0, c->stream>>>(fa); break;
-      case 4: k_project_fused<4><<<g, 256, 0, c->stream>>>(fa); break;
-      case 5: k_project_fused<5><<<g, 256, 0, c->stream>>>(fa); break;
-      case 6: k_project_fused<6><<<g, 256, 0, c->stream>>>(fa); break;
-      case 7: k_project_fused<7><<<g, 256, 0, c->stream>>>(fa); break;
-      default: k_project_fused<8><<<g, 256, 0, c->stream>>>(fa); break;
+      case 1: FUSED_LAUNCH(1); break;
+      case 2: FUSED_LAUNCH(2); break;
+      case 3: FUSED_LAUNCH(3); break;
+      case 4: FUSED_LAUNCH(4); break;
+      case 5: FUSED_LAUNCH(5); break;
+      case 6: FUSED_LAUNCH(6); break;
+      case 7: FUSED_LAUNCH(7); break;
+      default: FUSED_LAUNCH(8); break;
     }
+#undef FUSED_LAUNCH
     KCHECK(c);
     KEND();
     return UPSP_OK;
@@ -921,6 +920,14 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
             "projection stores node-major rows straight into peer buffers");
   CU(cudaStreamWaitEvent(c->stream, c->ev_push, 0));
   CU(cudaEventRecord(c->ev_pa, c->stream));
+  if (c->registration != UPSP_REG_NONE && count > 0) {
+    // OpenCV-style fixed-point warp tables of every frame of this call (one launch per camera)
+    for (auto& k : c->cams) {
+      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), count), 256, 0, c->stream>>>(
+          k.d_m6 + (size_t)off * 6, count, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
+      KCHECK(c);
+    }
+  }
   int done = 0;
   while (done < count) {
     const int o = off + done;
@@ -1453,9 +1460,9 @@ extern "C" int upsp_op_unpack(int device, const uint8_t* packed, int format, siz
   if (lut) TRY(S.put(&d_lut, lut, 1024));
   CU(cudaMemset(d_cnt, 0, sizeof(int)));
   if (format == UPSP_PIX_PACKED12)
-    k_unpack12_scan<<<dim3(cdiv(cdiv(npix, 8), 256), 1), 256>>>(d_in, nbytes, d_out, npix, 0x7fffffff, d_cnt, d_pos);
+    k_unpack12_scan<<<dim3(cdiv(cdiv(npix, 8), 256), 1), 256>>>(d_in, nbytes, d_out, npix, 0x7fffffff, d_cnt, d_pos, nullptr, 1, (int)npix);
   else
-    k_unpack10_scan<<<dim3(cdiv(cdiv(npix, 4), 256), 1), 256>>>(d_in, nbytes, d_out, npix, d_lut, 0x7fffffff, d_cnt, d_pos);
+    k_unpack10_scan<<<dim3(cdiv(cdiv(npix, 4), 256), 1), 256>>>(d_in, nbytes, d_out, npix, d_lut, 0x7fffffff, d_cnt, d_pos, nullptr, 1, (int)npix);
   CU(cudaGetLastError());
   CU(cudaMemcpy(out, d_out, npix * 2, cudaMemcpyDeviceToHost));
   return UPSP_OK;
@@ -1472,7 +1479,7 @@ extern "C" int upsp_op_fix_hot_pixels(int device, uint16_t* frames, int nf, int 
   TRY(S.alloc(&d_cnt, nf));
   TRY(S.alloc(&d_pos, (size_t)nf * UPSP_HOT_STORE));
   CU(cudaMemset(d_cnt, 0, sizeof(int) * nf));
-  k_copy16_scan<<<dim3(cdiv(cdiv(npix, 8), 256), nf), 256>>>(d_in, npix, d_out, npix, UPSP_HOT_THRESH, d_cnt, d_pos);
+  k_copy16_scan<<<dim3(cdiv(cdiv(npix, 8), 256), nf), 256>>>(d_in, npix, d_out, npix, UPSP_HOT_THRESH, d_cnt, d_pos, nullptr, rows, cols);
   CU(cudaGetLastError());
   k_fix_hot<<<cdiv(nf, 32), 32>>>(d_out, npix, rows, cols, nf, d_cnt, d_pos, UPSP_HOT_MIN_CHANGE, UPSP_HOT_MAX);
   CU(cudaGetLastError());
