@@ -60,12 +60,10 @@ __device__ __forceinline__ void hot_fix_tail(uint16_t* __restrict__ frame, int r
                                              int* __restrict__ hot_cnt, int* __restrict__ hot_pos,
                                              int* __restrict__ done, int f, int max_hot) {
   if (done == nullptr) return;
-  __shared__ int s_last;
-  __threadfence();          // this block's pixels + hot-pixel notes are visible device-wide
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(done + f, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  __syncthreads();          // every thread's stores precede thread 0's fence (CTA causality)
+  if (threadIdx.x != 0) return;
+  __threadfence();          // cumulative: the block's pixels + hot notes are visible device-wide
+  if (atomicAdd(done + f, 1) == (int)gridDim.x - 1) {
     __threadfence();
     const int n = *((volatile int*)(hot_cnt + f));
     if (n > 0 && n <= max_hot)
@@ -85,26 +83,26 @@ k_unpack12_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __re
   if (p0 >= npix) {
   } else if (p0 + 8 <= npix && ((in_stride | (size_t)(uintptr_t)in) & 3) == 0) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(src + g * 12);
-    uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-    // bytes b0..b11, MSB-first 12-bit fields: px0=b0<<4|b1>>4, px1=(b1&15)<<8|b2, ...
-    uint32_t b0 = w0 & 0xFF, b1 = (w0 >> 8) & 0xFF, b2 = (w0 >> 16) & 0xFF, b3 = w0 >> 24;
-    uint32_t b4 = w1 & 0xFF, b5 = (w1 >> 8) & 0xFF, b6 = (w1 >> 16) & 0xFF, b7 = w1 >> 24;
-    uint32_t b8 = w2 & 0xFF, b9 = (w2 >> 8) & 0xFF, b10 = (w2 >> 16) & 0xFF, b11 = w2 >> 24;
-    uint32_t px[8];
-    px[0] = (b0 << 4) | (b1 >> 4);
-    px[1] = ((b1 & 0xF) << 8) | b2;
-    px[2] = (b3 << 4) | (b4 >> 4);
-    px[3] = ((b4 & 0xF) << 8) | b5;
-    px[4] = (b6 << 4) | (b7 >> 4);
-    px[5] = ((b7 & 0xF) << 8) | b8;
-    px[6] = (b9 << 4) | (b10 >> 4);
-    px[7] = ((b10 & 0xF) << 8) | b11;
-    uint4 o = make_uint4(px[0] | (px[1] << 16), px[2] | (px[3] << 16), px[4] | (px[5] << 16),
-                         px[6] | (px[7] << 16));
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    // every 3 bytes b0 b1 b2 hold px_even = (b0<<8|b1)>>4 and px_odd = (b1<<8|b2)&0xFFF: one byte
+    // permute builds (b0<<8|b1) | (b1<<8|b2)<<16, one shift + two masks finish the pair.
+    const uint32_t v0 = __byte_perm(w0, w1, 0x1201);   // bytes 0,1,2
+    const uint32_t v1 = __byte_perm(w0, w1, 0x4534);   // bytes 3,4,5
+    const uint32_t v2 = __byte_perm(w1, w2, 0x3423);   // bytes 6,7,8  (w1 bytes 2,3 ; w2 byte 0)
+    const uint32_t v3 = __byte_perm(w2, w2, 0x2312);   // bytes 9,10,11
+    uint4 o;
+    o.x = ((v0 >> 4) & 0x00000FFFu) | (v0 & 0x0FFF0000u);
+    o.y = ((v1 >> 4) & 0x00000FFFu) | (v1 & 0x0FFF0000u);
+    o.z = ((v2 >> 4) & 0x00000FFFu) | (v2 & 0x0FFF0000u);
+    o.w = ((v3 >> 4) & 0x00000FFFu) | (v3 & 0x0FFF0000u);
     *reinterpret_cast<uint4*>(dst + p0) = o;
-    uint32_t mx = max(max(max(px[0], px[1]), max(px[2], px[3])),
-                      max(max(px[4], px[5]), max(px[6], px[7])));
-    if ((int)mx >= thresh) {
+    // packed >= test (values < 2^15, thresh <= 2^15): bit 15 of (px | 0x8000) - thresh
+    const uint32_t t2 = (uint32_t)min(thresh, 0x8000) * 0x00010001u;
+    const uint32_t hot = (((o.x | 0x80008000u) - t2) | ((o.y | 0x80008000u) - t2) |
+                          ((o.z | 0x80008000u) - t2) | ((o.w | 0x80008000u) - t2)) & 0x80008000u;
+    if (hot) {
+      const uint32_t px[8] = {o.x & 0xFFFF, o.x >> 16, o.y & 0xFFFF, o.y >> 16,
+                              o.z & 0xFFFF, o.z >> 16, o.w & 0xFFFF, o.w >> 16};
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         note_hot(px[k], p0 + k, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);

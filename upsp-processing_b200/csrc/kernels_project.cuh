@@ -182,9 +182,79 @@ __device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W
   return fminf(fmaxf(r, 0.0f), 65535.0f);
 }
 
+// U consecutive frames of one camera for one node: every global load of the group is issued
+// before any result is consumed (no divergent region between the loads), so a thread keeps
+// 2U table loads and then 4U tap loads in flight.  Border / nearest pixels are patched up
+// afterwards through the out-of-line slow path.
+template <int U, bool REG>
+__device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, int tx, int ty, int b,
+                                                int interp, int skip_frame, int bstride,
+                                                float (&v)[U]) {
+  if (code >= 0) {
+    if (REG) {
+      int X[U], Y[U];
+      const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (unsigned)b * (unsigned)(cam.W + cam.H);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int2 xa = __ldg(tb + tx), ya = __ldg(tb + ty);
+        X[j] = ya.x + xa.x;
+        Y[j] = ya.y + xa.y;
+        tb += cam.W + cam.H;
+      }
+      unsigned short t00[U], t01[U], t10[U], t11[U];
+      bool fast[U];
+      const uint16_t* fr = cam.frames + (size_t)((unsigned)b * (unsigned)cam.npix);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int sx = X[j] >> 10, sy = Y[j] >> 10;
+        fast[j] = (interp == 1) && (b + j != skip_frame) && (unsigned)sx < (unsigned)(cam.W - 1) &&
+                  (unsigned)sy < (unsigned)(cam.H - 1);
+        const int cx = min(max(sx, 0), cam.W - 2), cy = min(max(sy, 0), cam.H - 2);
+        const uint16_t* p = fr + (unsigned)(cy * cam.W + cx);
+        t00[j] = __ldg(p);
+        t01[j] = __ldg(p + 1);
+        t10[j] = __ldg(p + cam.W);
+        t11[j] = __ldg(p + cam.W + 1);
+        fr += cam.npix;
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int Xs = X[j] >> 5, Ys = Y[j] >> 5;
+        const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
+        const float gx = 1.0f - fx, gy = 1.0f - fy;
+        float r = __fadd_rn(__fmul_rn((float)t00[j], __fmul_rn(gy, gx)), __fmul_rn((float)t01[j], __fmul_rn(gy, fx)));
+        r = __fadd_rn(r, __fmul_rn((float)t10[j], __fmul_rn(fy, gx)));
+        r = __fadd_rn(r, __fmul_rn((float)t11[j], __fmul_rn(fy, fx)));
+        r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);   // rint (half to even)
+        v[j] = fminf(r, 65535.0f);                                 // r >= 0 by construction
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (!fast[j]) {
+          const uint16_t* f2 = cam.frames + (size_t)((unsigned)(b + j) * (unsigned)cam.npix);
+          v[j] = (b + j == skip_frame) ? (float)__ldg(f2 + code)
+                                       : warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], interp);
+        }
+      }
+    } else {
+      const uint16_t* p = cam.frames + (size_t)((unsigned)b * (unsigned)cam.npix) + code;
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        v[j] = (float)__ldg(p);
+        p += cam.npix;
+      }
+    }
+  } else if (code <= -2) {
+    const float* p = cam.pv + (size_t)(-2 - code) * bstride + b;
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
+  }
+}
+
 template <int NC, bool REG>
 __global__ void __launch_bounds__(256)
 k_project_fused(const FusedArgs a) {
+  constexpr int U = 4;
   __shared__ float tile[32][257];
   const int n = blockIdx.x * 256 + threadIdx.x;
   const bool live = n < a.n_nodes;
@@ -206,46 +276,36 @@ k_project_fused(const FusedArgs a) {
   for (int b0 = 0; b0 < a.nframes; b0 += 32) {
     const int nb = min(32, a.nframes - b0);
     if (live) {
-#pragma unroll 4
-      for (int u = 0; u < nb; ++u) {
-        const int b = b0 + u;
+      int u = 0;
+      for (; u + U <= nb; u += U) {
+        float sol[U];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float v[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) v[j] = 0.0f;
+          fused_cam_group<U, REG>(a.cam[c], code[c], tx[c], ty[c], b0 + u, a.interp, a.skip_frame, a.bstride, v);
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const float cs = (code[c] == -1) ? 0.0f : __fadd_rn(0.0f, __fmul_rn(val[c], v[j]));
+            sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          if (skipped) sol[j] = __int_as_float(0x7fc00000);
+          tile[u + j][threadIdx.x] = sol[j];
+          q += (double)__fmul_rn(sol[j], sol[j]);
+          s += (double)sol[j];
+        }
+      }
+      for (; u < nb; ++u) {   // tail frames of the batch, one at a time
         float sol = 0.0f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-          float cs = 0.0f;
-          const FusedCam& cam = a.cam[c];
-          if (code[c] >= 0) {
-            float v;
-            const unsigned fbase = (unsigned)b * (unsigned)cam.npix;   // batch-local pixel index (< 2^31)
-            if (REG && b != a.skip_frame) {
-              const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (unsigned)b * (unsigned)(cam.W + cam.H);
-              const int2 xa = __ldg(tb + tx[c]);
-              const int2 ya = __ldg(tb + ty[c]);
-              const int X = ya.x + xa.x, Y = ya.y + xa.y;
-              const int Xs = X >> 5, Ys = Y >> 5;
-              const int sx = X >> 10, sy = Y >> 10;
-              if (a.interp == 1 && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1)) {
-                const uint16_t* p = cam.frames + (fbase + (unsigned)(sy * cam.W + sx));
-                const uint16_t* p2 = p + cam.W;
-                const float t00 = (float)__ldg(p), t01 = (float)__ldg(p + 1);
-                const float t10 = (float)__ldg(p2), t11 = (float)__ldg(p2 + 1);
-                const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
-                const float gx = 1.0f - fx, gy = 1.0f - fy;
-                v = __fadd_rn(__fmul_rn(t00, __fmul_rn(gy, gx)), __fmul_rn(t01, __fmul_rn(gy, fx)));
-                v = __fadd_rn(v, __fmul_rn(t10, __fmul_rn(fy, gx)));
-                v = __fadd_rn(v, __fmul_rn(t11, __fmul_rn(fy, fx)));
-                v = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);   // rint (half to even)
-                v = fminf(v, 65535.0f);                                    // v >= 0 by construction
-              } else {
-                v = warp_px_slow(cam.frames + fbase, cam.W, cam.H, X, Y, a.interp);
-              }
-            } else {
-              v = (float)__ldg(cam.frames + (fbase + (unsigned)code[c]));
-            }
-            cs = __fadd_rn(0.0f, __fmul_rn(val[c], v));
-          } else if (code[c] <= -2) {
-            cs = __fadd_rn(0.0f, __fmul_rn(val[c], __ldg(cam.pv + (size_t)(-2 - code[c]) * a.bstride + b)));
-          }
+          float v[1] = {0.0f};
+          fused_cam_group<1, REG>(a.cam[c], code[c], tx[c], ty[c], b0 + u, a.interp, a.skip_frame, a.bstride, v);
+          const float cs = (code[c] == -1) ? 0.0f : __fadd_rn(0.0f, __fmul_rn(val[c], v[0]));
           sol = (c == 0) ? cs : __fadd_rn(sol, cs);
         }
         if (skipped) sol = __int_as_float(0x7fc00000);
