@@ -1,0 +1,71 @@
+"""Multi-GPU parity (needs >= 2 visible GPUs; skipped otherwise): two ranks in ONE process
+(upsp_gpu_connect_local), frames sharded by apportion(), node-major rows stored straight into
+the peer's buffer, rank-ordered sum/sum-sq over peer memory.  Compared with the oracle run with
+two simulated MPI ranks."""
+import numpy as np
+import pytest
+
+from chain import Case, cp_errors, monomial_mass, push_all, run_oracle, same_bits, setup_ctx
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_two_ranks(up, orc, case, keep_frame_major, same_device=False):
+    R = 2
+    ctxs, slices = [], []
+    for r in range(R):
+        g, sl = setup_ctx(up, orc, case, rank=r, n_ranks=R, device=0 if same_device else r,
+                          keep_frame_major=keep_frame_major)
+        ctxs.append(g)
+        slices.append(sl)
+    up.connect_local(ctxs)
+    for g, sl in zip(ctxs, slices):
+        push_all(up, orc, g, case, sl)
+    for g in ctxs:
+        g.sync()                      # == MPI_Barrier before the reduce
+    for g in ctxs:
+        g.finish_phase1()
+    for g in ctxs:
+        g.transpose()
+    for g in ctxs:
+        g.sync()                      # == MPI_Barrier after the transpose
+    out = dict(itrans=[], ptrans=[], rms2=[], avg2=[], gain=[])
+    stats = [g.read_phase1_stats() for g in ctxs]
+    for g in ctxs:
+        out["itrans"].append(g.read_intensity_transpose())
+        g.phase2(case.cal, case.qbar, case.ps, case.steady, case.temp, case.degree)
+        out["ptrans"].append(g.read_pressure_transpose())
+        r2, a2, g2 = g.read_phase2_stats()
+        out["rms2"].append(r2)
+        out["avg2"].append(a2)
+        out["gain"].append(g2)
+    res = {k: np.concatenate(v, 0) for k, v in out.items()}
+    res["avg"], res["rms"], res["coverage"] = stats[0]
+    # every rank must hold bit-identical phase-1 statistics (rank-ordered reduction)
+    for k in range(3):
+        assert same_bits(stats[0][k], stats[1][k])
+    for g in ctxs:
+        g.close()
+    return res
+
+
+@pytest.mark.parametrize("keep_frame_major", [False, True], ids=["fused", "frame-major+transpose"])
+@pytest.mark.parametrize("same_device", [False, True], ids=["2gpus", "2ranks-1gpu"])
+def test_two_ranks_match_oracle(up, orc, gpu, keep_frame_major, same_device):
+    if not same_device and gpu < 2:
+        pytest.skip("needs 2 GPUs")
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=75, n_nodes=3001, registration=True, patches=True, overlap=True,
+                seed=21, fmt="p12")
+    ref = run_oracle(orc, case, n_ranks=2)
+    got = _run_two_ranks(up, orc, case, keep_frame_major, same_device)
+    assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
+    assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact across ranks"
+    assert same_bits(got["gain"], ref["gain"])
+    exact = run_oracle(orc, case, n_ranks=2, exact_fit=True)
+    e_exact, _ = cp_errors(case, exact, got)
+    cond = 8 * np.finfo(np.float32).eps * monomial_mass(orc, ref)
+    assert np.all(e_exact <= 1e-6 + cond)
+    e_op, _ = cp_errors(case, ref, got)
+    noise, _ = cp_errors(case, ref, exact)
+    assert np.all(e_op <= 1e-5 + noise + cond)

@@ -165,6 +165,8 @@ struct FusedArgs {
   FusedCam cam[UPSP_MAX_CAMS];
   double* sum;
   double* sumsq;
+  const int* perm;                     // [N] processing order: nodes sorted by the Morton code of
+                                       // their pixel, so a warp / block gathers from a compact patch
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];
@@ -256,8 +258,11 @@ __global__ void __launch_bounds__(256)
 k_project_fused(const FusedArgs a) {
   constexpr int U = 4;
   __shared__ float tile[32][257];
-  const int n = blockIdx.x * 256 + threadIdx.x;
-  const bool live = n < a.n_nodes;
+  __shared__ int nodes[256];
+  const int gid = blockIdx.x * 256 + threadIdx.x;
+  const bool live = gid < a.n_nodes;
+  const int n = live ? __ldg(a.perm + gid) : -1;
+  nodes[threadIdx.x] = n;
   int code[NC], tx[NC], ty[NC];
   float val[NC];
   bool skipped = true;
@@ -315,25 +320,15 @@ k_project_fused(const FusedArgs a) {
       }
     }
     __syncthreads();
-    // warp w writes nodes [w*32, w*32+32) of the block: lane = frame -> 128-byte row segments
+    // warp w writes the block's nodes [w*32, w*32+32): lane = frame -> 128-byte row segments
     {
-      const int n0 = blockIdx.x * 256 + w * 32;
-      const int n1 = min(n0 + 32, a.n_nodes);
-      int r = 0;
-      while (r + 1 < a.n_ranks && n0 >= a.node_start[r + 1]) ++r;
       const size_t col = (size_t)a.col0 + b0 + lane;
-      float* p = a.dst[r] + (size_t)(n0 - a.node_start[r]) * a.f_total + col;
-      int next = a.node_start[r + 1];
-      for (int nn = n0; nn < n1; ++nn) {
-        if (nn >= next) {   // the warp's node run crosses into the next rank's slice
-          do {
-            ++r;
-            next = a.node_start[r + 1];
-          } while (nn >= next);
-          p = a.dst[r] + (size_t)(nn - a.node_start[r]) * a.f_total + col;
-        }
-        if (lane < nb) *p = tile[lane][nn - blockIdx.x * 256];
-        p += a.f_total;
+      for (int j = 0; j < 32; ++j) {
+        const int nn = nodes[w * 32 + j];
+        if (nn < 0) break;
+        int r = 0;
+        while (r + 1 < a.n_ranks && nn >= a.node_start[r + 1]) ++r;
+        if (lane < nb) a.dst[r][(size_t)(nn - a.node_start[r]) * a.f_total + col] = tile[lane][w * 32 + j];
       }
     }
     __syncthreads();

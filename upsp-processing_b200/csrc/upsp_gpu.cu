@@ -122,6 +122,7 @@ struct upsp_gpu_ctx {
   std::vector<int> remap;  // src_index or empty
   bool finalized = false, ell1 = true, fused = false;
   uint16_t* d_lut = nullptr;
+  int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
 
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
@@ -348,6 +349,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
     if (r != c->rank && c->peer_base[r] && c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
   for (auto& cam : c->cams) free_camera(cam);
   cudaFree(c->d_lut);
+  cudaFree(c->d_perm);
   cudaFree(c->d_intensity);
   cudaFree(c->d_shared);
   if (c->ptrans_owned) cudaFree(c->d_ptrans);
@@ -695,6 +697,36 @@ static int finalize(upsp_gpu_ctx* c) {
     }
   }
   CU(cudaMemcpy(c->d_cov, cov.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  if (c->fused) {
+    // processing order: Morton (Z-order) code of each node's pixel in the first camera that sees
+    // it; nodes without a plain pixel (skipped / patched-only) go last.  Pure locality hint.
+    auto spread = [](uint32_t v) {
+      v &= 0xFFFF;
+      v = (v | (v << 8)) & 0x00FF00FF;
+      v = (v | (v << 4)) & 0x0F0F0F0F;
+      v = (v | (v << 2)) & 0x33333333;
+      v = (v | (v << 1)) & 0x55555555;
+      return v;
+    };
+    std::vector<std::pair<uint64_t, int>> keyed(N);
+    for (int n = 0; n < N; ++n) {
+      uint64_t key = ~0ull;
+      const int sn = c->remap.empty() ? n : c->remap[n];
+      for (size_t ci = 0; ci < c->cams.size(); ++ci) {
+        const Camera& k = c->cams[ci];
+        if (k.rowptr[sn + 1] > k.rowptr[sn]) {
+          const int col = k.col[k.rowptr[sn]];
+          key = ((uint64_t)ci << 32) | (spread((uint32_t)(col % k.W)) | (spread((uint32_t)(col / k.W)) << 1));
+          break;
+        }
+      }
+      keyed[n] = {key, n};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int> perm(N);
+    for (int i = 0; i < N; ++i) perm[i] = keyed[i].second;
+    TRY(upload(&c->d_perm, perm.data(), perm.size()));
+  }
   // big buffers that depend on the mode
   {
     const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
@@ -870,6 +902,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.interp = c->interp;
     fa.sum = c->d_sum;
     fa.sumsq = c->d_sumsq;
+    fa.perm = c->d_perm;
     fa.n_ranks = c->R;
     fa.f_total = c->F;
     fa.col0 = c->f0 + off;
