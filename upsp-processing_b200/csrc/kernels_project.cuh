@@ -184,67 +184,80 @@ __device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W
   return fminf(fmaxf(r, 0.0f), 65535.0f);
 }
 
-// U consecutive frames of one camera for one node: every global load of the group is issued
-// before any result is consumed (no divergent region between the loads), so a thread keeps
-// 2U table loads and then 4U tap loads in flight.  Border / nearest pixels are patched up
-// afterwards through the out-of-line slow path.
-template <int U, bool REG>
-__device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, int tx, int ty, int b,
-                                                int interp, int skip_frame, int bstride,
+// U consecutive frames of one camera for one node.  Every global load of the group is issued
+// before any result is consumed (2U table loads, then 4U tap loads in flight per thread); the
+// rare border / nearest / unregistered-frame pixels are patched up afterwards through the
+// out-of-line slow path (one branch per group).
+// INT12: all pixels are < 2^14 (12/10-bit containers), so OpenCV's float bilinear sum
+// (weights k/1024, every product and partial sum exact in float) equals S/1024 with the integer
+// S = sum t_ij * w_ij; the kernel then rounds S half-to-even in integer arithmetic and never
+// touches the conversion (XU) pipe.  u16 containers keep the float sequence.
+template <int U, bool REG, bool INT12>
+__device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, const int2* __restrict__ ptx,
+                                                const int2* __restrict__ pty, const uint16_t* __restrict__ fr,
+                                                int b, int interp, int skip_frame, int bstride,
                                                 float (&v)[U]) {
   if (code >= 0) {
     if (REG) {
+      const size_t tstride = (size_t)(cam.W + cam.H);
       int X[U], Y[U];
-      const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (unsigned)b * (unsigned)(cam.W + cam.H);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int2 xa = __ldg(tb + tx), ya = __ldg(tb + ty);
+        const int2 xa = __ldg(ptx + j * tstride), ya = __ldg(pty + j * tstride);
         X[j] = ya.x + xa.x;
         Y[j] = ya.y + xa.y;
-        tb += cam.W + cam.H;
       }
       unsigned short t00[U], t01[U], t10[U], t11[U];
-      bool fast[U];
-      const uint16_t* fr = cam.frames + (size_t)((unsigned)b * (unsigned)cam.npix);
+      bool all_fast = true;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int sx = X[j] >> 10, sy = Y[j] >> 10;
-        fast[j] = (interp == 1) && (b + j != skip_frame) && (unsigned)sx < (unsigned)(cam.W - 1) &&
-                  (unsigned)sy < (unsigned)(cam.H - 1);
-        const int cx = min(max(sx, 0), cam.W - 2), cy = min(max(sy, 0), cam.H - 2);
-        const uint16_t* p = fr + (unsigned)(cy * cam.W + cx);
+        const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+        all_fast = all_fast && fast;
+        const unsigned idx = fast ? (unsigned)(sy * cam.W + sx) : 0u;
+        const uint16_t* p = fr + (j * cam.npix + idx);
+        const uint16_t* p2 = p + cam.W;
         t00[j] = __ldg(p);
         t01[j] = __ldg(p + 1);
-        t10[j] = __ldg(p + cam.W);
-        t11[j] = __ldg(p + cam.W + 1);
-        fr += cam.npix;
+        t10[j] = __ldg(p2);
+        t11[j] = __ldg(p2 + 1);
       }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int Xs = X[j] >> 5, Ys = Y[j] >> 5;
-        const float fx = frac32_exact(Xs & 31), fy = frac32_exact(Ys & 31);
-        const float gx = 1.0f - fx, gy = 1.0f - fy;
-        float r = __fadd_rn(__fmul_rn((float)t00[j], __fmul_rn(gy, gx)), __fmul_rn((float)t01[j], __fmul_rn(gy, fx)));
-        r = __fadd_rn(r, __fmul_rn((float)t10[j], __fmul_rn(fy, gx)));
-        r = __fadd_rn(r, __fmul_rn((float)t11[j], __fmul_rn(fy, fx)));
-        r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);   // rint (half to even)
-        v[j] = fminf(r, 65535.0f);                                 // r >= 0 by construction
+        const int fxi = (X[j] >> 5) & 31, fyi = (Y[j] >> 5) & 31;
+        if (INT12) {
+          const int gx = 32 - fxi, gy = 32 - fyi;
+          int S = (int)t00[j] * (gy * gx);
+          S += (int)t01[j] * (gy * fxi);
+          S += (int)t10[j] * (fyi * gx);
+          S += (int)t11[j] * (fyi * fxi);
+          const int qv = S >> 10, rem = S & 1023;
+          const int r = qv + ((rem + (qv & 1)) > 512);      // round half to even
+          v[j] = u2f_exact((uint32_t)r);
+        } else {
+          const float fx = frac32_exact(fxi), fy = frac32_exact(fyi);
+          const float gx = 1.0f - fx, gy = 1.0f - fy;
+          float r = __fadd_rn(__fmul_rn((float)t00[j], __fmul_rn(gy, gx)), __fmul_rn((float)t01[j], __fmul_rn(gy, fx)));
+          r = __fadd_rn(r, __fmul_rn((float)t10[j], __fmul_rn(fy, gx)));
+          r = __fadd_rn(r, __fmul_rn((float)t11[j], __fmul_rn(fy, fx)));
+          r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);   // rint (half to even)
+          v[j] = fminf(r, 65535.0f);                                 // r >= 0 by construction
+        }
       }
+      const bool has_skip = (unsigned)(skip_frame - b) < (unsigned)U;
+      if (!all_fast || interp != 1 || has_skip) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (!fast[j]) {
-          const uint16_t* f2 = cam.frames + (size_t)((unsigned)(b + j) * (unsigned)cam.npix);
-          v[j] = (b + j == skip_frame) ? (float)__ldg(f2 + code)
-                                       : warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], interp);
+        for (int j = 0; j < U; ++j) {
+          const int sx = X[j] >> 10, sy = Y[j] >> 10;
+          const bool fast = interp == 1 && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+          const uint16_t* f2 = fr + j * cam.npix;
+          if (b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
+          else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], interp);
         }
       }
     } else {
-      const uint16_t* p = cam.frames + (size_t)((unsigned)b * (unsigned)cam.npix) + code;
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        v[j] = (float)__ldg(p);
-        p += cam.npix;
-      }
+      for (int j = 0; j < U; ++j) v[j] = (float)__ldg(fr + (j * cam.npix + (size_t)code));
     }
   } else if (code <= -2) {
     const float* p = cam.pv + (size_t)(-2 - code) * bstride + b;
@@ -253,17 +266,27 @@ __device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, i
   }
 }
 
-template <int NC, bool REG>
+template <int NC, bool REG, bool INT12>
 __global__ void __launch_bounds__(256)
 k_project_fused(const FusedArgs a) {
   constexpr int U = 4;
   __shared__ float tile[32][257];
-  __shared__ int nodes[256];
+  __shared__ float* rowp[256];       // node-major row of each of the block's nodes (any rank)
   const int gid = blockIdx.x * 256 + threadIdx.x;
   const bool live = gid < a.n_nodes;
   const int n = live ? __ldg(a.perm + gid) : -1;
-  nodes[threadIdx.x] = n;
-  int code[NC], tx[NC], ty[NC];
+  {
+    float* rp = nullptr;
+    if (live) {
+      int r = 0;
+      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+    }
+    rowp[threadIdx.x] = rp;
+  }
+  int code[NC];
+  const int2* ptx[NC];
+  const int2* pty[NC];
   float val[NC];
   bool skipped = true;
 #pragma unroll
@@ -273,8 +296,8 @@ k_project_fused(const FusedArgs a) {
     skipped = skipped && (code[c] == -1);
     const int W = a.cam[c].W;
     const int px = code[c] >= 0 ? code[c] % W : 0, py = code[c] >= 0 ? code[c] / W : 0;
-    tx[c] = px;              // int2 index of (adelta,bdelta)[px] inside a frame's table
-    ty[c] = W + py;          // int2 index of (X0,Y0)[py]
+    ptx[c] = reinterpret_cast<const int2*>(a.cam[c].tab) + px;        // (adelta,bdelta)[px] of frame 0
+    pty[c] = reinterpret_cast<const int2*>(a.cam[c].tab) + W + py;    // (X0,Y0)[py] of frame 0
   }
   double s = 0.0, q = 0.0;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,7 +312,12 @@ k_project_fused(const FusedArgs a) {
           float v[U];
 #pragma unroll
           for (int j = 0; j < U; ++j) v[j] = 0.0f;
-          fused_cam_group<U, REG>(a.cam[c], code[c], tx[c], ty[c], b0 + u, a.interp, a.skip_frame, a.bstride, v);
+          const FusedCam& cam = a.cam[c];
+          const int b = b0 + u;
+          fused_cam_group<U, REG, INT12>(cam, code[c], ptx[c] + (size_t)b * (cam.W + cam.H),
+                                         pty[c] + (size_t)b * (cam.W + cam.H),
+                                         cam.frames + (size_t)b * cam.npix, b, a.interp, a.skip_frame,
+                                         a.bstride, v);
 #pragma unroll
           for (int j = 0; j < U; ++j) {
             const float cs = (code[c] == -1) ? 0.0f : __fadd_rn(0.0f, __fmul_rn(val[c], v[j]));
@@ -309,7 +337,12 @@ k_project_fused(const FusedArgs a) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           float v[1] = {0.0f};
-          fused_cam_group<1, REG>(a.cam[c], code[c], tx[c], ty[c], b0 + u, a.interp, a.skip_frame, a.bstride, v);
+          const FusedCam& cam = a.cam[c];
+          const int b = b0 + u;
+          fused_cam_group<1, REG, INT12>(cam, code[c], ptx[c] + (size_t)b * (cam.W + cam.H),
+                                         pty[c] + (size_t)b * (cam.W + cam.H),
+                                         cam.frames + (size_t)b * cam.npix, b, a.interp, a.skip_frame,
+                                         a.bstride, v);
           const float cs = (code[c] == -1) ? 0.0f : __fadd_rn(0.0f, __fmul_rn(val[c], v[0]));
           sol = (c == 0) ? cs : __fadd_rn(sol, cs);
         }
@@ -321,14 +354,12 @@ k_project_fused(const FusedArgs a) {
     }
     __syncthreads();
     // warp w writes the block's nodes [w*32, w*32+32): lane = frame -> 128-byte row segments
-    {
-      const size_t col = (size_t)a.col0 + b0 + lane;
+    if (lane < nb) {
+#pragma unroll 4
       for (int j = 0; j < 32; ++j) {
-        const int nn = nodes[w * 32 + j];
-        if (nn < 0) break;
-        int r = 0;
-        while (r + 1 < a.n_ranks && nn >= a.node_start[r + 1]) ++r;
-        if (lane < nb) a.dst[r][(size_t)(nn - a.node_start[r]) * a.f_total + col] = tile[lane][w * 32 + j];
+        float* rp = rowp[w * 32 + j];
+        if (rp == nullptr) break;
+        rp[b0 + lane] = tile[lane][w * 32 + j];
       }
     }
     __syncthreads();

@@ -122,6 +122,7 @@ struct upsp_gpu_ctx {
   std::vector<int> remap;  // src_index or empty
   bool finalized = false, ell1 = true, fused = false;
   uint16_t* d_lut = nullptr;
+  int lut_max = 0;        // largest entry of the 10->12-bit table (0 = no table)
   int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
 
   cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -468,7 +469,11 @@ extern "C" int upsp_gpu_set_unpack_lut(upsp_gpu_ctx* c, const uint16_t* lut) {
   ENTER(c);
   cudaFree(c->d_lut);
   c->d_lut = nullptr;
-  if (lut) TRY(upload(&c->d_lut, lut, 1024));
+  c->lut_max = 0;
+  if (lut) {
+    TRY(upload(&c->d_lut, lut, 1024));
+    for (int i = 0; i < 1024; ++i) c->lut_max = std::max(c->lut_max, (int)lut[i]);
+  }
   return UPSP_OK;
 }
 
@@ -914,9 +919,13 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     const unsigned g = cdiv(c->N, 256);
     KBEGIN(4);
     const bool regk = c->registration != UPSP_REG_NONE;
-#define FUSED_LAUNCH(NCAM)                                              \
-  if (regk) k_project_fused<NCAM, true><<<g, 256, 0, c->stream>>>(fa);  \
-  else k_project_fused<NCAM, false><<<g, 256, 0, c->stream>>>(fa)
+    bool int12 = true;   // every camera's container guarantees pixels < 2^14
+    for (auto& k : c->cams)
+      int12 = int12 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 16384));
+#define FUSED_LAUNCH(NCAM)                                                          \
+  if (regk && int12) k_project_fused<NCAM, true, true><<<g, 256, 0, c->stream>>>(fa);   \
+  else if (regk) k_project_fused<NCAM, true, false><<<g, 256, 0, c->stream>>>(fa);  \
+  else k_project_fused<NCAM, false, false><<<g, 256, 0, c->stream>>>(fa)
     switch (fa.n_cams) {
       case 1: FUSED_LAUNCH(1); break;
       case 2: FUSED_LAUNCH(2); break;
@@ -1006,10 +1015,14 @@ extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
   if (c->R > 1) {
     REQUIRE(c->peers_ready, UPSP_ERR_STATE,
             "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
+    // every rank lays its shared block out as [itrans N_r x F | sum N | sumsq N]: offsets depend on N_r
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     std::vector<double*> ptrs(2 * c->R);
     for (int r = 0; r < c->R; ++r) {
-      ptrs[r] = reinterpret_cast<double*>(c->peer_base[r] + c->off_sum);
-      ptrs[c->R + r] = reinterpret_cast<double*>(c->peer_base[r] + c->off_sumsq);
+      const size_t osum = al((size_t)c->n_count[r] * c->F * sizeof(float));
+      const size_t osq = osum + al((size_t)c->N * sizeof(double));
+      ptrs[r] = reinterpret_cast<double*>(c->peer_base[r] + osum);
+      ptrs[c->R + r] = reinterpret_cast<double*>(c->peer_base[r] + osq);
     }
     TRY(upload(&d_ptrs, ptrs.data(), ptrs.size()));
     TRY(dmalloc(&tsum, c->N));
