@@ -237,7 +237,7 @@ def bench_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # per-kernel launches of one step, CUDA-event mean duration (sampled inside the timed region),
     # algorithmic bytes per launch
-    B = args.batch if args.batch > 0 else 32
+    B = args.batch if args.batch > 0 else 128
     nbatch = -(-F_local // B)
     knames = ["k_unpack12_scan", "k_frame_prep", "k_warp_affine8_u16", "k_patch", "k_project_fused",
               "k_transpose_a2a", "k_phase2"]

@@ -263,7 +263,7 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
   c->n0 = c->n_start[c->rank];
   c->capacity = cfg->frame_capacity > 0 ? std::min(cfg->frame_capacity, std::max(c->F_local, 1))
                                         : std::max(c->F_local, 1);
-  c->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 32;
+  c->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 128;
   c->batch = std::min(c->batch, c->capacity);
   c->cams.resize(cfg->n_cams);
   *out = c;
