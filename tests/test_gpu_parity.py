@@ -122,10 +122,11 @@ def test_detrend_reference_unit_test_recipe(up, orc, gpu):
         assert np.abs(fit[p] - ofit).max() < 1e-4
 
 
-@pytest.mark.parametrize("F", [25, 1000, 20000, 70001])
+@pytest.mark.parametrize("F", [25, 1000, 20000, 40000, 70001, 410001])
 def test_detrend_long_series_vs_oracle(up, orc, gpu, F):
     """ratio-like series (1 + drift + noise): GPU fit vs the float-QR oracle fit and vs the
-    float64 least-squares fit; F=70001 exercises the not-in-shared-memory path."""
+    float64 least-squares fit.  F=40000 / 70001 run as 2- / 4-CTA clusters (row split over
+    distributed shared memory); F=410001 exceeds 8 x shared memory (two-HBM-pass path)."""
     rng = np.random.default_rng(6)
     t = np.arange(F) / F
     y = (1.0 + 0.02 * np.sin(2 * np.pi * t) + 0.01 * t + rng.normal(0, 4e-3, (3, F))).astype(np.float32)

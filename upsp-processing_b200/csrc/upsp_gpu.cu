@@ -1269,22 +1269,50 @@ static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
     }
 }
 
+template <int NC, bool ROW_SMEM, int CL>
+static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
+  constexpr int NT = 512;
+  auto kern = k_phase2<NC, ROW_SMEM, NT, CL>;
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)a.n_local * CL);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, a));
+  return UPSP_OK;
+}
+
 template <int NC>
 static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
-  constexpr int NT = 512;
-  const size_t row_bytes = (size_t)a.F * sizeof(float);
-  if (a.n_local == 0) return UPSP_OK;
-  cudaFuncAttributes fa;
-  CU(cudaFuncGetAttributes(&fa, k_phase2<NC, true, NT>));
-  const size_t smem_max = 227 * 1024 - fa.sharedSizeBytes - 1024;  // opt-in limit minus static part
-  if (row_bytes <= smem_max) {
-    CU(cudaFuncSetAttribute(k_phase2<NC, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)smem_max));
-    k_phase2<NC, true, NT><<<a.n_local, NT, row_bytes, st>>>(a);
-  } else {
-    k_phase2<NC, false, NT><<<a.n_local, NT, 0, st>>>(a);
-  }
   (void)c;
+  if (a.n_local == 0) return UPSP_OK;
+  // smallest cluster whose per-CTA segment leaves room for 2 CTAs per SM (<= 90 KB + 18.6 KB static each)
+  const size_t seg_budget = 90 * 1024, seg_max = 200 * 1024;
+  int rc = UPSP_OK;
+  bool done = false;
+  for (int cl = 1; cl <= 8 && !done; cl *= 2) {
+    const size_t seg = (size_t)(((a.F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
+    if (seg <= seg_budget || (cl == 8 && seg <= seg_max)) {
+      switch (cl) {
+        case 1: rc = launch_phase2_cl<NC, true, 1>(a, seg, st); break;
+        case 2: rc = launch_phase2_cl<NC, true, 2>(a, seg, st); break;
+        case 4: rc = launch_phase2_cl<NC, true, 4>(a, seg, st); break;
+        default: rc = launch_phase2_cl<NC, true, 8>(a, seg, st); break;
+      }
+      done = true;
+    }
+  }
+  if (!done) rc = launch_phase2_cl<NC, false, 1>(a, 0, st);   // two HBM passes
+  if (rc) return rc;
   ++*launches;
   CU(cudaGetLastError());
   return UPSP_OK;
