@@ -124,8 +124,12 @@ def dist_setup(n_gpus):
 
 
 def barrier(dist):
+    """Host-side rendezvous through the CPU (gloo) side of the process group: the data path has
+    no NCCL collective (peer stores / peer reads inside the library's own kernels)."""
     if dist is not None:
-        dist.barrier()
+        import torch
+        t = torch.zeros(1, dtype=torch.int32)
+        dist.all_reduce(t)
 
 
 def allmax(dist, v):
@@ -160,17 +164,25 @@ def configure(up, wl, args, rank, world, local, capacity, dist):
     return g
 
 
-def run_step_resident(g, wl, args, dist):
+def run_step_resident(g, wl, args, dist, trace=None):
+    t = [time.perf_counter()]
     g.reset_run()
     g.process_frames(0, g.n_frames)
     if dist is not None:
         g.sync()
+        t.append(time.perf_counter())
         barrier(dist)            # MPI_Barrier before the reduce (psp_process.cpp:1859)
+    t.append(time.perf_counter())
     g.finish_phase1()
     g.transpose()
+    t.append(time.perf_counter())
     if dist is not None:
         barrier(dist)            # psp_process.cpp:2034-2035
+    t.append(time.perf_counter())
     g.phase2(wl["cal"], wl["qbar"], wl["ps"], wl["steady"], wl["temp"], args.degree)
+    t.append(time.perf_counter())
+    if trace is not None:
+        trace.append([round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])])
 
 
 def bench_b200(args):
@@ -203,8 +215,9 @@ def bench_b200(args):
     stage = np.zeros(4)
     g.timer_start()
     t_wall = time.time()
+    trace = []
     for _ in range(args.steps):
-        run_step_resident(g, wl, args, dist)
+        run_step_resident(g, wl, args, dist, trace)
         stage += [g.stage_ms(i) for i in range(4)]
         if _ == args.steps - 1:
             kms = [g.kernel_ms(k) for k in range(7)]     # of the last timed step
@@ -213,6 +226,7 @@ def bench_b200(args):
     barrier(dist)
     wall_ms = (time.time() - t_wall) * 1e3
     clocks = sampler.stop() if sampler else None
+    log(f"[bench] rank {rank} host timeline per step (ms; process[, barrier], finish+transpose[, barrier], phase2): {trace}")
     launches = g.launch_count() - l0
     ms_dev = allmax(dist, ms_dev)
     stage /= args.steps

@@ -165,8 +165,8 @@ struct FusedArgs {
   FusedCam cam[UPSP_MAX_CAMS];
   double* sum;
   double* sumsq;
-  const int* perm;                     // [N] processing order: nodes sorted by the Morton code of
-                                       // their pixel, so a warp / block gathers from a compact patch
+  const int* perm;                     // [N] processing order: nodes sorted by pixel index (raster),
+                                       // so a warp gathers from one or two image rows
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];

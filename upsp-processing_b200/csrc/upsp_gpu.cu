@@ -273,6 +273,8 @@ struct upsp_gpu_ctx {
   double *d_rms2 = nullptr, *d_avg2 = nullptr, *d_gain2 = nullptr;     // [N_local]
   float *d_rms2f = nullptr, *d_avg2f = nullptr, *d_gain2f = nullptr;   // [N_local]
   size_t shared_bytes = 0, off_sum = 0, off_sumsq = 0;
+  double *d_tsum = nullptr, *d_tsq = nullptr;   // n_ranks > 1: all-reduced sums
+  double** d_peer_ptrs = nullptr;                // [2R] peers' sum / sumsq bases
 
   // peers: base of every rank's shared allocation as seen from this device
   char* peer_base[UPSP_MAX_RANKS] = {nullptr};
@@ -431,6 +433,11 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     TRY(dmalloc(&c->d_rms2f, c->N_local));
     TRY(dmalloc(&c->d_avg2f, c->N_local));
     TRY(dmalloc(&c->d_gain2f, c->N_local));
+    if (c->R > 1) {
+      TRY(dmalloc(&c->d_tsum, c->N));
+      TRY(dmalloc(&c->d_tsq, c->N));
+      TRY(dmalloc(&c->d_peer_ptrs, 2 * c->R));
+    }
     c->peer_base[c->rank] = c->d_shared;
     if (c->R == 1) c->peers_ready = true;
     CU(cudaStreamSynchronize(c->stream));
@@ -490,6 +497,9 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaFree(c->d_rms2f);
   cudaFree(c->d_avg2f);
   cudaFree(c->d_gain2f);
+  cudaFree(c->d_tsum);
+  cudaFree(c->d_tsq);
+  cudaFree(c->d_peer_ptrs);
   if (c->ev_push) cudaEventDestroy(c->ev_push);
   if (c->ev_proc) cudaEventDestroy(c->ev_proc);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -828,16 +838,11 @@ static int finalize(upsp_gpu_ctx* c) {
   }
   CU(cudaMemcpy(c->d_cov, cov.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
   if (c->fused) {
-    // processing order: Morton (Z-order) code of each node's pixel in the first camera that sees
-    // it; nodes without a plain pixel (skipped / patched-only) go last.  Pure locality hint.
-    auto spread = [](uint32_t v) {
-      v &= 0xFFFF;
-      v = (v | (v << 8)) & 0x00FF00FF;
-      v = (v | (v << 4)) & 0x0F0F0F0F;
-      v = (v | (v << 2)) & 0x33333333;
-      v = (v | (v << 1)) & 0x55555555;
-      return v;
-    };
+    // processing order: raster order of each node's pixel in the first camera that sees it, so
+    // the 32 nodes of a warp read (mostly) one image row: a warp-wide tap load then touches 1-2
+    // 128-byte lines instead of ~7 for a square (Z-order) patch or ~16 for mesh order -- the
+    // kernel is bound by L1 wavefronts, not bytes.  Nodes without a plain pixel (skipped /
+    // patched-only) go last.  Pure locality hint: results do not depend on it.
     std::vector<std::pair<uint64_t, int>> keyed(N);
     for (int n = 0; n < N; ++n) {
       uint64_t key = ~0ull;
@@ -846,7 +851,7 @@ static int finalize(upsp_gpu_ctx* c) {
         const Camera& k = c->cams[ci];
         if (k.rowptr[sn + 1] > k.rowptr[sn]) {
           const int col = k.col[k.rowptr[sn]];
-          key = ((uint64_t)ci << 32) | (spread((uint32_t)(col % k.W)) | (spread((uint32_t)(col / k.W)) << 1));
+          key = ((uint64_t)ci << 32) | (uint32_t)col;
           break;
         }
       }
@@ -1135,8 +1140,6 @@ extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
   REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
   CU(cudaEventRecord(c->ev_a, c->stream));
   const double *sum = c->d_sum, *sq = c->d_sumsq;
-  double *tsum = nullptr, *tsq = nullptr;
-  double** d_ptrs = nullptr;
   if (c->R > 1) {
     REQUIRE(c->peers_ready, UPSP_ERR_STATE,
             "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
@@ -1149,22 +1152,20 @@ extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
       ptrs[r] = reinterpret_cast<double*>(c->peer_base[r] + osum);
       ptrs[c->R + r] = reinterpret_cast<double*>(c->peer_base[r] + osq);
     }
-    TRY(upload(&d_ptrs, ptrs.data(), ptrs.size()));
-    TRY(dmalloc(&tsum, c->N));
-    TRY(dmalloc(&tsq, c->N));
-    k_allreduce_peer<<<cdiv(c->N, 256), 256, 0, c->stream>>>(d_ptrs, d_ptrs + c->R, c->R, c->N, tsum, tsq);
+    CU(cudaMemcpyAsync(c->d_peer_ptrs, ptrs.data(), ptrs.size() * sizeof(double*), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // ptrs is a stack object
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    k_allreduce_peer<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->d_peer_ptrs, c->d_peer_ptrs + c->R, c->R, c->N,
+                                                             c->d_tsum, c->d_tsq);
     KCHECK(c);
-    sum = tsum;
-    sq = tsq;
+    sum = c->d_tsum;
+    sq = c->d_tsq;
   }
   k_phase1_finals<<<cdiv(c->N, 256), 256, 0, c->stream>>>(sum, sq, c->N, (unsigned)c->F, c->d_avg, c->d_rms);
   KCHECK(c);
   CU(cudaEventRecord(c->ev_b, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&c->stage_ms[1], c->ev_a, c->ev_b));
-  cudaFree(tsum);
-  cudaFree(tsq);
-  cudaFree(d_ptrs);
   c->phase1_done = true;
   return UPSP_OK;
 }
