@@ -184,14 +184,92 @@ __device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W
   return fminf(fmaxf(r, 0.0f), 65535.0f);
 }
 
-// U consecutive frames of one camera for one node.  Every global load of the group is issued
-// before any result is consumed (2U table loads, then 4U tap loads in flight per thread); the
-// rare border / nearest / unregistered-frame pixels are patched up afterwards through the
+// ---- building blocks of the fused kernel: U consecutive frames of one camera for one node.
+// Every global load of a group is issued before any result is consumed (2U table loads, then
+// 4U tap loads in flight per thread); with one camera the table loads of group g+1 are issued
+// before the taps of group g are consumed, so the two dependent round trips overlap.  The rare
+// border / nearest / unregistered-frame pixels are patched up afterwards through the
 // out-of-line slow path (one branch per group).
 // INT12: all pixels are < 2^14 (12/10-bit containers), so OpenCV's float bilinear sum
 // (weights k/1024, every product and partial sum exact in float) equals S/1024 with the integer
 // S = sum t_ij * w_ij; the kernel then rounds S half-to-even in integer arithmetic and never
 // touches the conversion (XU) pipe.  u16 containers keep the float sequence.
+template <int U>
+struct Taps {
+  unsigned short t00[U], t01[U], t10[U], t11[U];
+  bool all_fast;
+};
+
+template <int U>
+__device__ __forceinline__ void fused_tabs(const FusedCam& cam, const int2* __restrict__ ptx,
+                                           const int2* __restrict__ pty, int (&X)[U], int (&Y)[U]) {
+  const size_t tstride = (size_t)(cam.W + cam.H);
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int2 xa = __ldg(ptx + j * tstride), ya = __ldg(pty + j * tstride);
+    X[j] = ya.x + xa.x;
+    Y[j] = ya.y + xa.y;
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void fused_taps(const FusedCam& cam, const uint16_t* __restrict__ fr,
+                                           const int (&X)[U], const int (&Y)[U], Taps<U>& t) {
+  t.all_fast = true;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int sx = X[j] >> 10, sy = Y[j] >> 10;
+    const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+    t.all_fast = t.all_fast && fast;
+    const unsigned idx = fast ? (unsigned)(sy * cam.W + sx) : 0u;
+    const uint16_t* p = fr + (j * cam.npix + idx);
+    const uint16_t* p2 = p + cam.W;
+    t.t00[j] = __ldg(p);
+    t.t01[j] = __ldg(p + 1);
+    t.t10[j] = __ldg(p2);
+    t.t11[j] = __ldg(p2 + 1);
+  }
+}
+
+template <int U, bool INT12>
+__device__ __forceinline__ void fused_finish(const FusedCam& cam, int code, const uint16_t* __restrict__ fr,
+                                             const int (&X)[U], const int (&Y)[U], const Taps<U>& t, int b,
+                                             int interp, int skip_frame, float (&v)[U]) {
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int fxi = (X[j] >> 5) & 31, fyi = (Y[j] >> 5) & 31;
+    if (INT12) {
+      const int gx = 32 - fxi, gy = 32 - fyi;
+      int S = (int)t.t00[j] * (gy * gx);
+      S += (int)t.t01[j] * (gy * fxi);
+      S += (int)t.t10[j] * (fyi * gx);
+      S += (int)t.t11[j] * (fyi * fxi);
+      const int qv = S >> 10, rem = S & 1023;
+      const int r = qv + ((rem + (qv & 1)) > 512);      // round half to even
+      v[j] = u2f_exact((uint32_t)r);
+    } else {
+      const float fx = frac32_exact(fxi), fy = frac32_exact(fyi);
+      const float gx = 1.0f - fx, gy = 1.0f - fy;
+      float r = __fadd_rn(__fmul_rn((float)t.t00[j], __fmul_rn(gy, gx)), __fmul_rn((float)t.t01[j], __fmul_rn(gy, fx)));
+      r = __fadd_rn(r, __fmul_rn((float)t.t10[j], __fmul_rn(fy, gx)));
+      r = __fadd_rn(r, __fmul_rn((float)t.t11[j], __fmul_rn(fy, fx)));
+      r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);   // rint (half to even)
+      v[j] = fminf(r, 65535.0f);                                 // r >= 0 by construction
+    }
+  }
+  const bool has_skip = (unsigned)(skip_frame - b) < (unsigned)U;
+  if (!t.all_fast || interp != 1 || has_skip) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int sx = X[j] >> 10, sy = Y[j] >> 10;
+      const bool fast = interp == 1 && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+      const uint16_t* f2 = fr + j * cam.npix;
+      if (b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
+      else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], interp);
+    }
+  }
+}
+
 template <int U, bool REG, bool INT12>
 __device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, const int2* __restrict__ ptx,
                                                 const int2* __restrict__ pty, const uint16_t* __restrict__ fr,
@@ -199,62 +277,11 @@ __device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, c
                                                 float (&v)[U]) {
   if (code >= 0) {
     if (REG) {
-      const size_t tstride = (size_t)(cam.W + cam.H);
       int X[U], Y[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int2 xa = __ldg(ptx + j * tstride), ya = __ldg(pty + j * tstride);
-        X[j] = ya.x + xa.x;
-        Y[j] = ya.y + xa.y;
-      }
-      unsigned short t00[U], t01[U], t10[U], t11[U];
-      bool all_fast = true;
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int sx = X[j] >> 10, sy = Y[j] >> 10;
-        const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
-        all_fast = all_fast && fast;
-        const unsigned idx = fast ? (unsigned)(sy * cam.W + sx) : 0u;
-        const uint16_t* p = fr + (j * cam.npix + idx);
-        const uint16_t* p2 = p + cam.W;
-        t00[j] = __ldg(p);
-        t01[j] = __ldg(p + 1);
-        t10[j] = __ldg(p2);
-        t11[j] = __ldg(p2 + 1);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int fxi = (X[j] >> 5) & 31, fyi = (Y[j] >> 5) & 31;
-        if (INT12) {
-          const int gx = 32 - fxi, gy = 32 - fyi;
-          int S = (int)t00[j] * (gy * gx);
-          S += (int)t01[j] * (gy * fxi);
-          S += (int)t10[j] * (fyi * gx);
-          S += (int)t11[j] * (fyi * fxi);
-          const int qv = S >> 10, rem = S & 1023;
-          const int r = qv + ((rem + (qv & 1)) > 512);      // round half to even
-          v[j] = u2f_exact((uint32_t)r);
-        } else {
-          const float fx = frac32_exact(fxi), fy = frac32_exact(fyi);
-          const float gx = 1.0f - fx, gy = 1.0f - fy;
-          float r = __fadd_rn(__fmul_rn((float)t00[j], __fmul_rn(gy, gx)), __fmul_rn((float)t01[j], __fmul_rn(gy, fx)));
-          r = __fadd_rn(r, __fmul_rn((float)t10[j], __fmul_rn(fy, gx)));
-          r = __fadd_rn(r, __fmul_rn((float)t11[j], __fmul_rn(fy, fx)));
-          r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);   // rint (half to even)
-          v[j] = fminf(r, 65535.0f);                                 // r >= 0 by construction
-        }
-      }
-      const bool has_skip = (unsigned)(skip_frame - b) < (unsigned)U;
-      if (!all_fast || interp != 1 || has_skip) {
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const int sx = X[j] >> 10, sy = Y[j] >> 10;
-          const bool fast = interp == 1 && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
-          const uint16_t* f2 = fr + j * cam.npix;
-          if (b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
-          else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], interp);
-        }
-      }
+      Taps<U> t;
+      fused_tabs<U>(cam, ptx, pty, X, Y);
+      fused_taps<U>(cam, fr, X, Y, t);
+      fused_finish<U, INT12>(cam, code, fr, X, Y, t, b, interp, skip_frame, v);
     } else {
 #pragma unroll
       for (int j = 0; j < U; ++j) v[j] = (float)__ldg(fr + (j * cam.npix + (size_t)code));
@@ -266,10 +293,9 @@ __device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, c
   }
 }
 
-template <int NC, bool REG, bool INT12>
+template <int NC, bool REG, bool INT12, int U>
 __global__ void __launch_bounds__(256)
 k_project_fused(const FusedArgs a) {
-  constexpr int U = 4;
   __shared__ float tile[32][257];
   __shared__ float* rowp[256];       // node-major row of each of the block's nodes (any rank)
   const int gid = blockIdx.x * 256 + threadIdx.x;
@@ -301,10 +327,37 @@ k_project_fused(const FusedArgs a) {
   }
   double s = 0.0, q = 0.0;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool PIPE = (NC == 1) && REG;    // one camera: software-pipeline the table loads
   for (int b0 = 0; b0 < a.nframes; b0 += 32) {
     const int nb = min(32, a.nframes - b0);
     if (live) {
       int u = 0;
+      if (PIPE && code[0] >= 0) {
+        const FusedCam& cam = a.cam[0];
+        const size_t ts = (size_t)(cam.W + cam.H);
+        int X[U], Y[U], Xn[U], Yn[U];
+        if (U <= nb) fused_tabs<U>(cam, ptx[0] + (size_t)b0 * ts, pty[0] + (size_t)b0 * ts, X, Y);
+        for (; u + U <= nb; u += U) {
+          const int b = b0 + u;
+          const uint16_t* fr = cam.frames + (size_t)b * cam.npix;
+          Taps<U> t;
+          fused_taps<U>(cam, fr, X, Y, t);
+          // tables of the next group (clamped to this one at the end of the chunk: harmless reload)
+          const int bn = (u + 2 * U <= nb) ? b + U : b;
+          fused_tabs<U>(cam, ptx[0] + (size_t)bn * ts, pty[0] + (size_t)bn * ts, Xn, Yn);
+          float v[U];
+          fused_finish<U, INT12>(cam, code[0], fr, X, Y, t, b, a.interp, a.skip_frame, v);
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const float sol = __fadd_rn(0.0f, __fmul_rn(val[0], v[j]));
+            tile[u + j][threadIdx.x] = sol;
+            q += (double)__fmul_rn(sol, sol);
+            s += (double)sol;
+            X[j] = Xn[j];
+            Y[j] = Yn[j];
+          }
+        }
+      }
       for (; u + U <= nb; u += U) {
         float sol[U];
 #pragma unroll
