@@ -293,12 +293,12 @@ __device__ __forceinline__ void fused_cam_group(const FusedCam& cam, int code, c
   }
 }
 
-template <int NC, bool REG, bool INT12, int U>
-__global__ void __launch_bounds__(256)
+template <int NC, bool REG, bool INT12, int U, int BS>
+__global__ void __launch_bounds__(BS)
 k_project_fused(const FusedArgs a) {
-  __shared__ float tile[32][257];
-  __shared__ float* rowp[256];       // node-major row of each of the block's nodes (any rank)
-  const int gid = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float tile[32][BS + 1];
+  __shared__ float* rowp[BS];        // node-major row of each of the block's nodes (any rank)
+  const int gid = blockIdx.x * BS + threadIdx.x;
   const bool live = gid < a.n_nodes;
   const int n = live ? __ldg(a.perm + gid) : -1;
   {
@@ -327,7 +327,9 @@ k_project_fused(const FusedArgs a) {
   }
   double s = 0.0, q = 0.0;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool PIPE = (NC == 1) && REG;    // one camera: software-pipeline the table loads
+  // one camera: software-pipelining the table loads across groups was measured SLOWER (0.47 vs
+  // 0.37 ms per 128-frame batch: register pressure), so it stays off
+  constexpr bool PIPE = false;
   for (int b0 = 0; b0 < a.nframes; b0 += 32) {
     const int nb = min(32, a.nframes - b0);
     if (live) {

@@ -1050,15 +1050,15 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     const unsigned g = cdiv(c->N, 256);
     KBEGIN(4);
     const bool regk = c->registration != UPSP_REG_NONE;
-    static const int fused_u = getenv("UPSP_FUSED_U") ? atoi(getenv("UPSP_FUSED_U")) : 4;   // frames in flight per thread
+    static const int fused_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 256;   // tuning knob: nodes per block
     bool int12 = true;   // every camera's container guarantees pixels < 2^14
     for (auto& k : c->cams)
       int12 = int12 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 16384));
-#define FUSED_LAUNCH(NCAM)                                                          \
-  if (regk && int12 && fused_u == 8) k_project_fused<NCAM, true, true, 8><<<g, 256, 0, c->stream>>>(fa);   \
-  else if (regk && int12) k_project_fused<NCAM, true, true, 4><<<g, 256, 0, c->stream>>>(fa);   \
-  else if (regk) k_project_fused<NCAM, true, false, 4><<<g, 256, 0, c->stream>>>(fa);  \
-  else k_project_fused<NCAM, false, false, 8><<<g, 256, 0, c->stream>>>(fa)
+#define FUSED_LAUNCH(NCAM)                                                                          \
+  if (regk && int12 && fused_bs == 128) k_project_fused<NCAM, true, true, 4, 128><<<cdiv(c->N, 128), 128, 0, c->stream>>>(fa); \
+  else if (regk && int12) k_project_fused<NCAM, true, true, 4, 256><<<g, 256, 0, c->stream>>>(fa);   \
+  else if (regk) k_project_fused<NCAM, true, false, 4, 256><<<g, 256, 0, c->stream>>>(fa);           \
+  else k_project_fused<NCAM, false, false, 8, 256><<<g, 256, 0, c->stream>>>(fa)
     switch (fa.n_cams) {
       case 1: FUSED_LAUNCH(1); break;
       case 2: FUSED_LAUNCH(2); break;
