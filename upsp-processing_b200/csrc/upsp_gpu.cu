@@ -1050,12 +1050,13 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     const unsigned g = cdiv(c->N, 256);
     KBEGIN(4);
     const bool regk = c->registration != UPSP_REG_NONE;
-    static const int fused_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 256;   // tuning knob: nodes per block
+    static const int fused_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 128;   // tuning knob: nodes per block
     bool int12 = true;   // every camera's container guarantees pixels < 2^14
     for (auto& k : c->cams)
       int12 = int12 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 16384));
 #define FUSED_LAUNCH(NCAM)                                                                          \
-  if (regk && int12 && fused_bs == 128) k_project_fused<NCAM, true, true, 4, 128><<<cdiv(c->N, 128), 128, 0, c->stream>>>(fa); \
+  if (regk && int12 && fused_bs == 64) k_project_fused<NCAM, true, true, 4, 64><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa); \
+  else if (regk && int12 && fused_bs == 128) k_project_fused<NCAM, true, true, 4, 128><<<cdiv(c->N, 128), 128, 0, c->stream>>>(fa); \
   else if (regk && int12) k_project_fused<NCAM, true, true, 4, 256><<<g, 256, 0, c->stream>>>(fa);   \
   else if (regk) k_project_fused<NCAM, true, false, 4, 256><<<g, 256, 0, c->stream>>>(fa);           \
   else k_project_fused<NCAM, false, false, 8, 256><<<g, 256, 0, c->stream>>>(fa)
