@@ -1,0 +1,101 @@
+"""GPU ECC registration (registration = pixel): the on-device affine ECC solve against
+cv2.findTransformECC golden results and against the numpy restatement, and the full chain with
+the solve in the loop."""
+import os
+
+import numpy as np
+import pytest
+
+from chain import Case, cp_errors, monomial_mass, run_oracle, same_bits
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_ecc(up, frames_u16, ref_u16, batch=0):
+    """Run only the registration through a throw-away context (one node looking at pixel 0)."""
+    n, h, w = frames_u16.shape
+    g = up.PspGpu(1, 1, n, batch_frames=batch)
+    g.set_camera(0, w, h)
+    g.set_projection(0, np.array([0, 1], np.int32), np.array([0], np.int32), np.ones(1, np.float32))
+    g.set_options(registration=up.REG_PIXEL, hot_pixel_fix=False)
+    g.set_reference_frame(0, ref_u16)
+    g.push_frames(0, frames_u16, up.PIX_U16, 0, n)
+    g.process_frames(0, n)
+    m, rho, it = g.read_warp_matrices(0, with_ecc=True)
+    g.close()
+    return m, rho, it
+
+
+def test_ecc_matches_cv2_golden(up, orc, gpu):
+    g = np.load(os.path.join(GOLDEN, "ecc_golden.npz"))
+    fr = g["frames"]
+    m, rho, it = _gpu_ecc(up, fr, fr[0])
+    # global frame 0 is never registered (psp_process.cpp:1777): identity, 0 iterations
+    assert np.array_equal(m[0], [1, 0, 0, 0, 1, 0]) and it[0] == 0
+    for f in range(1, fr.shape[0]):
+        Mc = g["m6"][f - 1].reshape(2, 3)
+        M = m[f].reshape(2, 3)
+        assert abs(rho[f] - g["rho"][f - 1]) < 1e-5, f
+        assert np.abs(M[:, 2] - Mc[:, 2]).max() < 5e-4, f
+        assert np.abs(M[:, :2] - Mc[:, :2]).max() < 5e-6, f
+
+
+def test_ecc_matches_numpy_restatement_and_iteration_count(up, orc, gpu):
+    import upsp_b200
+    from oracle import ecc
+    frames, shifts = upsp_b200.synth.make_frames(40, 80, 112, seed=5, hot_frames=0.0)
+    m, rho, it = _gpu_ecc(up, frames, frames[0], batch=16)
+    ref32 = frames[0].astype(np.float32)
+    for f in range(1, frames.shape[0]):
+        M, r, n = ecc.find_transform_ecc(ref32, frames[f].astype(np.float32))
+        assert it[f] == n, (f, it[f], n)
+        assert abs(rho[f] - r) < 1e-5
+        assert np.abs(m[f].reshape(2, 3) - M).max() < 2e-5, f
+        assert np.abs(m[f].reshape(2, 3)[:, 2] + shifts[f]).max() < 0.08
+
+
+def test_chain_with_on_device_registration(up, orc, gpu):
+    """registration = pixel through the whole chain.  The solve is held to the tolerances above;
+    everything downstream of it is checked bit-exactly by handing the matrices the GPU found to
+    the oracle (which then runs the reference's warp / patch / project / transpose / phase 2)."""
+    import upsp_b200
+    from chain import push_all, setup_ctx
+    case = Case(upsp_b200.synth, n_frames=48, n_nodes=3000, patches=True, overlap=True, seed=31, fmt="p12")
+    g, sl = setup_ctx(up, orc, case)
+    g.close()
+    g = up.PspGpu(case.C, case.N, case.F)
+    g.set_camera(0, case.W, case.H)
+    g.set_projection(0, *case.csr[0])
+    g.set_overlap_remap(orc.overlap_remap(case.N, case.overlap))
+    g.set_options(registration=up.REG_PIXEL, patcher=up.PATCH_POLYNOMIAL)
+    g.set_patches(0, *case.synth.flatten_patches(*case.patch_lists[0]))
+    g.set_reference_frame(0, case.frames[0][0])
+    push_all(up, orc, g, case, slice(0, case.F))
+    g.finish_phase1()
+    m = g.read_warp_matrices(0)
+    got = dict(intensity=None)
+    got["avg"], got["rms"], got["coverage"] = g.read_phase1_stats()
+    g.transpose()
+    got["itrans"] = g.read_intensity_transpose()
+    g.phase2(case.cal, case.qbar, case.ps, case.steady, case.temp, case.degree)
+    got["ptrans"] = g.read_pressure_transpose()
+    got["rms2"], got["avg2"], got["gain"] = g.read_phase2_stats()
+    g.close()
+    # (1) the maps agree with cv2's (same entry point the reference calls) on every frame
+    import cv2
+    ref32 = case.frames[0][0].astype(np.float32)
+    for f in range(1, case.F):
+        hot_fixed, _ = orc.fix_hot_pixels(case.frames[0][f])
+        Mc, _ = orc.ecc_cv2(ref32, hot_fixed)
+        assert np.abs(m[f].reshape(2, 3)[:, 2] - Mc[:, 2]).max() < 5e-4, f
+        assert np.abs(m[f].reshape(2, 3)[:, :2] - Mc[:, :2]).max() < 5e-6, f
+    # (2) downstream of the solve: bit-exact against the oracle fed with the same maps
+    case.warp = [m]
+    ref = run_oracle(orc, case)
+    assert same_bits(got["itrans"], ref["itrans"])
+    assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
+    exact = run_oracle(orc, case, exact_fit=True)
+    e_exact, _ = cp_errors(case, exact, got)
+    cond = 8 * np.finfo(np.float32).eps * monomial_mass(orc, ref)
+    assert np.all(e_exact <= 1e-6 + cond)

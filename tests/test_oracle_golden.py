@@ -154,3 +154,38 @@ def test_phase2_matches_float64_model(orc):
     ok = cov != 0
     assert (np.abs(p32 - p64)[ok].max(1) / K[ok]).max() < 1e-5
     assert np.allclose(gain[ok], [orc.get_gain(cal, temp[i], qbar * steady[i] + ps) for i in np.nonzero(ok)[0]])
+
+
+def test_ecc_restatement_matches_cv2_golden(orc):
+    """oracle/ecc.py (numpy restatement of cv::findTransformECC) against cv2.findTransformECC
+    results stored by tests/golden/make_golden.py: same correlation to 1e-6, translation to
+    5e-4 px, linear part to 5e-6 (OpenCV inverts the 6x6 Hessian in float LU; the restatement in
+    double: that is the whole difference)."""
+    from oracle import ecc
+    g = np.load(os.path.join(GOLDEN, "ecc_golden.npz"))
+    fr = g["frames"]
+    ref32 = fr[0].astype(np.float32)
+    for f in range(1, fr.shape[0]):
+        M, rho, it = ecc.find_transform_ecc(ref32, fr[f].astype(np.float32))
+        Mc = g["m6"][f - 1].reshape(2, 3)
+        assert abs(rho - g["rho"][f - 1]) < 1e-6
+        assert np.abs(M[:, 2] - Mc[:, 2]).max() < 5e-4
+        assert np.abs(M[:, :2] - Mc[:, :2]).max() < 5e-6
+        # registration recovers the synthetic jitter (inverse map: opposite sign)
+        assert np.abs(M[:, 2] + g["shifts"][f]).max() < 0.06
+        assert 2 <= it <= 8
+
+
+def test_ecc_blur_and_gradient_match_live_cv2(orc):
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ecc
+    rng = np.random.default_rng(0)
+    # integer-valued f32 (a converted 12-bit frame, what register_pixel feeds ECC): every product
+    # with k/16 and every partial sum is exact in float, so the summation order cannot matter
+    img = rng.integers(0, 4096, (37, 53)).astype(np.float32)
+    b = cv2.GaussianBlur(img, (5, 5), 0)
+    assert np.array_equal(b, ecc.gaussian_blur5(img))
+    gx = cv2.filter2D(b, -1, np.array([[-0.5, 0, 0.5]], np.float32))
+    gy = cv2.filter2D(b, -1, np.array([[-0.5], [0], [0.5]], np.float32))
+    ogx, ogy = ecc.gradients(b)
+    assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy)

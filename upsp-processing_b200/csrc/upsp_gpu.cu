@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "host_qr.hpp"
 #include "kernels_frame.cuh"
+#include "kernels_ecc.cuh"
 #include "kernels_phase2.cuh"
 #include "kernels_project.cuh"
 #include "kernels_transpose.cuh"
@@ -210,6 +211,13 @@ struct Camera {
   int* d_tab = nullptr;       // [F_local][2W+2H] warp tables of every local frame
   uint8_t* d_skip = nullptr;  // [batch]
   uint16_t* d_ref16 = nullptr;
+  // ECC (registration = pixel)
+  float *d_eccT = nullptr, *d_eccI = nullptr, *d_eccTmp = nullptr;
+  float2* d_eccG = nullptr;
+  double* d_eccPart = nullptr;
+  EccState* d_eccState = nullptr;   // [F_local]
+  int* d_eccTab = nullptr;
+  int* d_nactive = nullptr;
   bool has_ref = false, has_m6 = false;
   // patches
   bool has_patches = false;
@@ -465,6 +473,14 @@ static void free_camera(Camera& cam) {
   cudaFree(cam.d_tab);
   cudaFree(cam.d_skip);
   cudaFree(cam.d_ref16);
+  cudaFree(cam.d_eccT);
+  cudaFree(cam.d_eccI);
+  cudaFree(cam.d_eccTmp);
+  cudaFree(cam.d_eccG);
+  cudaFree(cam.d_eccPart);
+  cudaFree(cam.d_eccState);
+  cudaFree(cam.d_eccTab);
+  cudaFree(cam.d_nactive);
   for (void* p : cam.patch_allocs) cudaFree(p);
   cudaFree(cam.d_cl_list);
   cudaFree(cam.d_scratch);
@@ -587,9 +603,6 @@ extern "C" int upsp_gpu_set_options(upsp_gpu_ctx* c, int registration, int inter
   NOT_FINAL(c);
   REQUIRE(registration >= UPSP_REG_NONE && registration <= UPSP_REG_GIVEN, UPSP_ERR_INVALID,
           "registration %d", registration);
-  REQUIRE(registration != UPSP_REG_PIXEL, UPSP_ERR_INVALID,
-          "registration=pixel (on-device ECC solve) is not built yet; solve on the host and "
-          "use UPSP_REG_GIVEN");
   REQUIRE(interp == UPSP_INTERP_NEAREST || interp == UPSP_INTERP_LINEAR, UPSP_ERR_INVALID,
           "interp %d", interp);
   REQUIRE(patcher == UPSP_PATCH_NONE || patcher == UPSP_PATCH_POLYNOMIAL, UPSP_ERR_INVALID,
@@ -832,6 +845,26 @@ static int finalize(upsp_gpu_ctx* c) {
       TRY(dmalloc(&k.d_tab, (size_t)std::max(c->F_local, 1) * (2 * k.W + 2 * k.H)));
       if (c->registration == UPSP_REG_GIVEN)
         REQUIRE(k.has_m6, UPSP_ERR_STATE, "registration=given but camera %zu has no warp matrices", ci);
+      if (c->registration == UPSP_REG_PIXEL) {
+        REQUIRE(k.has_ref, UPSP_ERR_STATE,
+                "registration=pixel needs the first frame of camera %zu (upsp_gpu_set_reference_frame)", ci);
+        const int eb = std::min(c->batch, ECC_BATCH);
+        if (!k.d_m6) TRY(dmalloc(&k.d_m6, (size_t)std::max(c->F_local, 1) * 6));
+        TRY(dmalloc(&k.d_eccT, k.npix));
+        TRY(dmalloc(&k.d_eccI, (size_t)eb * k.npix));
+        TRY(dmalloc(&k.d_eccTmp, (size_t)eb * k.npix));
+        TRY(dmalloc(&k.d_eccG, (size_t)eb * k.npix));
+        TRY(dmalloc(&k.d_eccPart, (size_t)eb * ECC_NBLK * ECC_NSUM));
+        TRY(dmalloc(&k.d_eccState, (size_t)std::max(c->F_local, 1)));
+        TRY(dmalloc(&k.d_eccTab, (size_t)eb * (2 * k.W + 2 * k.H)));
+        TRY(dmalloc(&k.d_nactive, 1));
+        // template = GaussianBlur(first frame as f32)  (ecc.cpp: templateFloat)
+        const dim3 g(cdiv(k.W, 256), k.H, 1);
+        k_ecc_blur_rows<uint16_t><<<g, 256, 0, c->stream>>>(k.d_ref16, k.d_eccTmp, k.W, k.H);
+        KCHECK(c);
+        k_ecc_blur_cols<<<g, 256, 0, c->stream>>>(k.d_eccTmp, k.d_eccT, k.W, k.H);
+        KCHECK(c);
+      }
     }
     if (use_patch && k.has_patches) {
       TRY(dmalloc(&k.d_pv, (size_t)std::max(k.total_internal, 1) * c->batch));
@@ -950,6 +983,49 @@ static void launch_project_ell1(upsp_gpu_ctx* c, const ProjArgs& a) {
   }
 }
 
+// cv::findTransformECC for local frames [off, off+nb) of one camera (decoded frames in d_work);
+// leaves the 2x3 maps in d_m6 and the per-frame outcome in d_eccState.
+static int ecc_run_batch(upsp_gpu_ctx* c, Camera& k, int off, int nb) {
+  const int max_iters = 50;       // psp_process.cpp:1779-1780
+  const float eps = 0.001f;
+  for (int s0 = 0; s0 < nb; s0 += ECC_BATCH) {
+    const int n = std::min(ECC_BATCH, nb - s0);
+    const uint16_t* fr = k.d_work + (size_t)s0 * k.npix;
+    float* m6 = k.d_m6 + (size_t)(off + s0) * 6;
+    EccState* st = k.d_eccState + off + s0;
+    const dim3 g(cdiv(k.W, 256), k.H, n);
+    k_ecc_blur_rows<uint16_t><<<g, 256, 0, c->stream>>>(fr, k.d_eccTmp, k.W, k.H);
+    KCHECK(c);
+    k_ecc_blur_cols<<<g, 256, 0, c->stream>>>(k.d_eccTmp, k.d_eccI, k.W, k.H);
+    KCHECK(c);
+    k_ecc_grad<<<g, 256, 0, c->stream>>>(k.d_eccI, k.d_eccG, k.W, k.H);
+    KCHECK(c);
+    // global frame 0 is never registered (psp_process.cpp:1777)
+    const int skip = (c->f0 + off + s0 == 0) ? 0 : -1;
+    k_ecc_init<<<cdiv(n, 64), 64, 0, c->stream>>>(st, m6, n, skip, eps);
+    KCHECK(c);
+    const int rows_per_block = (k.H + ECC_NBLK - 1) / ECC_NBLK;
+    const int nblk = (k.H + rows_per_block - 1) / rows_per_block;
+    for (int it = 1; it <= max_iters; ++it) {
+      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), n), 256, 0, c->stream>>>(m6, n, k.W, k.H, 1, k.d_eccTab);
+      KCHECK(c);
+      CU(cudaMemsetAsync(k.d_nactive, 0, sizeof(int), c->stream));
+      k_ecc_reduce<<<dim3(nblk, n), ECC_NT, 0, c->stream>>>(k.d_eccI, k.d_eccG, k.d_eccT, k.d_eccTab, st, k.W, k.H,
+                                                            rows_per_block, k.d_eccPart);
+      KCHECK(c);
+      k_ecc_solve<<<cdiv(n, 32), 32, 0, c->stream>>>(k.d_eccPart, nblk, n, m6, st, max_iters, eps, k.d_nactive);
+      KCHECK(c);
+      if (it >= 2) {   // frames typically converge in 2-6 iterations: poll the survivor count
+        int active = 0;
+        CU(cudaMemcpyAsync(&active, k.d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (active == 0) break;
+      }
+    }
+  }
+  return UPSP_OK;
+}
+
 // one batch: local frames [off, off+nb)
 static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   ProjArgs pa{};
@@ -985,6 +1061,12 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     KCHECK(c);
     KEND();
     const bool reg = c->registration != UPSP_REG_NONE;
+    if (c->registration == UPSP_REG_PIXEL) {
+      TRY(ecc_run_batch(c, k, off, nb));
+      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), nb), 256, 0, c->stream>>>(
+          k.d_m6 + (size_t)off * 6, nb, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
+      KCHECK(c);
+    }
     const int* tabs = reg ? k.d_tab + (size_t)off * (2 * k.W + 2 * k.H) : nullptr;   // this batch's tables
     const uint16_t* cur = k.d_work;
     // global frame 0 is never registered (psp_process.cpp:1777)
@@ -1096,7 +1178,7 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
             "projection stores node-major rows straight into peer buffers");
   CU(cudaStreamWaitEvent(c->stream, c->ev_push, 0));
   CU(cudaEventRecord(c->ev_pa, c->stream));
-  if (c->registration != UPSP_REG_NONE && count > 0) {
+  if (c->registration == UPSP_REG_GIVEN && count > 0) {
     // OpenCV-style fixed-point warp tables of every frame of this call (one launch per camera)
     for (auto& k : c->cams) {
       k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), count), 256, 0, c->stream>>>(
@@ -1142,6 +1224,17 @@ __global__ void k_allreduce_peer(double* const* bases_sum, double* const* bases_
 extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
   ENTER(c);
   REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
+  if (c->registration == UPSP_REG_PIXEL && c->F_local > 0) {
+    // the reference dies with cv::Exception when ECC does not converge (registration.cpp:64)
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<EccState> st(c->F_local);
+    for (size_t ci = 0; ci < c->cams.size(); ++ci) {
+      CU(cudaMemcpy(st.data(), c->cams[ci].d_eccState, st.size() * sizeof(EccState), cudaMemcpyDeviceToHost));
+      for (int f = 0; f < c->F_local; ++f)
+        REQUIRE(st[f].status != 2, UPSP_ERR_NUMERIC,
+                "ECC registration failed (NaN correlation or lambda_d <= 0) for camera %zu, frame %d", ci, c->f0 + f);
+    }
+  }
   CU(cudaEventRecord(c->ev_a, c->stream));
   const double *sum = c->d_sum, *sq = c->d_sumsq;
   if (c->R > 1) {
@@ -1455,13 +1548,14 @@ extern "C" int upsp_gpu_read_warp_matrices(upsp_gpu_ctx* c, int cam, int off, in
   REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID, "bad range");
   REQUIRE(k.d_m6, UPSP_ERR_STATE, "camera %d has no warp matrices", cam);
   if (m6) TRY(d2h(c, m6, k.d_m6 + (size_t)off * 6, (size_t)count * 6 * sizeof(float)));
-  if (rho) {
-    REQUIRE(k.d_rho, UPSP_ERR_STATE, "no ECC results");
-    TRY(d2h(c, rho, k.d_rho + off, (size_t)count * sizeof(float)));
-  }
-  if (iters) {
-    REQUIRE(k.d_iters, UPSP_ERR_STATE, "no ECC results");
-    TRY(d2h(c, iters, k.d_iters + off, (size_t)count * sizeof(int)));
+  if (rho || iters) {
+    REQUIRE(k.d_eccState, UPSP_ERR_STATE, "no ECC results (registration is not `pixel`)");
+    std::vector<EccState> st(count);
+    TRY(d2h(c, st.data(), k.d_eccState + off, (size_t)count * sizeof(EccState)));
+    for (int f = 0; f < count; ++f) {
+      if (rho) rho[f] = st[f].rho;
+      if (iters) iters[f] = st[f].iters;
+    }
   }
   return UPSP_OK;
 }

@@ -6,14 +6,22 @@ from __future__ import annotations
 import numpy as np
 
 
-def make_frames(n_frames, height, width, seed=0, hot_frames=0.25, jitter=True, noise=8.0):
-    """u16 [F,H,W]: 1800 + 600 sin(x/37) cos(y/53) + 300 gauss blob + N(0,noise), slow drift
-    over the run (so the detrend has something to remove), optional sub-pixel affine jitter
-    per frame, <= 5 injected hot pixels (4095) in a fraction of the frames.
+def make_frames(n_frames, height, width, seed=0, hot_frames=0.25, jitter=True, noise=8.0, texture=250.0):
+    """u16 [F,H,W]: 1800 + 600 sin(x/37) cos(y/53) + 300 gauss blob + a fixed fine texture (sum of
+    random sinusoids, wavelengths 5-40 px: paint speckle / model edges, what makes the image
+    registration well posed) + N(0,noise), slow drift over the run (so the detrend has something
+    to remove), optional sub-pixel translation jitter per frame (applied analytically), <= 5
+    injected hot pixels (4095) in a fraction of the frames.
     Returns (frames, true_shift[F,2])."""
     rng = np.random.default_rng(seed)
     y, x = np.mgrid[0:height, 0:width].astype(np.float32)
     cx, cy = 0.55 * width, 0.45 * height
+    K = 32
+    wl = rng.uniform(5.0, 40.0, K)
+    ang = rng.uniform(0, 2 * np.pi, K)
+    kx, ky = 2 * np.pi / wl * np.cos(ang), 2 * np.pi / wl * np.sin(ang)
+    ph = rng.uniform(0, 2 * np.pi, K)
+    amp = texture * rng.uniform(0.5, 1.0, K) / np.sqrt(K)
     frames = np.empty((n_frames, height, width), np.uint16)
     shifts = np.zeros((n_frames, 2), np.float32)
     for f in range(n_frames):
@@ -23,6 +31,11 @@ def make_frames(n_frames, height, width, seed=0, hot_frames=0.25, jitter=True, n
         t = f / max(n_frames, 1)
         base = (1800.0 + 600.0 * np.sin(xs / 37.0) * np.cos(ys / 53.0)
                 + 300.0 * np.exp(-(((xs - cx) / (0.2 * width)) ** 2 + ((ys - cy) / (0.2 * height)) ** 2)))
+        if texture:
+            tex = np.zeros_like(base)
+            for k in range(K):
+                tex += np.float32(amp[k]) * np.sin(np.float32(kx[k]) * xs + np.float32(ky[k]) * ys + np.float32(ph[k]))
+            base = base + tex
         base *= (1.0 + 0.03 * np.sin(2.0 * np.pi * t) + 0.02 * t)
         img = base + rng.normal(0.0, noise, base.shape)
         frames[f] = np.clip(np.rint(img), 0, 4095).astype(np.uint16)
