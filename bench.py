@@ -147,7 +147,7 @@ def configure(up, wl, args, rank, world, local, capacity, dist):
                   frame_capacity=capacity, batch_frames=args.batch)
     g.set_camera(0, args.width, args.height)
     g.set_projection(0, *wl["csr"])
-    reg = up.REG_GIVEN if args.registration == "given" else up.REG_NONE
+    reg = {"given": up.REG_GIVEN, "none": up.REG_NONE, "pixel": up.REG_PIXEL}[args.registration]
     g.set_options(registration=reg, interp=up.INTERP_LINEAR,
                   patcher=up.PATCH_POLYNOMIAL if args.targets else up.PATCH_NONE)
     if args.targets:
@@ -155,6 +155,8 @@ def configure(up, wl, args, rank, world, local, capacity, dist):
     if reg == up.REG_GIVEN:
         from upsp_b200 import synth
         g.set_warp_matrices(0, 0, synth.make_warps(g.n_frames, seed=5 + rank))
+    if reg == up.REG_PIXEL:
+        g.set_reference_frame(0, wl["frames"][0])
     if world > 1:
         import torch
         h = torch.frombuffer(bytearray(g.ipc_export()), dtype=torch.uint8).clone()
@@ -449,7 +451,7 @@ def main():
     ap.add_argument("--degree", type=int, default=CFG["degree"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--csr", default="surface", choices=["surface", "random"])
-    ap.add_argument("--registration", default="given", choices=["given", "none"])
+    ap.add_argument("--registration", default="given", choices=["given", "none", "pixel"])
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget (0 = skip)")
     ap.add_argument("--ref-frames", type=int, default=0)

@@ -186,9 +186,10 @@ MODES = pytest.mark.parametrize("keep_frame_major", [False, True], ids=["fused",
 
 @MODES
 def test_chain_config1_plain(up, orc, gpu, keep_frame_major):
-    """config 1: one camera, registration none, patcher none, u16 frames, 128 frames."""
+    """config 1: one camera, registration none, patcher none, u16 frames, 128 frames of a still
+    camera (clean series: the strict 1e-5 criterion against the float-QR oracle applies)."""
     import upsp_b200
-    case = Case(upsp_b200.synth, n_frames=128, n_nodes=5000)
+    case = Case(upsp_b200.synth, n_frames=128, n_nodes=5000, jitter=False)
     ref = run_oracle(orc, case)
     got = run_gpu(up, orc, case, keep_frame_major=keep_frame_major)
     _check_chain(case, ref, got, orc, strict=True)
