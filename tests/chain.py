@@ -10,10 +10,10 @@ class Case:
 
     def __init__(self, synth, *, n_cams=1, n_nodes=3000, n_frames=48, height=96, width=128,
                  registration=False, interp=1, patches=False, overlap=False, kind="surface",
-                 weights=False, multi_nnz=0, seed=0, degree=6, fmt="u16", overlap_pair=False, jitter=True):
+                 weights=False, multi_nnz=0, seed=0, degree=6, fmt="u16", overlap_pair=False, jitter=True, texture=250.0):
         self.C, self.N, self.F, self.H, self.W = n_cams, n_nodes, n_frames, height, width
         self.interp, self.degree, self.fmt = interp, degree, fmt
-        self.frames = [synth.make_frames(n_frames, height, width, seed=seed + 10 * c, jitter=jitter)[0]
+        self.frames = [synth.make_frames(n_frames, height, width, seed=seed + 10 * c, jitter=jitter, texture=texture)[0]
                        for c in range(n_cams)]
         if multi_nnz:
             self.csr = [synth.make_multi_nnz_projection(n_nodes, height, width, multi_nnz, seed=seed + 20 + c)
