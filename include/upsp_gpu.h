@@ -159,6 +159,21 @@ UPSP_API int upsp_gpu_read_intensity_transpose(upsp_gpu_ctx* ctx, int local_node
                                                float* host);
 UPSP_API int upsp_gpu_read_pressure_transpose(upsp_gpu_ctx* ctx, int local_node_off, int n_nodes,
                                               float* host);
+/* Streaming output (the reference's write-behind thread, psp_process.cpp:977-1007): asynchronous
+ * D2H of a COLUMN block of this rank's intensity_transpose -- rows [local_node_off, +n_nodes),
+ * GLOBAL frames [frame_off, +n_frames) -- into host[i * host_pitch + j] (host_pitch in floats;
+ * pinned memory for real overlap).  Columns of this rank's own frames must already have been
+ * submitted with process_frames; columns written by peer ranks are the caller's to order (read
+ * them after the post-transpose barrier).  Ordered after every process_frames
+ * call issued so far and executed on a dedicated copy stream, so it overlaps later pushes and
+ * processing (PCIe is full duplex).  Needs the fused projection (keep_frame_major = 0), where a
+ * node-major column is final as soon as its frames are processed.  upsp_gpu_wait_reads blocks
+ * until all such reads have landed. */
+UPSP_API int upsp_gpu_read_intensity_transpose_block_async(upsp_gpu_ctx* ctx, int local_node_off,
+                                                           int n_nodes, int frame_off,
+                                                           int n_frames, float* host,
+                                                           size_t host_pitch);
+UPSP_API int upsp_gpu_wait_reads(upsp_gpu_ctx* ctx);
 /* sol_avg_final, sol_rms_final, coverage: [n_nodes] each; any pointer may be NULL */
 UPSP_API int upsp_gpu_read_phase1_stats(upsp_gpu_ctx* ctx, float* avg, float* rms, float* coverage);
 /* rms_final, avg_final, gain_final of this rank's node slice: [n_local_nodes] each */

@@ -260,6 +260,32 @@ def test_frame_major_read_needs_keep_flag(up, orc, gpu):
     g.close()
 
 
+def test_streamed_column_block_reads(up, orc, gpu):
+    """upsp_gpu_read_intensity_transpose_block_async: column blocks read while later frames are
+    still being processed equal the final intensity_transpose."""
+    import upsp_b200
+    from chain import setup_ctx
+    case = Case(upsp_b200.synth, n_frames=64, n_nodes=700, registration=True, seed=23)
+    g, sl = setup_ctx(up, orc, case, batch_frames=8)
+    blocks = []
+    for o in range(0, 64, 16):
+        g.push_frames(0, case.frames[0][o:o + 16], up.PIX_U16, o, 16)
+        g.process_frames(o, 16)
+        buf = np.full((case.N, 20), -1.0, np.float32)       # pitch 20 > 16 columns
+        g.read_intensity_transpose_block_async(0, case.N, o, 16, buf.ctypes.data, 20)
+        blocks.append(buf)
+    g.wait_reads()
+    g.finish_phase1()
+    g.transpose()
+    full = g.read_intensity_transpose()
+    for i, buf in enumerate(blocks):
+        assert same_bits(buf[:, :16], full[:, 16 * i:16 * i + 16])
+        assert np.all(buf[:, 16:] == -1.0)
+    with pytest.raises(up.UpspGpuError):
+        g.read_intensity_transpose_block_async(0, case.N, 0, 65, blocks[0].ctypes.data, 80)
+    g.close()
+
+
 def test_error_behaviour(up, gpu):
     g = up.PspGpu(1, 10, 4)
     with pytest.raises(up.UpspGpuError):

@@ -209,6 +209,15 @@ class PspGpu:
               "pressure_transpose": lib().upsp_gpu_read_pressure_transpose}[which]
         _chk(fn(self._h, local_off, n, C.c_void_p(host_ptr)))
 
+    def read_intensity_transpose_block_async(self, local_node_off, n_nodes, frame_off, n_frames,
+                                             host_ptr, host_pitch):
+        _chk(lib().upsp_gpu_read_intensity_transpose_block_async(
+            self._h, local_node_off, n_nodes, frame_off, n_frames, C.c_void_p(host_ptr),
+            C.c_size_t(host_pitch)))
+
+    def wait_reads(self):
+        _chk(lib().upsp_gpu_wait_reads(self._h))
+
     def read_phase1_stats(self):
         avg, rms, cov = (np.empty(self.n_nodes, np.float32) for _ in range(3))
         _chk(lib().upsp_gpu_read_phase1_stats(self._h, _p(avg), _p(rms), _p(cov)))

@@ -251,7 +251,7 @@ struct upsp_gpu_ctx {
   int lut_max = 0;        // largest entry of the 10->12-bit table (0 = no table)
   int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
 
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
@@ -401,6 +401,7 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_proc, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev_a));
@@ -495,6 +496,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
   for (int r = 0; r < c->R; ++r)
     if (r != c->rank && c->peer_is_ipc[r]) vmm_free(c->peer_vmm[r]);
   for (auto& cam : c->cams) free_camera(cam);
@@ -529,6 +531,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (c->ev_pb) cudaEventDestroy(c->ev_pb);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
   return UPSP_OK;
 }
@@ -1513,6 +1516,33 @@ extern "C" int upsp_gpu_read_intensity_transpose(upsp_gpu_ctx* c, int off, int n
   REQUIRE(off >= 0 && n >= 0 && off + n <= c->N_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
   REQUIRE(c->transposed, UPSP_ERR_STATE, "transpose first");
   return d2h(c, host, c->d_itrans + (size_t)off * c->F, (size_t)n * c->F * sizeof(float));
+}
+
+extern "C" int upsp_gpu_read_intensity_transpose_block_async(upsp_gpu_ctx* c, int noff, int nn, int foff,
+                                                             int nf, float* host, size_t pitch) {
+  ENTER(c);
+  REQUIRE(noff >= 0 && nn >= 0 && noff + nn <= c->N_local, UPSP_ERR_INVALID, "bad node range");
+  REQUIRE(foff >= 0 && nf >= 0 && foff + nf <= c->F, UPSP_ERR_INVALID, "bad frame range");
+  REQUIRE((host && pitch >= (size_t)nf) || nn == 0 || nf == 0, UPSP_ERR_INVALID, "bad host buffer / pitch");
+  REQUIRE(c->finalized && c->fused, UPSP_ERR_STATE,
+          "column-block reads need the fused projection (keep_frame_major = 0)");
+  {
+    const int lo = std::max(foff, c->f0), hi = std::min(foff + nf, c->f0 + c->F_local);   // own frames in the block
+    REQUIRE(hi <= lo || hi - c->f0 <= c->frames_processed, UPSP_ERR_STATE,
+            "frames [%d,%d) have not been submitted to process_frames yet", lo, hi);
+  }
+  if (nn == 0 || nf == 0) return UPSP_OK;
+  CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_proc, 0));
+  CU(cudaMemcpy2DAsync(host, pitch * sizeof(float), c->d_itrans + (size_t)noff * c->F + foff,
+                       (size_t)c->F * sizeof(float), (size_t)nf * sizeof(float), (size_t)nn,
+                       cudaMemcpyDeviceToHost, c->d2h_stream));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_wait_reads(upsp_gpu_ctx* c) {
+  ENTER(c);
+  CU(cudaStreamSynchronize(c->d2h_stream));
+  return UPSP_OK;
 }
 
 extern "C" int upsp_gpu_read_pressure_transpose(upsp_gpu_ctx* c, int off, int n, float* host) {
