@@ -51,5 +51,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_BIN = os.path.join(HERE, "psp_process_b200")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ host driver (g++, links libupsp_gpu.so through its C ABI only)."""
+    src = os.path.join(HERE, "host", "psp_process_b200.cpp")
+    hdr = os.path.join(HERE, "host", "upsp_b200.hpp")
+    build()
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(
+            os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB)):
+        return HOST_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_BIN, src, "-L" + HERE, "-lupsp_gpu",
+           "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building psp_process_b200")
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

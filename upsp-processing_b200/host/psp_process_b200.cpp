@@ -1,0 +1,207 @@
+// psp_process_b200 -- C++ host driver of the GPU frame chain (single rank).
+//
+// Mirrors the control flow of the reference's psp_process (cpp/exec/psp_process.cpp): phase 1
+// (frame loop :1743-1851, reduction / finals :1866-1940, global_transpose :2032) and phase 2
+// (node loop :2452-2507, finals :2540-2547), and writes the reference's flat output files
+// (:524-540) with the same names and layout.  What it does NOT do is the reference's phase 0
+// (input deck, grid readers, camera calibration, BVH visibility -> projection matrix): those
+// products are read from a job directory of raw little-endian arrays instead (written by
+// upsp-processing_b200/synth.py: write_job, or by any tool that has run phase 0):
+//
+//   job.txt               key = value lines: cameras width height number_frames msize format
+//                         registration pixel_interpolation target_patcher qbar ps cal_a..cal_f degree
+//   cam<c>.frames         number_frames frames, u16 or 12-bit packed (format = u16 | p12)
+//   cam<c>.rowptr/.col/.val   projection matrix of camera c in CSR (i32, i32, f32)
+//   cam<c>.warp           registration = given : number_frames x 6 f32
+//   cam<c>.first          registration = pixel : raw first frame, u16
+//   cam<c>.patch_boff/.patch_bx/.patch_by/.patch_ioff/.patch_ix/.patch_iy   target_patcher = polynomial
+//   remap.i32             optional: static form of P3DModel::adjust_solution
+//   steady.f32 model_temp.f32   [msize]
+//
+//   psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+
+#include "upsp_b200.hpp"
+
+using namespace upsp_b200;
+
+template <typename T>
+static std::vector<T> read_all(const std::string& path, bool required = true) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) {
+    if (required) throw std::invalid_argument("Cannot open '" + path + "'");
+    return {};
+  }
+  const std::streamsize n = f.tellg();
+  f.seekg(0);
+  std::vector<T> v((size_t)n / sizeof(T));
+  f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+  return v;
+}
+
+static std::map<std::string, std::string> read_job(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) throw std::invalid_argument("Cannot open '" + path + "'");
+  std::map<std::string, std::string> kv;
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos || line[0] == '#') continue;
+    auto trim = [](std::string s) {
+      const size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+      return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+    };
+    kv[trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+  }
+  return kv;
+}
+
+int main(int argc, char** argv) {
+  std::string job_dir, out_dir;
+  int device = 0, chunk = 256;
+  for (int i = 1; i + 1 < argc; i += 2) {
+    const std::string k = argv[i];
+    if (k == "-job_dir") job_dir = argv[i + 1];
+    else if (k == "-out_dir") out_dir = argv[i + 1];
+    else if (k == "-device") device = atoi(argv[i + 1]);
+    else if (k == "-chunk") chunk = atoi(argv[i + 1]);
+  }
+  if (job_dir.empty() || out_dir.empty()) {
+    std::cerr << "usage: psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]" << std::endl;
+    return 1;
+  }
+  try {
+    auto job = read_job(job_dir + "/job.txt");
+    auto geti = [&](const char* k) { return atoi(job.at(k).c_str()); };
+    auto getf = [&](const char* k) { return (float)atof(job.at(k).c_str()); };
+    const int cameras = geti("cameras"), W = geti("width"), H = geti("height");
+    const int number_frames = geti("number_frames"), msize = geti("msize");
+    const bool p12 = job.at("format") == "p12";
+    const std::string reg = job.at("registration"), patcher = job.at("target_patcher");
+    const size_t frame_bytes = p12 ? (size_t)W * H * 3 / 2 : (size_t)W * H * 2;
+
+    upsp_gpu_config cfg{};
+    cfg.device = device;
+    cfg.n_cams = cameras;
+    cfg.n_nodes = msize;
+    cfg.n_frames_total = number_frames;
+    cfg.rank = 0;
+    cfg.n_ranks = 1;
+    cfg.frame_capacity = 2 * chunk;     // streaming ring: the reader stays ahead of the GPU
+    cfg.pressure_aliases_intensity = 1;
+    FrameChain chain(cfg);
+
+    std::cout << "Initializing projection / patches (phase 0 products from " << job_dir << ")" << std::endl;
+    for (int c = 0; c < cameras; ++c) {
+      const std::string b = job_dir + "/cam" + std::to_string(c);
+      chain.set_camera(c, W, H);
+      auto rowptr = read_all<int32_t>(b + ".rowptr"), col = read_all<int32_t>(b + ".col");
+      auto val = read_all<float>(b + ".val");
+      if ((int)rowptr.size() != msize + 1) throw std::invalid_argument("rowptr size inconsistent with msize");
+      chain.set_projection(c, rowptr.data(), col.data(), val.data());
+      if (patcher == "polynomial") {
+        auto boff = read_all<int32_t>(b + ".patch_boff"), ioff = read_all<int32_t>(b + ".patch_ioff");
+        auto bx = read_all<uint32_t>(b + ".patch_bx"), by = read_all<uint32_t>(b + ".patch_by");
+        auto ix = read_all<uint32_t>(b + ".patch_ix"), iy = read_all<uint32_t>(b + ".patch_iy");
+        chain.set_patches(c, (int)boff.size() - 1, boff.data(), bx.data(), by.data(), ioff.data(),
+                          ix.data(), iy.data());
+      }
+      if (reg == "pixel") chain.set_reference_frame(c, read_all<uint16_t>(b + ".first").data());
+    }
+    auto remap = read_all<int32_t>(job_dir + "/remap.i32", false);
+    if (!remap.empty()) chain.set_overlap_remap(remap.data());
+    const int regmode = reg == "pixel" ? UPSP_REG_PIXEL : (reg == "given" ? UPSP_REG_GIVEN : UPSP_REG_NONE);
+    chain.set_options(regmode, job.at("pixel_interpolation") == "nearest" ? UPSP_INTERP_NEAREST : UPSP_INTERP_LINEAR,
+                      patcher == "polynomial" ? UPSP_PATCH_POLYNOMIAL : UPSP_PATCH_NONE, true);
+    if (regmode == UPSP_REG_GIVEN)
+      for (int c = 0; c < cameras; ++c) {
+        auto m6 = read_all<float>(job_dir + "/cam" + std::to_string(c) + ".warp");
+        chain.set_warp_matrices(c, 0, number_frames, m6.data());
+      }
+
+    // ---- phase 1: frame loop (the async reader of psp_process.cpp:867-908 is this read loop) ----
+    std::cout << "Processing frames" << std::endl;
+    std::vector<std::ifstream> vids;
+    for (int c = 0; c < cameras; ++c) {
+      vids.emplace_back(job_dir + "/cam" + std::to_string(c) + ".frames", std::ios::binary);
+      if (!vids.back()) throw std::invalid_argument("Cannot open frames of camera " + std::to_string(c));
+    }
+    std::vector<uint8_t> buf((size_t)chunk * frame_bytes);
+    for (int off = 0; off < number_frames; off += chunk) {
+      const int n = std::min(chunk, number_frames - off);
+      if (off % 100 == 0) std::cout << "  Rank 0:: processing frame " << off << std::endl;
+      for (int c = 0; c < cameras; ++c) {
+        vids[c].read(reinterpret_cast<char*>(buf.data()), (std::streamsize)((size_t)n * frame_bytes));
+        if (!vids[c]) throw std::invalid_argument("frame file of camera " + std::to_string(c) + " is too short");
+        chain.push_frames(c, buf.data(), p12 ? UPSP_PIX_PACKED12 : UPSP_PIX_U16, off, n);
+        chain.sync();   // buf is reused for the next camera / chunk
+      }
+      chain.process_frames(off, n);
+    }
+    std::cout << "Global reduction of rms and avg .." << std::endl;
+    chain.finish_phase1();
+    std::vector<float> sol_avg_final(msize), sol_rms_final(msize), coverage(msize);
+    chain.read_phase1_stats(sol_avg_final.data(), sol_rms_final.data(), coverage.data());
+    FlatFiles out(out_dir, true);
+    out.write_vector("intensity_rms", sol_rms_final.data(), msize);
+    out.write_vector("intensity_avg", sol_avg_final.data(), msize);
+    out.write_vector("coverage", coverage.data(), msize);
+
+    std::cout << "Construct the transpose" << std::endl;
+    chain.global_transpose();
+    {
+      const size_t rows = std::max<size_t>(1, (256u << 20) / ((size_t)number_frames * 4));
+      std::vector<float> blk(rows * number_frames);
+      for (size_t n0 = 0; n0 < (size_t)msize; n0 += rows) {
+        const size_t n = std::min(rows, (size_t)msize - n0);
+        chain.read_intensity_transpose((int)n0, (int)n, blk.data());
+        out.write_block("intensity_transpose", blk.data(), n0, n, number_frames);
+      }
+    }
+
+    // ---- phase 2 ----
+    std::cout << "Beginning node processing" << std::endl;
+    upsp_phase2_params p{};
+    const char* names[6] = {"cal_a", "cal_b", "cal_c", "cal_d", "cal_e", "cal_f"};
+    for (int i = 0; i < 6; ++i) p.paint_cal[i] = getf(names[i]);
+    p.qbar = getf("qbar");
+    p.ps = getf("ps");
+    p.degree = geti("degree");
+    auto steady = read_all<float>(job_dir + "/steady.f32");
+    auto model_temp = read_all<float>(job_dir + "/model_temp.f32");
+    if ((int)steady.size() != msize || (int)model_temp.size() != msize)
+      throw std::invalid_argument("steady / model_temp inconsistent with msize");
+    chain.phase2(p, steady.data(), model_temp.data());
+    std::vector<float> rms(msize), avg(msize), gain(msize);
+    chain.read_phase2_stats(rms.data(), avg.data(), gain.data());
+    std::cout << "Writing pressure rms, average, gain flat files" << std::endl;
+    out.write_vector("rms", rms.data(), msize);
+    out.write_vector("avg", avg.data(), msize);
+    out.write_vector("gain", gain.data(), msize);
+    for (auto& s : steady)     // psp_process.cpp:2566-2570
+      if (s > 3.0f) s = std::numeric_limits<float>::quiet_NaN();
+    out.write_vector("steady_state", steady.data(), msize);
+    out.write_vector("model_temp", model_temp.data(), msize);
+    std::cout << "Write pressure transpose ..." << std::endl;
+    {
+      const size_t rows = std::max<size_t>(1, (256u << 20) / ((size_t)number_frames * 4));
+      std::vector<float> blk(rows * number_frames);
+      for (size_t n0 = 0; n0 < (size_t)msize; n0 += rows) {
+        const size_t n = std::min(rows, (size_t)msize - n0);
+        chain.read_pressure_transpose((int)n0, (int)n, blk.data());
+        out.write_block("pressure_transpose", blk.data(), n0, n, number_frames);
+      }
+    }
+    std::cerr << "## 'pressure_transpose' written" << std::endl;
+  } catch (const std::exception& e) {
+    std::cerr << "psp_process_b200: " << e.what() << std::endl;
+    return 1;   // psp_process.cpp:1397-1415
+  }
+  return 0;
+}

@@ -205,3 +205,44 @@ def make_frames_fast(n_frames, height, width, seed=0, noise=8.0, hot_frames=0.25
         if rng.random() < hot_frames:
             frames[f].reshape(-1)[rng.integers(0, height * width, int(rng.integers(1, 6)))] = 4095
     return frames
+
+
+def write_job(job_dir, *, frames, csr, fmt="p12", registration="none", interp="linear", warp=None,
+              patches=None, remap=None, cal=None, qbar=1.0, ps=1.0, steady=None, model_temp=None,
+              degree=6):
+    """Write a psp_process_b200 job directory (host/psp_process_b200.cpp documents the layout).
+    frames: list over cameras of u16 [F,H,W]; csr: list of (rowptr, col, val); patches: list of
+    flatten_patches() tuples or None; warp: list of [F,6] f32 (registration = given)."""
+    import os
+    os.makedirs(job_dir, exist_ok=True)
+    C = len(frames)
+    F, H, W = frames[0].shape
+    N = len(csr[0][0]) - 1
+    with open(os.path.join(job_dir, "job.txt"), "w") as f:
+        kv = dict(cameras=C, width=W, height=H, number_frames=F, msize=N, format=fmt,
+                  registration=registration, pixel_interpolation=interp,
+                  target_patcher="polynomial" if patches else "none", qbar=repr(float(qbar)),
+                  ps=repr(float(ps)), degree=degree)
+        for k, v in zip("abcdef", cal):
+            kv["cal_" + k] = repr(float(v))
+        for k, v in kv.items():
+            f.write(f"{k} = {v}\n")
+    for c in range(C):
+        b = os.path.join(job_dir, f"cam{c}")
+        fr = np.ascontiguousarray(frames[c], np.uint16)
+        (pack_12bit(fr.reshape(F, -1)) if fmt == "p12" else fr).tofile(b + ".frames")
+        np.asarray(csr[c][0], np.int32).tofile(b + ".rowptr")
+        np.asarray(csr[c][1], np.int32).tofile(b + ".col")
+        np.asarray(csr[c][2], np.float32).tofile(b + ".val")
+        if registration == "given":
+            np.asarray(warp[c], np.float32).tofile(b + ".warp")
+        if registration == "pixel":
+            fr[0].tofile(b + ".first")
+        if patches:
+            for name, arr, dt in zip(("boff", "bx", "by", "ioff", "ix", "iy"), patches[c],
+                                     (np.int32, np.uint32, np.uint32, np.int32, np.uint32, np.uint32)):
+                np.asarray(arr, dt).tofile(b + ".patch_" + name)
+    if remap is not None:
+        np.asarray(remap, np.int32).tofile(os.path.join(job_dir, "remap.i32"))
+    np.asarray(steady, np.float32).tofile(os.path.join(job_dir, "steady.f32"))
+    np.asarray(model_temp, np.float32).tofile(os.path.join(job_dir, "model_temp.f32"))
