@@ -110,6 +110,11 @@ UPSP_API int upsp_gpu_set_overlap_remap(upsp_gpu_ctx* ctx, const int32_t* src_in
  * upsp::fix_hot_pixels (thresh 4064, min_change 512, max_hot 5). */
 UPSP_API int upsp_gpu_set_options(upsp_gpu_ctx* ctx, int registration, int interp, int patcher,
                                   int hot_pixel_fix);
+/* deck @options filter / filter_size (psp_process.cpp:1802-1807): kind 0 none, 1 gaussian
+ * (cv::GaussianBlur(img, img, Size(k,k), 0)), 2 box (cv::blur(img, img, Size(k,k))); k odd.
+ * Gaussian sizes 3, 5, 7 (OpenCV's fixed sigma=0 kernels) are built.  A filter makes the chain
+ * materialise the registered image (no fused register+project kernel). */
+UPSP_API int upsp_gpu_set_filter(upsp_gpu_ctx* ctx, int kind, int ksize);
 /* PatchClusters geometry of camera `cam` (patches.h:74-90: bounds_x/y, internal_x/y per
  * cluster, after threshold_bounds).  Offsets are CSR-style [n_clusters+1]. */
 UPSP_API int upsp_gpu_set_patches(upsp_gpu_ctx* ctx, int cam, int n_clusters,

@@ -177,6 +177,23 @@ def patch_apply(img32: np.ndarray, p: Patches) -> np.ndarray:
     return out
 
 
+# ---------------------------------------------------------------- a5 filter
+def spatial_filter(img, kind, ksize):
+    """cv::GaussianBlur(img,(k,k),0) (kind 1) / cv::blur(img,(k,k)) (kind 2) on u16 or f32."""
+    h, w = img.shape
+    if img.dtype == np.uint16:
+        src = _c(img, np.uint16)
+        dst = np.empty_like(src)
+        rc = lib().orc_filter_u16(_p(src), _p(dst), w, h, kind, ksize)
+    else:
+        src = _c(img, np.float32)
+        dst = np.empty_like(src)
+        rc = lib().orc_filter_f32(_p(src), _p(dst), w, h, kind, ksize)
+    if rc:
+        raise ValueError("gaussian filter sizes other than 3, 5, 7 are not restated")
+    return dst
+
+
 # ---------------------------------------------------------------- a6 project
 def project_frame(rowptr, col, val, frame32) -> np.ndarray:
     rowptr, col, val = _c(rowptr, np.int32), _c(col, np.int32), _c(val, np.float32)
@@ -224,6 +241,7 @@ class _P1Args(C.Structure):
         ("n_clusters", C.c_void_p), ("bounds_off", C.c_void_p), ("bx", C.c_void_p),
         ("by", C.c_void_p), ("internal_off", C.c_void_p), ("ix", C.c_void_p), ("iy", C.c_void_p),
         ("n_skipped", C.c_int), ("skipped", C.c_void_p), ("remap", C.c_void_p),
+        ("filter_kind", C.c_int), ("filter_size", C.c_int),
     ]
 
 
@@ -235,7 +253,7 @@ def _ptr_array(arrs):
 
 
 def phase1(frames, csr, *, first_frame=0, warp=None, interp=1, patches=None, remap=None,
-           hot_pixel_fix=True, sum_=None, sumsq=None):
+           hot_pixel_fix=True, sum_=None, sumsq=None, filter_kind=0, filter_size=0):
     """The frame loop of cpp/exec/psp_process.cpp:1743-1851 for one rank's slice.
 
     frames : list over cameras of u16 [F, H, W]
@@ -278,6 +296,7 @@ def phase1(frames, csr, *, first_frame=0, warp=None, interp=1, patches=None, rem
         (a.bounds_off, a.bx, a.by, a.internal_off, a.ix, a.iy) = (C.cast(x, C.c_void_p) for x in arrs)
         keep += [ncl, arrs, empty_i, empty_u]
     a.n_skipped, a.skipped = skipped.size, skipped.ctypes.data
+    a.filter_kind, a.filter_size = int(filter_kind), int(filter_size)
     if remap is not None:
         remap = _c(remap, np.int32)
         a.remap = remap.ctypes.data

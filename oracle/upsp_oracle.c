@@ -428,6 +428,92 @@ ORC_API void orc_patch_apply(float* img, int width, int n_clusters, const int* b
 }
 
 /* ------------------------------------------------------------------------ */
+/* a5: optional spatial filter cpp/exec/psp_process.cpp:1802-1807:            */
+/*   cv::GaussianBlur(img, img, Size(k,k), 0) | cv::blur(img, img, Size(k,k)) */
+/* default border BORDER_REFLECT_101.  kind: 1 gaussian, 2 box.               */
+/* CV_16U gaussian = OpenCV's fixed-point path (16 fractional bits per pass,  */
+/* exact accumulation, one rounding) -- PINNED against cv2 goldens for        */
+/* k = 3,5,7 (sigma = 0 -> getGaussianKernel's fixed small kernels);          */
+/* CV_16U box = integer sum * (1/area) in double, cvRound; CV_32F gaussian =  */
+/* separable float filter in OpenCV's symmetric order (exact on 12-bit data,  */
+/* last-bit differences possible next to patched pixels: cv2 may use FMA);    */
+/* CV_32F box = double window sum * (1/area).                                 */
+/* ------------------------------------------------------------------------ */
+static inline int orc_reflect101(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * (n - 1) - i : i;
+}
+static const double* orc_small_gauss(int k) {
+  static const double k3[] = {0.25, 0.5, 0.25};
+  static const double k5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
+  static const double k7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+  return k == 3 ? k3 : (k == 5 ? k5 : (k == 7 ? k7 : NULL));
+}
+
+ORC_API int orc_filter_u16(const uint16_t* src, uint16_t* dst, int W, int H, int kind, int ksize) {
+  const int r = ksize / 2;
+  const double* kd = orc_small_gauss(ksize);
+  if (kind == 1 && !kd) return 1;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      if (kind == 1) {
+        long long S = 0;
+        for (int j = -r; j <= r; ++j) {
+          long long t = 0;
+          for (int i = -r; i <= r; ++i)
+            t += (long long)llrint(kd[i + r] * 65536.0) * src[(size_t)orc_reflect101(y + j, H) * W + orc_reflect101(x + i, W)];
+          S += (long long)llrint(kd[j + r] * 65536.0) * t;
+        }
+        long long v = (S + (1LL << 31)) >> 32;
+        dst[(size_t)y * W + x] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+      } else {
+        int S = 0;
+        for (int j = -r; j <= r; ++j)
+          for (int i = -r; i <= r; ++i) S += src[(size_t)orc_reflect101(y + j, H) * W + orc_reflect101(x + i, W)];
+        long v = lrint((double)S * (1.0 / (double)(ksize * ksize)));
+        dst[(size_t)y * W + x] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+      }
+    }
+  return 0;
+}
+
+ORC_API int orc_filter_f32(const float* src, float* dst, int W, int H, int kind, int ksize) {
+  const int r = ksize / 2;
+  const double* kd = orc_small_gauss(ksize);
+  if (kind == 1 && !kd) return 1;
+  if (kind == 1) {
+    float* tmp = (float*)malloc(sizeof(float) * (size_t)W * H);
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const float* row = src + (size_t)y * W;
+        float s = row[x] * (float)kd[r];
+        for (int i = 1; i <= r; ++i) s = s + (row[orc_reflect101(x - i, W)] + row[orc_reflect101(x + i, W)]) * (float)kd[r + i];
+        tmp[(size_t)y * W + x] = s;
+      }
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        float s = tmp[(size_t)y * W + x] * (float)kd[r];
+        for (int i = 1; i <= r; ++i)
+          s = s + (tmp[(size_t)orc_reflect101(y - i, H) * W + x] + tmp[(size_t)orc_reflect101(y + i, H) * W + x]) * (float)kd[r + i];
+        dst[(size_t)y * W + x] = s;
+      }
+    free(tmp);
+  } else {
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        double S = 0.0;
+        for (int j = -r; j <= r; ++j) {
+          double t = 0.0;
+          for (int i = -r; i <= r; ++i) t += (double)src[(size_t)orc_reflect101(y + j, H) * W + orc_reflect101(x + i, W)];
+          S += t;
+        }
+        dst[(size_t)y * W + x] = (float)(S * (1.0 / (double)(ksize * ksize)));
+      }
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* a6: upsp::project_frame cpp/lib/projection.ipp:884-908 -- Eigen row-major */
 /*     CSR * dense vector, out zero-initialised, one accumulator per row.    */
 /* ------------------------------------------------------------------------ */
@@ -489,6 +575,8 @@ typedef struct {
   int n_skipped;
   const int* skipped;
   const int* remap;
+  int filter_kind;   /* 0 none, 1 gaussian, 2 box (psp_process.cpp:1802-1807) */
+  int filter_size;
 } orc_phase1_args;
 
 ORC_API void orc_phase1(const orc_phase1_args* a, float* intensity, double* sum, double* sumsq) {
@@ -521,10 +609,23 @@ ORC_API void orc_phase1(const orc_phase1_args* a, float* intensity, double* sum,
           orc_warp_affine_u16(img16, w, h, a->warp[c] + (size_t)off * 6, a->interp, warp16, w, h);
           cur = warp16;
         }
+        const int patched = a->n_clusters && a->n_clusters[c] > 0;
+        if (a->filter_kind && !patched) {   /* the image is still CV_16U: OpenCV's integer filter */
+          uint16_t* other = (cur == img16) ? warp16 : img16;
+          orc_filter_u16(cur, other, w, h, a->filter_kind, a->filter_size);
+          cur = other;
+        }
         for (size_t i = 0; i < P; ++i) img32[i] = (float)cur[i];
-        if (a->n_clusters && a->n_clusters[c] > 0)
+        if (patched) {
           orc_patch_apply(img32, w, a->n_clusters[c], a->bounds_off[c], a->bx[c], a->by[c],
                           a->internal_off[c], a->ix[c], a->iy[c]);
+          if (a->filter_kind) {
+            float* t32 = (float*)malloc(sizeof(float) * P);
+            orc_filter_f32(img32, t32, w, h, a->filter_kind, a->filter_size);
+            memcpy(img32, t32, sizeof(float) * P);
+            free(t32);
+          }
+        }
         orc_project_frame(a->rowptr[c], a->col[c], a->val[c], N, img32, csol);
         if (c == 0)
           memcpy(sol, csol, sizeof(float) * (size_t)N);

@@ -10,9 +10,10 @@ class Case:
 
     def __init__(self, synth, *, n_cams=1, n_nodes=3000, n_frames=48, height=96, width=128,
                  registration=False, interp=1, patches=False, overlap=False, kind="surface",
-                 weights=False, multi_nnz=0, seed=0, degree=6, fmt="u16", overlap_pair=False, jitter=True, texture=250.0):
+                 weights=False, multi_nnz=0, seed=0, degree=6, fmt="u16", overlap_pair=False, jitter=True, texture=250.0, filter_kind=0, filter_size=0):
         self.C, self.N, self.F, self.H, self.W = n_cams, n_nodes, n_frames, height, width
         self.interp, self.degree, self.fmt = interp, degree, fmt
+        self.filter_kind, self.filter_size = filter_kind, filter_size
         self.frames = [synth.make_frames(n_frames, height, width, seed=seed + 10 * c, jitter=jitter, texture=texture)[0]
                        for c in range(n_cams)]
         if multi_nnz:
@@ -47,7 +48,8 @@ def run_oracle(orc, case: Case, n_ranks=1, exact_fit=False):
         sl = slice(int(fs[r]), int(fs[r] + fe[r]))
         it, s, q = orc.phase1([f[sl] for f in case.frames], case.csr, first_frame=int(fs[r]),
                               warp=[w[sl] for w in case.warp] if case.warp else None,
-                              interp=case.interp, patches=patches, remap=remap)
+                              interp=case.interp, patches=patches, remap=remap,
+                              filter_kind=case.filter_kind, filter_size=case.filter_size)
         inten.append(it)
         sum_ += s
         sumsq += q
@@ -84,6 +86,8 @@ def setup_ctx(up, orc_mod, case: Case, rank=0, n_ranks=1, device=0, batch_frames
         g.set_overlap_remap(orc_mod.overlap_remap(case.N, case.overlap))
     g.set_options(registration=up.REG_GIVEN if case.warp else up.REG_NONE, interp=case.interp,
                   patcher=up.PATCH_POLYNOMIAL if case.patch_lists else up.PATCH_NONE)
+    if case.filter_kind:
+        g.set_filter(case.filter_kind, case.filter_size)
     if case.patch_lists:
         for c in range(case.C):
             g.set_patches(c, *case.synth.flatten_patches(*case.patch_lists[c]))

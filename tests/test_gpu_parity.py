@@ -260,6 +260,22 @@ def test_frame_major_read_needs_keep_flag(up, orc, gpu):
     g.close()
 
 
+@pytest.mark.parametrize("kind,ksize", [(1, 3), (1, 5), (1, 7), (2, 3), (2, 5)])
+@pytest.mark.parametrize("patches", [False, True], ids=["u16-image", "f32-image(patched)"])
+def test_chain_spatial_filter(up, orc, gpu, kind, ksize, patches):
+    """deck @options filter = gaussian | box (psp_process.cpp:1802-1807) after registration and
+    patching: CV_16U image without the patcher (OpenCV's integer paths), CV_32F with it."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=24, n_nodes=2500, registration=True, patches=patches, seed=29,
+                filter_kind=kind, filter_size=ksize)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case, keep_frame_major=True)
+    _check_chain(case, ref, got, orc)
+    with pytest.raises(up.UpspGpuError):
+        g = up.PspGpu(1, 10, 4)
+        g.set_filter(1, 9)          # gaussian sizes beyond OpenCV's fixed kernels are not built
+
+
 def test_streamed_column_block_reads(up, orc, gpu):
     """upsp_gpu_read_intensity_transpose_block_async: column blocks read while later frames are
     still being processed equal the final intensity_transpose."""

@@ -189,3 +189,23 @@ def test_ecc_blur_and_gradient_match_live_cv2(orc):
     gy = cv2.filter2D(b, -1, np.array([[-0.5], [0], [0.5]], np.float32))
     ogx, ogy = ecc.gradients(b)
     assert np.array_equal(gx, ogx) and np.array_equal(gy, ogy)
+
+
+def test_spatial_filter_matches_live_cv2(orc):
+    """a5: GaussianBlur / blur on CV_16U and CV_32F (12-bit data) equal cv2 bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 4096, (41, 59)).astype(np.uint16)
+    f = img.astype(np.float32)
+    for ks in (3, 5, 7):
+        assert np.array_equal(orc.spatial_filter(img, 1, ks), cv2.GaussianBlur(img, (ks, ks), 0))
+        assert np.array_equal(orc.spatial_filter(img, 2, ks), cv2.blur(img, (ks, ks)))
+        assert np.array_equal(orc.spatial_filter(f, 1, ks), cv2.GaussianBlur(f, (ks, ks), 0))
+        assert np.array_equal(orc.spatial_filter(f, 2, ks), cv2.blur(f, (ks, ks)))
+    # non-integer f32 (next to patched pixels): within one ulp of cv2 (its SIMD path may fuse mul-add)
+    g = f + rng.random(f.shape).astype(np.float32)
+    for ks in (3, 5, 7):
+        a, b = orc.spatial_filter(g, 1, ks), cv2.GaussianBlur(g, (ks, ks), 0)
+        assert np.abs(a - b).max() <= 2.5e-7 * np.abs(b).max()
+    with pytest.raises(ValueError):
+        orc.spatial_filter(img, 1, 9)

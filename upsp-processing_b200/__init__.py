@@ -21,6 +21,7 @@ PIX_U16, PIX_PACKED12, PIX_PACKED10 = 0, 1, 2
 REG_NONE, REG_PIXEL, REG_GIVEN = 0, 1, 2
 INTERP_NEAREST, INTERP_LINEAR = 0, 1
 PATCH_NONE, PATCH_POLYNOMIAL = 0, 1
+FILTER_NONE, FILTER_GAUSSIAN, FILTER_BOX = 0, 1, 2
 XCHG_PEER, XCHG_NCCL = 0, 1
 IPC_HANDLE_BYTES = 64
 
@@ -129,6 +130,10 @@ class PspGpu:
     def set_options(self, registration=REG_NONE, interp=INTERP_LINEAR, patcher=PATCH_NONE,
                     hot_pixel_fix=True):
         _chk(lib().upsp_gpu_set_options(self._h, registration, interp, patcher, int(hot_pixel_fix)))
+
+    def set_filter(self, kind, ksize):
+        """kind: 0 none, 1 gaussian, 2 box (deck @options filter / filter_size)."""
+        _chk(lib().upsp_gpu_set_filter(self._h, int(kind), int(ksize)))
 
     def set_patches(self, cam, bounds_off, bx, by, internal_off, ix, iy):
         bo, io = _c(bounds_off, np.int32), _c(internal_off, np.int32)

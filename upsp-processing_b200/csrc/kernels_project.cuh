@@ -19,6 +19,7 @@ namespace upsp {
 // patches.ipp:104-108,159); -1 (ELL-1 table only) "no entry for this camera".
 struct ProjCam {
   const uint16_t* frames;  // [batch][npix] registered u16 frames of this batch
+  const float* frames32;   // or (filter after patching) the f32 image of the batch; overrides `frames`
   size_t npix;
   const float* pv;         // [slots][bstride] patch values of this batch (or nullptr)
   const int* code;         // ELL-1: [N]; CSR: [nnz]
@@ -34,8 +35,10 @@ struct ProjArgs {
 };
 
 __device__ __forceinline__ float fetch_px(const ProjCam& c, int code, int b, int bstride) {
-  return code >= 0 ? u2f_exact(__ldg(c.frames + (size_t)b * c.npix + code))
-                   : __ldg(c.pv + (size_t)(-2 - code) * bstride + b);
+  if (code >= 0)
+    return c.frames32 ? __ldg(c.frames32 + (size_t)b * c.npix + code)
+                      : u2f_exact(__ldg(c.frames + (size_t)b * c.npix + code));
+  return __ldg(c.pv + (size_t)(-2 - code) * bstride + b);
 }
 
 // ---- fast path: every (remapped) row has <= 1 entry per camera: the reference's own case

@@ -25,6 +25,7 @@
 #include "host_qr.hpp"
 #include "kernels_frame.cuh"
 #include "kernels_ecc.cuh"
+#include "kernels_filter.cuh"
 #include "kernels_phase2.cuh"
 #include "kernels_project.cuh"
 #include "kernels_transpose.cuh"
@@ -230,6 +231,10 @@ struct Camera {
   float* d_scratch = nullptr;
   float* d_pv = nullptr;
   std::unordered_map<int, int> pix2slot;  // interior pixel -> slot of the LAST active cluster
+  // spatial filter (unfused mode only)
+  float *d_img32 = nullptr, *d_img32b = nullptr;
+  uint16_t* d_filt16 = nullptr;
+  int* d_slot_pix = nullptr;   // [interior slots] pixel index, or -1 if a later cluster overwrites it
   // projection tables
   int* d_code = nullptr;
   float* d_val = nullptr;
@@ -244,6 +249,7 @@ struct upsp_gpu_ctx {
   int capacity = 0, batch = 32;
   int registration = UPSP_REG_NONE, interp = UPSP_INTERP_LINEAR, patcher = UPSP_PATCH_NONE;
   int hot_fix = 1;
+  FilterSpec filter{};   // kind 0 = none
   std::vector<Camera> cams;
   std::vector<int> remap;  // src_index or empty
   bool finalized = false, ell1 = true, fused = false;
@@ -486,6 +492,10 @@ static void free_camera(Camera& cam) {
   cudaFree(cam.d_cl_list);
   cudaFree(cam.d_scratch);
   cudaFree(cam.d_pv);
+  cudaFree(cam.d_img32);
+  cudaFree(cam.d_img32b);
+  cudaFree(cam.d_filt16);
+  cudaFree(cam.d_slot_pix);
   cudaFree(cam.d_code);
   cudaFree(cam.d_val);
   cudaFree(cam.d_rowptr);
@@ -614,6 +624,31 @@ extern "C" int upsp_gpu_set_options(upsp_gpu_ctx* c, int registration, int inter
   c->interp = interp;
   c->patcher = patcher;
   c->hot_fix = hot_pixel_fix != 0;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_set_filter(upsp_gpu_ctx* c, int kind, int ksize) {
+  ENTER(c);
+  NOT_FINAL(c);
+  REQUIRE(kind >= 0 && kind <= 2, UPSP_ERR_INVALID, "filter kind %d", kind);
+  c->filter = FilterSpec{};
+  if (kind == 0) return UPSP_OK;
+  REQUIRE(ksize >= 1 && (ksize & 1), UPSP_ERR_INVALID, "filter_size must be odd (psp_process.cpp:1296), got %d", ksize);
+  static const double k3[] = {0.25, 0.5, 0.25}, k5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                      k7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+  if (kind == 1) {
+    const double* k = ksize == 3 ? k3 : (ksize == 5 ? k5 : (ksize == 7 ? k7 : nullptr));
+    REQUIRE(k != nullptr, UPSP_ERR_INVALID,
+            "gaussian filter_size %d is not built (3, 5, 7: OpenCV's fixed sigma=0 kernels)", ksize);
+    for (int i = 0; i < ksize; ++i) {
+      c->filter.kq[i] = (int)llrint(k[i] * 65536.0);
+      c->filter.kf[i] = (float)k[i];
+    }
+  } else {
+    REQUIRE(ksize <= 31, UPSP_ERR_INVALID, "box filter_size %d too large", ksize);
+  }
+  c->filter.kind = kind;
+  c->filter.ksize = ksize;
   return UPSP_OK;
 }
 
@@ -789,12 +824,12 @@ static int finalize(upsp_gpu_ctx* c) {
   for (auto& k : c->cams)
     for (int n = 0; n < N && c->ell1; ++n)
       if (k.rowptr[n + 1] - k.rowptr[n] > 1) c->ell1 = false;
-  c->fused = c->ell1 && c->cfg.keep_frame_major == 0;
+  c->fused = c->ell1 && c->cfg.keep_frame_major == 0 && c->filter.kind == 0;
   std::vector<float> cov(N, 0.0f);
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
     auto code_of = [&](int col) -> int {
-      if (use_patch && k.has_patches) {
+      if (use_patch && k.has_patches && c->filter.kind == 0) {   // filtered images carry the patch in-pixel
         auto it = k.pix2slot.find(col);
         if (it != k.pix2slot.end()) return -2 - it->second;
       }
@@ -871,6 +906,17 @@ static int finalize(upsp_gpu_ctx* c) {
     }
     if (use_patch && k.has_patches) {
       TRY(dmalloc(&k.d_pv, (size_t)std::max(k.total_internal, 1) * c->batch));
+    }
+    if (c->filter.kind) {
+      if (use_patch && k.has_patches) {
+        TRY(dmalloc(&k.d_img32, (size_t)c->batch * k.npix));
+        TRY(dmalloc(&k.d_img32b, (size_t)c->batch * k.npix));
+        std::vector<int> slot_pix(std::max(k.total_internal, 1), -1);
+        for (auto& kv : k.pix2slot) slot_pix[kv.second] = kv.first;    // final writer of each pixel
+        TRY(upload(&k.d_slot_pix, slot_pix.data(), slot_pix.size()));
+      } else {
+        TRY(dmalloc(&k.d_filt16, (size_t)c->batch * k.npix));
+      }
     }
   }
   CU(cudaMemcpy(c->d_cov, cov.data(), (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
@@ -1099,9 +1145,37 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       }
       KEND();
     }
+    const float* cur32 = nullptr;
+    if (c->filter.kind) {   // only reachable in the unfused mode
+      const dim3 fg(cdiv(k.W, 256), k.H, nb);
+      if (patch) {
+        const size_t tot = (size_t)nb * k.npix;
+        k_u16_to_f32<<<cdiv(tot, 256), 256, 0, c->stream>>>(cur, k.d_img32, tot);
+        KCHECK(c);
+        k_scatter_patched<<<dim3(cdiv(k.total_internal, 256), nb), 256, 0, c->stream>>>(
+            k.d_pv, k.d_slot_pix, k.total_internal, c->batch, nb, k.npix, k.d_img32);
+        KCHECK(c);
+        if (c->filter.kind == 1) {
+          k_filter_f32<<<fg, 256, 0, c->stream>>>(k.d_img32, k.d_img32b, k.W, k.H, c->filter, 0);
+          KCHECK(c);
+          k_filter_f32<<<fg, 256, 0, c->stream>>>(k.d_img32b, k.d_img32, k.W, k.H, c->filter, 1);
+          KCHECK(c);
+          cur32 = k.d_img32;
+        } else {
+          k_filter_f32<<<fg, 256, 0, c->stream>>>(k.d_img32, k.d_img32b, k.W, k.H, c->filter, 0);
+          KCHECK(c);
+          cur32 = k.d_img32b;
+        }
+      } else {
+        k_filter_u16<<<fg, 256, 0, c->stream>>>(cur, k.d_filt16, k.W, k.H, c->filter);
+        KCHECK(c);
+        cur = k.d_filt16;
+      }
+    }
     pa.cam[ci].frames = cur;
+    pa.cam[ci].frames32 = cur32;
     pa.cam[ci].npix = k.npix;
-    pa.cam[ci].pv = patch ? k.d_pv : nullptr;
+    pa.cam[ci].pv = (patch && !c->filter.kind) ? k.d_pv : nullptr;
     pa.cam[ci].code = k.d_code;
     pa.cam[ci].val = k.d_val;
     pa.cam[ci].rowptr = k.d_rowptr;
