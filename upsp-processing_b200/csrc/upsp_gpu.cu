@@ -1388,11 +1388,12 @@ extern "C" int upsp_gpu_transpose(upsp_gpu_ctx* c) {
 // phase 2
 // ------------------------------------------------------------------------------------------
 // inverse Gram matrix of T_k(x_f), x_f as the device computes it, in long double
-static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
+static void cheb_ginv(int F, int nc, float xa, float xb, bool sym, double* ginv) {
   std::vector<long double> G((size_t)nc * nc, 0.0L);
   std::vector<long double> T(nc);
   for (int f = 0; f < F; ++f) {
-    const float xf = fmaf((float)f, xa, xb);
+    // symmetric kernel: the abscissa of a mirrored sample is minus its partner's
+    const float xf = (sym && f >= F / 2) ? -fmaf((float)(F - 1 - f), xa, xb) : fmaf((float)f, xa, xb);
     const long double x = (long double)xf;
     T[0] = 1.0L;
     if (nc > 1) T[1] = x;
@@ -1444,6 +1445,9 @@ static void cheb_ginv(int F, int nc, float xa, float xb, double* ginv) {
     }
 }
 
+static int phase2_cluster(int F);
+static bool phase2_symmetric(const Phase2Args& a);
+
 template <int NC, bool ROW_SMEM, int CL>
 static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
   constexpr int NT = 512;
@@ -1466,27 +1470,53 @@ static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
   return UPSP_OK;
 }
 
+template <int NC, int CL>
+static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
+  constexpr int NT = 512;
+  auto kern = k_phase2_sym<NC, NT, CL>;
+  const size_t smem = (size_t)(a.F / CL) * sizeof(float);
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)a.n_local * CL);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, a));
+  return UPSP_OK;
+}
+
 template <int NC>
 static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
   (void)c;
   if (a.n_local == 0) return UPSP_OK;
-  // smallest cluster whose per-CTA segment leaves room for 2 CTAs per SM (<= 90 KB + 18.6 KB static each)
-  const size_t seg_budget = 90 * 1024, seg_max = 200 * 1024;
+  const int cl = phase2_cluster(a.F);
   int rc = UPSP_OK;
-  bool done = false;
-  for (int cl = 1; cl <= 8 && !done; cl *= 2) {
-    const size_t seg = (size_t)(((a.F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
-    if (seg <= seg_budget || (cl == 8 && seg <= seg_max)) {
-      switch (cl) {
-        case 1: rc = launch_phase2_cl<NC, true, 1>(a, seg, st); break;
-        case 2: rc = launch_phase2_cl<NC, true, 2>(a, seg, st); break;
-        case 4: rc = launch_phase2_cl<NC, true, 4>(a, seg, st); break;
-        default: rc = launch_phase2_cl<NC, true, 8>(a, seg, st); break;
-      }
-      done = true;
+  if (phase2_symmetric(a)) {
+    switch (cl) {
+      case 1: rc = launch_phase2_sym<NC, 1>(a, st); break;
+      case 2: rc = launch_phase2_sym<NC, 2>(a, st); break;
+      case 4: rc = launch_phase2_sym<NC, 4>(a, st); break;
+      default: rc = launch_phase2_sym<NC, 8>(a, st); break;
     }
+  } else if (cl > 0) {
+    const size_t seg = (size_t)(((a.F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
+    switch (cl) {
+      case 1: rc = launch_phase2_cl<NC, true, 1>(a, seg, st); break;
+      case 2: rc = launch_phase2_cl<NC, true, 2>(a, seg, st); break;
+      case 4: rc = launch_phase2_cl<NC, true, 4>(a, seg, st); break;
+      default: rc = launch_phase2_cl<NC, true, 8>(a, seg, st); break;
+    }
+  } else {
+    rc = launch_phase2_cl<NC, false, 1>(a, 0, st);   // two HBM passes
   }
-  if (!done) rc = launch_phase2_cl<NC, false, 1>(a, 0, st);   // two HBM passes
   if (rc) return rc;
   ++*launches;
   CU(cudaGetLastError());
@@ -1508,12 +1538,28 @@ static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st
   return fail(UPSP_ERR_INVALID, "detrend degree %d not in [0,%d]", a.ncoef - 1, UPSP_MAX_COEF - 1);
 }
 
+// cluster size for a row of F frames: smallest CL in {1,2,4,8} whose per-CTA segment leaves room
+// for 2 CTAs per SM (<= 90 KB + 18.6 KB static each); 0 = does not fit even with 8 (two HBM passes)
+static int phase2_cluster(int F) {
+  const size_t seg_budget = 90 * 1024, seg_max = 200 * 1024;
+  for (int cl = 1; cl <= 8; cl *= 2) {
+    const size_t seg = (size_t)(((F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
+    if (seg <= seg_budget || (cl == 8 && seg <= seg_max)) return cl;
+  }
+  return 0;
+}
+static bool phase2_symmetric(const Phase2Args& a) {
+  const int cl = phase2_cluster(a.F);
+  return a.fit_out == nullptr && cl > 0 && a.F % (8 * cl) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.itrans) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ptrans) & 15) == 0;
+}
+
 static void fill_basis(Phase2Args& a, int F, int degree) {
   a.F = F;
   a.ncoef = degree + 1;
   a.xa = 2.0f / (float)F;
   a.xb = (1.0f - (float)F) / (float)F;
-  cheb_ginv(F, a.ncoef, a.xa, a.xb, a.ginv);
+  cheb_ginv(F, a.ncoef, a.xa, a.xb, phase2_symmetric(a), a.ginv);
 }
 
 extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, const float* steady,
