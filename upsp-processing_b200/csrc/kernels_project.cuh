@@ -170,6 +170,7 @@ struct FusedArgs {
   double* sumsq;
   const int* perm;                     // [N] processing order: nodes sorted by pixel index (raster),
                                        // so a warp gathers from one or two image rows
+  int perm_len;                        // staged kernel: padded length of its (tile-ordered) perm
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];
@@ -418,6 +419,187 @@ k_project_fused(const FusedArgs a) {
         float* rp = rowp[w * 32 + j];
         if (rp == nullptr) break;
         rp[b0 + lane] = tile[lane][w * 32 + j];
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    a.sum[n] += s;
+    a.sumsq[n] += q;
+  }
+}
+
+// ---- staged variant of the fused kernel (one camera, registration on, <= 14-bit pixels).
+// The nodes are processed in TILE order (64 x 16 pixel tiles, raster inside a tile, every tile
+// padded to whole 128-node blocks), so the pixels a block needs lie in a small rectangle that is
+// known at setup time (BlockInfo).  Per stage of `fps` frames the block copies that rectangle
+// (+ a registration margin) of the decoded frames, and the matching slices of the warp tables,
+// into shared memory with 16-byte cp.async transfers; the per-node work then runs entirely out
+// of shared memory (6 LDS instead of 6 scattered LDG per node-frame, no long-scoreboard
+// stalls).  Taps that fall outside the staged rectangle (shift larger than the margin, image
+// border) take the global slow path -- correctness never depends on the margin.
+struct BlockInfo {
+  short x0, y0;     // bounding box of the block's node pixels
+  short w, h;       // extents (w == 0: no plain-pixel node in this block)
+  short tx0, ty0;   // staged rectangle origin (tx0 multiple of 8)
+  short tw, th;     // staged extents (tw multiple of 8)
+  int fps;          // frames per stage (0: rectangle too large, use the global path)
+};
+constexpr int STAGE_MARGIN = 3;
+constexpr int STAGE_BYTES = 40 * 1024;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool INT12>
+__global__ void __launch_bounds__(128)
+k_project_staged(const FusedArgs a, const BlockInfo* __restrict__ binfo) {
+  constexpr int BS = 128;
+  extern __shared__ __align__(16) unsigned char stage[];   // [fps][th][tw] u16 | [fps][w] int2 | [fps][h] int2
+  __shared__ float tile[32][BS + 1];
+  __shared__ float* rowp[BS];
+  const FusedCam& cam = a.cam[0];
+  const int gid = blockIdx.x * BS + threadIdx.x;
+  const int n = gid < a.perm_len ? __ldg(a.perm + gid) : -1;    // perm is padded with -1
+  const bool live = n >= 0;
+  {
+    float* rp = nullptr;
+    if (live) {
+      int r = 0;
+      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+    }
+    rowp[threadIdx.x] = rp;
+  }
+  const BlockInfo bi = binfo[blockIdx.x];
+  const int code = live ? __ldg(cam.code + n) : -1;
+  const float val = live ? __ldg(cam.val + n) : 0.0f;
+  const int W = cam.W, H = cam.H;
+  const int px = code >= 0 ? code % W : 0, py = code >= 0 ? code / W : 0;
+  const int tw = bi.tw, th = bi.th, fps = bi.fps;
+  const size_t img_bytes = (size_t)tw * th * 2;
+  uint16_t* s_img = reinterpret_cast<uint16_t*>(stage);
+  int2* s_xa = reinterpret_cast<int2*>(stage + (size_t)fps * img_bytes);
+  int2* s_ya = s_xa + (size_t)fps * bi.w;
+  const int tstride = W + H;
+  double s = 0.0, q = 0.0;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
+    const int nb = min(32, a.nframes - b0);
+    for (int u0 = 0; u0 < nb; u0 += (fps > 0 ? fps : nb)) {
+      const int ns = fps > 0 ? min(fps, nb - u0) : nb - u0;
+      const int b = b0 + u0;
+      if (fps > 0) {
+        __syncthreads();   // previous stage fully consumed
+        // ---- stage: image rectangle, 16-byte chunks
+        const int cpr = tw / 8;                                   // chunks per row
+        const int nimg = ns * th * cpr;
+        for (int i = threadIdx.x; i < nimg; i += BS) {
+          const int j = i / (th * cpr), rem = i - j * th * cpr, ry = rem / cpr, cx = rem - ry * cpr;
+          cp_async16(s_img + ((size_t)j * th + ry) * tw + cx * 8,
+                     cam.frames + (size_t)(b + j) * cam.npix + (size_t)(bi.ty0 + ry) * W + bi.tx0 + cx * 8);
+        }
+        const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (size_t)b * tstride;
+        const int nxa = ns * bi.w;
+        for (int i = threadIdx.x; i < nxa; i += BS) {
+          const int j = i / bi.w, k = i - j * bi.w;
+          cp_async8(s_xa + j * bi.w + k, tb + (size_t)j * tstride + bi.x0 + k);
+        }
+        const int nya = ns * bi.h;
+        for (int i = threadIdx.x; i < nya; i += BS) {
+          const int j = i / bi.h, k = i - j * bi.h;
+          cp_async8(s_ya + j * bi.h + k, tb + (size_t)j * tstride + W + bi.y0 + k);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+      }
+      if (live) {
+        if (code >= 0) {
+#pragma unroll 4
+          for (int j = 0; j < ns; ++j) {
+            const int bj = b + j;
+            const uint16_t* fr = cam.frames + (size_t)bj * cam.npix;
+            float v;
+            if (bj == a.skip_frame) {
+              v = (float)__ldg(fr + code);
+            } else {
+              int2 xa, ya;
+              if (fps > 0) {
+                xa = s_xa[j * bi.w + (px - bi.x0)];
+                ya = s_ya[j * bi.h + (py - bi.y0)];
+              } else {
+                const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (size_t)bj * tstride;
+                xa = __ldg(tb + px);
+                ya = __ldg(tb + W + py);
+              }
+              const int X = ya.x + xa.x, Y = ya.y + xa.y;
+              const int sx = X >> 10, sy = Y >> 10;
+              const int lx = sx - bi.tx0, ly = sy - bi.ty0;
+              const bool in_frame = (unsigned)sx < (unsigned)(W - 1) && (unsigned)sy < (unsigned)(H - 1);
+              const bool in_tile = fps > 0 && (unsigned)lx < (unsigned)(tw - 1) && (unsigned)ly < (unsigned)(th - 1);
+              if (a.interp == 1 && in_frame && (in_tile || fps == 0)) {
+                unsigned t00, t01, t10, t11;
+                if (in_tile) {
+                  const uint16_t* p = s_img + ((size_t)j * th + ly) * tw + lx;
+                  t00 = p[0]; t01 = p[1]; t10 = p[tw]; t11 = p[tw + 1];
+                } else {
+                  const uint16_t* p = fr + (size_t)sy * W + sx;
+                  t00 = __ldg(p); t01 = __ldg(p + 1); t10 = __ldg(p + W); t11 = __ldg(p + W + 1);
+                }
+                const int fxi = (X >> 5) & 31, fyi = (Y >> 5) & 31;
+                if (INT12) {
+                  const int gx = 32 - fxi, gy = 32 - fyi;
+                  int S = (int)t00 * (gy * gx);
+                  S += (int)t01 * (gy * fxi);
+                  S += (int)t10 * (fyi * gx);
+                  S += (int)t11 * (fyi * fxi);
+                  const int qv = S >> 10, rem = S & 1023;
+                  v = u2f_exact((uint32_t)(qv + ((rem + (qv & 1)) > 512)));
+                } else {
+                  const float fx = frac32_exact(fxi), fy = frac32_exact(fyi);
+                  const float gx = 1.0f - fx, gy = 1.0f - fy;
+                  float r = __fadd_rn(__fmul_rn((float)t00, __fmul_rn(gy, gx)), __fmul_rn((float)t01, __fmul_rn(gy, fx)));
+                  r = __fadd_rn(r, __fmul_rn((float)t10, __fmul_rn(fy, gx)));
+                  r = __fadd_rn(r, __fmul_rn((float)t11, __fmul_rn(fy, fx)));
+                  r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);
+                  v = fminf(r, 65535.0f);
+                }
+              } else {
+                v = warp_px_slow(fr, W, H, X, Y, a.interp);
+              }
+            }
+            const float sol = __fadd_rn(0.0f, __fmul_rn(val, v));
+            tile[u0 + j][threadIdx.x] = sol;
+            q += (double)__fmul_rn(sol, sol);
+            s += (double)sol;
+          }
+        } else {
+          for (int j = 0; j < ns; ++j) {
+            float sol = __int_as_float(0x7fc00000);     // skipped node
+            if (code <= -2) sol = __fadd_rn(0.0f, __fmul_rn(val, __ldg(cam.pv + (size_t)(-2 - code) * a.bstride + b + j)));
+            tile[u0 + j][threadIdx.x] = sol;
+            q += (double)__fmul_rn(sol, sol);
+            s += (double)sol;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (lane < nb) {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        float* rp = rowp[w * 32 + j];
+        if (rp != nullptr) rp[b0 + lane] = tile[lane][w * 32 + j];
       }
     }
     __syncthreads();

@@ -255,6 +255,9 @@ struct upsp_gpu_ctx {
   bool finalized = false, ell1 = true, fused = false;
   uint16_t* d_lut = nullptr;
   int lut_max = 0;        // largest entry of the 10->12-bit table (0 = no table)
+  int* d_perm_tile = nullptr;     // staged kernel: tile-ordered, block-padded node order
+  BlockInfo* d_binfo = nullptr;   // staged kernel: per-block pixel rectangle
+  int perm_tile_len = 0;
   int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
 
   cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
@@ -512,6 +515,8 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   for (auto& cam : c->cams) free_camera(cam);
   cudaFree(c->d_lut);
   cudaFree(c->d_perm);
+  cudaFree(c->d_perm_tile);
+  cudaFree(c->d_binfo);
   cudaFree(c->d_intensity);
   if (c->shared_vmm.handle) vmm_free(c->shared_vmm); else cudaFree(c->d_shared);
   if (c->ptrans_owned) cudaFree(c->d_ptrans);
@@ -944,6 +949,75 @@ static int finalize(upsp_gpu_ctx* c) {
     std::vector<int> perm(N);
     for (int i = 0; i < N; ++i) perm[i] = keyed[i].second;
     TRY(upload(&c->d_perm, perm.data(), perm.size()));
+    // staged kernel (one camera, W % 8 == 0): tile order (64 x 16 px tiles, raster inside), every
+    // tile padded to whole 128-node blocks; per block the pixel rectangle to stage
+    const Camera& k0 = c->cams[0];
+    if (c->cams.size() == 1 && (k0.W % 8) == 0 && (k0.npix % 8) == 0 && k0.W < 32760 && k0.H < 32760) {
+      const int TW = 64, TH = 16, BS = 128;
+      const int ntx = (k0.W + TW - 1) / TW;
+      std::vector<std::pair<uint64_t, int>> tk(N);
+      for (int n = 0; n < N; ++n) {
+        const int sn = c->remap.empty() ? n : c->remap[n];
+        uint64_t key = ~0ull;
+        if (k0.rowptr[sn + 1] > k0.rowptr[sn]) {
+          const int col = k0.col[k0.rowptr[sn]];
+          const int x = col % k0.W, y = col / k0.W;
+          key = ((uint64_t)((y / TH) * ntx + x / TW) << 32) | (uint32_t)col;
+        }
+        tk[n] = {key, n};
+      }
+      std::sort(tk.begin(), tk.end());
+      std::vector<int> pt;
+      pt.reserve(N + N / 8);
+      uint64_t cur_tile = ~0ull - 1;
+      for (int i = 0; i < N; ++i) {
+        const uint64_t tile = tk[i].first == ~0ull ? ~0ull : (tk[i].first >> 32);
+        if (tile != cur_tile) {
+          while (pt.size() % BS) pt.push_back(-1);
+          cur_tile = tile;
+        }
+        pt.push_back(tk[i].second);
+      }
+      while (pt.size() % BS) pt.push_back(-1);
+      const int nblocks = (int)pt.size() / BS;
+      std::vector<BlockInfo> bis(nblocks);
+      // device-side code of a node (patched pixels carry no plain pixel)
+      auto plain_col = [&](int n) -> int {
+        const int sn = c->remap.empty() ? n : c->remap[n];
+        if (k0.rowptr[sn + 1] <= k0.rowptr[sn]) return -1;
+        const int col = k0.col[k0.rowptr[sn]];
+        if (use_patch && k0.has_patches && k0.pix2slot.count(col)) return -1;
+        return col;
+      };
+      for (int b = 0; b < nblocks; ++b) {
+        int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+        for (int i = 0; i < BS; ++i) {
+          const int n = pt[(size_t)b * BS + i];
+          const int col = n >= 0 ? plain_col(n) : -1;
+          if (col < 0) continue;
+          const int x = col % k0.W, y = col / k0.W;
+          x0 = std::min(x0, x); x1 = std::max(x1, x);
+          y0 = std::min(y0, y); y1 = std::max(y1, y);
+        }
+        BlockInfo bi{};
+        if (x1 >= 0) {
+          bi.x0 = (short)x0; bi.y0 = (short)y0;
+          bi.w = (short)(x1 - x0 + 1); bi.h = (short)(y1 - y0 + 1);
+          const int tx0 = std::max(0, x0 - STAGE_MARGIN) & ~7;
+          const int tx1 = std::min(k0.W, (x1 + STAGE_MARGIN + 2 + 7) & ~7);
+          const int ty0 = std::max(0, y0 - STAGE_MARGIN), ty1 = std::min(k0.H, y1 + STAGE_MARGIN + 2);
+          bi.tx0 = (short)tx0; bi.ty0 = (short)ty0;
+          bi.tw = (short)(tx1 - tx0); bi.th = (short)(ty1 - ty0);
+          const size_t per_frame = (size_t)bi.tw * bi.th * 2 + (size_t)bi.w * 8 + (size_t)bi.h * 8;
+          int fps = (int)std::min<size_t>(32, STAGE_BYTES / per_frame);
+          bi.fps = fps >= 4 ? (fps & ~3) : 0;
+        }
+        bis[b] = bi;
+      }
+      TRY(upload(&c->d_perm_tile, pt.data(), pt.size()));
+      TRY(upload(&c->d_binfo, bis.data(), bis.size()));
+      c->perm_tile_len = (int)pt.size();
+    }
   }
   // big buffers that depend on the mode
   {
@@ -1207,7 +1281,26 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     fa.node_start[c->R] = c->N;
     const unsigned g = cdiv(c->N, 256);
+    static const bool use_staged = !(getenv("UPSP_NO_STAGED") && atoi(getenv("UPSP_NO_STAGED")));
     KBEGIN(4);
+    if (use_staged && c->d_perm_tile && c->registration != UPSP_REG_NONE && c->interp == UPSP_INTERP_LINEAR) {
+      bool i12 = true;
+      for (auto& k : c->cams)
+        i12 = i12 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 16384));
+      fa.perm = c->d_perm_tile;
+      fa.perm_len = c->perm_tile_len;
+      const unsigned gs = (unsigned)(c->perm_tile_len / 128);
+      if (i12) {
+        CU(cudaFuncSetAttribute(k_project_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        k_project_staged<true><<<gs, 128, STAGE_BYTES, c->stream>>>(fa, c->d_binfo);
+      } else {
+        CU(cudaFuncSetAttribute(k_project_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        k_project_staged<false><<<gs, 128, STAGE_BYTES, c->stream>>>(fa, c->d_binfo);
+      }
+      KCHECK(c);
+      KEND();
+      return UPSP_OK;
+    }
     const bool regk = c->registration != UPSP_REG_NONE;
     static const int fused_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 128;   // tuning knob: nodes per block
     bool int12 = true;   // every camera's container guarantees pixels < 2^14
