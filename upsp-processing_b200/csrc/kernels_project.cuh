@@ -501,24 +501,23 @@ k_project_staged(const FusedArgs a, const BlockInfo* __restrict__ binfo) {
       const int b = b0 + u0;
       if (fps > 0) {
         __syncthreads();   // previous stage fully consumed
-        // ---- stage: image rectangle, 16-byte chunks
+        // ---- stage: warp `w` copies frames w, w+4, ... of the stage; lanes walk the rectangle in
+        // 16-byte chunks (no integer divisions: the chunk cursor is advanced incrementally)
         const int cpr = tw / 8;                                   // chunks per row
-        const int nimg = ns * th * cpr;
-        for (int i = threadIdx.x; i < nimg; i += BS) {
-          const int j = i / (th * cpr), rem = i - j * th * cpr, ry = rem / cpr, cx = rem - ry * cpr;
-          cp_async16(s_img + ((size_t)j * th + ry) * tw + cx * 8,
-                     cam.frames + (size_t)(b + j) * cam.npix + (size_t)(bi.ty0 + ry) * W + bi.tx0 + cx * 8);
-        }
-        const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (size_t)b * tstride;
-        const int nxa = ns * bi.w;
-        for (int i = threadIdx.x; i < nxa; i += BS) {
-          const int j = i / bi.w, k = i - j * bi.w;
-          cp_async8(s_xa + j * bi.w + k, tb + (size_t)j * tstride + bi.x0 + k);
-        }
-        const int nya = ns * bi.h;
-        for (int i = threadIdx.x; i < nya; i += BS) {
-          const int j = i / bi.h, k = i - j * bi.h;
-          cp_async8(s_ya + j * bi.h + k, tb + (size_t)j * tstride + W + bi.y0 + k);
+        const int2* tb0 = reinterpret_cast<const int2*>(cam.tab) + (size_t)b * tstride;
+        for (int j = w; j < ns; j += BS / 32) {
+          const uint16_t* gsrc = cam.frames + (size_t)(b + j) * cam.npix + (size_t)bi.ty0 * W + bi.tx0;
+          uint16_t* sdst = s_img + (size_t)j * th * tw;
+          int ry = 0, cx = lane;
+          while (cx >= cpr) { cx -= cpr; ++ry; }
+          while (ry < th) {
+            cp_async16(sdst + ry * tw + cx * 8, gsrc + (size_t)ry * W + cx * 8);
+            cx += 32;
+            while (cx >= cpr) { cx -= cpr; ++ry; }
+          }
+          const int2* tb = tb0 + (size_t)j * tstride;
+          for (int k = lane; k < bi.w; k += 32) cp_async8(s_xa + j * bi.w + k, tb + bi.x0 + k);
+          for (int k = lane; k < bi.h; k += 32) cp_async8(s_ya + j * bi.h + k, tb + W + bi.y0 + k);
         }
         cp_async_wait_all();
         __syncthreads();
