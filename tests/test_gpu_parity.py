@@ -276,6 +276,27 @@ def test_chain_spatial_filter(up, orc, gpu, kind, ksize, patches):
         g.set_filter(1, 9)          # gaussian sizes beyond OpenCV's fixed kernels are not built
 
 
+def test_staged_projection_variant_matches(up, orc, gpu):
+    """UPSP_STAGED=1 selects the experimental cp.async shared-memory variant of the fused
+    projection; it must produce the same bits (run in a subprocess: the knob is read once)."""
+    import subprocess, sys, textwrap
+    from conftest import ROOT
+    code = textwrap.dedent("""
+        import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+        import upsp_b200 as up
+        from oracle import oracle as orc
+        from chain import Case, run_gpu, run_oracle, same_bits
+        case = Case(up.synth, n_frames=40, n_nodes=6000, registration=True, patches=True, overlap=True, seed=7, fmt="p12")
+        ref = run_oracle(orc, case); got = run_gpu(up, orc, case)
+        assert same_bits(got["itrans"], ref["itrans"]) and same_bits(got["avg"], ref["avg"])
+        print("staged ok")
+    """ % (ROOT, ROOT))
+    import os
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, UPSP_STAGED="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "staged ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_streamed_column_block_reads(up, orc, gpu):
     """upsp_gpu_read_intensity_transpose_block_async: column blocks read while later frames are
     still being processed equal the final intensity_transpose."""

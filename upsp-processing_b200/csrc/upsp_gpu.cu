@@ -1281,7 +1281,10 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     fa.node_start[c->R] = c->N;
     const unsigned g = cdiv(c->N, 256);
-    static const bool use_staged = !(getenv("UPSP_NO_STAGED") && atoi(getenv("UPSP_NO_STAGED")));
+    // experimental (UPSP_STAGED=1): shared-memory staged variant.  Measured SLOWER in round 1
+    // (0.77 vs 0.29 ms per 128-frame batch: 212 instructions per node-frame, 12 warps/SM), so the
+    // register-path kernel below stays the default; see DESIGN.md section 7.
+    static const bool use_staged = getenv("UPSP_STAGED") && atoi(getenv("UPSP_STAGED"));
     KBEGIN(4);
     if (use_staged && c->d_perm_tile && c->registration != UPSP_REG_NONE && c->interp == UPSP_INTERP_LINEAR) {
       bool i12 = true;
