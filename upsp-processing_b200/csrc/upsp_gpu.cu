@@ -1655,7 +1655,24 @@ static void fill_basis(Phase2Args& a, int F, int degree) {
   a.ncoef = degree + 1;
   a.xa = 2.0f / (float)F;
   a.xb = (1.0f - (float)F) / (float)F;
-  cheb_ginv(F, a.ncoef, a.xa, a.xb, phase2_symmetric(a), a.ginv);
+  // the O(F * ncoef^2) long-double Gram matrix depends on (F, degree, symmetric) only: memoise it
+  // (10 ms at F = 80 000, which would otherwise sit in every phase-2 call)
+  struct Key { int F, nc, sym; double ginv[UPSP_MAX_COEF * UPSP_MAX_COEF]; };
+  static thread_local std::vector<Key> cache;
+  const int sym = phase2_symmetric(a) ? 1 : 0;
+  for (const Key& k : cache)
+    if (k.F == F && k.nc == a.ncoef && k.sym == sym) {
+      memcpy(a.ginv, k.ginv, sizeof a.ginv);
+      return;
+    }
+  cheb_ginv(F, a.ncoef, a.xa, a.xb, sym != 0, a.ginv);
+  Key k;
+  k.F = F;
+  k.nc = a.ncoef;
+  k.sym = sym;
+  memcpy(k.ginv, a.ginv, sizeof a.ginv);
+  if (cache.size() >= 8) cache.erase(cache.begin());
+  cache.push_back(k);
 }
 
 extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, const float* steady,
