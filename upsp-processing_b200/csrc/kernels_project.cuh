@@ -1,6 +1,8 @@
 // kernels_project.cuh -- K5: batched-frame CSR projection (pixel -> node gather) with the
 // camera blend, NaN fill, overlap remap, sum / sum-of-squares and row store fused in.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace upsp {
@@ -159,12 +161,14 @@ struct FusedCam {
   size_t npix;
   int W, H;
   const int* tab;          // [batch][2W+2H] warp tables, or nullptr (registration = none)
+  const float* m6;         // [batch][6] the 2x3 maps the tables were built from (k_project_fused3)
   const float* pv;         // [slots][bstride] patch values
   const int* code;         // [N]
   const float* val;        // [N]
 };
 struct FusedArgs {
   int n_cams, n_nodes, nframes, bstride, interp, skip_frame;
+  int dbg;                             // experiment switches (UPSP_FUSED_DBG): 1 no row stores, 2 taps from one hot line, 4 no statistics
   FusedCam cam[UPSP_MAX_CAMS];
   double* sum;
   double* sumsq;
@@ -419,6 +423,423 @@ k_project_fused(const FusedArgs a) {
         float* rp = rowp[w * 32 + j];
         if (rp == nullptr) break;
         rp[b0 + lane] = tile[lane][w * 32 + j];
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    a.sum[n] += s;
+    a.sumsq[n] += q;
+  }
+}
+
+// ---- k_project_fused2: the lean version of the fused kernel for the hot configuration
+// (registration on, bilinear, pixels < 2^13, i.e. 12-bit containers).  Same arithmetic, same
+// results bit for bit; what changed is the instruction budget per node-frame (87 -> ~45):
+//   * every address is base + 32-bit element offset (one IMAD.WIDE per load instead of 64-bit
+//     add chains); frame / table strides of the batch are warp-uniform;
+//   * the bilinear sum S = sum t_ij w_ij (integer, < 2^22) is accumulated on top of the float
+//     bit pattern of 2^23, so S never needs an int->float conversion: the float 2^23 + S times
+//     2^-10 plus (1.5 * 2^23 - 2^13) lands in [2^23, 2^24) where one FFMA rounds S/1024 half to
+//     even (OpenCV's saturate_cast<ushort>(float) = cvRound), and one FADD removes the offset;
+//   * val * v + 0 is one FFMA (x*y + 0.0 rounds once, exactly like the FMUL + FADD pair, and
+//     turns -0 into +0 the same way);
+//   * a thread stores its 4 frames of a group with one STS.128 into a [node][36] tile, and the
+//     write-out moves 4 frames per lane (LDS.128 + STG.128, 8 lanes = one 128-byte row segment).
+// Preconditions (host-checked): batch * npix < 2^31, registration tables present, interp linear.
+template <int U>
+struct Taps2 {
+  unsigned t00[U], t01[U], t10[U], t11[U];
+};
+
+template <int U>
+__device__ __forceinline__ void fused2_cam_group(const FusedCam& cam, int code, unsigned px, unsigned pyw,
+                                                 unsigned b, int skip_frame, float (&v)[U]) {
+  const int2* __restrict__ tab2 = reinterpret_cast<const int2*>(cam.tab);
+  const uint16_t* __restrict__ fr = cam.frames;
+  const unsigned ts = (unsigned)(cam.W + cam.H), W = (unsigned)cam.W, npix = (unsigned)cam.npix;
+  int X[U], Y[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const unsigned tb = (b + j) * ts;
+    const int2 xa = __ldg(tab2 + (tb + px)), ya = __ldg(tab2 + (tb + pyw));
+    X[j] = ya.x + xa.x;
+    Y[j] = ya.y + xa.y;
+  }
+  Taps2<U> t;
+  bool all_fast = true;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int sx = X[j] >> 10, sy = Y[j] >> 10;
+    const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+    all_fast = all_fast && fast;
+    const unsigned idx = (fast ? (unsigned)(sy * cam.W + sx) : 0u) + (b + j) * npix;
+    const uint16_t* p0 = fr + idx;
+    const uint16_t* p1 = fr + (idx + W);
+    t.t00[j] = __ldg(p0);
+    t.t01[j] = __ldg(p0 + 1);
+    t.t10[j] = __ldg(p1);
+    t.t11[j] = __ldg(p1 + 1);
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const unsigned fxi = ((unsigned)X[j] >> 5) & 31u, fyi = ((unsigned)Y[j] >> 5) & 31u;
+    const unsigned gx = 32u - fxi, gy = 32u - fyi;
+    const unsigned top = t.t00[j] * gx + t.t01[j] * fxi;
+    const unsigned bot = t.t10[j] * gx + t.t11[j] * fxi;
+    const unsigned sm = top * gy + 0x4B000000u + bot * fyi;          // bits of the float 2^23 + S
+    v[j] = __fadd_rn(__fmaf_rn(__uint_as_float(sm), 0.0009765625f, 12574720.0f), -12582912.0f);
+  }
+  const bool has_skip = (unsigned)(skip_frame - (int)b) < (unsigned)U;
+  if (!all_fast || has_skip) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int sx = X[j] >> 10, sy = Y[j] >> 10;
+      const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+      const uint16_t* f2 = fr + (size_t)(b + j) * cam.npix;
+      if ((int)b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
+      else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], 1);
+    }
+  }
+}
+
+template <int NC, int U>
+__device__ __forceinline__ void fused2_group(const FusedArgs& a, const int (&code)[NC], const float (&val)[NC],
+                                             const unsigned (&px)[NC], const unsigned (&pyw)[NC],
+                                             bool skipped, unsigned b, float (&sol)[U]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[j] = 0.0f;
+    const FusedCam& cam = a.cam[c];
+    if (code[c] >= 0) {
+      fused2_cam_group<U>(cam, code[c], px[c], pyw[c], b, a.skip_frame, v);
+    } else if (code[c] <= -2) {
+      const float* p = cam.pv + (size_t)(-2 - code[c]) * a.bstride + b;
+#pragma unroll
+      for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const float cs = (code[c] == -1) ? 0.0f : __fmaf_rn(val[c], v[j], 0.0f);
+      sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
+    }
+  }
+  if (skipped) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
+  }
+}
+
+template <int NC, int BS>
+__global__ void __launch_bounds__(BS)
+k_project_fused2(const FusedArgs a) {
+  constexpr int TS = 36;                              // tile row stride in floats (32 frames + pad, 16-byte aligned)
+  __shared__ __align__(16) float tile[BS * TS];       // [node][frame]
+  __shared__ float* rowp[BS];
+  const int gid = blockIdx.x * BS + threadIdx.x;
+  const bool live = gid < a.n_nodes;
+  const int n = live ? __ldg(a.perm + gid) : -1;
+  {
+    float* rp = nullptr;
+    if (live) {
+      int r = 0;
+      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+    }
+    rowp[threadIdx.x] = rp;
+  }
+  int code[NC];
+  float val[NC];
+  unsigned px[NC], pyw[NC];
+  bool skipped = true;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    code[c] = live ? __ldg(a.cam[c].code + n) : -1;
+    val[c] = live ? __ldg(a.cam[c].val + n) : 0.0f;
+    skipped = skipped && (code[c] == -1);
+    const int W = a.cam[c].W;
+    px[c] = code[c] >= 0 ? (unsigned)(code[c] % W) : 0u;
+    pyw[c] = (unsigned)W + (code[c] >= 0 ? (unsigned)(code[c] / W) : 0u);
+  }
+  double s = 0.0, q = 0.0;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
+  float* trow = tile + threadIdx.x * TS;
+  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
+    const int nb = min(32, a.nframes - b0);
+    if (live) {
+      int u = 0;
+      for (; u + 4 <= nb; u += 4) {
+        float sol[4];
+        fused2_group<NC, 4>(a, code, val, px, pyw, skipped, (unsigned)(b0 + u), sol);
+        *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q += (double)__fmul_rn(sol[j], sol[j]);
+          s += (double)sol[j];
+        }
+      }
+      for (; u < nb; ++u) {
+        float sol[1];
+        fused2_group<NC, 1>(a, code, val, px, pyw, skipped, (unsigned)(b0 + u), sol);
+        trow[u] = sol[0];
+        q += (double)__fmul_rn(sol[0], sol[0]);
+        s += (double)sol[0];
+      }
+    }
+    __syncthreads();
+    if (vec_ok && nb == 32) {
+      // warp w writes the block's nodes [w*32, w*32+32): 8 lanes = one node's 32 frames = 128 bytes
+      const int fq = (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int nl = w * 32 + it * 4 + (lane >> 3);
+        float* rp = rowp[nl];
+        if (rp != nullptr) {
+          const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
+          *reinterpret_cast<float4*>(rp + b0 + fq) = o;
+        }
+      }
+    } else if (lane < nb) {
+      for (int j = 0; j < 32; ++j) {
+        float* rp = rowp[w * 32 + j];
+        if (rp == nullptr) break;
+        rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    a.sum[n] += s;
+    a.sumsq[n] += q;
+  }
+}
+
+// ---- k_project_fused3: k_project_fused2 without the per-node-frame table gathers.
+// ncu on fused2: 1.3 GB of L2->L1 traffic per 128-frame batch, ~1 GB of it the (adelta,bdelta)[x]
+// table (every image row's nodes re-read the 8 KB x-table of every frame), two dependent global
+// round trips per group (table -> taps), issue 38 %, L1 wavefronts 43 %: latency bound.  Here
+//   * (adelta, bdelta)[x] = cvRound(M0*x*1024), cvRound(M3*x*1024) are evaluated in the thread
+//     (DMUL + F2I.S32.F64, exactly k_warp_tables' expression: M*1024 is an exact scaling) from the
+//     32 per-frame coefficient pairs of the chunk, staged in shared memory;
+//   * (X0, Y0)[y]: a block's nodes are consecutive in raster order, so they span a few image rows;
+//     the block copies those rows' entries for the chunk's 32 frames into shared memory (while the
+//     previous chunk is being written out) and the per-node-frame lookup is one LDS.64.  Blocks
+//     whose nodes span more than RY rows of a camera fall back to the global y-table.
+// The tap loads are then the only global loads of a group: one round trip instead of two.
+constexpr int FUSED3_RY = 4;
+
+template <int U>
+__device__ __forceinline__ void fused3_cam_group(const FusedCam& cam, int code, double dpx, const int2* __restrict__ ysrc,
+                                                 unsigned ystep, const double2* __restrict__ coef, unsigned b,
+                                                 int skip_frame, int dbg, float (&v)[U]) {
+  const uint16_t* __restrict__ fr = cam.frames;
+  const unsigned W = (unsigned)cam.W, npix = (unsigned)cam.npix;
+  int X[U], Y[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const double2 cf = coef[j];
+    const int2 ya = ysrc[j * ystep];
+    X[j] = ya.x + __double2int_rn(__dmul_rn(cf.x, dpx));
+    Y[j] = ya.y + __double2int_rn(__dmul_rn(cf.y, dpx));
+  }
+  Taps2<U> t;
+  bool all_fast = true;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int sx = X[j] >> 10, sy = Y[j] >> 10;
+    const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+    all_fast = all_fast && fast;
+    const unsigned idx = (dbg & 2) ? (unsigned)(sx & 63) : (fast ? (unsigned)(sy * cam.W + sx) : 0u) + (b + j) * npix;
+    const uint16_t* p0 = fr + idx;
+    const uint16_t* p1 = fr + (idx + W);
+    t.t00[j] = __ldg(p0);
+    t.t01[j] = __ldg(p0 + 1);
+    t.t10[j] = __ldg(p1);
+    t.t11[j] = __ldg(p1 + 1);
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const unsigned fxi = ((unsigned)X[j] >> 5) & 31u, fyi = ((unsigned)Y[j] >> 5) & 31u;
+    const unsigned gx = 32u - fxi, gy = 32u - fyi;
+    const unsigned top = t.t00[j] * gx + t.t01[j] * fxi;
+    const unsigned bot = t.t10[j] * gx + t.t11[j] * fxi;
+    const unsigned sm = top * gy + 0x4B000000u + bot * fyi;          // bits of the float 2^23 + S
+    v[j] = __fadd_rn(__fmaf_rn(__uint_as_float(sm), 0.0009765625f, 12574720.0f), -12582912.0f);
+  }
+  const bool has_skip = (unsigned)(skip_frame - (int)b) < (unsigned)U;
+  if (!all_fast || has_skip) {
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int sx = X[j] >> 10, sy = Y[j] >> 10;
+      const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+      const uint16_t* f2 = fr + (size_t)(b + j) * cam.npix;
+      if ((int)b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
+      else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], 1);
+    }
+  }
+}
+
+template <int NC, int BS, int MINB = 1024 / BS>
+__global__ void __launch_bounds__(BS, MINB)
+k_project_fused3(const FusedArgs a) {
+  constexpr int TS = 36;                              // tile row stride in floats (32 frames + pad)
+  constexpr int RY = FUSED3_RY;
+  __shared__ __align__(16) float tile[BS * TS];       // [node][frame]
+  __shared__ float* rowp[BS];
+  __shared__ __align__(16) double2 s_coef[NC][32];    // (M0, M3) * 1024 of the chunk's frames
+  __shared__ __align__(8) int2 s_y[NC][32 * RY];      // (X0, Y0)[y0 .. y0+RY) of the chunk's frames
+  __shared__ int s_ymin[NC], s_ymax[NC];
+  const int gid = blockIdx.x * BS + threadIdx.x;
+  const bool live = gid < a.n_nodes;
+  const int n = live ? __ldg(a.perm + gid) : -1;
+  if (threadIdx.x < NC) {
+    s_ymin[threadIdx.x] = 0x7fffffff;
+    s_ymax[threadIdx.x] = -1;
+  }
+  {
+    float* rp = nullptr;
+    if (live) {
+      int r = 0;
+      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+    }
+    rowp[threadIdx.x] = rp;
+  }
+  __syncthreads();
+  int code[NC];
+  float val[NC];
+  double dpx[NC];
+  int py[NC];
+  bool skipped = true;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    code[c] = live ? __ldg(a.cam[c].code + n) : -1;
+    val[c] = live ? __ldg(a.cam[c].val + n) : 0.0f;
+    skipped = skipped && (code[c] == -1);
+    const int W = a.cam[c].W;
+    dpx[c] = code[c] >= 0 ? (double)(code[c] % W) : 0.0;
+    py[c] = code[c] >= 0 ? code[c] / W : 0;
+    if (code[c] >= 0) {
+      atomicMin(&s_ymin[c], py[c]);
+      atomicMax(&s_ymax[c], py[c]);
+    }
+  }
+  __syncthreads();
+  int y0[NC];
+  bool ysm[NC];
+  const int2* ysrc[NC];        // this thread's (X0,Y0) entry of the chunk's first frame
+  unsigned ystep[NC];          // distance (in int2) between consecutive frames' entries
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    y0[c] = s_ymin[c];
+    ysm[c] = s_ymax[c] - y0[c] < RY;     // also true when the block has no plain-pixel node of this camera
+    ystep[c] = ysm[c] ? (unsigned)RY : (unsigned)(a.cam[c].W + a.cam[c].H);
+  }
+  // stage the coefficient pairs and the y-table rows of frames [b0, b0 + 32)
+  auto stage = [&](int b0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const FusedCam& cam = a.cam[c];
+      if (threadIdx.x < 32) {
+        const int f = min(b0 + (int)threadIdx.x, a.nframes - 1);
+        const float* M = cam.m6 + (size_t)f * 6;
+        s_coef[c][threadIdx.x] = make_double2((double)__ldg(M) * 1024.0, (double)__ldg(M + 3) * 1024.0);
+      }
+      if (ysm[c] && s_ymax[c] >= 0) {
+        const int2* tab2 = reinterpret_cast<const int2*>(cam.tab);
+        const unsigned ts = (unsigned)(cam.W + cam.H);
+        for (int i = threadIdx.x; i < 32 * RY; i += BS) {
+          const int f = min(b0 + i / RY, a.nframes - 1), r = i % RY;
+          const int yy = min(y0[c] + r, cam.H - 1);
+          s_y[c][i] = __ldg(tab2 + ((unsigned)f * ts + (unsigned)(cam.W + yy)));
+        }
+      }
+    }
+  };
+  stage(0);
+  __syncthreads();
+  double s = 0.0, q = 0.0;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
+  float* trow = tile + threadIdx.x * TS;
+  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
+    const int nb = min(32, a.nframes - b0);
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        ysrc[c] = ysm[c] ? &s_y[c][py[c] - y0[c]]
+                         : reinterpret_cast<const int2*>(a.cam[c].tab) +
+                               ((unsigned)b0 * ystep[c] + (unsigned)(a.cam[c].W + py[c]));
+      auto group = [&](auto UU, int u, float* sol) {
+        constexpr int U = decltype(UU)::value;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float v[U];
+#pragma unroll
+          for (int j = 0; j < U; ++j) v[j] = 0.0f;
+          const FusedCam& cam = a.cam[c];
+          if (code[c] >= 0) {
+            fused3_cam_group<U>(cam, code[c], dpx[c], ysrc[c] + (unsigned)u * ystep[c], ystep[c], &s_coef[c][u],
+                                (unsigned)(b0 + u), a.skip_frame, a.dbg, v);
+          } else if (code[c] <= -2) {
+            const float* p = cam.pv + (size_t)(-2 - code[c]) * a.bstride + (b0 + u);
+#pragma unroll
+            for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
+          }
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const float cs = (code[c] == -1) ? 0.0f : __fmaf_rn(val[c], v[j], 0.0f);
+            sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
+          }
+        }
+        if (skipped) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
+        }
+      };
+      int u = 0;
+      for (; u + 4 <= nb; u += 4) {
+        float sol[4];
+        group(std::integral_constant<int, 4>{}, u, sol);
+        *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
+        if (!(a.dbg & 4)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            q += (double)__fmul_rn(sol[j], sol[j]);
+            s += (double)sol[j];
+          }
+        }
+      }
+      for (; u < nb; ++u) {
+        float sol[1];
+        group(std::integral_constant<int, 1>{}, u, sol);
+        trow[u] = sol[0];
+        q += (double)__fmul_rn(sol[0], sol[0]);
+        s += (double)sol[0];
+      }
+    }
+    __syncthreads();
+    if (b0 + 32 < a.nframes) stage(b0 + 32);      // the compute loop is done with this chunk's tables
+    if (vec_ok && nb == 32) {
+      // warp w writes the block's nodes [w*32, w*32+32): 8 lanes = one node's 32 frames = 128 bytes
+      const int fq = (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int nl = w * 32 + it * 4 + (lane >> 3);
+        float* rp = rowp[nl];
+        if (rp != nullptr && !(a.dbg & 1)) {
+          const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
+          *reinterpret_cast<float4*>(rp + b0 + fq) = o;
+        }
+      }
+    } else if (lane < nb) {
+      for (int j = 0; j < 32; ++j) {
+        float* rp = rowp[w * 32 + j];
+        if (rp == nullptr) break;
+        rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
       }
     }
     __syncthreads();

@@ -1258,6 +1258,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.cam[ci].W = k.W;
     fa.cam[ci].H = k.H;
     fa.cam[ci].tab = tabs;
+    fa.cam[ci].m6 = reg ? k.d_m6 + (size_t)off * 6 : nullptr;
     fa.cam[ci].pv = patch ? k.d_pv : nullptr;
     fa.cam[ci].code = k.d_code;
     fa.cam[ci].val = k.d_val;
@@ -1269,6 +1270,8 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.nframes = nb;
     fa.bstride = c->batch;
     fa.interp = c->interp;
+    static const int fused_dbg = getenv("UPSP_FUSED_DBG") ? atoi(getenv("UPSP_FUSED_DBG")) : 0;
+    fa.dbg = fused_dbg;
     fa.sum = c->d_sum;
     fa.sumsq = c->d_sumsq;
     fa.perm = c->d_perm;
@@ -1315,6 +1318,54 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   else if (regk && int12) k_project_fused<NCAM, true, true, 4, 256><<<g, 256, 0, c->stream>>>(fa);   \
   else if (regk) k_project_fused<NCAM, true, false, 4, 256><<<g, 256, 0, c->stream>>>(fa);           \
   else k_project_fused<NCAM, false, false, 8, 256><<<g, 256, 0, c->stream>>>(fa)
+    // lean kernel for the hot configuration (bilinear registration, 12-bit containers); UPSP_FUSED_V1=1
+    // keeps the first-generation kernel for A/B measurements
+    static const bool fused_v1 = getenv("UPSP_FUSED_V1") && atoi(getenv("UPSP_FUSED_V1"));
+    bool pix13 = true;   // pixels < 2^13: the bilinear sum fits under the float bit pattern of 2^23
+    size_t max_elems = 0;
+    for (auto& k : c->cams) {
+      pix13 = pix13 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 8192));
+      max_elems = std::max(max_elems, (size_t)c->batch * k.npix);
+      max_elems = std::max(max_elems, (size_t)c->batch * (size_t)(k.W + k.H));
+    }
+    if (!fused_v1 && regk && pix13 && c->interp == UPSP_INTERP_LINEAR && max_elems < ((size_t)1 << 31)) {
+      const unsigned g2 = cdiv(c->N, 128);
+      // UPSP_FUSED_V=2: table-gather variant (k_project_fused2); default: k_project_fused3
+      static const int fused_v = getenv("UPSP_FUSED_V") ? atoi(getenv("UPSP_FUSED_V")) : 3;
+#define FUSED23(NCAM)                                                              \
+  if (fused_v == 2) k_project_fused2<NCAM, 128><<<g2, 128, 0, c->stream>>>(fa);    \
+  else k_project_fused3<NCAM, 128><<<g2, 128, 0, c->stream>>>(fa)
+      // experiment knobs (one camera): UPSP_FUSED_BS nodes per block, UPSP_FUSED_OCC resident blocks per SM
+      static const int f3_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 128;
+      static const int f3_occ = getenv("UPSP_FUSED_OCC") ? atoi(getenv("UPSP_FUSED_OCC")) : 0;
+      if (fa.n_cams == 1 && fused_v == 3 && (f3_bs != 128 || f3_occ != 0)) {
+        if (f3_bs == 128 && f3_occ == 10) k_project_fused3<1, 128, 10><<<g2, 128, 0, c->stream>>>(fa);
+        else if (f3_bs == 128 && f3_occ == 12) k_project_fused3<1, 128, 12><<<g2, 128, 0, c->stream>>>(fa);
+        else if (f3_bs == 64 && f3_occ == 20) k_project_fused3<1, 64, 20><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
+        else if (f3_bs == 64 && f3_occ == 24) k_project_fused3<1, 64, 24><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
+        else if (f3_bs == 64) k_project_fused3<1, 64, 16><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
+        else if (f3_bs == 256 && f3_occ == 5) k_project_fused3<1, 256, 5><<<cdiv(c->N, 256), 256, 0, c->stream>>>(fa);
+        else if (f3_bs == 256) k_project_fused3<1, 256, 4><<<cdiv(c->N, 256), 256, 0, c->stream>>>(fa);
+        else k_project_fused3<1, 128, 8><<<g2, 128, 0, c->stream>>>(fa);
+        KCHECK(c);
+        KEND();
+        return UPSP_OK;
+      }
+      switch (fa.n_cams) {
+        case 1: FUSED23(1); break;
+        case 2: FUSED23(2); break;
+        case 3: FUSED23(3); break;
+        case 4: FUSED23(4); break;
+        case 5: FUSED23(5); break;
+        case 6: FUSED23(6); break;
+        case 7: FUSED23(7); break;
+        default: FUSED23(8); break;
+      }
+#undef FUSED23
+      KCHECK(c);
+      KEND();
+      return UPSP_OK;
+    }
     switch (fa.n_cams) {
       case 1: FUSED_LAUNCH(1); break;
       case 2: FUSED_LAUNCH(2); break;
