@@ -276,9 +276,15 @@ def test_chain_spatial_filter(up, orc, gpu, kind, ksize, patches):
         g.set_filter(1, 9)          # gaussian sizes beyond OpenCV's fixed kernels are not built
 
 
-def test_staged_projection_variant_matches(up, orc, gpu):
-    """UPSP_STAGED=1 selects the experimental cp.async shared-memory variant of the fused
-    projection; it must produce the same bits (run in a subprocess: the knob is read once)."""
+@pytest.mark.parametrize("env", [{"UPSP_FUSED_V1": "1"}, {"UPSP_PIPELINE": "0"}, {"UPSP_PIPELINE": "0", "UPSP_DECODE_P": "1"}],
+                         ids=["fused-v1", "no-pipeline", "persistent-decode-serial"])
+def test_kernel_variants_match(up, orc, gpu, env):
+    """The first-generation fused kernel (UPSP_FUSED_V1=1), the single-stream schedule
+    (UPSP_PIPELINE=0) and the persistent decoder outside the pipeline must produce the same bits as
+    the default path does against the oracle (subprocess: the knobs are read once).  Frames span
+    several batches so that both buffer sets of the two-stream pipeline are exercised, one frame
+    carries hot pixels, and the 96x128 frames keep npix % 32 == 0 so the persistent decoder is
+    eligible."""
     import subprocess, sys, textwrap
     from conftest import ROOT
     code = textwrap.dedent("""
@@ -286,15 +292,29 @@ def test_staged_projection_variant_matches(up, orc, gpu):
         import upsp_b200 as up
         from oracle import oracle as orc
         from chain import Case, run_gpu, run_oracle, same_bits
-        case = Case(up.synth, n_frames=40, n_nodes=6000, registration=True, patches=True, overlap=True, seed=7, fmt="p12")
-        ref = run_oracle(orc, case); got = run_gpu(up, orc, case)
-        assert same_bits(got["itrans"], ref["itrans"]) and same_bits(got["avg"], ref["avg"])
-        print("staged ok")
+        for seed, ncam in ((7, 1), (8, 2)):
+            case = Case(up.synth, n_frames=40, n_nodes=6000, n_cams=ncam, registration=True, patches=True,
+                        overlap=True, seed=seed, fmt="p12")
+            ref = run_oracle(orc, case); got = run_gpu(up, orc, case, batch_frames=8)
+            assert same_bits(got["itrans"], ref["itrans"]) and same_bits(got["avg"], ref["avg"])
+            assert same_bits(got["rms"], ref["rms"])
+        print("variant ok")
     """ % (ROOT, ROOT))
     import os
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, UPSP_STAGED="1"),
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env),
                        capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "staged ok" in r.stdout, r.stderr[-2000:]
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_phase2_mid_length_rows(up, orc, gpu):
+    """Rows whose dynamic shared memory alone is below 48 KB but static + dynamic is above it
+    (F = 8192: 32 KB + 18.5 KB) need the opt-in attribute as well: regression test for the
+    'invalid argument' launch failure."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=8192, n_nodes=40, registration=False, seed=31, height=32, width=32)
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got, orc)
 
 
 def test_streamed_column_block_reads(up, orc, gpu):

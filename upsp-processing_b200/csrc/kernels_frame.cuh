@@ -123,6 +123,84 @@ k_unpack12_scan(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __re
   hot_fix_tail(dst, rows, cols, hot_cnt, hot_pos, done, f, UPSP_HOT_MAX);
 }
 
+__device__ __noinline__ void fix_hot_frame_noinline(uint16_t* img, int rows, int cols, int n, int* pos, int min_change) {
+  fix_hot_frame(img, rows, cols, n, pos, min_change);
+}
+
+__device__ __noinline__ void note_hot_item(const uint16_t* px, size_t pix0, int thresh, int* cnt, int* pos) {
+  for (int k = 0; k < 32; ++k) note_hot(px[k], pix0 + k, thresh, cnt, pos);   // the thread's own stores
+}
+
+// Persistent variant of k_unpack12_scan for the two-stream pipeline: the decode of batch i+1 runs
+// on a second (high-priority) stream WHILE the fused projection of batch i -- which is bound by
+// instruction issue, not by HBM -- occupies most of every SM.  A small grid of long-lived blocks
+// (2 per SM) streams the packed frames with 128-bit loads: one thread-iteration = 48 packed bytes
+// -> 32 pixels -> four 16-byte stores, the next iteration's loads already in flight.  Block b
+// owns the contiguous item range [b*chunk, (b+1)*chunk) of the batch (item = 32 pixels).
+// Hot-pixel hand-over: `done[f]` counts finished items of frame f; the block that completes a
+// frame applies its fixes.  Requires npix % 32 == 0, 16-byte aligned frames (host-checked).
+__device__ __forceinline__ void unpack12_x8(uint32_t w0, uint32_t w1, uint32_t w2, uint4& o) {
+  const uint32_t v0 = __byte_perm(w0, w1, 0x1201);
+  const uint32_t v1 = __byte_perm(w0, w1, 0x4534);
+  const uint32_t v2 = __byte_perm(w1, w2, 0x3423);
+  const uint32_t v3 = __byte_perm(w2, w2, 0x2312);
+  o.x = ((v0 >> 4) & 0x00000FFFu) | (v0 & 0x0FFF0000u);
+  o.y = ((v1 >> 4) & 0x00000FFFu) | (v1 & 0x0FFF0000u);
+  o.z = ((v2 >> 4) & 0x00000FFFu) | (v2 & 0x0FFF0000u);
+  o.w = ((v3 >> 4) & 0x00000FFFu) | (v3 & 0x0FFF0000u);
+}
+
+__global__ void __launch_bounds__(256, 6)
+k_unpack12_scan_p(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __restrict__ out,
+                  size_t npix, int nframes, int thresh, int* __restrict__ hot_cnt,
+                  int* __restrict__ hot_pos, int* __restrict__ done, int rows, int cols) {
+  const unsigned ipf = (unsigned)(npix / 32);                   // items per frame
+  const unsigned total = ipf * (unsigned)nframes;               // < 2^31 (host-checked)
+  const unsigned chunk = (total + gridDim.x - 1) / gridDim.x;
+  unsigned it0 = blockIdx.x * chunk;
+  const unsigned it1 = min(total, it0 + chunk);
+  const uint32_t t2 = (uint32_t)min(thresh, 0x8000) * 0x00010001u;
+  while (it0 < it1) {
+    const unsigned f = it0 / ipf;
+    const unsigned fbeg = f * ipf;
+    const unsigned seg_end = min(it1, fbeg + ipf);
+    const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)f * in_stride);
+    uint4* dst4 = reinterpret_cast<uint4*>(out + (size_t)f * npix);
+    const unsigned iend = seg_end - fbeg;
+    for (unsigned i = it0 - fbeg + threadIdx.x; i < iend; i += 256) {
+      const uint4 b0 = ld_stream_u4(src + 3 * i), b1 = ld_stream_u4(src + 3 * i + 1), b2 = ld_stream_u4(src + 3 * i + 2);
+      const uint32_t w[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+      uint32_t hot = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 o;
+        unpack12_x8(w[3 * k], w[3 * k + 1], w[3 * k + 2], o);
+        dst4[4 * i + k] = o;
+        hot |= (((o.x | 0x80008000u) - t2) | ((o.y | 0x80008000u) - t2) |
+                ((o.z | 0x80008000u) - t2) | ((o.w | 0x80008000u) - t2));
+      }
+      if (hot & 0x80008000u)         // rare: re-read the item's 32 pixels and note the hot ones
+        note_hot_item(reinterpret_cast<const uint16_t*>(dst4 + 4 * i), (size_t)i * 32, thresh, hot_cnt + f,
+                      hot_pos + f * UPSP_HOT_STORE);
+    }
+    if (done != nullptr) {
+      __syncthreads();          // every thread's stores precede thread 0's fence (CTA causality)
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const int items = (int)(seg_end - it0);
+        if (atomicAdd(done + f, items) + items == (int)ipf) {
+          __threadfence();
+          const int n = *((volatile int*)(hot_cnt + f));
+          if (n > 0 && n <= UPSP_HOT_MAX)
+            fix_hot_frame_noinline(reinterpret_cast<uint16_t*>(dst4), rows, cols, n, hot_pos + f * UPSP_HOT_STORE,
+                                   UPSP_HOT_MIN_CHANGE);
+        }
+      }
+    }
+    it0 = seg_end;
+  }
+}
+
 // 10-bit packed (5 bytes -> 4 px) with the optional 10->12-bit table
 // (cpp/lib/CineReader.cpp:409-425).  One thread = one 5-byte group.
 __global__ void __launch_bounds__(256)

@@ -168,13 +168,11 @@ struct FusedCam {
 };
 struct FusedArgs {
   int n_cams, n_nodes, nframes, bstride, interp, skip_frame;
-  int dbg;                             // experiment switches (UPSP_FUSED_DBG): 1 no row stores, 2 taps from one hot line, 4 no statistics
   FusedCam cam[UPSP_MAX_CAMS];
   double* sum;
   double* sumsq;
   const int* perm;                     // [N] processing order: nodes sorted by pixel index (raster),
                                        // so a warp gathers from one or two image rows
-  int perm_len;                        // staged kernel: padded length of its (tile-ordered) perm
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];
@@ -433,45 +431,59 @@ k_project_fused(const FusedArgs a) {
   }
 }
 
-// ---- k_project_fused2: the lean version of the fused kernel for the hot configuration
-// (registration on, bilinear, pixels < 2^13, i.e. 12-bit containers).  Same arithmetic, same
-// results bit for bit; what changed is the instruction budget per node-frame (87 -> ~45):
+// ---- Lean fused kernels for the hot configuration (registration on, bilinear, pixels < 2^13, i.e.
+// 12-bit containers).  Same arithmetic as k_project_fused, same results bit for bit; what changed is
+// the cost per node-frame:
 //   * every address is base + 32-bit element offset (one IMAD.WIDE per load instead of 64-bit
-//     add chains); frame / table strides of the batch are warp-uniform;
+//     add chains); frame strides of the batch are warp-uniform;
 //   * the bilinear sum S = sum t_ij w_ij (integer, < 2^22) is accumulated on top of the float
 //     bit pattern of 2^23, so S never needs an int->float conversion: the float 2^23 + S times
 //     2^-10 plus (1.5 * 2^23 - 2^13) lands in [2^23, 2^24) where one FFMA rounds S/1024 half to
 //     even (OpenCV's saturate_cast<ushort>(float) = cvRound), and one FADD removes the offset;
 //   * val * v + 0 is one FFMA (x*y + 0.0 rounds once, exactly like the FMUL + FADD pair, and
 //     turns -0 into +0 the same way);
-//   * a thread stores its 4 frames of a group with one STS.128 into a [node][36] tile, and the
-//     write-out moves 4 frames per lane (LDS.128 + STG.128, 8 lanes = one 128-byte row segment).
+//   * a thread stores its 4 frames of a group with one STS.128 into a [node][frame] tile, and the
+//     write-out moves 4 frames per lane (LDS.128 + STG.128).
 // Preconditions (host-checked): batch * npix < 2^31, registration tables present, interp linear.
 template <int U>
 struct Taps2 {
   unsigned t00[U], t01[U], t10[U], t11[U];
 };
 
-template <int U>
-__device__ __forceinline__ void fused2_cam_group(const FusedCam& cam, int code, unsigned px, unsigned pyw,
-                                                 unsigned b, int skip_frame, float (&v)[U]) {
-  const int2* __restrict__ tab2 = reinterpret_cast<const int2*>(cam.tab);
+// The warp coordinates of a node-frame are NOT gathered from the per-frame tables (measured: 1.3 GB
+// of L2->L1 traffic per 128-frame batch, ~1 GB of it the (adelta,bdelta)[x] table that every image
+// row's nodes re-read, and two dependent global round trips per group):
+//   * (adelta, bdelta)[x] = cvRound(M0*x*1024), cvRound(M3*x*1024) are evaluated in the thread
+//     (DMUL + F2I.S32.F64, exactly k_warp_tables' expression: M*1024 is an exact scaling) from the
+//     per-frame coefficient pairs staged in shared memory;
+//   * (X0, Y0)[y]: a block's nodes are consecutive in raster order, so they span a few image rows;
+//     the block copies those rows' entries into shared memory and the per-node-frame lookup is one
+//     LDS.64.  Blocks whose nodes span more than RY rows of a camera fall back to the global y-table.
+// The tap loads are then the only global loads of a group: one round trip instead of two.
+constexpr int FUSED3_RY = 4;
+
+template <int U, bool CHK = true>
+__device__ __forceinline__ void fused3_cam_group(const FusedCam& cam, int code, double dpx, const int2* __restrict__ ysrc,
+                                                 unsigned ystep, const double2* __restrict__ coef, unsigned b,
+                                                 int skip_frame, float (&v)[U]) {
   const uint16_t* __restrict__ fr = cam.frames;
-  const unsigned ts = (unsigned)(cam.W + cam.H), W = (unsigned)cam.W, npix = (unsigned)cam.npix;
+  const unsigned W = (unsigned)cam.W, npix = (unsigned)cam.npix;
   int X[U], Y[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    const unsigned tb = (b + j) * ts;
-    const int2 xa = __ldg(tab2 + (tb + px)), ya = __ldg(tab2 + (tb + pyw));
-    X[j] = ya.x + xa.x;
-    Y[j] = ya.y + xa.y;
+    const double2 cf = coef[j];
+    const int2 ya = ysrc[j * ystep];
+    X[j] = ya.x + __double2int_rn(__dmul_rn(cf.x, dpx));
+    Y[j] = ya.y + __double2int_rn(__dmul_rn(cf.y, dpx));
   }
   Taps2<U> t;
   bool all_fast = true;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int sx = X[j] >> 10, sy = Y[j] >> 10;
-    const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+    // CHK = false: the block has proven (fused4, per frame, from the corners of its pixel box) that
+    // every tap of every one of its nodes lies inside the image
+    const bool fast = !CHK || ((unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1));
     all_fast = all_fast && fast;
     const unsigned idx = (fast ? (unsigned)(sy * cam.W + sx) : 0u) + (b + j) * npix;
     const uint16_t* p0 = fr + idx;
@@ -490,8 +502,8 @@ __device__ __forceinline__ void fused2_cam_group(const FusedCam& cam, int code, 
     const unsigned sm = top * gy + 0x4B000000u + bot * fyi;          // bits of the float 2^23 + S
     v[j] = __fadd_rn(__fmaf_rn(__uint_as_float(sm), 0.0009765625f, 12574720.0f), -12582912.0f);
   }
-  const bool has_skip = (unsigned)(skip_frame - (int)b) < (unsigned)U;
-  if (!all_fast || has_skip) {
+  const bool has_skip = CHK && (unsigned)(skip_frame - (int)b) < (unsigned)U;
+  if (CHK && (!all_fast || has_skip)) {
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int sx = X[j] >> 10, sy = Y[j] >> 10;
@@ -503,201 +515,39 @@ __device__ __forceinline__ void fused2_cam_group(const FusedCam& cam, int code, 
   }
 }
 
-template <int NC, int U>
-__device__ __forceinline__ void fused2_group(const FusedArgs& a, const int (&code)[NC], const float (&val)[NC],
-                                             const unsigned (&px)[NC], const unsigned (&pyw)[NC],
-                                             bool skipped, unsigned b, float (&sol)[U]) {
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    float v[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) v[j] = 0.0f;
-    const FusedCam& cam = a.cam[c];
-    if (code[c] >= 0) {
-      fused2_cam_group<U>(cam, code[c], px[c], pyw[c], b, a.skip_frame, v);
-    } else if (code[c] <= -2) {
-      const float* p = cam.pv + (size_t)(-2 - code[c]) * a.bstride + b;
-#pragma unroll
-      for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const float cs = (code[c] == -1) ? 0.0f : __fmaf_rn(val[c], v[j], 0.0f);
-      sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
-    }
-  }
-  if (skipped) {
-#pragma unroll
-    for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
-  }
-}
+// ---- k_project_fused4: the fused kernel of the hot configuration, with warp-private output tiles.
+// A warp computes 32 nodes and writes out the same 32 nodes, so the [node][frame] staging tile is
+// private to the warp and the compute -> write-out hand-over needs __syncwarp only: the main loop
+// has no block barrier (with a block-wide tile 8 % of the warp time sat in BAR, and a block ran at
+// the pace of its slowest warp).  The per-frame tables (coefficient pairs, y-table rows) are staged once per STAGE
+// frames (the whole 128-frame batch for one camera) instead of once per 32-frame chunk.  Chunks are
+// 16 frames (64-byte row segments, two chunks fill a 128-byte line back to back), which halves the
+// tile: shared memory per block drops from 21 KB to 17 KB and the unified L1 keeps ~30 KB more for
+// the tap lines.
+constexpr int F4_CH = 16;       // frames per chunk
+constexpr int F4_TS = 20;       // tile row stride in floats (16 frames + pad; STS.128 conflict-free)
 
-template <int NC, int BS>
-__global__ void __launch_bounds__(BS)
-k_project_fused2(const FusedArgs a) {
-  constexpr int TS = 36;                              // tile row stride in floats (32 frames + pad, 16-byte aligned)
-  __shared__ __align__(16) float tile[BS * TS];       // [node][frame]
-  __shared__ float* rowp[BS];
-  const int gid = blockIdx.x * BS + threadIdx.x;
-  const bool live = gid < a.n_nodes;
-  const int n = live ? __ldg(a.perm + gid) : -1;
-  {
-    float* rp = nullptr;
-    if (live) {
-      int r = 0;
-      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
-    }
-    rowp[threadIdx.x] = rp;
-  }
-  int code[NC];
-  float val[NC];
-  unsigned px[NC], pyw[NC];
-  bool skipped = true;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    code[c] = live ? __ldg(a.cam[c].code + n) : -1;
-    val[c] = live ? __ldg(a.cam[c].val + n) : 0.0f;
-    skipped = skipped && (code[c] == -1);
-    const int W = a.cam[c].W;
-    px[c] = code[c] >= 0 ? (unsigned)(code[c] % W) : 0u;
-    pyw[c] = (unsigned)W + (code[c] >= 0 ? (unsigned)(code[c] / W) : 0u);
-  }
-  double s = 0.0, q = 0.0;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
-  float* trow = tile + threadIdx.x * TS;
-  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
-    const int nb = min(32, a.nframes - b0);
-    if (live) {
-      int u = 0;
-      for (; u + 4 <= nb; u += 4) {
-        float sol[4];
-        fused2_group<NC, 4>(a, code, val, px, pyw, skipped, (unsigned)(b0 + u), sol);
-        *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          q += (double)__fmul_rn(sol[j], sol[j]);
-          s += (double)sol[j];
-        }
-      }
-      for (; u < nb; ++u) {
-        float sol[1];
-        fused2_group<NC, 1>(a, code, val, px, pyw, skipped, (unsigned)(b0 + u), sol);
-        trow[u] = sol[0];
-        q += (double)__fmul_rn(sol[0], sol[0]);
-        s += (double)sol[0];
-      }
-    }
-    __syncthreads();
-    if (vec_ok && nb == 32) {
-      // warp w writes the block's nodes [w*32, w*32+32): 8 lanes = one node's 32 frames = 128 bytes
-      const int fq = (lane & 7) * 4;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int nl = w * 32 + it * 4 + (lane >> 3);
-        float* rp = rowp[nl];
-        if (rp != nullptr) {
-          const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
-          *reinterpret_cast<float4*>(rp + b0 + fq) = o;
-        }
-      }
-    } else if (lane < nb) {
-      for (int j = 0; j < 32; ++j) {
-        float* rp = rowp[w * 32 + j];
-        if (rp == nullptr) break;
-        rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
-      }
-    }
-    __syncthreads();
-  }
-  if (live) {
-    a.sum[n] += s;
-    a.sumsq[n] += q;
-  }
-}
-
-// ---- k_project_fused3: k_project_fused2 without the per-node-frame table gathers.
-// ncu on fused2: 1.3 GB of L2->L1 traffic per 128-frame batch, ~1 GB of it the (adelta,bdelta)[x]
-// table (every image row's nodes re-read the 8 KB x-table of every frame), two dependent global
-// round trips per group (table -> taps), issue 38 %, L1 wavefronts 43 %: latency bound.  Here
-//   * (adelta, bdelta)[x] = cvRound(M0*x*1024), cvRound(M3*x*1024) are evaluated in the thread
-//     (DMUL + F2I.S32.F64, exactly k_warp_tables' expression: M*1024 is an exact scaling) from the
-//     32 per-frame coefficient pairs of the chunk, staged in shared memory;
-//   * (X0, Y0)[y]: a block's nodes are consecutive in raster order, so they span a few image rows;
-//     the block copies those rows' entries for the chunk's 32 frames into shared memory (while the
-//     previous chunk is being written out) and the per-node-frame lookup is one LDS.64.  Blocks
-//     whose nodes span more than RY rows of a camera fall back to the global y-table.
-// The tap loads are then the only global loads of a group: one round trip instead of two.
-constexpr int FUSED3_RY = 4;
-
-template <int U>
-__device__ __forceinline__ void fused3_cam_group(const FusedCam& cam, int code, double dpx, const int2* __restrict__ ysrc,
-                                                 unsigned ystep, const double2* __restrict__ coef, unsigned b,
-                                                 int skip_frame, int dbg, float (&v)[U]) {
-  const uint16_t* __restrict__ fr = cam.frames;
-  const unsigned W = (unsigned)cam.W, npix = (unsigned)cam.npix;
-  int X[U], Y[U];
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    const double2 cf = coef[j];
-    const int2 ya = ysrc[j * ystep];
-    X[j] = ya.x + __double2int_rn(__dmul_rn(cf.x, dpx));
-    Y[j] = ya.y + __double2int_rn(__dmul_rn(cf.y, dpx));
-  }
-  Taps2<U> t;
-  bool all_fast = true;
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    const int sx = X[j] >> 10, sy = Y[j] >> 10;
-    const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
-    all_fast = all_fast && fast;
-    const unsigned idx = (dbg & 2) ? (unsigned)(sx & 63) : (fast ? (unsigned)(sy * cam.W + sx) : 0u) + (b + j) * npix;
-    const uint16_t* p0 = fr + idx;
-    const uint16_t* p1 = fr + (idx + W);
-    t.t00[j] = __ldg(p0);
-    t.t01[j] = __ldg(p0 + 1);
-    t.t10[j] = __ldg(p1);
-    t.t11[j] = __ldg(p1 + 1);
-  }
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    const unsigned fxi = ((unsigned)X[j] >> 5) & 31u, fyi = ((unsigned)Y[j] >> 5) & 31u;
-    const unsigned gx = 32u - fxi, gy = 32u - fyi;
-    const unsigned top = t.t00[j] * gx + t.t01[j] * fxi;
-    const unsigned bot = t.t10[j] * gx + t.t11[j] * fxi;
-    const unsigned sm = top * gy + 0x4B000000u + bot * fyi;          // bits of the float 2^23 + S
-    v[j] = __fadd_rn(__fmaf_rn(__uint_as_float(sm), 0.0009765625f, 12574720.0f), -12582912.0f);
-  }
-  const bool has_skip = (unsigned)(skip_frame - (int)b) < (unsigned)U;
-  if (!all_fast || has_skip) {
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int sx = X[j] >> 10, sy = Y[j] >> 10;
-      const bool fast = (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
-      const uint16_t* f2 = fr + (size_t)(b + j) * cam.npix;
-      if ((int)b + j == skip_frame) v[j] = (float)__ldg(f2 + code);
-      else if (!fast) v[j] = warp_px_slow(f2, cam.W, cam.H, X[j], Y[j], 1);
-    }
-  }
-}
-
-template <int NC, int BS, int MINB = 1024 / BS>
-__global__ void __launch_bounds__(BS, MINB)
-k_project_fused3(const FusedArgs a) {
-  constexpr int TS = 36;                              // tile row stride in floats (32 frames + pad)
+template <int NC, int BS, int GU = 4>
+__global__ void __launch_bounds__(BS, 1024 / BS)
+k_project_fused4(const FusedArgs a) {
   constexpr int RY = FUSED3_RY;
-  __shared__ __align__(16) float tile[BS * TS];       // [node][frame]
+  constexpr int S = NC == 1 ? 128 : NC == 2 ? 64 : 32;      // frames per table stage
+  constexpr int CH = F4_CH, TS = F4_TS;
+  __shared__ __align__(16) float tile[BS * TS];        // [node][frame], rows [w*32, w*32+32) private to warp w
   __shared__ float* rowp[BS];
-  __shared__ __align__(16) double2 s_coef[NC][32];    // (M0, M3) * 1024 of the chunk's frames
-  __shared__ __align__(8) int2 s_y[NC][32 * RY];      // (X0, Y0)[y0 .. y0+RY) of the chunk's frames
+  __shared__ __align__(16) double2 s_coef[NC][S];      // (M0, M3) * 1024 of the stage's frames
+  __shared__ __align__(8) int2 s_y[NC][S * RY];        // (X0, Y0)[y0 .. y0+RY) of the stage's frames
   __shared__ int s_ymin[NC], s_ymax[NC];
+  __shared__ int s_xmin[NC], s_xmax[NC];               // column range of the block's node pixels
+  __shared__ __align__(4) unsigned char s_fast[NC][S]; // per frame: all taps of all the block's nodes are interior
   const int gid = blockIdx.x * BS + threadIdx.x;
   const bool live = gid < a.n_nodes;
   const int n = live ? __ldg(a.perm + gid) : -1;
   if (threadIdx.x < NC) {
     s_ymin[threadIdx.x] = 0x7fffffff;
     s_ymax[threadIdx.x] = -1;
+    s_xmin[threadIdx.x] = 0x7fffffff;
+    s_xmax[threadIdx.x] = -1;
   }
   {
     float* rp = nullptr;
@@ -725,304 +575,179 @@ k_project_fused3(const FusedArgs a) {
     if (code[c] >= 0) {
       atomicMin(&s_ymin[c], py[c]);
       atomicMax(&s_ymax[c], py[c]);
+      atomicMin(&s_xmin[c], code[c] % W);
+      atomicMax(&s_xmax[c], code[c] % W);
     }
   }
   __syncthreads();
   int y0[NC];
   bool ysm[NC];
-  const int2* ysrc[NC];        // this thread's (X0,Y0) entry of the chunk's first frame
-  unsigned ystep[NC];          // distance (in int2) between consecutive frames' entries
+  unsigned ystep[NC];          // distance (in int2) between consecutive frames' y entries
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     y0[c] = s_ymin[c];
     ysm[c] = s_ymax[c] - y0[c] < RY;     // also true when the block has no plain-pixel node of this camera
     ystep[c] = ysm[c] ? (unsigned)RY : (unsigned)(a.cam[c].W + a.cam[c].H);
   }
-  // stage the coefficient pairs and the y-table rows of frames [b0, b0 + 32)
-  auto stage = [&](int b0) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0.0, q = 0.0;
+  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
+  float* trow = tile + threadIdx.x * TS;
+
+  for (int s0 = 0; s0 < a.nframes; s0 += S) {
+    const int ns = min(S, a.nframes - s0);
+    if (s0 > 0) __syncthreads();       // every warp is done with the previous stage's tables
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const FusedCam& cam = a.cam[c];
-      if (threadIdx.x < 32) {
-        const int f = min(b0 + (int)threadIdx.x, a.nframes - 1);
-        const float* M = cam.m6 + (size_t)f * 6;
-        s_coef[c][threadIdx.x] = make_double2((double)__ldg(M) * 1024.0, (double)__ldg(M + 3) * 1024.0);
+      for (int i = threadIdx.x; i < S; i += BS) {
+        bool fast = false;
+        if (i < ns) {
+          const float* M = cam.m6 + (size_t)(s0 + i) * 6;
+          const double2 cf = make_double2((double)__ldg(M) * 1024.0, (double)__ldg(M + 3) * 1024.0);
+          s_coef[c][i] = cf;
+          // X(x,y) = cvRound(M0 x 1024) + X0[y] is monotone in x and in y (same for Y), so over the
+          // block's pixel box it is extremal at the four corners
+          if (s_ymax[c] >= 0 && s0 + i != a.skip_frame) {
+            const int2* tab2 = reinterpret_cast<const int2*>(cam.tab);
+            const unsigned tb = (unsigned)(s0 + i) * (unsigned)(cam.W + cam.H) + (unsigned)cam.W;
+            const int2 ylo = __ldg(tab2 + (tb + (unsigned)s_ymin[c])), yhi = __ldg(tab2 + (tb + (unsigned)s_ymax[c]));
+            const double xl = (double)s_xmin[c], xh = (double)s_xmax[c];
+            const int axl = __double2int_rn(cf.x * xl), axh = __double2int_rn(cf.x * xh);
+            const int bxl = __double2int_rn(cf.y * xl), bxh = __double2int_rn(cf.y * xh);
+            fast = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int sx = (((k & 1) ? axh : axl) + ((k & 2) ? yhi.x : ylo.x)) >> 10;
+              const int sy = (((k & 1) ? bxh : bxl) + ((k & 2) ? yhi.y : ylo.y)) >> 10;
+              fast = fast && (unsigned)sx < (unsigned)(cam.W - 1) && (unsigned)sy < (unsigned)(cam.H - 1);
+            }
+          }
+        }
+        s_fast[c][i] = fast ? 1 : 0;
       }
       if (ysm[c] && s_ymax[c] >= 0) {
         const int2* tab2 = reinterpret_cast<const int2*>(cam.tab);
         const unsigned ts = (unsigned)(cam.W + cam.H);
-        for (int i = threadIdx.x; i < 32 * RY; i += BS) {
-          const int f = min(b0 + i / RY, a.nframes - 1), r = i % RY;
+        for (int i = threadIdx.x; i < ns * RY; i += BS) {
+          const int f = s0 + i / RY, r = i % RY;
           const int yy = min(y0[c] + r, cam.H - 1);
           s_y[c][i] = __ldg(tab2 + ((unsigned)f * ts + (unsigned)(cam.W + yy)));
         }
       }
     }
-  };
-  stage(0);
-  __syncthreads();
-  double s = 0.0, q = 0.0;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
-  float* trow = tile + threadIdx.x * TS;
-  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
-    const int nb = min(32, a.nframes - b0);
-    if (live) {
+    __syncthreads();
+    for (int c0 = 0; c0 < ns; c0 += CH) {
+      const int nb = min(CH, ns - c0);
+      const int b0 = s0 + c0;
+      if (live) {
+        const int2* ysrc[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-        ysrc[c] = ysm[c] ? &s_y[c][py[c] - y0[c]]
-                         : reinterpret_cast<const int2*>(a.cam[c].tab) +
-                               ((unsigned)b0 * ystep[c] + (unsigned)(a.cam[c].W + py[c]));
-      auto group = [&](auto UU, int u, float* sol) {
-        constexpr int U = decltype(UU)::value;
+        for (int c = 0; c < NC; ++c)
+          ysrc[c] = ysm[c] ? &s_y[c][c0 * RY + (py[c] - y0[c])]
+                           : reinterpret_cast<const int2*>(a.cam[c].tab) +
+                                 ((unsigned)b0 * ystep[c] + (unsigned)(a.cam[c].W + py[c]));
+        auto group = [&](auto UU, int u, float* sol) {
+          constexpr int U = decltype(UU)::value;
+          if constexpr (NC == 1) {
+            if (code[0] >= 0) {
+              float v[U];
+              bool nochk = false;
+              if constexpr (U == 4) nochk = *reinterpret_cast<const unsigned*>(&s_fast[0][c0 + u]) == 0x01010101u;
+              if (nochk)
+                fused3_cam_group<U, false>(a.cam[0], code[0], dpx[0], ysrc[0] + (unsigned)u * ystep[0], ystep[0],
+                                           &s_coef[0][c0 + u], (unsigned)(b0 + u), a.skip_frame, v);
+              else
+                fused3_cam_group<U>(a.cam[0], code[0], dpx[0], ysrc[0] + (unsigned)u * ystep[0], ystep[0],
+                                    &s_coef[0][c0 + u], (unsigned)(b0 + u), a.skip_frame, v);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          float v[U];
+              for (int j = 0; j < U; ++j) sol[j] = __fmaf_rn(val[0], v[j], 0.0f);
+            } else if (code[0] <= -2) {
+              const float* p = a.cam[0].pv + (size_t)(-2 - code[0]) * a.bstride + (b0 + u);
 #pragma unroll
-          for (int j = 0; j < U; ++j) v[j] = 0.0f;
-          const FusedCam& cam = a.cam[c];
-          if (code[c] >= 0) {
-            fused3_cam_group<U>(cam, code[c], dpx[c], ysrc[c] + (unsigned)u * ystep[c], ystep[c], &s_coef[c][u],
-                                (unsigned)(b0 + u), a.skip_frame, a.dbg, v);
-          } else if (code[c] <= -2) {
-            const float* p = cam.pv + (size_t)(-2 - code[c]) * a.bstride + (b0 + u);
+              for (int j = 0; j < U; ++j) sol[j] = __fmaf_rn(val[0], __ldg(p + j), 0.0f);
+            } else {
 #pragma unroll
-            for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
+              for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              float v[U];
+#pragma unroll
+              for (int j = 0; j < U; ++j) v[j] = 0.0f;
+              const FusedCam& cam = a.cam[c];
+              if (code[c] >= 0) {
+                bool nochk = false;
+                if constexpr (U == 4) nochk = *reinterpret_cast<const unsigned*>(&s_fast[c][c0 + u]) == 0x01010101u;
+                if (nochk)
+                  fused3_cam_group<U, false>(cam, code[c], dpx[c], ysrc[c] + (unsigned)u * ystep[c], ystep[c],
+                                             &s_coef[c][c0 + u], (unsigned)(b0 + u), a.skip_frame, v);
+                else
+                  fused3_cam_group<U>(cam, code[c], dpx[c], ysrc[c] + (unsigned)u * ystep[c], ystep[c],
+                                      &s_coef[c][c0 + u], (unsigned)(b0 + u), a.skip_frame, v);
+              } else if (code[c] <= -2) {
+                const float* p = cam.pv + (size_t)(-2 - code[c]) * a.bstride + (b0 + u);
+#pragma unroll
+                for (int j = 0; j < U; ++j) v[j] = __ldg(p + j);
+              }
+#pragma unroll
+              for (int j = 0; j < U; ++j) {
+                const float cs = (code[c] == -1) ? 0.0f : __fmaf_rn(val[c], v[j], 0.0f);
+                sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
+              }
+            }
+            if (skipped) {
+#pragma unroll
+              for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
+            }
+          }
+        };
+        int u = 0;
+        for (; u + GU <= nb; u += GU) {
+          float sol[GU];
+          group(std::integral_constant<int, GU>{}, u, sol);
+          if constexpr (GU == 4) *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
+          else if constexpr (GU == 2) *reinterpret_cast<float2*>(trow + u) = make_float2(sol[0], sol[1]);
+          else {
+#pragma unroll
+            for (int j = 0; j < GU; ++j) trow[u + j] = sol[j];
           }
 #pragma unroll
-          for (int j = 0; j < U; ++j) {
-            const float cs = (code[c] == -1) ? 0.0f : __fmaf_rn(val[c], v[j], 0.0f);
-            sol[j] = (c == 0) ? cs : __fadd_rn(sol[j], cs);
-          }
-        }
-        if (skipped) {
-#pragma unroll
-          for (int j = 0; j < U; ++j) sol[j] = __int_as_float(0x7fc00000);
-        }
-      };
-      int u = 0;
-      for (; u + 4 <= nb; u += 4) {
-        float sol[4];
-        group(std::integral_constant<int, 4>{}, u, sol);
-        *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
-        if (!(a.dbg & 4)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < GU; ++j) {
             q += (double)__fmul_rn(sol[j], sol[j]);
             s += (double)sol[j];
           }
         }
+        for (; u < nb; ++u) {
+          float sol[1];
+          group(std::integral_constant<int, 1>{}, u, sol);
+          trow[u] = sol[0];
+          q += (double)__fmul_rn(sol[0], sol[0]);
+          s += (double)sol[0];
+        }
       }
-      for (; u < nb; ++u) {
-        float sol[1];
-        group(std::integral_constant<int, 1>{}, u, sol);
-        trow[u] = sol[0];
-        q += (double)__fmul_rn(sol[0], sol[0]);
-        s += (double)sol[0];
-      }
-    }
-    __syncthreads();
-    if (b0 + 32 < a.nframes) stage(b0 + 32);      // the compute loop is done with this chunk's tables
-    if (vec_ok && nb == 32) {
-      // warp w writes the block's nodes [w*32, w*32+32): 8 lanes = one node's 32 frames = 128 bytes
-      const int fq = (lane & 7) * 4;
+      __syncwarp();
+      if (vec_ok && nb == CH) {
+        // 4 lanes = one node's 16 frames = 64 bytes; 8 nodes per pass
+        const int fq = (lane & 3) * 4;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int nl = w * 32 + it * 4 + (lane >> 3);
-        float* rp = rowp[nl];
-        if (rp != nullptr && !(a.dbg & 1)) {
-          const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
-          *reinterpret_cast<float4*>(rp + b0 + fq) = o;
-        }
-      }
-    } else if (lane < nb) {
-      for (int j = 0; j < 32; ++j) {
-        float* rp = rowp[w * 32 + j];
-        if (rp == nullptr) break;
-        rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
-      }
-    }
-    __syncthreads();
-  }
-  if (live) {
-    a.sum[n] += s;
-    a.sumsq[n] += q;
-  }
-}
-
-// ---- staged variant of the fused kernel (one camera, registration on, <= 14-bit pixels).
-// The nodes are processed in TILE order (64 x 16 pixel tiles, raster inside a tile, every tile
-// padded to whole 128-node blocks), so the pixels a block needs lie in a small rectangle that is
-// known at setup time (BlockInfo).  Per stage of `fps` frames the block copies that rectangle
-// (+ a registration margin) of the decoded frames, and the matching slices of the warp tables,
-// into shared memory with 16-byte cp.async transfers; the per-node work then runs entirely out
-// of shared memory (6 LDS instead of 6 scattered LDG per node-frame, no long-scoreboard
-// stalls).  Taps that fall outside the staged rectangle (shift larger than the margin, image
-// border) take the global slow path -- correctness never depends on the margin.
-struct BlockInfo {
-  short x0, y0;     // bounding box of the block's node pixels
-  short w, h;       // extents (w == 0: no plain-pixel node in this block)
-  short tx0, ty0;   // staged rectangle origin (tx0 multiple of 8)
-  short tw, th;     // staged extents (tw multiple of 8)
-  int fps;          // frames per stage (0: rectangle too large, use the global path)
-};
-constexpr int STAGE_MARGIN = 3;
-constexpr int STAGE_BYTES = 40 * 1024;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-template <bool INT12>
-__global__ void __launch_bounds__(128)
-k_project_staged(const FusedArgs a, const BlockInfo* __restrict__ binfo) {
-  constexpr int BS = 128;
-  extern __shared__ __align__(16) unsigned char stage[];   // [fps][th][tw] u16 | [fps][w] int2 | [fps][h] int2
-  __shared__ float tile[32][BS + 1];
-  __shared__ float* rowp[BS];
-  const FusedCam& cam = a.cam[0];
-  const int gid = blockIdx.x * BS + threadIdx.x;
-  const int n = gid < a.perm_len ? __ldg(a.perm + gid) : -1;    // perm is padded with -1
-  const bool live = n >= 0;
-  {
-    float* rp = nullptr;
-    if (live) {
-      int r = 0;
-      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
-    }
-    rowp[threadIdx.x] = rp;
-  }
-  const BlockInfo bi = binfo[blockIdx.x];
-  const int code = live ? __ldg(cam.code + n) : -1;
-  const float val = live ? __ldg(cam.val + n) : 0.0f;
-  const int W = cam.W, H = cam.H;
-  const int px = code >= 0 ? code % W : 0, py = code >= 0 ? code / W : 0;
-  const int tw = bi.tw, th = bi.th, fps = bi.fps;
-  const size_t img_bytes = (size_t)tw * th * 2;
-  uint16_t* s_img = reinterpret_cast<uint16_t*>(stage);
-  int2* s_xa = reinterpret_cast<int2*>(stage + (size_t)fps * img_bytes);
-  int2* s_ya = s_xa + (size_t)fps * bi.w;
-  const int tstride = W + H;
-  double s = 0.0, q = 0.0;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  for (int b0 = 0; b0 < a.nframes; b0 += 32) {
-    const int nb = min(32, a.nframes - b0);
-    for (int u0 = 0; u0 < nb; u0 += (fps > 0 ? fps : nb)) {
-      const int ns = fps > 0 ? min(fps, nb - u0) : nb - u0;
-      const int b = b0 + u0;
-      if (fps > 0) {
-        __syncthreads();   // previous stage fully consumed
-        // ---- stage: warp `w` copies frames w, w+4, ... of the stage; lanes walk the rectangle in
-        // 16-byte chunks (no integer divisions: the chunk cursor is advanced incrementally)
-        const int cpr = tw / 8;                                   // chunks per row
-        const int2* tb0 = reinterpret_cast<const int2*>(cam.tab) + (size_t)b * tstride;
-        for (int j = w; j < ns; j += BS / 32) {
-          const uint16_t* gsrc = cam.frames + (size_t)(b + j) * cam.npix + (size_t)bi.ty0 * W + bi.tx0;
-          uint16_t* sdst = s_img + (size_t)j * th * tw;
-          int ry = 0, cx = lane;
-          while (cx >= cpr) { cx -= cpr; ++ry; }
-          while (ry < th) {
-            cp_async16(sdst + ry * tw + cx * 8, gsrc + (size_t)ry * W + cx * 8);
-            cx += 32;
-            while (cx >= cpr) { cx -= cpr; ++ry; }
-          }
-          const int2* tb = tb0 + (size_t)j * tstride;
-          for (int k = lane; k < bi.w; k += 32) cp_async8(s_xa + j * bi.w + k, tb + bi.x0 + k);
-          for (int k = lane; k < bi.h; k += 32) cp_async8(s_ya + j * bi.h + k, tb + W + bi.y0 + k);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-      }
-      if (live) {
-        if (code >= 0) {
-#pragma unroll 4
-          for (int j = 0; j < ns; ++j) {
-            const int bj = b + j;
-            const uint16_t* fr = cam.frames + (size_t)bj * cam.npix;
-            float v;
-            if (bj == a.skip_frame) {
-              v = (float)__ldg(fr + code);
-            } else {
-              int2 xa, ya;
-              if (fps > 0) {
-                xa = s_xa[j * bi.w + (px - bi.x0)];
-                ya = s_ya[j * bi.h + (py - bi.y0)];
-              } else {
-                const int2* tb = reinterpret_cast<const int2*>(cam.tab) + (size_t)bj * tstride;
-                xa = __ldg(tb + px);
-                ya = __ldg(tb + W + py);
-              }
-              const int X = ya.x + xa.x, Y = ya.y + xa.y;
-              const int sx = X >> 10, sy = Y >> 10;
-              const int lx = sx - bi.tx0, ly = sy - bi.ty0;
-              const bool in_frame = (unsigned)sx < (unsigned)(W - 1) && (unsigned)sy < (unsigned)(H - 1);
-              const bool in_tile = fps > 0 && (unsigned)lx < (unsigned)(tw - 1) && (unsigned)ly < (unsigned)(th - 1);
-              if (a.interp == 1 && in_frame && (in_tile || fps == 0)) {
-                unsigned t00, t01, t10, t11;
-                if (in_tile) {
-                  const uint16_t* p = s_img + ((size_t)j * th + ly) * tw + lx;
-                  t00 = p[0]; t01 = p[1]; t10 = p[tw]; t11 = p[tw + 1];
-                } else {
-                  const uint16_t* p = fr + (size_t)sy * W + sx;
-                  t00 = __ldg(p); t01 = __ldg(p + 1); t10 = __ldg(p + W); t11 = __ldg(p + W + 1);
-                }
-                const int fxi = (X >> 5) & 31, fyi = (Y >> 5) & 31;
-                if (INT12) {
-                  const int gx = 32 - fxi, gy = 32 - fyi;
-                  int S = (int)t00 * (gy * gx);
-                  S += (int)t01 * (gy * fxi);
-                  S += (int)t10 * (fyi * gx);
-                  S += (int)t11 * (fyi * fxi);
-                  const int qv = S >> 10, rem = S & 1023;
-                  v = u2f_exact((uint32_t)(qv + ((rem + (qv & 1)) > 512)));
-                } else {
-                  const float fx = frac32_exact(fxi), fy = frac32_exact(fyi);
-                  const float gx = 1.0f - fx, gy = 1.0f - fy;
-                  float r = __fadd_rn(__fmul_rn((float)t00, __fmul_rn(gy, gx)), __fmul_rn((float)t01, __fmul_rn(gy, fx)));
-                  r = __fadd_rn(r, __fmul_rn((float)t10, __fmul_rn(fy, gx)));
-                  r = __fadd_rn(r, __fmul_rn((float)t11, __fmul_rn(fy, fx)));
-                  r = __fadd_rn(__fadd_rn(r, 12582912.0f), -12582912.0f);
-                  v = fminf(r, 65535.0f);
-                }
-              } else {
-                v = warp_px_slow(fr, W, H, X, Y, a.interp);
-              }
-            }
-            const float sol = __fadd_rn(0.0f, __fmul_rn(val, v));
-            tile[u0 + j][threadIdx.x] = sol;
-            q += (double)__fmul_rn(sol, sol);
-            s += (double)sol;
-          }
-        } else {
-          for (int j = 0; j < ns; ++j) {
-            float sol = __int_as_float(0x7fc00000);     // skipped node
-            if (code <= -2) sol = __fadd_rn(0.0f, __fmul_rn(val, __ldg(cam.pv + (size_t)(-2 - code) * a.bstride + b + j)));
-            tile[u0 + j][threadIdx.x] = sol;
-            q += (double)__fmul_rn(sol, sol);
-            s += (double)sol;
+        for (int it = 0; it < 4; ++it) {
+          const int nl = w * 32 + it * 8 + (lane >> 2);
+          float* rp = rowp[nl];
+          if (rp != nullptr) {
+            const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
+            *reinterpret_cast<float4*>(rp + b0 + fq) = o;
           }
         }
+      } else if (lane < nb) {
+        for (int j = 0; j < 32; ++j) {
+          float* rp = rowp[w * 32 + j];
+          if (rp != nullptr) rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
+        }
       }
+      __syncwarp();
     }
-    __syncthreads();
-    if (lane < nb) {
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-        float* rp = rowp[w * 32 + j];
-        if (rp != nullptr) rp[b0 + lane] = tile[lane][w * 32 + j];
-      }
-    }
-    __syncthreads();
   }
   if (live) {
     a.sum[n] += s;

@@ -230,6 +230,11 @@ struct Camera {
   int total_bounds = 0, total_internal = 0, max_bounds = 0;
   float* d_scratch = nullptr;
   float* d_pv = nullptr;
+  // two-stream pipeline: second set of per-batch buffers (set 0 = the members above)
+  uint16_t* d_work2 = nullptr;
+  int* d_hot_cnt2 = nullptr;
+  int* d_hot_pos2 = nullptr;
+  float* d_pv2 = nullptr;
   std::unordered_map<int, int> pix2slot;  // interior pixel -> slot of the LAST active cluster
   // spatial filter (unfused mode only)
   float *d_img32 = nullptr, *d_img32b = nullptr;
@@ -255,12 +260,16 @@ struct upsp_gpu_ctx {
   bool finalized = false, ell1 = true, fused = false;
   uint16_t* d_lut = nullptr;
   int lut_max = 0;        // largest entry of the 10->12-bit table (0 = no table)
-  int* d_perm_tile = nullptr;     // staged kernel: tile-ordered, block-padded node order
-  BlockInfo* d_binfo = nullptr;   // staged kernel: per-block pixel rectangle
-  int perm_tile_len = 0;
   int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
 
   cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+  // front-end stream (decode + hot pixels + patch of batch i+1 while the fused projection of batch i
+  // runs on `stream`); high priority so its few long-lived blocks get SM slots as soon as they free up
+  cudaStream_t stream_b = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr}, ev_tabs = nullptr;
+  bool pipelined = false;
+  long pipe_batches = 0;
+  int n_sm = 148;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
@@ -320,7 +329,7 @@ static int set_dev(const upsp_gpu_ctx* c) {
   } while (0)
 
 // sampled kernel timing: KBEGIN/KEND bracket one launch with events when `on`
-static int kprof_begin(upsp_gpu_ctx* c, bool on, int cls) {
+static int kprof_begin(upsp_gpu_ctx* c, bool on, int cls, cudaStream_t st = nullptr) {
   if (!on) return UPSP_OK;
   if (2 * c->kn + 2 > c->kev.size()) {
     if (c->kev.size() >= 16384) return UPSP_OK;  // pool exhausted: stop sampling
@@ -332,17 +341,19 @@ static int kprof_begin(upsp_gpu_ctx* c, bool on, int cls) {
     c->kcls.push_back(cls);
   }
   c->kcls[c->kn] = cls;
-  CU(cudaEventRecord(c->kev[2 * c->kn], c->stream));
+  CU(cudaEventRecord(c->kev[2 * c->kn], st ? st : c->stream));
   return UPSP_OK;
 }
-static int kprof_end(upsp_gpu_ctx* c, bool on) {
+static int kprof_end(upsp_gpu_ctx* c, bool on, cudaStream_t st = nullptr) {
   if (!on || 2 * c->kn + 2 > c->kev.size()) return UPSP_OK;
-  CU(cudaEventRecord(c->kev[2 * c->kn + 1], c->stream));
+  CU(cudaEventRecord(c->kev[2 * c->kn + 1], st ? st : c->stream));
   c->kn++;
   return UPSP_OK;
 }
 #define KBEGIN(cls) TRY(kprof_begin(c, prof, cls))
 #define KEND() TRY(kprof_end(c, prof))
+#define KBEGIN_ON(cls, st) TRY(kprof_begin(c, prof, cls, st))
+#define KEND_ON(st) TRY(kprof_end(c, prof, st))
 
 template <typename T>
 static int dmalloc(T** p, size_t count) {
@@ -411,6 +422,17 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, hi));
+      for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_back[i], cudaEventDisableTiming));
+      }
+      CU(cudaEventCreateWithFlags(&c->ev_tabs, cudaEventDisableTiming));
+      CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_proc, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev_a));
@@ -474,6 +496,10 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
 static void free_camera(Camera& cam) {
   cudaFree(cam.d_in);
   cudaFree(cam.d_work);
+  cudaFree(cam.d_work2);
+  cudaFree(cam.d_hot_cnt2);
+  cudaFree(cam.d_hot_pos2);
+  cudaFree(cam.d_pv2);
   cudaFree(cam.d_warp);
   cudaFree(cam.d_hot_cnt);
   cudaFree(cam.d_hot_pos);
@@ -507,6 +533,7 @@ static void free_camera(Camera& cam) {
 extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (!c) return UPSP_OK;
   cudaSetDevice(c->cfg.device);
+  if (c->stream_b) cudaStreamSynchronize(c->stream_b);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
@@ -515,8 +542,6 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   for (auto& cam : c->cams) free_camera(cam);
   cudaFree(c->d_lut);
   cudaFree(c->d_perm);
-  cudaFree(c->d_perm_tile);
-  cudaFree(c->d_binfo);
   cudaFree(c->d_intensity);
   if (c->shared_vmm.handle) vmm_free(c->shared_vmm); else cudaFree(c->d_shared);
   if (c->ptrans_owned) cudaFree(c->d_ptrans);
@@ -544,6 +569,12 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   for (auto& r : c->proc_recs) if (r.ev) cudaEventDestroy(r.ev);
   for (auto e : c->kev) cudaEventDestroy(e);
   if (c->ev_pb) cudaEventDestroy(c->ev_pb);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_front[i]) cudaEventDestroy(c->ev_front[i]);
+    if (c->ev_back[i]) cudaEventDestroy(c->ev_back[i]);
+  }
+  if (c->ev_tabs) cudaEventDestroy(c->ev_tabs);
+  if (c->stream_b) cudaStreamDestroy(c->stream_b);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
@@ -830,6 +861,11 @@ static int finalize(upsp_gpu_ctx* c) {
     for (int n = 0; n < N && c->ell1; ++n)
       if (k.rowptr[n + 1] - k.rowptr[n] > 1) c->ell1 = false;
   c->fused = c->ell1 && c->cfg.keep_frame_major == 0 && c->filter.kind == 0;
+  // two-stream pipeline: front end (decode, hot pixels, patch) of batch i+1 overlaps the fused
+  // projection of batch i.  Not with the device ECC solve (its blur/moment kernels want the whole
+  // GPU) and not in the unfused modes.  UPSP_PIPELINE=0 turns it off.
+  c->pipelined = c->fused && c->registration != UPSP_REG_PIXEL &&
+                 !(getenv("UPSP_PIPELINE") && atoi(getenv("UPSP_PIPELINE")) == 0);
   std::vector<float> cov(N, 0.0f);
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
@@ -883,6 +919,11 @@ static int finalize(upsp_gpu_ctx* c) {
     TRY(dmalloc(&k.d_work, (size_t)c->batch * k.npix));
     TRY(dmalloc(&k.d_hot_cnt, (size_t)2 * c->batch));   // [hot counts | finished-block tickets]
     TRY(dmalloc(&k.d_hot_pos, (size_t)c->batch * UPSP_HOT_STORE));
+    if (c->pipelined) {
+      TRY(dmalloc(&k.d_work2, (size_t)c->batch * k.npix));
+      TRY(dmalloc(&k.d_hot_cnt2, (size_t)2 * c->batch));
+      TRY(dmalloc(&k.d_hot_pos2, (size_t)c->batch * UPSP_HOT_STORE));
+    }
     if (c->registration != UPSP_REG_NONE) {
       if (!c->fused) TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
       TRY(dmalloc(&k.d_tab, (size_t)std::max(c->F_local, 1) * (2 * k.W + 2 * k.H)));
@@ -911,6 +952,7 @@ static int finalize(upsp_gpu_ctx* c) {
     }
     if (use_patch && k.has_patches) {
       TRY(dmalloc(&k.d_pv, (size_t)std::max(k.total_internal, 1) * c->batch));
+      if (c->pipelined) TRY(dmalloc(&k.d_pv2, (size_t)std::max(k.total_internal, 1) * c->batch));
     }
     if (c->filter.kind) {
       if (use_patch && k.has_patches) {
@@ -949,75 +991,6 @@ static int finalize(upsp_gpu_ctx* c) {
     std::vector<int> perm(N);
     for (int i = 0; i < N; ++i) perm[i] = keyed[i].second;
     TRY(upload(&c->d_perm, perm.data(), perm.size()));
-    // staged kernel (one camera, W % 8 == 0): tile order (64 x 16 px tiles, raster inside), every
-    // tile padded to whole 128-node blocks; per block the pixel rectangle to stage
-    const Camera& k0 = c->cams[0];
-    if (c->cams.size() == 1 && (k0.W % 8) == 0 && (k0.npix % 8) == 0 && k0.W < 32760 && k0.H < 32760) {
-      const int TW = 64, TH = 16, BS = 128;
-      const int ntx = (k0.W + TW - 1) / TW;
-      std::vector<std::pair<uint64_t, int>> tk(N);
-      for (int n = 0; n < N; ++n) {
-        const int sn = c->remap.empty() ? n : c->remap[n];
-        uint64_t key = ~0ull;
-        if (k0.rowptr[sn + 1] > k0.rowptr[sn]) {
-          const int col = k0.col[k0.rowptr[sn]];
-          const int x = col % k0.W, y = col / k0.W;
-          key = ((uint64_t)((y / TH) * ntx + x / TW) << 32) | (uint32_t)col;
-        }
-        tk[n] = {key, n};
-      }
-      std::sort(tk.begin(), tk.end());
-      std::vector<int> pt;
-      pt.reserve(N + N / 8);
-      uint64_t cur_tile = ~0ull - 1;
-      for (int i = 0; i < N; ++i) {
-        const uint64_t tile = tk[i].first == ~0ull ? ~0ull : (tk[i].first >> 32);
-        if (tile != cur_tile) {
-          while (pt.size() % BS) pt.push_back(-1);
-          cur_tile = tile;
-        }
-        pt.push_back(tk[i].second);
-      }
-      while (pt.size() % BS) pt.push_back(-1);
-      const int nblocks = (int)pt.size() / BS;
-      std::vector<BlockInfo> bis(nblocks);
-      // device-side code of a node (patched pixels carry no plain pixel)
-      auto plain_col = [&](int n) -> int {
-        const int sn = c->remap.empty() ? n : c->remap[n];
-        if (k0.rowptr[sn + 1] <= k0.rowptr[sn]) return -1;
-        const int col = k0.col[k0.rowptr[sn]];
-        if (use_patch && k0.has_patches && k0.pix2slot.count(col)) return -1;
-        return col;
-      };
-      for (int b = 0; b < nblocks; ++b) {
-        int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
-        for (int i = 0; i < BS; ++i) {
-          const int n = pt[(size_t)b * BS + i];
-          const int col = n >= 0 ? plain_col(n) : -1;
-          if (col < 0) continue;
-          const int x = col % k0.W, y = col / k0.W;
-          x0 = std::min(x0, x); x1 = std::max(x1, x);
-          y0 = std::min(y0, y); y1 = std::max(y1, y);
-        }
-        BlockInfo bi{};
-        if (x1 >= 0) {
-          bi.x0 = (short)x0; bi.y0 = (short)y0;
-          bi.w = (short)(x1 - x0 + 1); bi.h = (short)(y1 - y0 + 1);
-          const int tx0 = std::max(0, x0 - STAGE_MARGIN) & ~7;
-          const int tx1 = std::min(k0.W, (x1 + STAGE_MARGIN + 2 + 7) & ~7);
-          const int ty0 = std::max(0, y0 - STAGE_MARGIN), ty1 = std::min(k0.H, y1 + STAGE_MARGIN + 2);
-          bi.tx0 = (short)tx0; bi.ty0 = (short)ty0;
-          bi.tw = (short)(tx1 - tx0); bi.th = (short)(ty1 - ty0);
-          const size_t per_frame = (size_t)bi.tw * bi.th * 2 + (size_t)bi.w * 8 + (size_t)bi.h * 8;
-          int fps = (int)std::min<size_t>(32, STAGE_BYTES / per_frame);
-          bi.fps = fps >= 4 ? (fps & ~3) : 0;
-        }
-        bis[b] = bi;
-      }
-      TRY(upload(&c->d_perm_tile, pt.data(), pt.size()));
-      TRY(upload(&c->d_binfo, bis.data(), bis.size()));
-      c->perm_tile_len = (int)pt.size();
-    }
   }
   // big buffers that depend on the mode
   {
@@ -1150,7 +1123,7 @@ static int ecc_run_batch(upsp_gpu_ctx* c, Camera& k, int off, int nb) {
 }
 
 // one batch: local frames [off, off+nb)
-static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
+static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   ProjArgs pa{};
   pa.n_cams = (int)c->cams.size();
   pa.n_nodes = c->N;
@@ -1163,26 +1136,42 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   const int slot = off % c->capacity;
   REQUIRE(slot + nb <= c->capacity, UPSP_ERR_STATE, "batch wraps the input ring");
   const bool prof = c->sample_every > 0 && (c->batch_counter++ % c->sample_every) == 0;
+  // pipeline: buffer set `bs`, front end on stream SB; it may start once the fused kernel that last
+  // read this buffer set (two batches ago) is done
+  const int bs = c->pipelined ? (int)(c->pipe_batches & 1) : 0;
+  cudaStream_t SB = c->pipelined ? c->stream_b : c->stream;
+  if (c->pipelined) CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
     REQUIRE(k.format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
+    uint16_t* const w_work = bs ? k.d_work2 : k.d_work;
+    int* const w_hot_cnt = bs ? k.d_hot_cnt2 : k.d_hot_cnt;
+    int* const w_hot_pos = bs ? k.d_hot_pos2 : k.d_hot_pos;
+    float* const w_pv = bs ? k.d_pv2 : k.d_pv;
     const int thresh = c->hot_fix ? UPSP_HOT_THRESH : 0x7fffffff;
-    CU(cudaMemsetAsync(k.d_hot_cnt, 0, (size_t)2 * c->batch * sizeof(int), c->stream));
-    int* done = c->hot_fix ? k.d_hot_cnt + c->batch : nullptr;
+    CU(cudaMemsetAsync(w_hot_cnt, 0, (size_t)2 * c->batch * sizeof(int), SB));
+    int* done = c->hot_fix ? w_hot_cnt + c->batch : nullptr;
     const uint8_t* in = k.d_in + (size_t)slot * k.frame_bytes;
-    KBEGIN(0);
-    if (k.format == UPSP_PIX_PACKED12) {
-      k_unpack12_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
-          in, k.frame_bytes, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
+    KBEGIN_ON(0, SB);
+    static const int decode_p = getenv("UPSP_DECODE_P") ? atoi(getenv("UPSP_DECODE_P")) : -1;
+    const bool persistent = (decode_p < 0 ? c->pipelined : decode_p != 0) && k.format == UPSP_PIX_PACKED12 &&
+                            k.npix % 32 == 0 && k.frame_bytes % 16 == 0 && (k.npix / 32) * (size_t)nb < ((size_t)1 << 31);
+    if (persistent) {
+      static const int decode_bpsm = getenv("UPSP_DECODE_BPSM") ? atoi(getenv("UPSP_DECODE_BPSM")) : 2;
+      k_unpack12_scan_p<<<c->n_sm * decode_bpsm, 256, 0, SB>>>(in, k.frame_bytes, w_work, k.npix, nb, thresh,
+                                                              w_hot_cnt, w_hot_pos, done, k.H, k.W);
+    } else if (k.format == UPSP_PIX_PACKED12) {
+      k_unpack12_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, SB>>>(
+          in, k.frame_bytes, w_work, k.npix, thresh, w_hot_cnt, w_hot_pos, done, k.H, k.W);
     } else if (k.format == UPSP_PIX_PACKED10) {
-      k_unpack10_scan<<<dim3(cdiv(cdiv(k.npix, 4), 256), nb), 256, 0, c->stream>>>(
-          in, k.frame_bytes, k.d_work, k.npix, c->d_lut, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
+      k_unpack10_scan<<<dim3(cdiv(cdiv(k.npix, 4), 256), nb), 256, 0, SB>>>(
+          in, k.frame_bytes, w_work, k.npix, c->d_lut, thresh, w_hot_cnt, w_hot_pos, done, k.H, k.W);
     } else {
-      k_copy16_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, c->stream>>>(
-          (const uint16_t*)in, k.npix, k.d_work, k.npix, thresh, k.d_hot_cnt, k.d_hot_pos, done, k.H, k.W);
+      k_copy16_scan<<<dim3(cdiv(cdiv(k.npix, 8), 256), nb), 256, 0, SB>>>(
+          (const uint16_t*)in, k.npix, w_work, k.npix, thresh, w_hot_cnt, w_hot_pos, done, k.H, k.W);
     }
     KCHECK(c);
-    KEND();
+    KEND_ON(SB);
     const bool reg = c->registration != UPSP_REG_NONE;
     if (c->registration == UPSP_REG_PIXEL) {
       TRY(ecc_run_batch(c, k, off, nb));
@@ -1191,13 +1180,13 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       KCHECK(c);
     }
     const int* tabs = reg ? k.d_tab + (size_t)off * (2 * k.W + 2 * k.H) : nullptr;   // this batch's tables
-    const uint16_t* cur = k.d_work;
+    const uint16_t* cur = w_work;
     // global frame 0 is never registered (psp_process.cpp:1777)
     const int skip_frame = (c->f0 + off == 0) ? 0 : -1;
     if (reg && !c->fused) {
       KBEGIN(2);
       k_warp_affine8_u16<<<dim3(cdiv(k.W, 1024), k.H, nb), 128, 0, c->stream>>>(
-          k.d_work, k.d_warp, k.W, k.H, tabs, c->interp, skip_frame);
+          w_work, k.d_warp, k.W, k.H, tabs, c->interp, skip_frame);
       KCHECK(c);
       KEND();
       cur = k.d_warp;
@@ -1208,16 +1197,16 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       REQUIRE(sm <= 200 * 1024, UPSP_ERR_INVALID, "patch cluster with %d boundary pixels is too large", k.max_bounds);
       if (sm > 48 * 1024)
         CU(cudaFuncSetAttribute(k_patch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      KBEGIN(3);
+      KBEGIN_ON(3, SB);
       for (size_t l = 0; l + 1 < k.level_off.size(); ++l) {
         const int ncl = k.level_off[l + 1] - k.level_off[l];
         if (!ncl) continue;
-        k_patch<<<dim3(ncl, cdiv(nb, PATCH_WARPS)), 32 * PATCH_WARPS, sm, c->stream>>>(
+        k_patch<<<dim3(ncl, cdiv(nb, PATCH_WARPS)), 32 * PATCH_WARPS, sm, SB>>>(
             k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, k.W, k.H,
-            (reg && c->fused) ? tabs : nullptr, c->interp, skip_frame, nb, c->batch, k.d_pv);
+            (reg && c->fused) ? tabs : nullptr, c->interp, skip_frame, nb, c->batch, w_pv);
         KCHECK(c);
       }
-      KEND();
+      KEND_ON(SB);
     }
     const float* cur32 = nullptr;
     if (c->filter.kind) {   // only reachable in the unfused mode
@@ -1227,7 +1216,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
         k_u16_to_f32<<<cdiv(tot, 256), 256, 0, c->stream>>>(cur, k.d_img32, tot);
         KCHECK(c);
         k_scatter_patched<<<dim3(cdiv(k.total_internal, 256), nb), 256, 0, c->stream>>>(
-            k.d_pv, k.d_slot_pix, k.total_internal, c->batch, nb, k.npix, k.d_img32);
+            w_pv, k.d_slot_pix, k.total_internal, c->batch, nb, k.npix, k.d_img32);
         KCHECK(c);
         if (c->filter.kind == 1) {
           k_filter_f32<<<fg, 256, 0, c->stream>>>(k.d_img32, k.d_img32b, k.W, k.H, c->filter, 0);
@@ -1249,20 +1238,24 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     pa.cam[ci].frames = cur;
     pa.cam[ci].frames32 = cur32;
     pa.cam[ci].npix = k.npix;
-    pa.cam[ci].pv = (patch && !c->filter.kind) ? k.d_pv : nullptr;
+    pa.cam[ci].pv = (patch && !c->filter.kind) ? w_pv : nullptr;
     pa.cam[ci].code = k.d_code;
     pa.cam[ci].val = k.d_val;
     pa.cam[ci].rowptr = k.d_rowptr;
-    fa.cam[ci].frames = k.d_work;
+    fa.cam[ci].frames = w_work;
     fa.cam[ci].npix = k.npix;
     fa.cam[ci].W = k.W;
     fa.cam[ci].H = k.H;
     fa.cam[ci].tab = tabs;
     fa.cam[ci].m6 = reg ? k.d_m6 + (size_t)off * 6 : nullptr;
-    fa.cam[ci].pv = patch ? k.d_pv : nullptr;
+    fa.cam[ci].pv = patch ? w_pv : nullptr;
     fa.cam[ci].code = k.d_code;
     fa.cam[ci].val = k.d_val;
     fa.skip_frame = skip_frame;
+  }
+  if (c->pipelined) {
+    CU(cudaEventRecord(c->ev_front[bs], SB));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_front[bs], 0));
   }
   if (c->fused) {
     fa.n_cams = pa.n_cams;
@@ -1270,8 +1263,6 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     fa.nframes = nb;
     fa.bstride = c->batch;
     fa.interp = c->interp;
-    static const int fused_dbg = getenv("UPSP_FUSED_DBG") ? atoi(getenv("UPSP_FUSED_DBG")) : 0;
-    fa.dbg = fused_dbg;
     fa.sum = c->d_sum;
     fa.sumsq = c->d_sumsq;
     fa.perm = c->d_perm;
@@ -1284,29 +1275,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     fa.node_start[c->R] = c->N;
     const unsigned g = cdiv(c->N, 256);
-    // experimental (UPSP_STAGED=1): shared-memory staged variant.  Measured SLOWER in round 1
-    // (0.77 vs 0.29 ms per 128-frame batch: 212 instructions per node-frame, 12 warps/SM), so the
-    // register-path kernel below stays the default; see DESIGN.md section 7.
-    static const bool use_staged = getenv("UPSP_STAGED") && atoi(getenv("UPSP_STAGED"));
     KBEGIN(4);
-    if (use_staged && c->d_perm_tile && c->registration != UPSP_REG_NONE && c->interp == UPSP_INTERP_LINEAR) {
-      bool i12 = true;
-      for (auto& k : c->cams)
-        i12 = i12 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 16384));
-      fa.perm = c->d_perm_tile;
-      fa.perm_len = c->perm_tile_len;
-      const unsigned gs = (unsigned)(c->perm_tile_len / 128);
-      if (i12) {
-        CU(cudaFuncSetAttribute(k_project_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
-        k_project_staged<true><<<gs, 128, STAGE_BYTES, c->stream>>>(fa, c->d_binfo);
-      } else {
-        CU(cudaFuncSetAttribute(k_project_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
-        k_project_staged<false><<<gs, 128, STAGE_BYTES, c->stream>>>(fa, c->d_binfo);
-      }
-      KCHECK(c);
-      KEND();
-      return UPSP_OK;
-    }
     const bool regk = c->registration != UPSP_REG_NONE;
     static const int fused_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 128;   // tuning knob: nodes per block
     bool int12 = true;   // every camera's container guarantees pixels < 2^14
@@ -1318,8 +1287,9 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   else if (regk && int12) k_project_fused<NCAM, true, true, 4, 256><<<g, 256, 0, c->stream>>>(fa);   \
   else if (regk) k_project_fused<NCAM, true, false, 4, 256><<<g, 256, 0, c->stream>>>(fa);           \
   else k_project_fused<NCAM, false, false, 8, 256><<<g, 256, 0, c->stream>>>(fa)
-    // lean kernel for the hot configuration (bilinear registration, 12-bit containers); UPSP_FUSED_V1=1
-    // keeps the first-generation kernel for A/B measurements
+    // hot configuration (bilinear registration, 12-bit containers): k_project_fused4.  UPSP_FUSED_V1=1
+    // keeps the first-generation kernel (A/B measurements, and the parity test that pins the two to
+    // identical bits)
     static const bool fused_v1 = getenv("UPSP_FUSED_V1") && atoi(getenv("UPSP_FUSED_V1"));
     bool pix13 = true;   // pixels < 2^13: the bilinear sum fits under the float bit pattern of 2^23
     size_t max_elems = 0;
@@ -1330,38 +1300,16 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
     }
     if (!fused_v1 && regk && pix13 && c->interp == UPSP_INTERP_LINEAR && max_elems < ((size_t)1 << 31)) {
       const unsigned g2 = cdiv(c->N, 128);
-      // UPSP_FUSED_V=2: table-gather variant (k_project_fused2); default: k_project_fused3
-      static const int fused_v = getenv("UPSP_FUSED_V") ? atoi(getenv("UPSP_FUSED_V")) : 3;
-#define FUSED23(NCAM)                                                              \
-  if (fused_v == 2) k_project_fused2<NCAM, 128><<<g2, 128, 0, c->stream>>>(fa);    \
-  else k_project_fused3<NCAM, 128><<<g2, 128, 0, c->stream>>>(fa)
-      // experiment knobs (one camera): UPSP_FUSED_BS nodes per block, UPSP_FUSED_OCC resident blocks per SM
-      static const int f3_bs = getenv("UPSP_FUSED_BS") ? atoi(getenv("UPSP_FUSED_BS")) : 128;
-      static const int f3_occ = getenv("UPSP_FUSED_OCC") ? atoi(getenv("UPSP_FUSED_OCC")) : 0;
-      if (fa.n_cams == 1 && fused_v == 3 && (f3_bs != 128 || f3_occ != 0)) {
-        if (f3_bs == 128 && f3_occ == 10) k_project_fused3<1, 128, 10><<<g2, 128, 0, c->stream>>>(fa);
-        else if (f3_bs == 128 && f3_occ == 12) k_project_fused3<1, 128, 12><<<g2, 128, 0, c->stream>>>(fa);
-        else if (f3_bs == 64 && f3_occ == 20) k_project_fused3<1, 64, 20><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
-        else if (f3_bs == 64 && f3_occ == 24) k_project_fused3<1, 64, 24><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
-        else if (f3_bs == 64) k_project_fused3<1, 64, 16><<<cdiv(c->N, 64), 64, 0, c->stream>>>(fa);
-        else if (f3_bs == 256 && f3_occ == 5) k_project_fused3<1, 256, 5><<<cdiv(c->N, 256), 256, 0, c->stream>>>(fa);
-        else if (f3_bs == 256) k_project_fused3<1, 256, 4><<<cdiv(c->N, 256), 256, 0, c->stream>>>(fa);
-        else k_project_fused3<1, 128, 8><<<g2, 128, 0, c->stream>>>(fa);
-        KCHECK(c);
-        KEND();
-        return UPSP_OK;
-      }
       switch (fa.n_cams) {
-        case 1: FUSED23(1); break;
-        case 2: FUSED23(2); break;
-        case 3: FUSED23(3); break;
-        case 4: FUSED23(4); break;
-        case 5: FUSED23(5); break;
-        case 6: FUSED23(6); break;
-        case 7: FUSED23(7); break;
-        default: FUSED23(8); break;
+        case 1: k_project_fused4<1, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 2: k_project_fused4<2, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 3: k_project_fused4<3, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 4: k_project_fused4<4, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 5: k_project_fused4<5, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 6: k_project_fused4<6, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 7: k_project_fused4<7, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        default: k_project_fused4<8, 128><<<g2, 128, 0, c->stream>>>(fa); break;
       }
-#undef FUSED23
       KCHECK(c);
       KEND();
       return UPSP_OK;
@@ -1391,6 +1339,15 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   return UPSP_OK;
 }
 
+static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
+  TRY(process_batch_impl(c, off, nb));
+  if (c->pipelined) {   // the projection of this batch is the last reader of its buffer set
+    CU(cudaEventRecord(c->ev_back[c->pipe_batches & 1], c->stream));
+    c->pipe_batches++;
+  }
+  return UPSP_OK;
+}
+
 extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
   ENTER(c);
   REQUIRE(off >= 0 && count >= 0 && off + count <= c->F_local, UPSP_ERR_INVALID,
@@ -1409,6 +1366,11 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
           k.d_m6 + (size_t)off * 6, count, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
       KCHECK(c);
     }
+  }
+  if (c->pipelined) {   // the front-end stream needs the pushed frames and (patch kernel) the warp tables
+    CU(cudaStreamWaitEvent(c->stream_b, c->ev_push, 0));
+    CU(cudaEventRecord(c->ev_tabs, c->stream));
+    CU(cudaStreamWaitEvent(c->stream_b, c->ev_tabs, 0));
   }
   int done = 0;
   while (done < count) {
@@ -1599,7 +1561,8 @@ template <int NC, bool ROW_SMEM, int CL>
 static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
   constexpr int NT = 512;
   auto kern = k_phase2<NC, ROW_SMEM, NT, CL>;
-  if (smem > 48 * 1024)
+  // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
+  if (smem > 24 * 1024)
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)a.n_local * CL);
@@ -1622,7 +1585,8 @@ static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
   constexpr int NT = 512;
   auto kern = k_phase2_sym<NC, NT, CL>;
   const size_t smem = (size_t)(a.F / CL) * sizeof(float);
-  if (smem > 48 * 1024)
+  // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
+  if (smem > 24 * 1024)
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)a.n_local * CL);
