@@ -63,7 +63,7 @@ typedef struct {
   int rank, n_ranks;  /* my_mpi_rank, num_mpi_ranks: frame / node slices by apportion()   */
   int frame_capacity; /* device input slots per camera; 0 => this rank's frame count
                          (whole slice resident).  Frame `o` lives in slot o % capacity.  */
-  int batch_frames;   /* frames per internal launch batch; 0 => default (128)             */
+  int batch_frames;   /* frames per internal launch batch; 0 => default (256)             */
   int pressure_aliases_intensity; /* 1: pressure_transpose reuses the frame-major
                          intensity storage when that buffer exists (saves one F x N buffer);
                          0: separate buffer                                              */

@@ -176,7 +176,21 @@ struct FusedArgs {
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];
+  // staged exchange (n_ranks > 1, pipelined): rows of nodes owned by OTHER ranks are written to a local
+  // [N][stage_stride] staging block (column = frame inside the batch) and shipped to their owners
+  // by copy engines afterwards, so the projection never waits on NVLink stores.  nullptr: rows go
+  // straight into the peer-mapped buffers.
+  float* stage;
+  int stage_stride, rank;
 };
+
+// where a block writes node n's row segment of this batch (frame b of the batch at [b])
+__device__ __forceinline__ float* fused_row_ptr(const FusedArgs& a, int n) {
+  int r = 0;
+  while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+  if (a.stage != nullptr && r != a.rank) return a.stage + (size_t)n * a.stage_stride;
+  return a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+}
 
 // border / nearest-neighbour pixels: rare, kept out of the hot loop's code
 __device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W, int H, int X, int Y,
@@ -308,13 +322,7 @@ k_project_fused(const FusedArgs a) {
   const bool live = gid < a.n_nodes;
   const int n = live ? __ldg(a.perm + gid) : -1;
   {
-    float* rp = nullptr;
-    if (live) {
-      int r = 0;
-      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
-    }
-    rowp[threadIdx.x] = rp;
+    rowp[threadIdx.x] = live ? fused_row_ptr(a, n) : nullptr;
   }
   int code[NC];
   const int2* ptx[NC];
@@ -524,15 +532,15 @@ __device__ __forceinline__ void fused3_cam_group(const FusedCam& cam, int code, 
 // 16 frames (64-byte row segments, two chunks fill a 128-byte line back to back), which halves the
 // tile: shared memory per block drops from 21 KB to 17 KB and the unified L1 keeps ~30 KB more for
 // the tap lines.
-constexpr int F4_CH = 16;       // frames per chunk
-constexpr int F4_TS = 20;       // tile row stride in floats (16 frames + pad; STS.128 conflict-free)
-
-template <int NC, int BS, int GU = 4>
+// CH = 32 (128-byte row segments) is used when rows go straight into peer memory: NVLink write
+// efficiency halves with 64-byte segments (measured at 8 GPUs: 0.73 vs 0.40 ms per 128 frames).
+template <int NC, int BS, int CH = 16, int GU = 4>
 __global__ void __launch_bounds__(BS, 1024 / BS)
 k_project_fused4(const FusedArgs a) {
   constexpr int RY = FUSED3_RY;
   constexpr int S = NC == 1 ? 128 : NC == 2 ? 64 : 32;      // frames per table stage
-  constexpr int CH = F4_CH, TS = F4_TS;
+  constexpr int TS = CH + 4;      // tile row stride in floats (frames + pad; STS.128 conflict-free for 20 and 36)
+  static_assert(CH == 16 || CH == 32, "chunk of 16 or 32 frames");
   __shared__ __align__(16) float tile[BS * TS];        // [node][frame], rows [w*32, w*32+32) private to warp w
   __shared__ float* rowp[BS];
   __shared__ __align__(16) double2 s_coef[NC][S];      // (M0, M3) * 1024 of the stage's frames
@@ -550,13 +558,7 @@ k_project_fused4(const FusedArgs a) {
     s_xmax[threadIdx.x] = -1;
   }
   {
-    float* rp = nullptr;
-    if (live) {
-      int r = 0;
-      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-      rp = a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
-    }
-    rowp[threadIdx.x] = rp;
+    rowp[threadIdx.x] = live ? fused_row_ptr(a, n) : nullptr;
   }
   __syncthreads();
   int code[NC];
@@ -729,11 +731,12 @@ k_project_fused4(const FusedArgs a) {
       }
       __syncwarp();
       if (vec_ok && nb == CH) {
-        // 4 lanes = one node's 16 frames = 64 bytes; 8 nodes per pass
-        const int fq = (lane & 3) * 4;
+        // LPN lanes = one node's CH frames (64 or 128 bytes); 32 / LPN nodes per pass
+        constexpr int LPN = CH / 4;
+        const int fq = (lane % LPN) * 4;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int nl = w * 32 + it * 8 + (lane >> 2);
+        for (int it = 0; it < LPN; ++it) {
+          const int nl = w * 32 + it * (32 / LPN) + lane / LPN;
           float* rp = rowp[nl];
           if (rp != nullptr) {
             const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);

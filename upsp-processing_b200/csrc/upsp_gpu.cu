@@ -270,6 +270,14 @@ struct upsp_gpu_ctx {
   bool pipelined = false;
   long pipe_batches = 0;
   int n_sm = 148;
+  // staged exchange (n_ranks > 1, pipelined): the projection writes other ranks' rows into a local
+  // staging block; copy engines ship them (one strided 2-D copy per peer and batch) on stream_x
+  float* d_stage[2] = {nullptr, nullptr};
+  int stage_stride = 0;
+  static constexpr int NX = 4;     // exchange streams: strided peer copies in flight on several copy engines
+  cudaStream_t stream_x[NX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_x[2][NX] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  bool staged_xchg = false;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
@@ -413,7 +421,7 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
   c->n0 = c->n_start[c->rank];
   c->capacity = cfg->frame_capacity > 0 ? std::min(cfg->frame_capacity, std::max(c->F_local, 1))
                                         : std::max(c->F_local, 1);
-  c->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 128;
+  c->batch = cfg->batch_frames > 0 ? cfg->batch_frames : 256;
   c->batch = std::min(c->batch, c->capacity);
   c->cams.resize(cfg->n_cams);
   *out = c;
@@ -431,6 +439,10 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
         CU(cudaEventCreateWithFlags(&c->ev_back[i], cudaEventDisableTiming));
       }
       CU(cudaEventCreateWithFlags(&c->ev_tabs, cudaEventDisableTiming));
+      for (int j = 0; j < upsp_gpu_ctx::NX; ++j) {
+        CU(cudaStreamCreateWithFlags(&c->stream_x[j], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_x[i][j], cudaEventDisableTiming));
+      }
       CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     }
     CU(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
@@ -534,6 +546,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (!c) return UPSP_OK;
   cudaSetDevice(c->cfg.device);
   if (c->stream_b) cudaStreamSynchronize(c->stream_b);
+  for (auto sx : c->stream_x) if (sx) cudaStreamSynchronize(sx);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
@@ -574,6 +587,11 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
     if (c->ev_back[i]) cudaEventDestroy(c->ev_back[i]);
   }
   if (c->ev_tabs) cudaEventDestroy(c->ev_tabs);
+  for (int i = 0; i < 2; ++i) {
+    for (auto e : c->ev_x[i]) if (e) cudaEventDestroy(e);
+    cudaFree(c->d_stage[i]);
+  }
+  for (auto sx : c->stream_x) if (sx) cudaStreamDestroy(sx);
   if (c->stream_b) cudaStreamDestroy(c->stream_b);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -992,6 +1010,18 @@ static int finalize(upsp_gpu_ctx* c) {
     for (int i = 0; i < N; ++i) perm[i] = keyed[i].second;
     TRY(upload(&c->d_perm, perm.data(), perm.size()));
   }
+  // Staged exchange or direct peer stores from the projection kernel?  Measured on 8 x B200 (NVSwitch):
+  // one GPU pair moves ~300 GB/s whichever way it is driven, and so do the copy engines in total.
+  // With 2 ranks the copy engines therefore win (the projection kernel no longer waits on NVLink
+  // stores: 82 -> 56 ms per 20k frames); with >= 3 ranks the SMs' direct stores fan out over all
+  // pairs (~570 GB/s per GPU at 8 ranks) and beat the copy engines' ~290 GB/s.  UPSP_STAGED_XCHG=0/1
+  // overrides.
+  c->staged_xchg = c->pipelined && c->R == 2;
+  if (getenv("UPSP_STAGED_XCHG")) c->staged_xchg = c->pipelined && c->R > 1 && atoi(getenv("UPSP_STAGED_XCHG")) != 0;
+  if (c->staged_xchg) {
+    c->stage_stride = (c->batch + 3) & ~3;
+    for (int i = 0; i < 2; ++i) TRY(dmalloc(&c->d_stage[i], (size_t)c->N * c->stage_stride));
+  }
   // big buffers that depend on the mode
   {
     const size_t fn = (size_t)c->F_local * c->N, nf = (size_t)c->N_local * c->F;
@@ -1269,6 +1299,11 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     fa.n_ranks = c->R;
     fa.f_total = c->F;
     fa.col0 = c->f0 + off;
+    fa.rank = c->rank;
+    fa.stage = c->staged_xchg ? c->d_stage[bs] : nullptr;
+    fa.stage_stride = c->stage_stride;
+    if (c->staged_xchg)   // copies of two batches ago are out
+      for (auto e : c->ev_x[bs]) CU(cudaStreamWaitEvent(c->stream, e, 0));
     for (int r = 0; r < c->R; ++r) {
       fa.dst[r] = reinterpret_cast<float*>(c->peer_base[r]);
       fa.node_start[r] = c->n_start[r];
@@ -1300,16 +1335,22 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     }
     if (!fused_v1 && regk && pix13 && c->interp == UPSP_INTERP_LINEAR && max_elems < ((size_t)1 << 31)) {
       const unsigned g2 = cdiv(c->N, 128);
+      // rows stored straight into peer memory (>= 3 ranks, or staging off): 128-byte segments
+      const bool seg128 = c->R > 1 && !c->staged_xchg;
+#define FUSED4(NCAM)                                                               \
+  if (seg128) k_project_fused4<NCAM, 128, 32><<<g2, 128, 0, c->stream>>>(fa);      \
+  else k_project_fused4<NCAM, 128, 16><<<g2, 128, 0, c->stream>>>(fa)
       switch (fa.n_cams) {
-        case 1: k_project_fused4<1, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 2: k_project_fused4<2, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 3: k_project_fused4<3, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 4: k_project_fused4<4, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 5: k_project_fused4<5, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 6: k_project_fused4<6, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        case 7: k_project_fused4<7, 128><<<g2, 128, 0, c->stream>>>(fa); break;
-        default: k_project_fused4<8, 128><<<g2, 128, 0, c->stream>>>(fa); break;
+        case 1: FUSED4(1); break;
+        case 2: FUSED4(2); break;
+        case 3: FUSED4(3); break;
+        case 4: FUSED4(4); break;
+        case 5: FUSED4(5); break;
+        case 6: FUSED4(6); break;
+        case 7: FUSED4(7); break;
+        default: FUSED4(8); break;
       }
+#undef FUSED4
       KCHECK(c);
       KEND();
       return UPSP_OK;
@@ -1342,7 +1383,30 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
 static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
   TRY(process_batch_impl(c, off, nb));
   if (c->pipelined) {   // the projection of this batch is the last reader of its buffer set
-    CU(cudaEventRecord(c->ev_back[c->pipe_batches & 1], c->stream));
+    const int bs = (int)(c->pipe_batches & 1);
+    CU(cudaEventRecord(c->ev_back[bs], c->stream));
+    if (c->staged_xchg) {
+      // ship the other ranks' rows: [N_s rows x nb frames] block of the staging buffer -> columns
+      // [f0+off, f0+off+nb) of rank s's node-major buffer, one strided copy per peer (copy engines)
+      constexpr int NX = upsp_gpu_ctx::NX;
+      for (int j = 0; j < NX; ++j) CU(cudaStreamWaitEvent(c->stream_x[j], c->ev_back[bs], 0));
+      // every peer's row block is cut into `parts` pieces so that NX copies are in flight at any time
+      const int parts = std::max(1, (NX + c->R - 2) / (c->R - 1));
+      int q = 0;
+      for (int d = 1; d < c->R; ++d) {
+        const int s = (c->rank + d) % c->R;
+        for (int part = 0; part < parts; ++part) {
+          const int r0 = (int)((long long)c->n_count[s] * part / parts), r1 = (int)((long long)c->n_count[s] * (part + 1) / parts);
+          if (r1 <= r0) continue;
+          float* dst = reinterpret_cast<float*>(c->peer_base[s]) + (size_t)r0 * c->F + (size_t)(c->f0 + off);
+          const float* src = c->d_stage[bs] + (size_t)(c->n_start[s] + r0) * c->stage_stride;
+          CU(cudaMemcpy2DAsync(dst, (size_t)c->F * sizeof(float), src, (size_t)c->stage_stride * sizeof(float),
+                               (size_t)nb * sizeof(float), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice,
+                               c->stream_x[q++ % NX]));
+        }
+      }
+      for (int j = 0; j < NX; ++j) CU(cudaEventRecord(c->ev_x[bs][j], c->stream_x[j]));
+    }
     c->pipe_batches++;
   }
   return UPSP_OK;
@@ -1379,6 +1443,10 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
     nb = std::min(nb, c->capacity - (o % c->capacity));
     TRY(process_batch(c, o, nb));
     done += nb;
+  }
+  if (c->staged_xchg) {   // the call is complete when the last two batches' rows have left
+    for (int i = 0; i < 2; ++i)
+      for (auto e : c->ev_x[i]) CU(cudaStreamWaitEvent(c->stream, e, 0));
   }
   CU(cudaEventRecord(c->ev_pb, c->stream));
   CU(cudaEventRecord(c->ev_proc, c->stream));
