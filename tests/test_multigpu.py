@@ -10,12 +10,11 @@ from chain import Case, cp_errors, monomial_mass, push_all, run_oracle, same_bit
 pytestmark = pytest.mark.gpu
 
 
-def _run_two_ranks(up, orc, case, keep_frame_major, same_device=False):
-    R = 2
+def _run_ranks(up, orc, case, keep_frame_major, same_device=False, R=2, **kw):
     ctxs, slices = [], []
     for r in range(R):
         g, sl = setup_ctx(up, orc, case, rank=r, n_ranks=R, device=0 if same_device else r,
-                          keep_frame_major=keep_frame_major)
+                          keep_frame_major=keep_frame_major, **kw)
         ctxs.append(g)
         slices.append(sl)
     up.connect_local(ctxs)
@@ -42,8 +41,9 @@ def _run_two_ranks(up, orc, case, keep_frame_major, same_device=False):
     res = {k: np.concatenate(v, 0) for k, v in out.items()}
     res["avg"], res["rms"], res["coverage"] = stats[0]
     # every rank must hold bit-identical phase-1 statistics (rank-ordered reduction)
-    for k in range(3):
-        assert same_bits(stats[0][k], stats[1][k])
+    for r in range(1, R):
+        for k in range(3):
+            assert same_bits(stats[0][k], stats[r][k])
     for g in ctxs:
         g.close()
     return res
@@ -58,7 +58,7 @@ def test_two_ranks_match_oracle(up, orc, gpu, keep_frame_major, same_device):
     case = Case(upsp_b200.synth, n_frames=75, n_nodes=3001, registration=True, patches=True, overlap=True,
                 seed=21, fmt="p12")
     ref = run_oracle(orc, case, n_ranks=2)
-    got = _run_two_ranks(up, orc, case, keep_frame_major, same_device)
+    got = _run_ranks(up, orc, case, keep_frame_major, same_device)
     assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
     assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact across ranks"
     assert same_bits(got["gain"], ref["gain"])
@@ -69,3 +69,21 @@ def test_two_ranks_match_oracle(up, orc, gpu, keep_frame_major, same_device):
     e_op, _ = cp_errors(case, ref, got)
     noise, _ = cp_errors(case, ref, exact)
     assert np.all(e_op <= 1e-5 + noise + cond)
+
+
+@pytest.mark.parametrize("R,staged", [(3, None), (4, "1"), (8, "3"), (8, None)])
+def test_many_ranks_one_gpu(up, orc, gpu, R, staged, monkeypatch):
+    """R ranks as R contexts on one device.  >= 3 ranks store rows straight into the owners' buffers
+    in 128-byte segments (default); UPSP_STAGED_PEERS=k sends the next k ranks' rows through the
+    staging block + copy engines instead (mixed exchange).  Small batches so that both staging
+    buffers and several exchange rounds are used."""
+    import upsp_b200
+    if staged is not None:
+        monkeypatch.setenv("UPSP_STAGED_PEERS", staged)
+    case = Case(upsp_b200.synth, n_frames=96, n_nodes=2003, registration=True, patches=True, overlap=True,
+                seed=33, fmt="p12")
+    ref = run_oracle(orc, case, n_ranks=R)
+    got = _run_ranks(up, orc, case, False, True, R=R, batch_frames=8)
+    assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
+    assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact across ranks"
+    assert same_bits(got["gain"], ref["gain"])

@@ -176,19 +176,20 @@ struct FusedArgs {
   int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
   float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
   int node_start[UPSP_MAX_RANKS + 1];
-  // staged exchange (n_ranks > 1, pipelined): rows of nodes owned by OTHER ranks are written to a local
-  // [N][stage_stride] staging block (column = frame inside the batch) and shipped to their owners
-  // by copy engines afterwards, so the projection never waits on NVLink stores.  nullptr: rows go
-  // straight into the peer-mapped buffers.
+  // staged exchange (n_ranks > 1, pipelined): rows of nodes owned by the ranks in `stage_mask` are
+  // written to a local [N][stage_stride] staging block (column = frame inside the batch) and shipped
+  // to their owners by copy engines afterwards; the other ranks' rows go straight into the
+  // peer-mapped buffers.  Copy engines and SM stores then drive NVLink side by side.
   float* stage;
   int stage_stride, rank;
+  unsigned stage_mask;                 // bit r set: rank r's rows go through the staging block
 };
 
 // where a block writes node n's row segment of this batch (frame b of the batch at [b])
 __device__ __forceinline__ float* fused_row_ptr(const FusedArgs& a, int n) {
   int r = 0;
   while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-  if (a.stage != nullptr && r != a.rank) return a.stage + (size_t)n * a.stage_stride;
+  if (a.stage != nullptr && ((a.stage_mask >> r) & 1u)) return a.stage + (size_t)n * a.stage_stride;
   return a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
 }
 

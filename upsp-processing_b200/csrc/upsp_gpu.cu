@@ -278,6 +278,8 @@ struct upsp_gpu_ctx {
   cudaStream_t stream_x[NX] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_x[2][NX] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
   bool staged_xchg = false;
+  unsigned stage_mask = 0;         // ranks whose rows travel through the staging block
+  int staged_peers = 0;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
@@ -1011,13 +1013,20 @@ static int finalize(upsp_gpu_ctx* c) {
     TRY(upload(&c->d_perm, perm.data(), perm.size()));
   }
   // Staged exchange or direct peer stores from the projection kernel?  Measured on 8 x B200 (NVSwitch):
-  // one GPU pair moves ~300 GB/s whichever way it is driven, and so do the copy engines in total.
-  // With 2 ranks the copy engines therefore win (the projection kernel no longer waits on NVLink
-  // stores: 82 -> 56 ms per 20k frames); with >= 3 ranks the SMs' direct stores fan out over all
-  // pairs (~570 GB/s per GPU at 8 ranks) and beat the copy engines' ~290 GB/s.  UPSP_STAGED_XCHG=0/1
-  // overrides.
-  c->staged_xchg = c->pipelined && c->R == 2;
-  if (getenv("UPSP_STAGED_XCHG")) c->staged_xchg = c->pipelined && c->R > 1 && atoi(getenv("UPSP_STAGED_XCHG")) != 0;
+  // one GPU pair moves ~300 GB/s whichever way it is driven, and the copy engines move ~290 GB/s per
+  // GPU in total, while the SMs' direct stores fan out over all pairs (~570 GB/s per GPU at 8 ranks)
+  // but make the projection kernel wait on NVLink.
+  //   2 ranks: copy engines win (phase 1 of 20k frames/GPU: 82 ms direct, 56 ms staged);
+  //   8 ranks: direct stores in 128-byte segments win (78.7 ms; all staged 121 ms; mixed 3 staged +
+  //            4 direct 86 ms, 2 + 5: 87 ms).
+  // So: `staged_peers` = 1 at 2 ranks, 0 otherwise; UPSP_STAGED_PEERS=k routes the next k ranks' rows
+  // through the staging block (0: all direct).
+  c->staged_peers = c->R == 2 ? 1 : 0;
+  if (getenv("UPSP_STAGED_PEERS")) c->staged_peers = std::min(std::max(atoi(getenv("UPSP_STAGED_PEERS")), 0), c->R - 1);
+  if (!c->pipelined || c->R <= 1) c->staged_peers = 0;
+  c->staged_xchg = c->staged_peers > 0;
+  c->stage_mask = 0;
+  for (int d = 1; d <= c->staged_peers; ++d) c->stage_mask |= 1u << ((c->rank + d) % c->R);
   if (c->staged_xchg) {
     c->stage_stride = (c->batch + 3) & ~3;
     for (int i = 0; i < 2; ++i) TRY(dmalloc(&c->d_stage[i], (size_t)c->N * c->stage_stride));
@@ -1302,6 +1311,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     fa.rank = c->rank;
     fa.stage = c->staged_xchg ? c->d_stage[bs] : nullptr;
     fa.stage_stride = c->stage_stride;
+    fa.stage_mask = c->stage_mask;
     if (c->staged_xchg)   // copies of two batches ago are out
       for (auto e : c->ev_x[bs]) CU(cudaStreamWaitEvent(c->stream, e, 0));
     for (int r = 0; r < c->R; ++r) {
@@ -1336,7 +1346,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     if (!fused_v1 && regk && pix13 && c->interp == UPSP_INTERP_LINEAR && max_elems < ((size_t)1 << 31)) {
       const unsigned g2 = cdiv(c->N, 128);
       // rows stored straight into peer memory (>= 3 ranks, or staging off): 128-byte segments
-      const bool seg128 = c->R > 1 && !c->staged_xchg;
+      const bool seg128 = c->R > 1 && c->staged_peers < c->R - 1;
 #define FUSED4(NCAM)                                                               \
   if (seg128) k_project_fused4<NCAM, 128, 32><<<g2, 128, 0, c->stream>>>(fa);      \
   else k_project_fused4<NCAM, 128, 16><<<g2, 128, 0, c->stream>>>(fa)
@@ -1391,9 +1401,9 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       constexpr int NX = upsp_gpu_ctx::NX;
       for (int j = 0; j < NX; ++j) CU(cudaStreamWaitEvent(c->stream_x[j], c->ev_back[bs], 0));
       // every peer's row block is cut into `parts` pieces so that NX copies are in flight at any time
-      const int parts = std::max(1, (NX + c->R - 2) / (c->R - 1));
+      const int parts = std::max(1, (NX + c->staged_peers - 1) / c->staged_peers);
       int q = 0;
-      for (int d = 1; d < c->R; ++d) {
+      for (int d = 1; d <= c->staged_peers; ++d) {
         const int s = (c->rank + d) % c->R;
         for (int part = 0; part < parts; ++part) {
           const int r0 = (int)((long long)c->n_count[s] * part / parts), r1 = (int)((long long)c->n_count[s] * (part + 1) / parts);
