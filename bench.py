@@ -212,13 +212,17 @@ def bench_b200(args):
     g.sync()
     barrier(dist)
     sampler = ClockSampler(local) if rank == 0 else None
-    g.set_kernel_sampling(8)          # CUDA events around every 8th batch's kernels (+ phase 2)
+    # per-kernel CUDA events in the LAST timed step only: every 8th batch runs un-overlapped (the
+    # library serialises a sampled batch so that event durations are the kernels' own) + phase 2
+    g.set_kernel_sampling(0)
     l0 = g.launch_count()
     stage = np.zeros(4)
     g.timer_start()
     t_wall = time.time()
     trace = []
     for _ in range(args.steps):
+        if _ == args.steps - 1:
+            g.set_kernel_sampling(8)
         run_step_resident(g, wl, args, dist, trace)
         stage += [g.stage_ms(i) for i in range(4)]
         if _ == args.steps - 1:
@@ -253,10 +257,10 @@ def bench_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # per-kernel launches of one step, CUDA-event mean duration (sampled inside the timed region),
     # algorithmic bytes per launch
-    B = args.batch if args.batch > 0 else 128
+    B = args.batch if args.batch > 0 else 256     # library default (upsp_gpu_config.batch_frames = 0)
     nbatch = -(-F_local // B)
-    knames = ["k_unpack12_scan", "k_frame_prep", "k_warp_affine8_u16", "k_patch", "k_project_fused",
-              "k_transpose_a2a", "k_phase2"]
+    knames = ["k_unpack12_scan_p", "k_frame_prep", "k_warp_affine8_u16", "k_patch", "k_project_fused4",
+              "k_transpose_a2a", "k_phase2_sym"]
     kalg = [B * 3.5 * P, 0.0, B * 4.0 * P, 0.0, B * (2.0 * P + 4.0 * N), 8.0 * N * F_local,
             8.0 * (N / world) * F_total]
     klaunch = [nbatch, nbatch, nbatch, nbatch, nbatch, 1, 1]
@@ -268,6 +272,15 @@ def bench_b200(args):
                            "sampled": ns}
     dom = max((k for k in kernels if kernels[k]["alg_bytes_per_launch"]), key=lambda k: kernels[k]["ms_per_step"])
     achieved = kernels[dom]["gbs"]
+    # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture
+    # (profiles/r01_traffic.json, written by scripts/ncu_summary.py at the same batch size), else null
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get(dom, {}).get("batch_frames") == B and tr[dom].get("nodes") == N:
+            traffic = tr[dom]["dram_bytes_per_launch"]
+    except (OSError, ValueError):
+        pass
     names = ["process_frames", "finish_phase1", "transpose", "phase2"]
     chain_bytes = (1.5 * P + 20.0 * N) * F_local
     chain_gbs = chain_bytes / (ms_dev / args.steps * 1e-3) / 1e9
@@ -289,7 +302,7 @@ def bench_b200(args):
                           "projection writes node-major rows directly, so the implementation moves 8N less"},
         "kernels": kernels,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
                      "launch_ms": kernels[dom]["mean_ms"], "share_of_step": round(kernels[dom]["ms_per_step"] / (ms_dev / args.steps), 3)},

@@ -268,6 +268,7 @@ struct upsp_gpu_ctx {
   cudaStream_t stream_b = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr}, ev_tabs = nullptr;
   bool pipelined = false;
+  bool last_sampled = false;   // the previous batch ran un-overlapped for kernel timing
   long pipe_batches = 0;
   int n_sm = 148;
   // staged exchange (n_ranks > 1, pipelined): the projection writes other ranks' rows into a local
@@ -1177,9 +1178,16 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   const bool prof = c->sample_every > 0 && (c->batch_counter++ % c->sample_every) == 0;
   // pipeline: buffer set `bs`, front end on stream SB; it may start once the fused kernel that last
   // read this buffer set (two batches ago) is done
+  // A batch whose kernels are being timed (upsp_gpu_set_kernel_sampling) runs un-overlapped: its
+  // front end goes on the main stream, and the next batch's front end waits for its projection, so the
+  // CUDA-event durations are those of the kernels alone (they are what the roofline figures use).
   const int bs = c->pipelined ? (int)(c->pipe_batches & 1) : 0;
-  cudaStream_t SB = c->pipelined ? c->stream_b : c->stream;
-  if (c->pipelined) CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
+  cudaStream_t SB = (c->pipelined && !prof) ? c->stream_b : c->stream;
+  if (c->pipelined) {
+    CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
+    if (c->last_sampled) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
+    c->last_sampled = prof;
+  }
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
     REQUIRE(k.format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
