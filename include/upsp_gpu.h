@@ -198,7 +198,9 @@ UPSP_API int upsp_gpu_timer_stop(upsp_gpu_ctx* ctx, float* ms);
  * phase-2 launch) is bracketed with CUDA events on the launching stream.  kernel_class:
  * 0 decode(+scan), 1 frame prep, 2 warp (unfused mode), 3 patch, 4 projection (fused: +transpose
  * +exchange), 5 transpose, 6 phase 2.  Returns the mean launch duration and the number of
- * sampled launches since the last upsp_gpu_reset_run / create. */
+ * sampled launches since the last upsp_gpu_reset_run / create.  A sampled batch is taken out of
+ * the two-stream pipeline (its decode / patch run on the main stream, the next batch's front end
+ * waits for its projection) so that the durations are those of the kernels alone. */
 UPSP_API int upsp_gpu_set_kernel_sampling(upsp_gpu_ctx* ctx, int sample_every);
 UPSP_API int upsp_gpu_kernel_ms(upsp_gpu_ctx* ctx, int kernel_class, float* mean_ms, int* n_sampled);
 /* start a new run on the same context (same setup, same device buffers): zeroes the
