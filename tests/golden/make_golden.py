@@ -12,6 +12,13 @@ Outputs (small, committed):
                     pixels the reference's Python reader (python/upsp/video/util.py
                     unpack_12bpp) decodes from them + CRC32 of both full decoded frames
   ecc_golden.npz    cv2.findTransformECC warp matrices / rho for synthetic frame pairs
+  synthetic10.cine / synthetic12.cine   tiny Vision Research cine files (3 frames 64x32, 10- and
+                    12-bit packed, one tagged exposure block) assembled from the reference's own
+                    ctypes header structures (python/upsp/video/cine.py)
+  tiny12.mraw / tiny12.cih   tiny Photron pair (2 frames 32x16, 12-bit)
+  video_golden.npz  what the reference's Python readers (upsp.video.CineReader / MrawReader) decode
+                    from those files, their properties, and the 10->12-bit table
+  ../../upsp-processing_b200/host/cine_lut.inc   the same table as a C initialiser list
 """
 import os
 import sys
@@ -46,6 +53,86 @@ def warp_golden():
     np.savez_compressed(os.path.join(HERE, "warp_f32_golden.npz"), src=src32, m6=m.reshape(nf, 6), linear=lin32)
 
 
+def video_golden():
+    """Synthetic containers written with the reference's header structures, decoded with the
+    reference's Python readers."""
+    import ctypes
+    import struct
+    from upsp.video import cine, mraw
+    rng = np.random.default_rng(77)
+    W, H, NF = 64, 32, 3
+    out = {}
+    for bpp in (10, 12):
+        vals = rng.integers(0, 1 << bpp, (NF, H * W)).astype(np.uint32)
+        frames = []
+        for f in range(NF):                       # pack exactly as PSPVideo.cpp:111-150 unpacks
+            v = vals[f]
+            if bpp == 12:
+                a, b = v[0::2], v[1::2]
+                by = np.stack([a >> 4, ((a & 0xF) << 4) | (b >> 8), b & 0xFF], 1)
+            else:
+                a, b, c, d = v[0::4], v[1::4], v[2::4], v[3::4]
+                by = np.stack([a >> 2, ((a & 3) << 6) | (b >> 4), ((b & 0xF) << 4) | (c >> 6),
+                               ((c & 0x3F) << 2) | (d >> 8), d & 0xFF], 1)
+            frames.append(by.astype(np.uint8).tobytes())
+        cf, bm, st = cine.CINEFILEHEADER(), cine.BITMAPINFOHEADER(), cine.SETUP()
+        st.Length = ctypes.sizeof(st)
+        st.Mark = 0x5453
+        st.FrameRate16 = 5000
+        st.FrameRate = 5000
+        st.ImWidth, st.ImHeight, st.RealBPP = W, H, bpp
+        st.LensAperture = 2.8
+        tagged = struct.pack("<IHH", 8 + 4 * NF, 0x3eb, 0) + struct.pack("<%dI" % NF, *([int(2 ** 32 * 25e-6)] * NF))
+        cf.Type = 0x4943
+        cf.Headersize = ctypes.sizeof(cf)
+        cf.Version = 1
+        cf.TotalImageCount = cf.ImageCount = NF
+        cf.OffImageHeader = ctypes.sizeof(cf)
+        cf.OffSetup = ctypes.sizeof(cf) + ctypes.sizeof(bm)
+        cf.OffImageOffsets = cf.OffSetup + st.Length + len(tagged)
+        bm.biSize = ctypes.sizeof(bm)
+        bm.biWidth, bm.biHeight, bm.biPlanes, bm.biBitCount = W, H, 1, 16
+        bm.biCompression = 256 if bpp == 10 else 1024
+        bm.biSizeImage = len(frames[0])
+        first = cf.OffImageOffsets + 8 * NF
+        offs = [first + i * (8 + len(frames[0])) for i in range(NF)]
+        path = os.path.join(HERE, "synthetic%d.cine" % bpp)
+        with open(path, "wb") as fd:
+            fd.write(bytes(cf) + bytes(bm) + bytes(st) + tagged + struct.pack("<%dq" % NF, *offs))
+            for fr in frames:
+                fd.write(struct.pack("<II", 8, len(fr)) + fr)
+        with cine.CineReader(path) as rd:
+            dec = np.stack([np.asarray(rd.read_frame(i)) for i in range(NF)]).astype(np.uint16)
+            out["cine%d_frames" % bpp] = dec
+            out["cine%d_props" % bpp] = np.array([rd.width, rd.height, rd.bit_depth, rd.frame_count, rd.frame_rate])
+        out["cine%d_crc" % bpp] = np.array([zlib.crc32(fr) for fr in frames], np.uint64)
+    lut = np.asarray(cine._LUT_10BIT).astype(np.uint16)
+    out["lut10"] = lut
+    with open(os.path.join(HERE, "..", "..", "upsp-processing_b200", "host", "cine_lut.inc"), "w") as fd:
+        fd.write("// 10 -> 12-bit table of packed 10-bit cines; generated by tests/golden/make_golden.py from the\n"
+                 "// reference's python/upsp/video/cine.py (_LUT_10BIT == CINE2_LUT, cpp/lib/CineReader.cpp:23-87)\n")
+        for i in range(0, 1024, 16):
+            fd.write(", ".join(str(int(x)) for x in lut[i:i + 16]) + ",\n")
+    # Photron pair
+    w, h, nf = 32, 16, 2
+    vals = rng.integers(0, 4096, (nf, h * w)).astype(np.uint32)
+    raw = b""
+    for f in range(nf):
+        a, b = vals[f][0::2], vals[f][1::2]
+        raw += np.stack([a >> 4, ((a & 0xF) << 4) | (b >> 8), b & 0xFF], 1).astype(np.uint8).tobytes()
+    open(os.path.join(HERE, "tiny12.mraw"), "wb").write(raw)
+    open(os.path.join(HERE, "tiny12.cih"), "w", newline="").write(
+        "#Camera Information Header\r\nDate : 2020/9/1\r\nCamera Type : FASTCAM synthetic\r\nScene Name : \r\n"
+        "Record Rate(fps) : 1000\r\nShutter Speed(s) : 1/1000\r\nTotal Frame : %d\r\nImage Width : %d\r\n"
+        "Image Height : %d\r\nColor Type : Mono\r\nColor Bit : 12\r\nFile Format : MRaw\r\nEffectiveBit Depth : 12\r\n"
+        "#END\r\n" % (nf, w, h))
+    with mraw.MrawReader(os.path.join(HERE, "tiny12.mraw")) as rd:
+        out["mraw_frames"] = np.stack([np.asarray(rd.read_frame(i)) for i in range(nf)]).astype(np.uint16)
+        out["mraw_props"] = np.array([rd.width, rd.height, rd.bit_depth, rd.frame_count, rd.frame_rate])
+    out["mraw_crc"] = np.array([zlib.crc32(raw[i * len(raw) // nf:(i + 1) * len(raw) // nf]) for i in range(nf)], np.uint64)
+    np.savez_compressed(os.path.join(HERE, "video_golden.npz"), **out)
+
+
 def mraw_golden():
     from upsp.video import util
     raw = np.fromfile(os.path.join(REF, "cpp/test/mraw/12bitMRAW.mraw"), dtype=np.uint8)
@@ -77,8 +164,12 @@ def ecc_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "video":     # only the container fixtures
+        video_golden()
+        sys.exit(0)
     warp_golden()
     mraw_golden()
     ecc_golden()
+    video_golden()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -64,3 +64,78 @@ def test_host_driver_writes_reference_flat_files(up, orc, gpu, tmp_path, registr
     assert np.all(e_exact <= 1e-6 + cond)
     st = rd("steady_state")
     assert np.array_equal(np.isnan(st), case.steady > 3.0) and same_bits(rd("model_temp"), case.temp)
+
+
+def _write_cine(path, codes, bpp, width, height):
+    """Minimal Vision Research cine (CINEFILEHEADER 44 B, BITMAPINFOHEADER 40 B, SETUP 7240 B, offset
+    table, {annotation size, image size, image} per frame) holding packed 10- or 12-bit `codes`."""
+    import struct
+    nf = codes.shape[0]
+    frames = []
+    for f in range(nf):
+        v = codes[f].reshape(-1).astype(np.uint32)
+        if bpp == 12:
+            a, b = v[0::2], v[1::2]
+            by = np.stack([a >> 4, ((a & 0xF) << 4) | (b >> 8), b & 0xFF], 1)
+        else:
+            a, b, c, d = v[0::4], v[1::4], v[2::4], v[3::4]
+            by = np.stack([a >> 2, ((a & 3) << 6) | (b >> 4), ((b & 0xF) << 4) | (c >> 6),
+                           ((c & 0x3F) << 2) | (d >> 8), d & 0xFF], 1)
+        frames.append(by.astype(np.uint8).tobytes())
+    setup = bytearray(7240)
+    struct.pack_into("<H", setup, 0, 1000)        # FrameRate16
+    struct.pack_into("<H", setup, 140, 0x5453)    # Mark
+    struct.pack_into("<H", setup, 142, 7240)      # Length
+    struct.pack_into("<HH", setup, 737, width, height)
+    struct.pack_into("<I", setup, 896, bpp)       # RealBPP
+    off_offsets = 44 + 40 + 7240
+    cfh = struct.pack("<HHHHiIiIIII", 0x4943, 44, 0, 1, 0, nf, 0, nf, 44, 84, off_offsets) + bytes(8)
+    bmi = struct.pack("<IiiHHIIiiII", 40, width, height, 1, 16, 256, len(frames[0]), 0, 0, 0, 0)
+    first = off_offsets + 8 * nf
+    offs = [first + i * (8 + len(frames[0])) for i in range(nf)]
+    with open(path, "wb") as fd:
+        fd.write(cfh + bmi + bytes(setup) + struct.pack("<%dq" % nf, *offs))
+        for fr in frames:
+            fd.write(struct.pack("<II", 8, len(fr)) + fr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("container", ["mraw", "cine10"])
+def test_host_driver_reads_camera_files(up, orc, gpu, tmp_path, container):
+    """job.txt `video0 = file`: the driver reads a Photron .mraw / Vision Research .cine with
+    host/video_readers.hpp and pushes the stored bytes; decode, the 10->12-bit table and everything
+    after it run on the GPU.  Results must equal the oracle run on the decoded frames."""
+    import upsp_b200
+    synth = upsp_b200.synth
+    case = Case(synth, n_frames=24, n_nodes=1500, registration=True, patches=True, seed=43)
+    lut = np.load(os.path.join(os.path.dirname(__file__), "golden", "video_golden.npz"))["lut10"]
+    job, out = tmp_path / "job", tmp_path / "out"
+    out.mkdir()
+    if container == "cine10":      # frames become table[codes]: the oracle sees what the reference would decode
+        rng = np.random.default_rng(9)
+        codes = np.clip(case.frames[0].astype(np.int64) // 4 + rng.integers(-2, 3, case.frames[0].shape), 0, 1023)
+        case.frames = [lut[codes].astype(np.uint16)]
+    synth.write_job(str(job), frames=case.frames, csr=case.csr, fmt="p12", registration="given",
+                    warp=case.warp, patches=[synth.flatten_patches(*p) for p in case.patch_lists], remap=None,
+                    cal=case.cal, qbar=case.qbar, ps=case.ps, steady=case.steady, model_temp=case.temp)
+    os.remove(job / "cam0.frames")
+    if container == "mraw":
+        synth.pack_12bit(case.frames[0].reshape(case.F, -1)).tofile(job / "cam0.mraw")
+        (job / "cam0.cih").write_text("#Camera Information Header\r\nRecord Rate(fps) : 1000\r\nTotal Frame : %d\r\n"
+                                      "Image Width : %d\r\nImage Height : %d\r\nColor Bit : 12\r\n" % (case.F, case.W, case.H))
+        name = "cam0.mraw"
+    else:
+        _write_cine(job / "cam0.cine", codes, 10, case.W, case.H)
+        name = "cam0.cine"
+    with open(job / "job.txt", "a") as fd:
+        fd.write("video0 = %s\n" % name)
+    exe = up.build.build_host()
+    r = subprocess.run([exe, "-job_dir", str(job), "-out_dir", str(out), "-chunk", "8"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ref = run_oracle(orc, case)
+    rd = lambda n, shape=None: (np.fromfile(out / n, np.float32).reshape(shape) if shape
+                                else np.fromfile(out / n, np.float32))
+    assert same_bits(rd("intensity_transpose", (case.N, case.F)), ref["itrans"])
+    assert same_bits(rd("intensity_avg"), ref["avg"]) and same_bits(rd("intensity_rms"), ref["rms"])
+    assert same_bits(rd("gain"), ref["gain"])

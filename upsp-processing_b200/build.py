@@ -72,6 +72,24 @@ def build_host(force: bool = False) -> str:
     return HOST_BIN
 
 
+PROBE_BIN = os.path.join(HERE, "video_probe")
+
+
+def build_probe(force: bool = False) -> str:
+    """host/video_probe.cpp: container readers (cine / mraw) exercised from the tests; plain g++."""
+    src = os.path.join(HERE, "host", "video_probe.cpp")
+    deps = [src, os.path.join(HERE, "host", "video_readers.hpp"), os.path.join(HERE, "host", "cine_lut.inc")]
+    if not force and os.path.exists(PROBE_BIN) and os.path.getmtime(PROBE_BIN) >= max(map(os.path.getmtime, deps)):
+        return PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", PROBE_BIN, src], capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building video_probe")
+    return PROBE_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
     print(build_host(force="--force" in sys.argv))
+    print(build_probe(force="--force" in sys.argv))

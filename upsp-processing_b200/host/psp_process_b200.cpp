@@ -11,6 +11,9 @@
 //   job.txt               key = value lines: cameras width height number_frames msize format
 //                         registration pixel_interpolation target_patcher qbar ps cal_a..cal_f degree
 //   cam<c>.frames         number_frames frames, u16 or 12-bit packed (format = u16 | p12)
+//   video<c> = PATH       (job.txt, instead of cam<c>.frames) a Vision Research .cine or Photron .mraw
+//                         file, read with host/video_readers.hpp as the reference's CineReader /
+//                         MrawReader do; `first_frame` (1-based, default 1) as the deck's start frame
 //   cam<c>.rowptr/.col/.val   projection matrix of camera c in CSR (i32, i32, f32)
 //   cam<c>.warp           registration = given : number_frames x 6 f32
 //   cam<c>.first          registration = pixel : raw first frame, u16
@@ -28,6 +31,7 @@
 #include <sstream>
 
 #include "upsp_b200.hpp"
+#include "video_readers.hpp"
 
 using namespace upsp_b200;
 
@@ -82,8 +86,26 @@ int main(int argc, char** argv) {
     auto getf = [&](const char* k) { return (float)atof(job.at(k).c_str()); };
     const int cameras = geti("cameras"), W = geti("width"), H = geti("height");
     const int number_frames = geti("number_frames"), msize = geti("msize");
-    const bool p12 = job.at("format") == "p12";
     const std::string reg = job.at("registration"), patcher = job.at("target_patcher");
+    // frame sources: raw dumps (cam<c>.frames) or camera files (video<c> = path)
+    std::vector<std::unique_ptr<VideoReader>> readers(cameras);
+    bool any_video = false;
+    for (int c = 0; c < cameras; ++c) {
+      auto it = job.find("video" + std::to_string(c));
+      if (it == job.end()) continue;
+      readers[c] = open_video(it->second.front() == '/' ? it->second : job_dir + "/" + it->second);
+      any_video = true;
+      const auto& vp = readers[c]->properties();
+      if ((int)vp.width != W || (int)vp.height != H)
+        throw std::invalid_argument("video" + std::to_string(c) + " is " + std::to_string(vp.width) + "x" +
+                                    std::to_string(vp.height) + ", job.txt says " + std::to_string(W) + "x" + std::to_string(H));
+    }
+    const int first_frame = job.count("first_frame") ? geti("first_frame") : 1;
+    for (int c = 0; c < cameras; ++c)
+      if (readers[c] && first_frame - 1 + number_frames > (int)readers[c]->properties().num_frames)
+        throw std::invalid_argument("video" + std::to_string(c) + " has fewer frames than first_frame + number_frames");
+    const bool p12 = job.count("format") ? job.at("format") == "p12" : false;
+    if (!any_video && !job.count("format")) throw std::invalid_argument("job.txt: neither format nor video<c> given");
     const size_t frame_bytes = p12 ? (size_t)W * H * 3 / 2 : (size_t)W * H * 2;
 
     upsp_gpu_config cfg{};
@@ -127,19 +149,30 @@ int main(int argc, char** argv) {
 
     // ---- phase 1: frame loop (the async reader of psp_process.cpp:867-908 is this read loop) ----
     std::cout << "Processing frames" << std::endl;
-    std::vector<std::ifstream> vids;
+    std::vector<std::ifstream> vids(cameras);
+    size_t max_fb = frame_bytes;
     for (int c = 0; c < cameras; ++c) {
-      vids.emplace_back(job_dir + "/cam" + std::to_string(c) + ".frames", std::ios::binary);
-      if (!vids.back()) throw std::invalid_argument("Cannot open frames of camera " + std::to_string(c));
+      if (readers[c]) {
+        max_fb = std::max(max_fb, readers[c]->frame_bytes());
+        if (readers[c]->unpack_lut()) chain.set_unpack_lut(readers[c]->unpack_lut());   // 10-bit cine
+        continue;
+      }
+      vids[c].open(job_dir + "/cam" + std::to_string(c) + ".frames", std::ios::binary);
+      if (!vids[c]) throw std::invalid_argument("Cannot open frames of camera " + std::to_string(c));
     }
-    std::vector<uint8_t> buf((size_t)chunk * frame_bytes);
+    std::vector<uint8_t> buf((size_t)chunk * max_fb);
     for (int off = 0; off < number_frames; off += chunk) {
       const int n = std::min(chunk, number_frames - off);
       if (off % 100 == 0) std::cout << "  Rank 0:: processing frame " << off << std::endl;
       for (int c = 0; c < cameras; ++c) {
-        vids[c].read(reinterpret_cast<char*>(buf.data()), (std::streamsize)((size_t)n * frame_bytes));
-        if (!vids[c]) throw std::invalid_argument("frame file of camera " + std::to_string(c) + " is too short");
-        chain.push_frames(c, buf.data(), p12 ? UPSP_PIX_PACKED12 : UPSP_PIX_U16, off, n);
+        if (readers[c]) {     // stored bytes straight to the GPU: decode / table / hot pixels happen there
+          readers[c]->read_packed((unsigned)(first_frame + off), (unsigned)n, buf.data());
+          chain.push_frames(c, buf.data(), readers[c]->pixel_format(), off, n);
+        } else {
+          vids[c].read(reinterpret_cast<char*>(buf.data()), (std::streamsize)((size_t)n * frame_bytes));
+          if (!vids[c]) throw std::invalid_argument("frame file of camera " + std::to_string(c) + " is too short");
+          chain.push_frames(c, buf.data(), p12 ? UPSP_PIX_PACKED12 : UPSP_PIX_U16, off, n);
+        }
         chain.sync();   // buf is reused for the next camera / chunk
       }
       chain.process_frames(off, n);

@@ -134,6 +134,8 @@ class FrameChain {
   void set_warp_matrices(int cam, int local_offset, int count, const float* m6) {
     check(upsp_gpu_set_warp_matrices(ctx_, cam, local_offset, count, m6));
   }
+  /* 10 -> 12-bit table of packed 10-bit cines (CineReader.cpp:409-425) */
+  void set_unpack_lut(const uint16_t* lut1024) { check(upsp_gpu_set_unpack_lut(ctx_, lut1024)); }
   void push_frames(int cam, const void* frames, int format, int local_offset, int count) {
     check(upsp_gpu_push_frames(ctx_, cam, frames, format, local_offset, count));
   }
