@@ -139,3 +139,34 @@ def test_host_driver_reads_camera_files(up, orc, gpu, tmp_path, container):
     assert same_bits(rd("intensity_transpose", (case.N, case.F)), ref["itrans"])
     assert same_bits(rd("intensity_avg"), ref["avg"]) and same_bits(rd("intensity_rms"), ref["rms"])
     assert same_bits(rd("gain"), ref["gain"])
+
+
+def test_transpose_tool_fails_loudly(up, tmp_path):
+    exe = up.build.build_transpose_tool()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr
+    r = subprocess.run([exe, "5", "7", "0", str(tmp_path / "nope"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot open" in r.stderr
+    (tmp_path / "short").write_bytes(bytes(12))
+    r = subprocess.run([exe, "5", "7", "0", str(tmp_path / "short"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "expected msize*number_frames*4" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag,block", [(0, None), (1, None), (0, "4000"), (1, "3000")])
+def test_transpose_tool_matches_numpy(up, gpu, tmp_path, flag, block):
+    """upsp_matrix_transpose (cpp/exec/upsp_matrix_transpose.cpp): pressure [F x N] <-> pressure_transpose
+    [N x F], whole matrix at once and in several row blocks; ragged sizes as in test_general_utils.cpp."""
+    msize, nframes = 1237, 301
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((nframes, msize) if flag == 0 else (msize, nframes)).astype(np.float32)
+    a.tofile(tmp_path / "in")
+    exe = up.build.build_transpose_tool()
+    env = dict(os.environ)
+    if block:
+        env["UPSP_XPOSE_BLOCK_FLOATS"] = block
+    r = subprocess.run([exe, str(msize), str(nframes), str(flag), str(tmp_path / "in"), str(tmp_path)],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(tmp_path / ("pressure_transpose" if flag == 0 else "pressure"), np.float32)
+    assert np.array_equal(out.reshape(a.T.shape), a.T)

@@ -72,6 +72,25 @@ def build_host(force: bool = False) -> str:
     return HOST_BIN
 
 
+XPOSE_BIN = os.path.join(HERE, "upsp_matrix_transpose_b200")
+
+
+def build_transpose_tool(force: bool = False) -> str:
+    """host/upsp_matrix_transpose_b200.cpp: the reference's stand-alone transpose tool on the C ABI."""
+    src = os.path.join(HERE, "host", "upsp_matrix_transpose_b200.cpp")
+    build()
+    if not force and os.path.exists(XPOSE_BIN) and os.path.getmtime(XPOSE_BIN) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return XPOSE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", XPOSE_BIN, src, "-L" + HERE, "-lupsp_gpu",
+           "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building upsp_matrix_transpose_b200")
+    return XPOSE_BIN
+
+
 PROBE_BIN = os.path.join(HERE, "video_probe")
 
 
@@ -93,3 +112,4 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
     print(build_host(force="--force" in sys.argv))
     print(build_probe(force="--force" in sys.argv))
+    print(build_transpose_tool(force="--force" in sys.argv))
