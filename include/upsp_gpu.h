@@ -246,6 +246,30 @@ UPSP_API int upsp_op_transpose(int device, const float* src, int x_extent, int y
 UPSP_API int upsp_op_polyfit_detrend(int device, const float* data, int n_pts, int n_frames,
                                      int degree, float* fit);
 
+/* ---- phase-0 product on the GPU: the pixel-to-node projection matrix.
+ * create_projection_mat (cpp/exec/psp_process.cpp:168-355): every data node is projected with the
+ * camera calibration (cv::projectPoints, CameraCal.ipp:227-239), kept if it lands inside the frame,
+ * if the nearest triangle hit by the ray from the camera centre (rt::BVH::intersect,
+ * pspRT.cpp:359-430; six jittered retries) contains the node, and if the angle between the node
+ * normal and the ray exceeds oblique_thresh; its row of the matrix is then the single entry
+ * (nearest pixel, 1.0).
+ *   xyz, normals [n_nodes][3] (Model::get_position / get_n), is_datanode [n_nodes],
+ *   tri_nodes [n_tris][3] node indices of every triangle (the reference's triNodes),
+ *   code [n_nodes]: pixel index y*width + x of the node's entry, or -1 (empty row),
+ *   uv [2*n_nodes]: normalised image coordinates as psp_process writes them (0 for empty rows). */
+typedef struct {
+  double rvec[3], tvec[3];        /* CameraCal rvec_/tvec_ */
+  double fx, fy, cx, cy;          /* cameraMatrix_ */
+  double dist[8];                 /* distCoeffs_: k1 k2 p1 p2 k3 k4 k5 k6 (4, 5 or 8 used; rest 0) */
+  int width, height;
+} upsp_camera_model;
+UPSP_API int upsp_op_create_projection(int device, const upsp_camera_model* cam, const float* xyz,
+                                       const float* normals, const uint8_t* is_datanode, int n_nodes,
+                                       const int32_t* tri_nodes, int n_tris, float oblique_thresh,
+                                       int32_t* code, float* uv);
+/* cv::projectPoints for n float points (CameraCal::map_points_to_image): uv [n][2] */
+UPSP_API int upsp_op_project_points(int device, const upsp_camera_model* cam, const float* xyz, int n, float* uv);
+
 #ifdef __cplusplus
 }
 #endif

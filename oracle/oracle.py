@@ -22,8 +22,8 @@ _LIB_PATH = os.path.join(_HERE, "libupsp_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "upsp_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("upsp_oracle.c", "upsp_oracle_setup.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -388,3 +388,56 @@ def phase2(itrans, avg_final, coverage_, steady, model_temp, cal, qbar, ps, degr
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+# ---------------------------------------------------------------- phase 0: projection matrix
+class Camera(C.Structure):
+    """orc_camera (upsp_oracle_setup.c): CameraCal's rvec/tvec/cameraMatrix/distCoeffs + frame size"""
+    _fields_ = [("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("k", C.c_double * 8), ("width", C.c_int), ("height", C.c_int)]
+
+
+def make_camera(rvec, tvec, K, dist, width, height) -> Camera:
+    cam = Camera()
+    cam.rvec[:] = [float(v) for v in rvec]
+    cam.tvec[:] = [float(v) for v in tvec]
+    K = np.asarray(K, np.float64)
+    cam.fx, cam.fy, cam.cx, cam.cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    d = list(np.asarray(dist, np.float64).ravel()) + [0.0] * 8
+    cam.k[:] = d[:8]
+    cam.width, cam.height = int(width), int(height)
+    return cam
+
+
+def project_points(cam: Camera, xyz: np.ndarray) -> np.ndarray:
+    """cv::projectPoints as CameraCal::map_points_to_image calls it (cpp/lib/CameraCal.ipp:227-230)"""
+    p = _c(xyz, np.float32).reshape(-1, 3)
+    uv = np.empty((p.shape[0], 2), np.float32)
+    lib().orc_project_points(C.byref(cam), _p(p), C.c_int(p.shape[0]), _p(uv))
+    return uv
+
+
+def cam_center(cam: Camera) -> np.ndarray:
+    c = np.empty(3, np.float32)
+    lib().orc_cam_center(C.byref(cam), _p(c))
+    return c
+
+
+def create_projection(cam: Camera, xyz, normals, is_data, tri, oblique_thresh):
+    """create_projection_mat (cpp/exec/psp_process.cpp:168-355): (code[N] pixel index or -1, uv[N,2])"""
+    p = _c(xyz, np.float32).reshape(-1, 3)
+    nr = _c(normals, np.float32).reshape(-1, 3)
+    isd = _c(is_data, np.uint8)
+    t = _c(tri, np.int32).reshape(-1, 3)
+    code = np.empty(p.shape[0], np.int32)
+    uv = np.empty((p.shape[0], 2), np.float32)
+    lib().orc_create_projection(C.byref(cam), _p(p), _p(nr), _p(isd), C.c_int(p.shape[0]), _p(t), C.c_int(t.shape[0]),
+                                C.c_float(oblique_thresh), _p(code), _p(uv))
+    return code, uv
+
+
+def projection_csr(code: np.ndarray):
+    """the Eigen matrix setFromTriplets builds from the accepted nodes: one entry (pixel, 1.0) per row"""
+    has = code >= 0
+    rowptr = np.concatenate([[0], np.cumsum(has)]).astype(np.int32)
+    return rowptr, code[has].astype(np.int32), np.ones(int(has.sum()), np.float32)

@@ -16,6 +16,7 @@ Outputs (small, committed):
                     12-bit packed, one tagged exposure block) assembled from the reference's own
                     ctypes header structures (python/upsp/video/cine.py)
   tiny12.mraw / tiny12.cih   tiny Photron pair (2 frames 32x16, 12-bit)
+  setup_golden.npz  cv2.projectPoints / cv2.Rodrigues for random calibrations (phase-0 camera model)
   video_golden.npz  what the reference's Python readers (upsp.video.CineReader / MrawReader) decode
                     from those files, their properties, and the 10->12-bit table
   ../../upsp-processing_b200/host/cine_lut.inc   the same table as a C initialiser list
@@ -51,6 +52,29 @@ def warp_golden():
     lin32 = np.stack([cv2.warpAffine(src32[f], m[f], (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP)
                       for f in range(nf)])
     np.savez_compressed(os.path.join(HERE, "warp_f32_golden.npz"), src=src32, m6=m.reshape(nf, 6), linear=lin32)
+
+
+def setup_golden():
+    """cv2.projectPoints (the call of CameraCal::map_points_to_image, cpp/lib/CameraCal.ipp:227-230)
+    and cv2.Rodrigues for random calibrations with 4, 5 and 8 distortion coefficients."""
+    rng = np.random.default_rng(2024)
+    cams, pts, uvs, rots = [], [], [], []
+    for trial in range(12):
+        rvec = rng.normal(0, 0.5, 3)
+        tvec = np.array([rng.normal(0, 2), rng.normal(0, 2), 30 + rng.normal(0, 5)])
+        K = np.array([[1200 + rng.normal(0, 50), 0, 512 + rng.normal(0, 5)], [0, 1190 + rng.normal(0, 50), 500 + rng.normal(0, 5)],
+                      [0, 0, 1]])
+        nd = [4, 5, 8][trial % 3]
+        d = np.concatenate([rng.normal(0, 0.05, 2), rng.normal(0, 0.002, 2), rng.normal(0, 0.01, 1), rng.normal(0, 0.01, 3)])
+        d[nd:] = 0.0
+        p = rng.normal(0, 6, (64, 3)).astype(np.float32)
+        uv = cv2.projectPoints(p.reshape(-1, 1, 3), rvec, tvec, K, d[:nd])[0].reshape(-1, 2).astype(np.float32)
+        cams.append(np.concatenate([rvec, tvec, [K[0, 0], K[1, 1], K[0, 2], K[1, 2]], d]))
+        pts.append(p)
+        uvs.append(uv)
+        rots.append(cv2.Rodrigues(rvec)[0].reshape(9))
+    np.savez_compressed(os.path.join(HERE, "setup_golden.npz"), cams=np.array(cams), pts=np.array(pts), uv=np.array(uvs),
+                        rot=np.array(rots), cv2_version=cv2.__version__)
 
 
 def video_golden():
@@ -167,9 +191,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "video":     # only the container fixtures
         video_golden()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "setup":     # only the camera-model fixtures
+        setup_golden()
+        sys.exit(0)
     warp_golden()
     mraw_golden()
     ecc_golden()
     video_golden()
+    setup_golden()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

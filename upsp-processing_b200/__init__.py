@@ -338,3 +338,41 @@ def op_polyfit_detrend(data, degree=6, device=0):
     out = np.empty_like(a)
     _chk(lib().upsp_op_polyfit_detrend(device, _p(a), n_pts, F, degree, _p(out)))
     return out
+
+
+class CameraModel(C.Structure):
+    """upsp_camera_model (include/upsp_gpu.h)"""
+    _fields_ = [("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("dist", C.c_double * 8), ("width", C.c_int), ("height", C.c_int)]
+
+
+def camera_model(rvec, tvec, K, dist, width, height) -> CameraModel:
+    cam = CameraModel()
+    cam.rvec[:] = [float(v) for v in rvec]
+    cam.tvec[:] = [float(v) for v in tvec]
+    K = np.asarray(K, np.float64)
+    cam.fx, cam.fy, cam.cx, cam.cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    d = list(np.asarray(dist, np.float64).ravel()) + [0.0] * 8
+    cam.dist[:] = d[:8]
+    cam.width, cam.height = int(width), int(height)
+    return cam
+
+
+def op_project_points(cam: CameraModel, xyz, device=0):
+    p = _c(xyz, np.float32).reshape(-1, 3)
+    uv = np.empty((p.shape[0], 2), np.float32)
+    _chk(lib().upsp_op_project_points(device, C.byref(cam), _p(p), p.shape[0], _p(uv)))
+    return uv
+
+
+def op_create_projection(cam: CameraModel, xyz, normals, is_datanode, tri_nodes, oblique_thresh, device=0):
+    """create_projection_mat on the GPU: (code[N] = pixel index of the node's single entry or -1, uv[N,2])"""
+    p = _c(xyz, np.float32).reshape(-1, 3)
+    nr = _c(normals, np.float32).reshape(-1, 3)
+    isd = _c(is_datanode, np.uint8)
+    t = _c(tri_nodes, np.int32).reshape(-1, 3)
+    code = np.empty(p.shape[0], np.int32)
+    uv = np.empty((p.shape[0], 2), np.float32)
+    _chk(lib().upsp_op_create_projection(device, C.byref(cam), _p(p), _p(nr), _p(isd), p.shape[0], _p(t), t.shape[0],
+                                         C.c_float(oblique_thresh), _p(code), _p(uv)))
+    return code, uv

@@ -28,6 +28,7 @@
 #include "kernels_filter.cuh"
 #include "kernels_phase2.cuh"
 #include "kernels_project.cuh"
+#include "kernels_setup.cuh"
 #include "kernels_transpose.cuh"
 
 using namespace upsp;
@@ -2269,5 +2270,147 @@ extern "C" int upsp_op_polyfit_detrend(int device, const float* data, int n_pts,
   TRY(dispatch_phase2(nullptr, a, 0, &l));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(fit, d_fit, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase-0 product: projection matrix (kernels_setup.cuh)
+// ------------------------------------------------------------------------------------------
+static void rodrigues_f64(const double r[3], double R[9]) {   // cv::Rodrigues(rvec -> R)
+  const double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (theta < 2.220446049250313e-16) {
+    for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, itheta = 1.0 / theta;
+  const double x = r[0] * itheta, y = r[1] * itheta, z = r[2] * itheta;
+  const double rrt[9] = {x * x, x * y, x * z, x * y, y * y, y * z, x * z, y * z, z * z};
+  const double rx[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int k = 0; k < 9; ++k) R[k] = c * I[k] + c1 * rrt[k] + s * rx[k];
+}
+
+static int fill_setup_cam(const upsp_camera_model* cam, SetupCam& sc) {
+  REQUIRE(cam && cam->width > 0 && cam->height > 0, UPSP_ERR_INVALID, "camera model");
+  rodrigues_f64(cam->rvec, sc.R);
+  for (int i = 0; i < 3; ++i) sc.t[i] = cam->tvec[i];
+  sc.fx = cam->fx; sc.fy = cam->fy; sc.cx = cam->cx; sc.cy = cam->cy;
+  for (int i = 0; i < 8; ++i) sc.k[i] = cam->dist[i];
+  for (int i = 0; i < 3; ++i)   // CameraCal::get_cam_center: -R^T t (double), narrowed to float
+    sc.orig[i] = (float)(-(sc.R[0 + i] * cam->tvec[0] + sc.R[3 + i] * cam->tvec[1] + sc.R[6 + i] * cam->tvec[2]));
+  sc.width = cam->width;
+  sc.height = cam->height;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_project_points(int device, const upsp_camera_model* cam, const float* xyz, int n, float* uv) {
+  OP_ENTER(device);
+  REQUIRE(xyz && uv && n > 0, UPSP_ERR_INVALID, "null/empty argument");
+  SetupCam sc{};
+  TRY(fill_setup_cam(cam, sc));
+  float *d_xyz, *d_uv;
+  TRY(S.put(&d_xyz, xyz, (size_t)3 * n));
+  TRY(S.alloc(&d_uv, (size_t)2 * n));
+  k_project_points<<<cdiv(n, 128), 128>>>(sc, d_xyz, n, d_uv);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(uv, d_uv, (size_t)2 * n * sizeof(float), cudaMemcpyDeviceToHost));
+  return UPSP_OK;
+}
+
+extern "C" int upsp_op_create_projection(int device, const upsp_camera_model* cam, const float* xyz,
+                                         const float* normals, const uint8_t* is_datanode, int n_nodes,
+                                         const int32_t* tri_nodes, int n_tris, float oblique_thresh,
+                                         int32_t* code, float* uv) {
+  OP_ENTER(device);
+  REQUIRE(xyz && normals && is_datanode && tri_nodes && code && uv && n_nodes > 0 && n_tris > 0, UPSP_ERR_INVALID,
+          "null/empty argument");
+  for (size_t i = 0; i < (size_t)3 * n_tris; ++i)
+    REQUIRE(tri_nodes[i] >= 0 && tri_nodes[i] < n_nodes, UPSP_ERR_INVALID, "triangle %zu references node %d", i / 3, tri_nodes[i]);
+  SetupCam sc{};
+  TRY(fill_setup_cam(cam, sc));
+  // ---- direction-space grid (host, once): pinhole coordinates of every vertex seen from the ray origin
+  std::vector<double> xn(n_nodes), yn(n_nodes);
+  std::vector<uint8_t> front(n_nodes);
+  double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+  for (int i = 0; i < n_nodes; ++i) {
+    const double w[3] = {(double)xyz[3 * i] - (double)sc.orig[0], (double)xyz[3 * i + 1] - (double)sc.orig[1],
+                         (double)xyz[3 * i + 2] - (double)sc.orig[2]};
+    const double qx = sc.R[0] * w[0] + sc.R[1] * w[1] + sc.R[2] * w[2], qy = sc.R[3] * w[0] + sc.R[4] * w[1] + sc.R[5] * w[2];
+    const double qz = sc.R[6] * w[0] + sc.R[7] * w[1] + sc.R[8] * w[2];
+    const double len = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    front[i] = qz > 1e-3 * len;             // well in front of the camera plane (within ~89.9 deg of the axis)
+    if (!front[i]) continue;
+    xn[i] = qx / qz;
+    yn[i] = qy / qz;
+    lo[0] = std::min(lo[0], xn[i]); hi[0] = std::max(hi[0], xn[i]);
+    lo[1] = std::min(lo[1], yn[i]); hi[1] = std::max(hi[1], yn[i]);
+  }
+  SetupGrid grid{};
+  std::vector<int> cell_start(1, 0), cell_tris, always;
+  if (lo[0] <= hi[0]) {
+    const int G = std::max(8, std::min(2048, (int)sqrt((double)n_tris / 2.0)));
+    const double ex = std::max(hi[0] - lo[0], 1e-9), ey = std::max(hi[1] - lo[1], 1e-9);
+    grid.gx = grid.gy = G;
+    // the gridded range is padded by one cell on every side so that jittered rays stay inside
+    const double cwx = ex / (G - 2), cwy = ey / (G - 2);
+    grid.x0 = lo[0] - cwx;
+    grid.y0 = lo[1] - cwy;
+    grid.inv_cell_x = 1.0 / cwx;
+    grid.inv_cell_y = 1.0 / cwy;
+    auto cell_range = [&](double a, double b, double o, double inv, int g, int& c0, int& c1) {
+      // margin of a quarter cell: orders of magnitude above the float error of the edge tests and
+      // above the 1e-4 jitter of the retry rays
+      c0 = std::max(0, (int)floor((a - o) * inv - 0.25));
+      c1 = std::min(g - 1, (int)floor((b - o) * inv + 0.25));
+    };
+    std::vector<int> count((size_t)G * G + 1, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int k = 0; k < n_tris; ++k) {
+        const int a = tri_nodes[3 * k], b = tri_nodes[3 * k + 1], c = tri_nodes[3 * k + 2];
+        if (!(front[a] && front[b] && front[c])) {
+          if (pass == 0) always.push_back(k);
+          continue;
+        }
+        int x0, x1, y0, y1;
+        cell_range(std::min({xn[a], xn[b], xn[c]}), std::max({xn[a], xn[b], xn[c]}), grid.x0, grid.inv_cell_x, G, x0, x1);
+        cell_range(std::min({yn[a], yn[b], yn[c]}), std::max({yn[a], yn[b], yn[c]}), grid.y0, grid.inv_cell_y, G, y0, y1);
+        for (int y = y0; y <= y1; ++y)
+          for (int x = x0; x <= x1; ++x) {
+            if (pass == 0) count[(size_t)y * G + x + 1]++;
+            else cell_tris[(size_t)cell_start[(size_t)y * G + x] + count[(size_t)y * G + x]++] = k;
+          }
+      }
+      if (pass == 0) {
+        cell_start.assign((size_t)G * G + 1, 0);
+        for (size_t i = 0; i < (size_t)G * G; ++i) cell_start[i + 1] = cell_start[i] + count[i + 1];
+        cell_tris.resize((size_t)cell_start.back());
+        std::fill(count.begin(), count.end(), 0);
+      }
+    }
+  }
+  float *d_xyz, *d_nrm, *d_uv;
+  uint8_t* d_isd;
+  int *d_tri, *d_code, *d_cs = nullptr, *d_ct = nullptr, *d_al = nullptr;
+  TRY(S.put(&d_xyz, xyz, (size_t)3 * n_nodes));
+  TRY(S.put(&d_nrm, normals, (size_t)3 * n_nodes));
+  TRY(S.put(&d_isd, is_datanode, (size_t)n_nodes));
+  TRY(S.put(&d_tri, tri_nodes, (size_t)3 * n_tris));
+  TRY(S.alloc(&d_code, (size_t)n_nodes));
+  TRY(S.alloc(&d_uv, (size_t)2 * n_nodes));
+  if (grid.gx) {
+    TRY(S.put(&d_cs, cell_start.data(), cell_start.size()));
+    if (!cell_tris.empty()) TRY(S.put(&d_ct, cell_tris.data(), cell_tris.size()));
+    else TRY(S.alloc(&d_ct, 1));
+  }
+  if (!always.empty()) TRY(S.put(&d_al, always.data(), always.size()));
+  grid.cell_start = d_cs;
+  grid.cell_tris = d_ct;
+  grid.always = d_al;
+  grid.n_always = (int)always.size();
+  k_create_projection<<<cdiv(n_nodes, 128), 128>>>(sc, grid, d_xyz, d_nrm, d_isd, n_nodes, d_tri, n_tris, oblique_thresh,
+                                                   d_code, d_uv);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(code, d_code, (size_t)n_nodes * sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(uv, d_uv, (size_t)2 * n_nodes * sizeof(float), cudaMemcpyDeviceToHost));
   return UPSP_OK;
 }

@@ -246,3 +246,47 @@ def write_job(job_dir, *, frames, csr, fmt="p12", registration="none", interp="l
         np.asarray(remap, np.int32).tofile(os.path.join(job_dir, "remap.i32"))
     np.asarray(steady, np.float32).tofile(os.path.join(job_dir, "steady.f32"))
     np.asarray(model_temp, np.float32).tofile(os.path.join(job_dir, "model_temp.f32"))
+
+
+def make_sphere_mesh(n_lat=24, n_lon=48, radius=5.0, center=(0.0, 0.0, 0.0), bump=0.0, seed=0):
+    """Closed triangulated sphere (optionally with a smooth radial bump so that it self-occludes a
+    little): xyz [N,3] f32, outward unit vertex normals [N,3] f32, triangles [T,3] i32 of node indices
+    (the reference's triNodes for an unstructured .tri grid)."""
+    rng = np.random.default_rng(seed)
+    th = np.linspace(0.0, np.pi, n_lat + 2)[1:-1]
+    ph = np.linspace(0.0, 2 * np.pi, n_lon, endpoint=False)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3)
+    d = np.concatenate([[[0, 0, 1.0]], d, [[0, 0, -1.0]]])
+    r = radius * (1.0 + bump * np.sin(3 * np.arctan2(d[:, 1], d[:, 0])) * np.sin(2 * np.arccos(np.clip(d[:, 2], -1, 1))))
+    xyz = (d * r[:, None] + np.asarray(center)[None, :] + rng.normal(0, 1e-4, d.shape)).astype(np.float32)
+    tri = []
+    idx = lambda i, j: 1 + i * n_lon + (j % n_lon)
+    for j in range(n_lon):
+        tri.append([0, idx(0, j), idx(0, j + 1)])
+        tri.append([len(d) - 1, idx(n_lat - 1, j + 1), idx(n_lat - 1, j)])
+    for i in range(n_lat - 1):
+        for j in range(n_lon):
+            tri.append([idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)])
+            tri.append([idx(i, j), idx(i + 1, j + 1), idx(i, j + 1)])
+    return xyz, d.astype(np.float32), np.asarray(tri, np.int32)
+
+
+def make_projection_scene(n_lat=40, n_lon=80, seed=0):
+    """A model (bumpy sphere) with a small occluding sphere between it and the camera, a camera
+    with lens distortion looking at it, and some non-data nodes: everything create_projection_mat
+    consumes.  Returns dict(xyz, normals, tri, is_data, rvec, tvec, K, dist, width, height, thresh)."""
+    rng = np.random.default_rng(seed)
+    x1, n1, t1 = make_sphere_mesh(n_lat, n_lon, 5.0, (0, 0, 0), bump=0.12, seed=seed)
+    x2, n2, t2 = make_sphere_mesh(8, 16, 0.9, (1.5, 1.0, -8.0), seed=seed + 1)
+    xyz = np.concatenate([x1, x2])
+    normals = np.concatenate([n1, n2])
+    tri = np.concatenate([t1, t2 + len(x1)])
+    is_data = np.ones(len(xyz), np.uint8)
+    is_data[rng.choice(len(xyz), len(xyz) // 50, replace=False)] = 0
+    rvec = np.array([0.05, -0.08, 0.3])
+    tvec = np.array([0.3, -0.2, 30.0])
+    K = np.array([[2400.0, 0, 255.3], [0, 2390.0, 250.8], [0, 0, 1]])
+    dist = np.array([-0.12, 0.06, 0.001, -0.0007, 0.01])
+    return dict(xyz=xyz, normals=normals, tri=tri, is_data=is_data, rvec=rvec, tvec=tvec, K=K, dist=dist,
+                width=512, height=512, thresh=float(np.deg2rad(100.0)))
