@@ -91,6 +91,23 @@ def build_transpose_tool(force: bool = False) -> str:
     return XPOSE_BIN
 
 
+PATCH_PROBE_BIN = os.path.join(HERE, "patch_geometry_probe")
+
+
+def build_patch_probe(force: bool = False) -> str:
+    """host/patch_geometry_probe.cpp: phase-0 patch geometry (host C++) exercised from the tests."""
+    src = os.path.join(HERE, "host", "patch_geometry_probe.cpp")
+    deps = [src, os.path.join(HERE, "host", "patch_geometry.hpp")]
+    if not force and os.path.exists(PATCH_PROBE_BIN) and os.path.getmtime(PATCH_PROBE_BIN) >= max(map(os.path.getmtime, deps)):
+        return PATCH_PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", PATCH_PROBE_BIN, src], capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building patch_geometry_probe")
+    return PATCH_PROBE_BIN
+
+
 PROBE_BIN = os.path.join(HERE, "video_probe")
 
 
@@ -113,3 +130,4 @@ if __name__ == "__main__":
     print(build_host(force="--force" in sys.argv))
     print(build_probe(force="--force" in sys.argv))
     print(build_transpose_tool(force="--force" in sys.argv))
+    print(build_patch_probe(force="--force" in sys.argv))

@@ -18,6 +18,11 @@
 //   cam<c>.warp           registration = given : number_frames x 6 f32
 //   cam<c>.first          registration = pixel : raw first frame, u16
 //   cam<c>.patch_boff/.patch_bx/.patch_by/.patch_ioff/.patch_ix/.patch_iy   target_patcher = polynomial
+//   cam<c>.targets        (instead of the six patch_* files) text, one projected target "u v diameter" per
+//                         line: the pixel lists are then built here as InitializeImagePatches does
+//                         (psp_process.cpp:2125-2163) with host/patch_geometry.hpp; job.txt keys
+//                         bound_thickness (2), buffer_thickness (0), patch_thresh (optional: boundary
+//                         pixels near values of cam<c>.first below it are dropped, offset 2)
 //   remap.i32             optional: static form of P3DModel::adjust_solution
 //   steady.f32 model_temp.f32   [msize]
 //
@@ -30,6 +35,7 @@
 #include <limits>
 #include <sstream>
 
+#include "patch_geometry.hpp"
 #include "upsp_b200.hpp"
 #include "video_readers.hpp"
 
@@ -127,7 +133,27 @@ int main(int argc, char** argv) {
       auto val = read_all<float>(b + ".val");
       if ((int)rowptr.size() != msize + 1) throw std::invalid_argument("rowptr size inconsistent with msize");
       chain.set_projection(c, rowptr.data(), col.data(), val.data());
-      if (patcher == "polynomial") {
+      std::ifstream targets_file(b + ".targets");
+      if (patcher == "polynomial" && targets_file) {
+        std::vector<Target> targs;
+        Target t;
+        while (targets_file >> t.u >> t.v >> t.diameter) targs.push_back(t);
+        const unsigned bt = job.count("bound_thickness") ? (unsigned)geti("bound_thickness") : 2u;
+        const unsigned bf = job.count("buffer_thickness") ? (unsigned)geti("buffer_thickness") : 0u;
+        std::vector<std::vector<Target>> clusters;
+        cluster_points(targs, clusters, (int)(bt + bf));
+        PatchClusters pc(clusters, W, H, bt, bf);
+        if (job.count("patch_thresh")) {
+          auto first = read_all<uint16_t>(b + ".first");
+          if (first.size() != (size_t)W * H) throw std::invalid_argument("cam.first has the wrong size");
+          pc.threshold_bounds(first.data(), (unsigned)geti("patch_thresh"), 2u);
+        }
+        std::vector<int32_t> boff, ioff;
+        std::vector<uint32_t> bx, by, ix, iy;
+        pc.flatten(boff, bx, by, ioff, ix, iy);
+        std::cout << "Sorted " << targs.size() << " targets into " << clusters.size() << " clusters" << std::endl;
+        chain.set_patches(c, (int)clusters.size(), boff.data(), bx.data(), by.data(), ioff.data(), ix.data(), iy.data());
+      } else if (patcher == "polynomial") {
         auto boff = read_all<int32_t>(b + ".patch_boff"), ioff = read_all<int32_t>(b + ".patch_ioff");
         auto bx = read_all<uint32_t>(b + ".patch_bx"), by = read_all<uint32_t>(b + ".patch_by");
         auto ix = read_all<uint32_t>(b + ".patch_ix"), iy = read_all<uint32_t>(b + ".patch_iy");
