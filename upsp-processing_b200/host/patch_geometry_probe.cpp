@@ -1,5 +1,5 @@
 // patch_geometry_probe -- runs host/patch_geometry.hpp on a target list and prints the resulting
-// cluster pixel lists (tests/test_patch_geometry.py compares them with the oracle's restatement).
+// cluster pixel lists (tests/test_patch_geometry.py compares them with an independent restatement).
 //   patch_geometry_probe targets.txt width height boundary_thickness buffer_thickness [ref.u16 thresh offset]
 // targets.txt: one "u v diameter" per line.  Output: "cluster i n_targets", then "b x y" / "i x y" lines.
 #include <cstdio>
