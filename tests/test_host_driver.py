@@ -170,3 +170,46 @@ def test_transpose_tool_matches_numpy(up, gpu, tmp_path, flag, block):
     assert r.returncode == 0, r.stderr
     out = np.fromfile(tmp_path / ("pressure_transpose" if flag == 0 else "pressure"), np.float32)
     assert np.array_equal(out.reshape(a.T.shape), a.T)
+
+
+@pytest.mark.gpu
+def test_host_driver_builds_patches_from_targets(up, orc, gpu, tmp_path):
+    """job directory with cam0.targets (projected fiducials u v diameter) instead of precomputed
+    pixel lists: the driver clusters them and builds the boundary / interior lists with
+    host/patch_geometry.hpp (InitializeImagePatches, psp_process.cpp:2125-2163); the run must equal
+    the oracle run with the lists of the oracle's own restatement of that geometry."""
+    import upsp_b200
+    from oracle import setup_patches as sp
+    synth = upsp_b200.synth
+    case = Case(synth, n_frames=24, n_nodes=1500, registration=True, patches=False, seed=47)
+    rng = np.random.default_rng(5)
+    targs = [(rng.uniform(12, case.W - 12), rng.uniform(12, case.H - 12), rng.uniform(3, 6)) for _ in range(6)]
+    targs += [(40.0, 30.0, 5.0), (46.0, 31.0, 4.0), (2.0, 50.0, 5.0)]           # a two-target cluster and a border target
+    targs = [tuple(np.float32(x) for x in t) for t in targs]
+    bt, bf = 2, 1
+    first = case.frames[0][0]
+    thresh = int(np.percentile(first, 2))
+    lists = sp.patch_clusters(sp.cluster_points(targs, bt + bf), case.W, case.H, bt, bf, first, thresh, 2)
+    xy = lambda pts: (np.array([p[0] for p in pts], np.uint32), np.array([p[1] for p in pts], np.uint32))
+    case.patch_lists = [([xy(b) for b, _ in lists], [xy(i) for _, i in lists])]
+    job, out = tmp_path / "job", tmp_path / "out"
+    out.mkdir()
+    synth.write_job(str(job), frames=case.frames, csr=case.csr, fmt="p12", registration="given", warp=case.warp,
+                    patches=[synth.flatten_patches(*case.patch_lists[0])], remap=None, cal=case.cal, qbar=case.qbar,
+                    ps=case.ps, steady=case.steady, model_temp=case.temp)
+    for f in os.listdir(job):
+        if ".patch_" in f:
+            os.remove(job / f)
+    (job / "cam0.targets").write_text("".join("%.9g %.9g %.9g\n" % tuple(float(x) for x in t) for t in targs))
+    first.astype("<u2").tofile(job / "cam0.first")
+    with open(job / "job.txt", "a") as fd:
+        fd.write("bound_thickness = %d\nbuffer_thickness = %d\npatch_thresh = %d\n" % (bt, bf, thresh))
+    exe = up.build.build_host()
+    r = subprocess.run([exe, "-job_dir", str(job), "-out_dir", str(out), "-chunk", "8"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Sorted 9 targets into 8 clusters" in r.stdout
+    ref = run_oracle(orc, case)
+    got = np.fromfile(out / "intensity_transpose", np.float32).reshape(case.N, case.F)
+    assert same_bits(got, ref["itrans"])
+    assert same_bits(np.fromfile(out / "intensity_avg", np.float32), ref["avg"])
