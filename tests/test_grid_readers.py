@@ -1,0 +1,93 @@
+"""host/grid_readers.hpp: the unstructured .tri grid reader (TriModel_::load_grid,
+cpp/lib/TriModel.ipp:115-225) and the node normals (calcNormals, :1428-1506).  Known answers come
+from the reference's own unit tests (cpp/test/test_trimodel.cpp:26-100: node / face / component
+counts of its sphere fixtures); the arrays are checked against a numpy reading of the same
+Fortran-unformatted records.  CPU only."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+
+def write_tri(path, xyz, tri, comps=None):
+    """Cart3D-style unformatted .tri: {n_node, n_tri}, xyz float32, 1-based faces int32[, components]"""
+    rec = lambda payload: struct.pack("<i", len(payload)) + payload + struct.pack("<i", len(payload))
+    with open(path, "wb") as f:
+        f.write(rec(struct.pack("<ii", len(xyz), len(tri))))
+        f.write(rec(np.ascontiguousarray(xyz, "<f4").tobytes()))
+        f.write(rec(np.ascontiguousarray(tri + 1, "<i4").tobytes()))
+        if comps is not None:
+            f.write(rec(np.ascontiguousarray(comps, "<i4").tobytes()))
+
+
+def run_probe(probe, path, prefix=None):
+    r = subprocess.run([probe, str(path)] + ([str(prefix)] if prefix else []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return {l.split()[0]: int(l.split()[1]) for l in r.stdout.splitlines()}
+
+
+def numpy_normals(xyz, tri):
+    """calcNormals in float32, faces accumulated in ascending order"""
+    xyz = xyz.astype(np.float32)
+    p0, p1, p2 = xyz[tri[:, 0]], xyz[tri[:, 1]], xyz[tri[:, 2]]
+    u, v = p2 - p1, p0 - p1
+    n = np.stack([u[:, 1] * v[:, 2] - v[:, 1] * u[:, 2], v[:, 0] * u[:, 2] - u[:, 0] * v[:, 2],
+                  u[:, 0] * v[:, 1] - v[:, 0] * u[:, 1]], 1).astype(np.float32)
+    m = np.sqrt((n.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+    n = np.where(m[:, None] != 0, n / np.where(m == 0, 1, m)[:, None], n).astype(np.float32)
+    acc = np.zeros_like(xyz)
+    for t in range(len(tri)):                     # ordered accumulation, float32
+        for k in range(3):
+            acc[tri[t, k]] = acc[tri[t, k]] + n[t]
+    m = np.sqrt((acc.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+    return np.where(m[:, None] != 0, acc / np.where(m == 0, 1, m)[:, None], acc).astype(np.float32)
+
+
+@pytest.mark.parametrize("with_comps", [False, True])
+def test_tri_reader_and_normals(up, tmp_path, with_comps):
+    probe = up.build.build_grid_probe()
+    xyz, _, tri = up.synth.make_sphere_mesh(10, 20, 3.0, (0.5, -1.0, 2.0), bump=0.1, seed=4)
+    xyz = np.concatenate([xyz, [[9.0, 9.0, 9.0]]]).astype(np.float32)        # a node no triangle uses
+    comps = (np.arange(len(tri)) % 3 + 1).astype(np.int32) if with_comps else None
+    write_tri(tmp_path / "g.tri", xyz, tri, comps)
+    info = run_probe(probe, tmp_path / "g.tri", tmp_path / "d")
+    assert info == dict(n_nodes=len(xyz), n_tris=len(tri), n_comps=3 if with_comps else 1, has_comps=int(with_comps))
+    assert np.array_equal(np.fromfile(tmp_path / "d.xyz", np.float32).reshape(-1, 3), xyz)
+    assert np.array_equal(np.fromfile(tmp_path / "d.tri", np.int32).reshape(-1, 3), tri)
+    if with_comps:
+        assert np.array_equal(np.fromfile(tmp_path / "d.comp", np.int32), comps)
+    nrm = np.fromfile(tmp_path / "d.nrm", np.float32).reshape(-1, 3)
+    want = numpy_normals(xyz, tri)
+    assert np.array_equal(nrm.view(np.uint32), want.view(np.uint32))
+    assert np.all(nrm[-1] == 0) and np.allclose(np.linalg.norm(nrm[:-1], axis=1), 1.0, atol=1e-6)
+    centre = np.float32([0.5, -1.0, 2.0])
+    assert np.all(np.einsum("ij,ij->i", nrm[:-1], xyz[:-1] - centre) > 0)    # outward for this winding
+
+
+def test_reference_sphere_fixtures(up):
+    """cpp/test/test_trimodel.cpp:64-70, 86-92, 26-32 (build container only)"""
+    base = "/root/reference/cpp/test/inputs/"
+    if not os.path.exists(base + "sphere_unf_single.tri"):
+        pytest.skip("reference fixtures not present on this machine")
+    probe = up.build.build_grid_probe()
+    assert run_probe(probe, base + "sphere_unf_single.tri") == dict(n_nodes=594, n_tris=1024, n_comps=1, has_comps=1)
+    assert run_probe(probe, base + "sphere_unf_single.i.tri") == dict(n_nodes=514, n_tris=1024, n_comps=1, has_comps=1)
+    multi = run_probe(probe, base + "sphere_unf_multi.i.tri")
+    assert (multi["n_nodes"], multi["n_tris"], multi["n_comps"]) == (514, 1024, 6)
+
+
+def test_tri_reader_errors(up, tmp_path):
+    probe = up.build.build_grid_probe()
+    r = subprocess.run([probe, str(tmp_path / "none.tri")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot open tri grid file" in r.stderr
+    xyz, _, tri = up.synth.make_sphere_mesh(4, 8)
+    write_tri(tmp_path / "g.tri", xyz, tri)
+    raw = (tmp_path / "g.tri").read_bytes()
+    (tmp_path / "cut.tri").write_bytes(raw[:len(raw) // 2])
+    r = subprocess.run([probe, str(tmp_path / "cut.tri")], capture_output=True, text=True)
+    assert r.returncode == 1 and "inconsistent number of" in r.stderr
+    (tmp_path / "bad.tri").write_bytes(struct.pack("<i", 12) + raw[4:])
+    r = subprocess.run([probe, str(tmp_path / "bad.tri")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unable to read tri grid file" in r.stderr

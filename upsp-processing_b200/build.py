@@ -108,6 +108,24 @@ def build_patch_probe(force: bool = False) -> str:
     return PATCH_PROBE_BIN
 
 
+GRID_PROBE_BIN = os.path.join(HERE, "grid_probe")
+
+
+def build_grid_probe(force: bool = False) -> str:
+    """host/grid_probe.cpp: .tri grid reader + node normals (host C++) exercised from the tests."""
+    src = os.path.join(HERE, "host", "grid_probe.cpp")
+    deps = [src, os.path.join(HERE, "host", "grid_readers.hpp")]
+    if not force and os.path.exists(GRID_PROBE_BIN) and os.path.getmtime(GRID_PROBE_BIN) >= max(map(os.path.getmtime, deps)):
+        return GRID_PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-o", GRID_PROBE_BIN, src],
+                       capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building grid_probe")
+    return GRID_PROBE_BIN
+
+
 PROBE_BIN = os.path.join(HERE, "video_probe")
 
 
@@ -131,3 +149,4 @@ if __name__ == "__main__":
     print(build_probe(force="--force" in sys.argv))
     print(build_transpose_tool(force="--force" in sys.argv))
     print(build_patch_probe(force="--force" in sys.argv))
+    print(build_grid_probe(force="--force" in sys.argv))

@@ -1,0 +1,38 @@
+// grid_probe -- reads a .tri grid with host/grid_readers.hpp, prints its sizes and dumps
+// xyz | normals | tris (0-based) as raw little-endian arrays for tests/test_grid_readers.py.
+//   grid_probe FILE.tri [dump_prefix]
+#include <cstdio>
+#include <iostream>
+
+#include "grid_readers.hpp"
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::cerr << "usage: grid_probe FILE.tri [dump_prefix]\n";
+    return 1;
+  }
+  try {
+    const auto g = upsp_b200::read_tri_grid(argv[1]);
+    std::vector<float> nrm;
+    upsp_b200::calc_normals(g, nrm);
+    std::printf("n_nodes %d\nn_tris %d\nn_comps %d\nhas_comps %d\n", g.n_nodes, g.n_tris, g.number_of_components(),
+                g.comps.empty() ? 0 : 1);
+    if (argc > 2) {
+      const std::string p = argv[2];
+      auto dump = [&](const std::string& name, const void* d, size_t bytes) {
+        FILE* f = std::fopen((p + name).c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot write " + p + name);
+        std::fwrite(d, 1, bytes, f);
+        std::fclose(f);
+      };
+      dump(".xyz", g.xyz.data(), g.xyz.size() * 4);
+      dump(".nrm", nrm.data(), nrm.size() * 4);
+      dump(".tri", g.tris.data(), g.tris.size() * 4);
+      dump(".comp", g.comps.data(), g.comps.size() * 4);
+    }
+  } catch (const std::exception& e) {
+    std::cerr << "grid_probe: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}
