@@ -91,3 +91,102 @@ def test_tri_reader_errors(up, tmp_path):
     (tmp_path / "bad.tri").write_bytes(struct.pack("<i", 12) + raw[4:])
     r = subprocess.run([probe, str(tmp_path / "bad.tri")], capture_output=True, text=True)
     assert r.returncode == 1 and "Unable to read tri grid file" in r.stderr
+
+
+# ---------------------------------------------------------------- structured plot3d grids
+def write_p3d(path, zones, dp=False, big=False, iblank=False, multi=None):
+    """zones: list of (x, y, z) arrays of shape (k, j, i).  Unformatted plot3d as plot3d.h:30-60."""
+    e = ">" if big else "<"
+    ft = e + ("f8" if dp else "f4")
+    rec = lambda payload: struct.pack(e + "i", len(payload)) + payload + struct.pack(e + "i", len(payload))
+    multi = len(zones) > 1 if multi is None else multi
+    with open(path, "wb") as f:
+        if multi:
+            f.write(rec(struct.pack(e + "i", len(zones))))
+        f.write(rec(b"".join(struct.pack(e + "iii", *z[0].shape[::-1]) for z in zones)))
+        for x, y, z in zones:
+            payload = b"".join(np.ascontiguousarray(a, ft).tobytes() for a in (x, y, z))
+            if iblank:
+                payload += np.ones(x.size, e + "i4").tobytes()
+            f.write(rec(payload))
+
+
+def _zones(seed, shapes):
+    rng = np.random.default_rng(seed)
+    return [tuple(rng.normal(0, 5, s).astype(np.float32) for _ in range(3)) for s in shapes]
+
+
+@pytest.mark.parametrize("shapes", [[(1, 7, 9)], [(1, 5, 4), (2, 3, 6), (1, 1, 8)]], ids=["single", "multi"])
+def test_plot3d_reader_all_variants_round_trip(up, tmp_path, shapes):
+    """The reference's own test (cpp/test/test_plot3d.cpp ReadWriteGridFiles): whatever the variant
+    read (precision, endianness, IBLANK), writing it back gives the little-endian file of the
+    requested precision, byte for byte."""
+    probe = up.build.build_grid_probe()
+    zones = _zones(len(shapes), shapes)
+    write_p3d(tmp_path / "le_sp.x", zones)
+    write_p3d(tmp_path / "le_dp.x", zones, dp=True)
+    for dp in (False, True):
+        for big in (False, True):
+            for ib in (False, True):
+                src = tmp_path / f"v_{dp}_{big}_{ib}.x"
+                write_p3d(src, zones, dp=dp, big=big, iblank=ib)
+                for out_dp in (False, True):
+                    out = tmp_path / "o.x"
+                    r = subprocess.run([probe, str(src), "dp" if out_dp else "sp", str(out)], capture_output=True, text=True)
+                    assert r.returncode == 0, r.stderr
+                    assert out.read_bytes() == (tmp_path / ("le_dp.x" if out_dp else "le_sp.x")).read_bytes()
+                    lines = r.stdout.splitlines()
+                    assert lines[0] == f"n_zones {len(shapes)}" and lines[1] == f"n_points {sum(int(np.prod(s)) for s in shapes)}"
+                    assert [tuple(map(int, l.split()[2:])) for l in lines[2:]] == [s[::-1] for s in shapes]
+
+
+def test_plot3d_reference_fixtures(up, tmp_path):
+    """cpp/test/test_plot3d.cpp:36-118 on the reference's fixtures, plus the reference's Python reader
+    (python/upsp/processing/plot3d.py read_p3d_grid) on the single-precision multi-zone file."""
+    base = "/root/reference/cpp/test/inputs/sphere_unf_"
+    if not os.path.exists(base + "multi_integration_sp.x"):
+        pytest.skip("reference fixtures not present on this machine")
+    probe = up.build.build_grid_probe()
+    for kind in ("single", "multi"):
+        variants = ["sp", "dp", "sp_bigend", "dp_bigend"] + (["sp_iblank", "dp_iblank"] if kind == "multi" else [])
+        for v in variants:
+            for prec in ("sp", "dp"):
+                out = tmp_path / "o.x"
+                r = subprocess.run([probe, f"{base}{kind}_integration_{v}.x", prec, str(out)], capture_output=True, text=True)
+                assert r.returncode == 0, r.stderr
+                assert out.read_bytes() == open(f"{base}{kind}_integration_{prec}.x", "rb").read()
+    import sys
+    sys.path.insert(0, "/root/reference/python")
+    try:
+        from upsp.processing import plot3d
+    except Exception:
+        return
+    if not hasattr(np, "product"):
+        np.product = np.prod          # the reference predates numpy 2
+    g = plot3d.read_p3d_grid(base + "multi_integration_sp.x")
+    out = tmp_path / "m.x"
+    subprocess.run([probe, base + "multi_integration_sp.x", "sp", str(out)], check=True, capture_output=True)
+    raw = out.read_bytes()
+    nz = struct.unpack("<i", raw[4:8])[0]
+    assert nz == len(g.sz) == 4
+    pos, xs = 12 + 4 + 12 * nz + 4, []
+    for z in range(nz):
+        n = int(np.prod(g.sz[z]))
+        pos += 4
+        xs.append(np.frombuffer(raw, "<f4", 3 * n, pos)[:n])
+        pos += 12 * n + 4
+    assert np.array_equal(np.concatenate(xs), np.asarray(g.x, np.float32))
+
+
+def test_plot3d_reader_errors(up, tmp_path):
+    probe = up.build.build_grid_probe()
+    r = subprocess.run([probe, str(tmp_path / "none.x"), "sp"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot open plot3d grid file" in r.stderr
+    (tmp_path / "junk.x").write_bytes(struct.pack("<i", 77) + bytes(100))
+    r = subprocess.run([probe, str(tmp_path / "junk.x"), "sp"], capture_output=True, text=True)
+    assert r.returncode == 1 and "bad header record" in r.stderr
+    write_p3d(tmp_path / "ok.x", _zones(1, [(1, 3, 4)]))
+    raw = (tmp_path / "ok.x").read_bytes()
+    (tmp_path / "cut.x").write_bytes(raw[:-20])
+    r = subprocess.run([probe, str(tmp_path / "cut.x"), "sp"], capture_output=True, text=True)
+    assert r.returncode == 1 and "truncated zone data" in r.stderr

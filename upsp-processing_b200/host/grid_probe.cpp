@@ -1,6 +1,8 @@
 // grid_probe -- reads a .tri grid with host/grid_readers.hpp, prints its sizes and dumps
-// xyz | normals | tris (0-based) as raw little-endian arrays for tests/test_grid_readers.py.
+// xyz | normals | tris (0-based) as raw little-endian arrays for tests/test_grid_readers.py; or reads
+// an unformatted plot3d grid and re-writes it in single or double precision.
 //   grid_probe FILE.tri [dump_prefix]
+//   grid_probe FILE.x sp|dp [OUT.x]
 #include <cstdio>
 #include <iostream>
 
@@ -12,6 +14,27 @@ int main(int argc, char** argv) {
     return 1;
   }
   try {
+    const std::string name = argv[1];
+    if (name.size() > 2 && name.compare(name.size() - 2, 2, ".x") == 0) {
+      const bool dp = argc > 2 && std::string(argv[2]) == "dp";
+      auto report = [](const auto& g) {
+        std::printf("n_zones %u\nn_points %zu\n", g.num_zones(), g.size());
+        for (unsigned z = 0; z < g.num_zones(); ++z)
+          std::printf("zone %u %u %u %u\n", z, g.grid_size[z][0], g.grid_size[z][1], g.grid_size[z][2]);
+      };
+      if (dp) {
+        upsp_b200::StructuredGrid<double> g;
+        upsp_b200::read_plot3d_grid_file(name, g);
+        report(g);
+        if (argc > 3) upsp_b200::write_plot3d_grid_file(argv[3], g);
+      } else {
+        upsp_b200::StructuredGrid<float> g;
+        upsp_b200::read_plot3d_grid_file(name, g);
+        report(g);
+        if (argc > 3) upsp_b200::write_plot3d_grid_file(argv[3], g);
+      }
+      return 0;
+    }
     const auto g = upsp_b200::read_tri_grid(argv[1]);
     std::vector<float> nrm;
     upsp_b200::calc_normals(g, nrm);

@@ -7,8 +7,10 @@
 //       unit normals of the triangles around the node, in ascending triangle order)
 // The outputs are exactly what upsp_op_create_projection consumes: xyz, normals, triNodes.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <fstream>
 #include <set>
 #include <stdexcept>
@@ -95,6 +97,136 @@ inline void calc_normals(const TriGrid& g, std::vector<float>& normals) {
     float* v = &normals[3 * (size_t)n];
     const float m = norm3(v[0], v[1], v[2]);
     if (m != 0.f) { v[0] /= m; v[1] /= m; v[2] /= m; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Structured grids: unformatted plot3d (cpp/include/plot3d.h:30-110, read_plot3d_grid_file /
+// write_plot3d_grid_file): Fortran records; single zone = {IDIM,JDIM,KDIM} then one x|y|z record;
+// multi zone = {NZONES}, {3*NZONES dims}, one x|y|z[|iblank] record per zone; single or double
+// precision, little or big endian, IBLANKs skipped.  The precision / endianness / IBLANK variant is
+// recognised from the record lengths.  StructuredGrid<FP> mirrors upsp::StructuredGrid<FP>.
+template <typename FP>
+struct StructuredGrid {
+  typedef FP data_type;
+  std::vector<std::vector<unsigned>> grid_size;   // per zone {i, j, k}
+  std::vector<FP> x, y, z;                        // all zones back to back, i fastest
+  unsigned num_zones() const { return (unsigned)grid_size.size(); }
+  unsigned zone_size(unsigned zn) const { return grid_size[zn][0] * grid_size[zn][1] * grid_size[zn][2]; }
+  size_t size() const { return x.size(); }
+};
+
+namespace p3d_detail {
+inline uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24); }
+inline void swap_bytes(void* p, size_t elem, size_t n) {
+  unsigned char* b = static_cast<unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t k = 0; k < elem / 2; ++k) std::swap(b[i * elem + k], b[i * elem + elem - 1 - k]);
+}
+}  // namespace p3d_detail
+
+template <typename StructGrid>
+void read_plot3d_grid_file(const std::string& filename, StructGrid& grid) {
+  typedef typename StructGrid::data_type FP;
+  std::ifstream ifs(filename, std::ios::in | std::ios::binary);
+  if (!ifs) throw std::invalid_argument("Cannot open plot3d grid file '" + filename + "'");
+  bool swap = false;
+  auto rd_i32 = [&](int32_t* dst, size_t n) {
+    ifs.read(reinterpret_cast<char*>(dst), (std::streamsize)(n * 4));
+    if (!ifs) throw std::invalid_argument("Unable to read plot3d grid file '" + filename + "'");
+    if (swap) p3d_detail::swap_bytes(dst, 4, n);
+  };
+  int32_t len = 0;
+  rd_i32(&len, 1);
+  if (len != 4 && len != 12) {                     // not a native-endian header record: try the other endianness
+    len = (int32_t)p3d_detail::bswap32((uint32_t)len);
+    swap = true;
+    if (len != 4 && len != 12) throw std::invalid_argument("Unable to read plot3d grid file '" + filename + "': bad header record");
+  }
+  int32_t nz = 1, tail = 0;
+  std::vector<int32_t> dims;
+  if (len == 4) {                                   // multi-zone
+    rd_i32(&nz, 1);
+    rd_i32(&tail, 1);
+    if (tail != len || nz <= 0) throw std::invalid_argument("Unable to read plot3d grid file, bad zone count");
+    rd_i32(&len, 1);
+    if (len != 12 * nz) throw std::invalid_argument("Unable to read plot3d grid file, inconsistent zone dimensions");
+  }
+  dims.resize((size_t)3 * nz);
+  rd_i32(dims.data(), dims.size());
+  rd_i32(&tail, 1);
+  if (tail != len) throw std::invalid_argument("Unable to read plot3d grid file, inconsistent zone dimensions");
+  grid.grid_size.clear();
+  grid.x.clear(); grid.y.clear(); grid.z.clear();
+  for (int zn = 0; zn < nz; ++zn) {
+    if (dims[3 * zn] <= 0 || dims[3 * zn + 1] <= 0 || dims[3 * zn + 2] <= 0)
+      throw std::invalid_argument("Unable to read plot3d grid file, non-positive zone dimension");
+    grid.grid_size.push_back({(unsigned)dims[3 * zn], (unsigned)dims[3 * zn + 1], (unsigned)dims[3 * zn + 2]});
+  }
+  for (int zn = 0; zn < nz; ++zn) {
+    const size_t npts = (size_t)grid.zone_size((unsigned)zn);
+    uint32_t rlen = 0;
+    ifs.read(reinterpret_cast<char*>(&rlen), 4);
+    if (!ifs) throw std::invalid_argument("Unable to read plot3d grid file, missing zone data");
+    if (swap) rlen = p3d_detail::bswap32(rlen);
+    size_t elem = 0;
+    bool iblank = false;
+    if (rlen == 12 * npts) elem = 4;
+    else if (rlen == 24 * npts) elem = 8;
+    else if (rlen == 16 * npts) { elem = 4; iblank = true; }
+    else if (rlen == 28 * npts) { elem = 8; iblank = true; }
+    else throw std::invalid_argument("Unable to read plot3d grid file, zone record length matches no precision");
+    std::vector<unsigned char> buf(3 * npts * elem);
+    ifs.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size());
+    if (!ifs) throw std::invalid_argument("Unable to read plot3d grid file, truncated zone data");
+    if (swap) p3d_detail::swap_bytes(buf.data(), elem, 3 * npts);
+    if (iblank) ifs.seekg((std::streamoff)(4 * npts), std::ios::cur);
+    uint32_t rtail = 0;
+    ifs.read(reinterpret_cast<char*>(&rtail), 4);
+    if (swap) rtail = p3d_detail::bswap32(rtail);
+    if (!ifs || rtail != rlen) throw std::invalid_argument("Unable to read plot3d grid file, inconsistent zone record");
+    std::vector<FP>* out[3] = {&grid.x, &grid.y, &grid.z};
+    for (int c = 0; c < 3; ++c)
+      for (size_t i = 0; i < npts; ++i) {
+        if (elem == 4) {
+          float v;
+          std::memcpy(&v, &buf[(c * npts + i) * 4], 4);
+          out[c]->push_back((FP)v);
+        } else {
+          double v;
+          std::memcpy(&v, &buf[(c * npts + i) * 8], 8);
+          out[c]->push_back((FP)v);
+        }
+      }
+  }
+}
+
+/* machine-endian, precision of StructGrid::data_type, single-zone layout when there is one zone */
+template <typename StructGrid>
+void write_plot3d_grid_file(const std::string& filename, const StructGrid& grid) {
+  typedef typename StructGrid::data_type FP;
+  std::ofstream ofs(filename, std::ios::out | std::ios::binary);
+  if (!ofs) throw std::invalid_argument("Cannot open plot3d grid file '" + filename + "' for writing");
+  auto rec = [&](const void* p, size_t bytes) {
+    const int32_t n = (int32_t)bytes;
+    ofs.write(reinterpret_cast<const char*>(&n), 4);
+    ofs.write(reinterpret_cast<const char*>(p), (std::streamsize)bytes);
+    ofs.write(reinterpret_cast<const char*>(&n), 4);
+  };
+  const int32_t nz = (int32_t)grid.num_zones();
+  if (nz != 1) rec(&nz, 4);
+  std::vector<int32_t> dims;
+  for (const auto& g : grid.grid_size) dims.insert(dims.end(), {(int32_t)g[0], (int32_t)g[1], (int32_t)g[2]});
+  rec(dims.data(), dims.size() * 4);
+  size_t off = 0;
+  for (int32_t zn = 0; zn < nz; ++zn) {
+    const size_t npts = grid.zone_size((unsigned)zn);
+    std::vector<FP> buf;
+    buf.insert(buf.end(), grid.x.begin() + (std::ptrdiff_t)off, grid.x.begin() + (std::ptrdiff_t)(off + npts));
+    buf.insert(buf.end(), grid.y.begin() + (std::ptrdiff_t)off, grid.y.begin() + (std::ptrdiff_t)(off + npts));
+    buf.insert(buf.end(), grid.z.begin() + (std::ptrdiff_t)off, grid.z.begin() + (std::ptrdiff_t)(off + npts));
+    rec(buf.data(), buf.size() * sizeof(FP));
+    off += npts;
   }
 }
 
