@@ -126,6 +126,26 @@ def build_grid_probe(force: bool = False) -> str:
     return GRID_PROBE_BIN
 
 
+SETUP_BIN = os.path.join(HERE, "psp_setup_b200")
+
+
+def build_setup_tool(force: bool = False) -> str:
+    """host/psp_setup_b200.cpp: grid + calibration -> projection matrix (phase 0 on the GPU)."""
+    src = os.path.join(HERE, "host", "psp_setup_b200.cpp")
+    deps = [src, os.path.join(HERE, "host", "camera_cal.hpp"), os.path.join(HERE, "host", "grid_readers.hpp")]
+    build()
+    if not force and os.path.exists(SETUP_BIN) and os.path.getmtime(SETUP_BIN) >= max([os.path.getmtime(LIB)] + list(map(os.path.getmtime, deps))):
+        return SETUP_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-o", SETUP_BIN, src, "-L" + HERE, "-lupsp_gpu",
+           "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building psp_setup_b200")
+    return SETUP_BIN
+
+
 PROBE_BIN = os.path.join(HERE, "video_probe")
 
 
@@ -150,3 +170,4 @@ if __name__ == "__main__":
     print(build_transpose_tool(force="--force" in sys.argv))
     print(build_patch_probe(force="--force" in sys.argv))
     print(build_grid_probe(force="--force" in sys.argv))
+    print(build_setup_tool(force="--force" in sys.argv))
