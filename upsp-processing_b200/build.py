@@ -146,6 +146,24 @@ def build_setup_tool(force: bool = False) -> str:
     return SETUP_BIN
 
 
+WEIGHTS_PROBE_BIN = os.path.join(HERE, "projection_weights_probe")
+
+
+def build_weights_probe(force: bool = False) -> str:
+    """host/projection_weights_probe.cpp: multi-camera blending weights (host C++) exercised from the tests."""
+    src = os.path.join(HERE, "host", "projection_weights_probe.cpp")
+    deps = [src, os.path.join(HERE, "host", "projection_weights.hpp")]
+    if not force and os.path.exists(WEIGHTS_PROBE_BIN) and os.path.getmtime(WEIGHTS_PROBE_BIN) >= max(map(os.path.getmtime, deps)):
+        return WEIGHTS_PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-o", WEIGHTS_PROBE_BIN, src],
+                       capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building projection_weights_probe")
+    return WEIGHTS_PROBE_BIN
+
+
 PROBE_BIN = os.path.join(HERE, "video_probe")
 
 
@@ -171,3 +189,4 @@ if __name__ == "__main__":
     print(build_patch_probe(force="--force" in sys.argv))
     print(build_grid_probe(force="--force" in sys.argv))
     print(build_setup_tool(force="--force" in sys.argv))
+    print(build_weights_probe(force="--force" in sys.argv))
