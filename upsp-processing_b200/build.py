@@ -126,6 +126,25 @@ def build_grid_probe(force: bool = False) -> str:
     return GRID_PROBE_BIN
 
 
+INPUTS_PROBE_BIN = os.path.join(HERE, "inputs_probe")
+
+
+def build_inputs_probe(force: bool = False) -> str:
+    """host/inputs_probe.cpp: deck / paint calibration / wtd / targets / p3d function / histogram readers and
+    the structured model's seam detection (host C++) exercised from the tests."""
+    src = os.path.join(HERE, "host", "inputs_probe.cpp")
+    deps = [src] + [os.path.join(HERE, "host", h) for h in ("upsp_inputs.hpp", "run_inputs.hpp", "p3d_model.hpp", "grid_readers.hpp")]
+    if not force and os.path.exists(INPUTS_PROBE_BIN) and os.path.getmtime(INPUTS_PROBE_BIN) >= max(map(os.path.getmtime, deps)):
+        return INPUTS_PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-o", INPUTS_PROBE_BIN, src],
+                       capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building inputs_probe")
+    return INPUTS_PROBE_BIN
+
+
 SETUP_BIN = os.path.join(HERE, "psp_setup_b200")
 
 
@@ -190,3 +209,4 @@ if __name__ == "__main__":
     print(build_grid_probe(force="--force" in sys.argv))
     print(build_setup_tool(force="--force" in sys.argv))
     print(build_weights_probe(force="--force" in sys.argv))
+    print(build_inputs_probe(force="--force" in sys.argv))
