@@ -1,0 +1,115 @@
+"""psp_setup_b200 deck mode (host/psp_setup_b200.cpp: run_deck): psp_process's own command line and input deck
+(ParseOpts cpp/exec/psp_process.cpp:1192-1310, InitializeVideoStreams :392-470, phase-2 start-up :2270-2385) turned
+into a job directory of psp_process_b200.  CPU: everything except the projection matrix (`-no_projection`)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_grid_readers import write_tri
+from test_p3d_model import reference_fixture, write_p3d
+from test_setup_tool import _cal_json
+
+
+def job_kv(path):
+    out = {}
+    for line in open(path):
+        if "=" in line and not line.startswith("#"):
+            k, _, v = line.partition("=")
+            out[k.strip()] = v.strip()
+    return out
+
+
+def make_inputs(up, d, grid="tri", registration="none", frames=-1, cameras=1, extra_all=""):
+    """a run directory in the reference's layout; the camera file is the committed 2-frame 32x16 Photron pair"""
+    if grid == "tri":
+        xyz, _, tri = up.synth.make_sphere_mesh(8, 16, 2.0, (0, 0, 6.0), seed=3)
+        write_tri(d / "model.tri", xyz.astype(np.float32), tri, np.ones(len(tri), np.int32))
+        gname, n = "model.tri", len(xyz)
+    else:
+        write_p3d(d / "model.grid", reference_fixture())
+        gname, n = "model.grid", 52
+    (d / "run.wtd").write_text(open(os.path.join(GOLDEN, "sample.wtd")).read())
+    (d / "model.tgts").write_text(open(os.path.join(GOLDEN, "sample.tgts")).read())
+    (d / "paint.cal").write_text("a = 1.5\nb = -0.002\nc = 1e-6\nd = 0.5\ne = 0.001\nf = -2e-7\n")
+    for c in range(cameras):
+        _cal_json(d / f"cam{c + 1:02d}.json", np.eye(3), [0.1 * c, 0, 0], [[40, 0, 16], [0, 40, 8], [0, 0, 1]], [0, 0, 0, 0], (32, 16))
+        for ext in ("mraw", "cih"):
+            (d / f"v{c + 1}.{ext}").write_bytes(open(os.path.join(GOLDEN, "tiny12." + ext), "rb").read())
+    (d / "out").mkdir(exist_ok=True)
+    cams = "".join(f"@camera\n\tnumber = {c + 1}\n\tfilename = $d/v{c + 1}.mraw\n\tcalibration = $d/cam{c + 1:02d}.json\n" for c in range(cameras))
+    deck = (f"%Version 0.0\n@general\n\ttest = t-b200\n\trun = 12\n\tsequence = 3\n\ttunnel = ames_unitary\n@vars\n\td = {d}\n"
+            f"@all\n\tgrid = $d/{gname}\n\tsds = $d/run.wtd\n\ttargets = $d/model.tgts\n{extra_all}{cams}"
+            f"@options\n\ttarget_patcher = none\n\tregistration = {registration}\n\tfilter = none\n\tfilter_size = 1\n"
+            f"\toblique_angle = 70\n\tnumber_frames = {frames}\n\toverlap = best_view\n@output\n\tdir = $d/out\n\tname = run12\n")
+    (d / "deck.inp").write_text(deck)
+    return n
+
+
+def setup(up, d, *extra, ok=True):
+    job = d / "job"
+    job.mkdir(exist_ok=True)
+    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(d / "deck.inp"), "-paint_cal", str(d / "paint.cal"),
+                        "-job_dir", str(job)] + [str(a) for a in extra], capture_output=True, text=True)
+    assert (r.returncode == 0) == ok, r.stdout + r.stderr
+    return r, job
+
+
+def test_deck_to_job_unstructured(up, tmp_path):
+    n = make_inputs(up, tmp_path, "tri", registration="pixel")
+    r, job = setup(up, tmp_path, "-no_projection")
+    kv = job_kv(job / "job.txt")
+    assert kv["cameras"] == "1" and kv["width"] == "32" and kv["height"] == "16" and kv["msize"] == str(n)
+    assert kv["number_frames"] == "2"                                   # -1 in the deck: every frame all cameras have
+    assert kv["video0"] == str(tmp_path / "v1.mraw") and kv["registration"] == "pixel" and kv["target_patcher"] == "none"
+    assert kv["bound_thickness"] == "2" and kv["buffer_thickness"] == "1" and kv["degree"] == "6"
+    assert np.float32(kv["qbar"]) == np.float32(657.9153) and np.float32(kv["ps"]) == np.float32(1332.0421)
+    assert [np.float32(kv["cal_" + k]) for k in "abcdef"] == [np.float32(v) for v in (1.5, -0.002, 1e-6, 0.5, 0.001, -2e-7)]
+    assert np.array_equal(np.fromfile(job / "steady.f32", np.float32), np.zeros(n, np.float32))       # wind-off
+    assert np.array_equal(np.fromfile(job / "model_temp.f32", np.float32), np.full(n, 88.125, np.float32))   # TCAVG
+    assert not (job / "remap.i32").exists() and np.fromfile(job / "xyz.f32", np.float32).size == 3 * n
+    assert "Will process (2) frames" in r.stdout and "thermocouple average" in r.stdout
+
+
+def test_deck_to_job_structured(up, tmp_path):
+    n = make_inputs(up, tmp_path, "p3d", frames=1)
+    vals = (np.arange(n, dtype=np.float32) * 0.01 - 0.2).astype(np.float32)
+    with open(tmp_path / "steady.f", "wb") as f:                        # no record markers
+        f.write(struct.pack("<i", 3) + b"".join(struct.pack("<4i", j, k, 1, 1) for j, k in ((4, 5), (3, 4), (5, 4))) + vals.tobytes())
+    r, job = setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f")
+    kv = job_kv(job / "job.txt")
+    assert kv["msize"] == "52" and kv["number_frames"] == "1"
+    remap = np.fromfile(job / "remap.i32", np.int32)
+    assert sorted(np.nonzero(remap != np.arange(52))[0]) == [20, 23, 26, 29, 41, 46, 51]
+    assert np.array_equal(np.fromfile(job / "steady.f32", np.float32), vals)
+    (tmp_path / "short.f").write_bytes(struct.pack("<i", 1) + struct.pack("<4i", 2, 2, 1, 1) + np.zeros(4, np.float32).tobytes())
+    r, _ = setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "short.f", ok=False)
+    assert "Steady-state function file inconsistent with grid (expect 52 values, got 4)" in r.stderr
+
+
+def test_deck_mode_rejections(up, tmp_path):
+    make_inputs(up, tmp_path, "tri", frames=3)
+    r, _ = setup(up, tmp_path, "-no_projection", ok=False)
+    assert "(3) frames requested but only (2) frames available" in r.stderr
+    r, _ = setup(up, tmp_path, "-no_projection", "-frames", "2")          # -frames overrides the deck
+    make_inputs(up, tmp_path, "tri", registration="point")
+    assert "Unsupported registration type" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+    make_inputs(up, tmp_path, "tri")
+    (tmp_path / "deck.inp").write_text((tmp_path / "deck.inp").read_text().replace("ames_unitary", "langley"))
+    assert "Unrecognized tunnel name 'langley'" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+    make_inputs(up, tmp_path, "tri")
+    (tmp_path / "deck.inp").write_text((tmp_path / "deck.inp").read_text().replace("filter_size = 1", "filter_size = 4"))
+    assert "Filter size must be odd" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+    make_inputs(up, tmp_path, "tri")
+    os.remove(tmp_path / "run.wtd")
+    assert "SDS file" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+    make_inputs(up, tmp_path, "tri")
+    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(tmp_path / "deck.inp"), "-job_dir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Must specify -paint_cal" in r.stderr
+    make_inputs(up, tmp_path, "tri")
+    (tmp_path / "steady.f").write_bytes(b"\0" * 64)
+    assert "unstructured grid" in setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f", ok=False)[0].stderr

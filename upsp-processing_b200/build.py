@@ -57,13 +57,13 @@ HOST_BIN = os.path.join(HERE, "psp_process_b200")
 def build_host(force: bool = False) -> str:
     """The C++ host driver (g++, links libupsp_gpu.so through its C ABI only)."""
     src = os.path.join(HERE, "host", "psp_process_b200.cpp")
-    hdr = os.path.join(HERE, "host", "upsp_b200.hpp")
+    hdrs = [os.path.join(HERE, "host", h) for h in ("upsp_b200.hpp", "patch_geometry.hpp", "run_inputs.hpp", "video_readers.hpp")]
     build()
     if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(
-            os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB)):
+            [os.path.getmtime(src), os.path.getmtime(LIB)] + list(map(os.path.getmtime, hdrs))):
         return HOST_BIN
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_BIN, src, "-L" + HERE, "-lupsp_gpu",
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-o", HOST_BIN, src, "-L" + HERE, "-lupsp_gpu",
            "-Wl,-rpath,$ORIGIN", "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
@@ -151,7 +151,9 @@ SETUP_BIN = os.path.join(HERE, "psp_setup_b200")
 def build_setup_tool(force: bool = False) -> str:
     """host/psp_setup_b200.cpp: grid + calibration -> projection matrix (phase 0 on the GPU)."""
     src = os.path.join(HERE, "host", "psp_setup_b200.cpp")
-    deps = [src, os.path.join(HERE, "host", "camera_cal.hpp"), os.path.join(HERE, "host", "grid_readers.hpp")]
+    deps = [src] + [os.path.join(HERE, "host", h) for h in (
+        "camera_cal.hpp", "grid_readers.hpp", "p3d_model.hpp", "projection_weights.hpp", "run_inputs.hpp", "upsp_inputs.hpp",
+        "video_readers.hpp")]
     build()
     if not force and os.path.exists(SETUP_BIN) and os.path.getmtime(SETUP_BIN) >= max([os.path.getmtime(LIB)] + list(map(os.path.getmtime, deps))):
         return SETUP_BIN

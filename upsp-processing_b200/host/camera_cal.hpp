@@ -6,6 +6,7 @@
 // assumes rmat is orthonormal to rounding (it is written by the calibration tools with 16 digits) and
 // applies the same axis-angle formulas, which reproduces cv2.Rodrigues to ~1e-15 (tests pin 1e-12).
 #pragma once
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
@@ -64,6 +65,29 @@ inline void rodrigues_from_matrix(const double R[9], double r[3]) {
     const double vth = 1. / (2 * s) * theta;
     r[0] = rx * vth; r[1] = ry * vth; r[2] = rz * vth;
   }
+}
+
+/* cv::Rodrigues(rvec -> R), the arithmetic of the library's own fill_setup_cam */
+inline void rodrigues_to_matrix(const double r[3], double R[9]) {
+  const double theta = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (theta < 2.220446049250313e-16) {
+    for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double c = std::cos(theta), s = std::sin(theta), c1 = 1.0 - c, itheta = 1.0 / theta;
+  const double x = r[0] * itheta, y = r[1] * itheta, z = r[2] * itheta;
+  const double rrt[9] = {x * x, x * y, x * z, x * y, y * y, y * z, x * z, y * z, z * z};
+  const double rx[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  for (int k = 0; k < 9; ++k) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * rx[k];
+}
+
+/* CameraCal::get_cam_center (cpp/lib/CameraCal.cpp:193-204): -R^T t */
+inline std::array<double, 3> get_cam_center(const upsp_camera_model& cam) {
+  double R[9];
+  rodrigues_to_matrix(cam.rvec, R);
+  std::array<double, 3> c{};
+  for (int i = 0; i < 3; ++i) c[(size_t)i] = -(R[0 + i] * cam.tvec[0] + R[3 + i] * cam.tvec[1] + R[6 + i] * cam.tvec[2]);
+  return c;
 }
 
 inline upsp_camera_model read_json_camera_calibration(const std::string& cfg_file) {

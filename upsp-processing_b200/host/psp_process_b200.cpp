@@ -23,7 +23,13 @@
 //                         (psp_process.cpp:2125-2163) with host/patch_geometry.hpp; job.txt keys
 //                         bound_thickness (2), buffer_thickness (0), patch_thresh (optional: boundary
 //                         pixels near values of cam<c>.first below it are dropped, offset 2)
+//   auto_patch_thresh = 1 (job.txt) the threshold of the reference instead of patch_thresh: first-frame histogram,
+//                         edges[first_min_threshold(counts, 5)] + 5 (psp_process.cpp:2150-2155, host/run_inputs.hpp)
+//   filter / filter_size  (job.txt) deck @options filter: none | gaussian | box
 //   remap.i32             optional: static form of P3DModel::adjust_solution
+//   xyz.f32               optional [msize][3]: written out as the X, Y, Z flat files (psp_process.cpp:1549-1556)
+//   A job directory is either assembled by hand / synth.py, or written by `psp_setup_b200 -input_file DECK ...`
+//   from the reference's own inputs (deck, grid, calibrations, paint calibration, .wtd, steady-state file).
 //   steady.f32 model_temp.f32   [msize]
 //
 //   psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]
@@ -36,6 +42,7 @@
 #include <sstream>
 
 #include "patch_geometry.hpp"
+#include "run_inputs.hpp"
 #include "upsp_b200.hpp"
 #include "video_readers.hpp"
 
@@ -114,6 +121,24 @@ int main(int argc, char** argv) {
     if (!any_video && !job.count("format")) throw std::invalid_argument("job.txt: neither format nor video<c> given");
     const size_t frame_bytes = p12 ? (size_t)W * H * 3 / 2 : (size_t)W * H * 2;
 
+    // first_frames_raw of the reference (psp_process.cpp:877-884): frame `first_frame`, decoded, hot pixels fixed
+    auto first_frame_of = [&](int c) {
+      const std::string b = job_dir + "/cam" + std::to_string(c);
+      if (!readers[c]) {
+        auto first = read_all<uint16_t>(b + ".first");
+        if (first.size() != (size_t)W * H) throw std::invalid_argument("cam.first has the wrong size");
+        return first;
+      }
+      std::vector<uint8_t> packed(readers[c]->frame_bytes());
+      readers[c]->read_packed((unsigned)first_frame, packed.data());
+      std::vector<uint16_t> first((size_t)W * H);
+      if (upsp_op_unpack(device, packed.data(), readers[c]->pixel_format(), first.size(), readers[c]->unpack_lut(), first.data()) != UPSP_OK)
+        throw std::runtime_error(upsp_gpu_last_error());
+      int n_hot = 0;
+      if (upsp_op_fix_hot_pixels(device, first.data(), 1, H, W, &n_hot) != UPSP_OK) throw std::runtime_error(upsp_gpu_last_error());
+      return first;
+    };
+
     upsp_gpu_config cfg{};
     cfg.device = device;
     cfg.n_cams = cameras;
@@ -143,10 +168,12 @@ int main(int argc, char** argv) {
         std::vector<std::vector<Target>> clusters;
         cluster_points(targs, clusters, (int)(bt + bf));
         PatchClusters pc(clusters, W, H, bt, bf);
-        if (job.count("patch_thresh")) {
-          auto first = read_all<uint16_t>(b + ".first");
-          if (first.size() != (size_t)W * H) throw std::invalid_argument("cam.first has the wrong size");
-          pc.threshold_bounds(first.data(), (unsigned)geti("patch_thresh"), 2u);
+        if (job.count("patch_thresh") || (job.count("auto_patch_thresh") && geti("auto_patch_thresh"))) {
+          const auto first = first_frame_of(c);
+          const unsigned bit_depth = readers[c] ? readers[c]->properties().bit_depth : 12u;
+          const unsigned thresh = job.count("patch_thresh") ? (unsigned)geti("patch_thresh")
+                                                            : patch_threshold(first.data(), first.size(), bit_depth);
+          pc.threshold_bounds(first.data(), thresh, 2u);
         }
         std::vector<int32_t> boff, ioff;
         std::vector<uint32_t> bx, by, ix, iy;
@@ -160,13 +187,18 @@ int main(int argc, char** argv) {
         chain.set_patches(c, (int)boff.size() - 1, boff.data(), bx.data(), by.data(), ioff.data(),
                           ix.data(), iy.data());
       }
-      if (reg == "pixel") chain.set_reference_frame(c, read_all<uint16_t>(b + ".first").data());
+      if (reg == "pixel") chain.set_reference_frame(c, first_frame_of(c).data());
     }
     auto remap = read_all<int32_t>(job_dir + "/remap.i32", false);
     if (!remap.empty()) chain.set_overlap_remap(remap.data());
     const int regmode = reg == "pixel" ? UPSP_REG_PIXEL : (reg == "given" ? UPSP_REG_GIVEN : UPSP_REG_NONE);
     chain.set_options(regmode, job.at("pixel_interpolation") == "nearest" ? UPSP_INTERP_NEAREST : UPSP_INTERP_LINEAR,
                       patcher == "polynomial" ? UPSP_PATCH_POLYNOMIAL : UPSP_PATCH_NONE, true);
+    if (job.count("filter") && job.at("filter") != "none") {
+      const std::string f = job.at("filter");
+      if (f != "gaussian" && f != "box") throw std::invalid_argument("job.txt: filter must be none, gaussian or box");
+      chain.set_filter(f == "gaussian" ? 1 : 2, geti("filter_size"));
+    }
     if (regmode == UPSP_REG_GIVEN)
       for (int c = 0; c < cameras; ++c) {
         auto m6 = read_all<float>(job_dir + "/cam" + std::to_string(c) + ".warp");
@@ -212,16 +244,32 @@ int main(int argc, char** argv) {
     out.write_vector("intensity_avg", sol_avg_final.data(), msize);
     out.write_vector("coverage", coverage.data(), msize);
 
+    {
+      auto xyz = read_all<float>(job_dir + "/xyz.f32", false);   // psp_process.cpp:1549-1556
+      if (xyz.size() == (size_t)msize * 3) {
+        std::vector<float> axis(msize);
+        const char* names[3] = {"X", "Y", "Z"};
+        for (int d = 0; d < 3; ++d) {
+          for (int n = 0; n < msize; ++n) axis[n] = xyz[(size_t)n * 3 + d];
+          out.write_vector(names[d], axis.data(), msize);
+        }
+      }
+    }
+
     std::cout << "Construct the transpose" << std::endl;
     chain.global_transpose();
     {
       const size_t rows = std::max<size_t>(1, (256u << 20) / ((size_t)number_frames * 4));
-      std::vector<float> blk(rows * number_frames);
+      std::vector<float> blk(rows * number_frames), sol1(msize);
       for (size_t n0 = 0; n0 < (size_t)msize; n0 += rows) {
         const size_t n = std::min(rows, (size_t)msize - n0);
         chain.read_intensity_transpose((int)n0, (int)n, blk.data());
         out.write_block("intensity_transpose", blk.data(), n0, n, number_frames);
+        for (size_t r = 0; r < n; ++r) sol1[n0 + r] = blk[r * number_frames];     // frame 1 of every node
       }
+      // "a sample Iref/I for frame 1" (psp_process.cpp:1946-1951): avg / sol1 in float, - 1.0 in double
+      for (int i = 0; i < msize; ++i) sol1[i] = (float)((double)(sol_avg_final[i] / sol1[i]) - 1.0);
+      out.write_vector("intensity_ratio_0", sol1.data(), msize);
     }
 
     // ---- phase 2 ----

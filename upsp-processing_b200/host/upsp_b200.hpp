@@ -124,6 +124,8 @@ class FrameChain {
   void set_options(int registration, int interp, int patcher, bool hot_pixel_fix = true) {
     check(upsp_gpu_set_options(ctx_, registration, interp, patcher, hot_pixel_fix));
   }
+  /* deck @options filter / filter_size: kind 0 none, 1 gaussian, 2 box */
+  void set_filter(int kind, int ksize) { check(upsp_gpu_set_filter(ctx_, kind, ksize)); }
   void set_patches(int cam, int n_clusters, const int32_t* boff, const uint32_t* bx, const uint32_t* by,
                    const int32_t* ioff, const uint32_t* ix, const uint32_t* iy) {
     check(upsp_gpu_set_patches(ctx_, cam, n_clusters, boff, bx, by, ioff, ix, iy));
