@@ -81,3 +81,78 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
         ratio0 = ((ref["avg"] / ref["itrans"][:, 0]).astype(np.float32).astype(np.float64) - 1.0).astype(np.float32)
     assert same_bits(rd("intensity_ratio_0"), ratio0)
     assert same_bits(rd("model_temp"), case.temp) and np.array_equal(rd("steady_state"), case.steady)
+
+
+@pytest.mark.gpu
+def test_deck_with_polynomial_patcher(up, orc, gpu, tmp_path):
+    """deck target_patcher = polynomial: .tgts -> visible / projected / sized targets (host/targets.hpp, setup tool) ->
+    clusters, histogram threshold on the first frame decoded from the video, pixel lists (driver) -> patched chain."""
+    import cv2
+    from oracle import setup_patches as sp
+    synth = up.synth
+    sc = synth.make_projection_scene(n_lat=24, n_lon=48, seed=11)
+    W, H, F = sc["width"], sc["height"], 10
+    d = tmp_path
+    write_tri(d / "model.tri", sc["xyz"], sc["tri"], np.ones(len(sc["tri"]), np.int32))
+    _cal_json(d / "cam01.json", cv2.Rodrigues(np.asarray(sc["rvec"], float))[0], sc["tvec"], sc["K"], sc["dist"], (W, H))
+    frames = synth.make_frames(F, H, W, seed=6)[0]
+    synth.pack_12bit(frames.reshape(F, -1)).tofile(d / "v1.mraw")
+    (d / "v1.cih").write_text("#Camera Information Header\r\nRecord Rate(fps) : 1000\r\nTotal Frame : %d\r\n"
+                              "Image Width : %d\r\nImage Height : %d\r\nColor Bit : 12\r\n" % (F, W, H))
+    (d / "run.wtd").write_text(open(os.path.join(GOLDEN, "sample.wtd")).read())
+    # fiducials painted on visible grid nodes (so that nodes do read patched pixels) + one on the far side
+    subprocess.run([up.build.build_grid_probe(), str(d / "model.tri"), str(d / "g")], check=True, capture_output=True)
+    nrm = np.fromfile(d / "g.nrm", np.float32).reshape(-1, 3)
+    ocam = orc.make_camera(sc["rvec"], sc["tvec"], sc["K"], sc["dist"], W, H)
+    code, _ = orc.create_projection(ocam, sc["xyz"], nrm, np.ones(len(sc["xyz"]), np.uint8), sc["tri"], float(np.float32(110 * np.pi / 180)))
+    vis = np.nonzero(code >= 0)[0]
+    inner = [n for n in vis if 40 < code[n] % W < W - 40 and 40 < code[n] // W < H - 40]
+    picks = [inner[i] for i in np.linspace(0, len(inner) - 1, 6).astype(int)]
+    pts = [sc["xyz"][n] for n in picks] + [np.array([0.0, 0.0, 5.0])]
+    rows = []
+    for i, p in enumerate(pts):
+        rows.append("%4d %10.4f %10.4f %10.4f 0.0 0.0 1.0 %6.3f 1 2 3 st%02d\n" % (i + 1, p[0], p[1], p[2], 0.05 + 0.004 * i, i + 1))
+    (d / "model.tgts").write_text("*Targets\n" + "".join(rows[:5]) + "*Fiducials\n" + "".join(rows[5:]))
+    cal = np.array([0.62, -1.3e-3, 2.1e-6, 2.4e-4, 3.0e-7, -1.1e-9], np.float32)
+    (d / "paint.cal").write_text("".join("%s = %.9g\n" % (k, v) for k, v in zip("abcdef", cal)))
+    (d / "out").mkdir()
+    (d / "job").mkdir()
+    (d / "deck.inp").write_text(
+        f"@general\n\ttest = t\n\trun = 1\n\tsequence = 1\n\ttunnel = ames_unitary\n@all\n\tgrid = {d}/model.tri\n\tsds = {d}/run.wtd\n"
+        f"\ttargets = {d}/model.tgts\n@camera\n\tnumber = 1\n\tfilename = {d}/v1.mraw\n\tcalibration = {d}/cam01.json\n"
+        f"@options\n\ttarget_patcher = polynomial\n\tregistration = none\n\tfilter = none\n\tfilter_size = 1\n\toblique_angle = 70\n"
+        f"\tnumber_frames = {F}\n@output\n\tdir = {d}/out\n\tname = r\n")
+    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(d / "deck.inp"), "-paint_cal", str(d / "paint.cal"),
+                        "-job_dir", str(d / "job")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    targs = [tuple(np.float32(x) for x in row) for row in np.loadtxt(d / "job" / "cam0.targets", dtype=np.float32).reshape(-1, 3)]
+    assert len(targs) == 6                                       # the far-side target is hidden
+    r = subprocess.run([up.build.build_host(), "-job_dir", str(d / "job"), "-out_dir", str(d / "out"), "-chunk", "8"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert f"Sorted {len(targs)} targets into" in r.stdout
+
+    first = orc.fix_hot_pixels(frames[0])[0]
+    first.astype("<u2").tofile(d / "first.u16")
+    hp = subprocess.run([up.build.build_inputs_probe(), "hist", str(d / "first.u16"), "12"], capture_output=True, text=True)
+    thresh = int([l for l in hp.stdout.splitlines() if l.startswith("threshold")][0].split()[1])
+    bt, bf = 2, 1
+    lists = sp.patch_clusters(sp.cluster_points(targs, bt + bf), W, H, bt, bf, first, thresh, 2)
+    xy = lambda pts: (np.array([p[0] for p in pts], np.uint32), np.array([p[1] for p in pts], np.uint32))
+    N = len(sc["xyz"])
+    case = Case.__new__(Case)
+    case.C, case.N, case.F, case.H, case.W = 1, N, F, H, W
+    case.interp, case.degree, case.fmt, case.filter_kind, case.filter_size = 1, 6, "p12", 0, 0
+    csr = tuple(np.fromfile(d / "job" / ("cam0." + k), t) for k, t in (("rowptr", np.int32), ("col", np.int32), ("val", np.float32)))
+    case.frames, case.csr, case.warp, case.overlap, case.synth = [frames], [csr], None, None, synth
+    case.patch_lists = [([xy(b) for b, _ in lists], [xy(i) for _, i in lists])]
+    case.cal, case.qbar, case.ps = cal, np.float32(657.9153), np.float32(1332.0421)
+    case.steady, case.temp = np.zeros(N, np.float32), np.full(N, 88.125, np.float32)
+    ref = run_oracle(orc, case)
+    got = np.fromfile(d / "out" / "intensity_transpose", np.float32).reshape(N, F)
+    assert same_bits(got, ref["itrans"])
+    assert same_bits(np.fromfile(d / "out" / "intensity_avg", np.float32), ref["avg"])
+    plain = Case.__new__(Case)
+    plain.__dict__.update(case.__dict__)
+    plain.patch_lists = None
+    assert not same_bits(got, run_oracle(orc, plain)["itrans"])   # the patches did touch pixels that nodes read

@@ -153,7 +153,7 @@ def build_setup_tool(force: bool = False) -> str:
     src = os.path.join(HERE, "host", "psp_setup_b200.cpp")
     deps = [src] + [os.path.join(HERE, "host", h) for h in (
         "camera_cal.hpp", "grid_readers.hpp", "p3d_model.hpp", "projection_weights.hpp", "run_inputs.hpp", "upsp_inputs.hpp",
-        "video_readers.hpp")]
+        "video_readers.hpp", "targets.hpp", "patch_geometry.hpp")]
     build()
     if not force and os.path.exists(SETUP_BIN) and os.path.getmtime(SETUP_BIN) >= max([os.path.getmtime(LIB)] + list(map(os.path.getmtime, deps))):
         return SETUP_BIN

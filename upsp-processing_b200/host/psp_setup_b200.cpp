@@ -11,7 +11,8 @@
 // (ParseOpts, cpp/exec/psp_process.cpp:1192-1310) to a complete job directory for psp_process_b200:
 //
 //   psp_setup_b200 -input_file DECK -paint_cal FILE -job_dir DIR [-steady_p3d FILE] [-model_temp_p3d FILE]
-//                  [-frames N] [-cutoff_x_max X] [-bound_pts 2] [-buffer_pts 1] [-device 0] [-no_projection]
+//                  [-frames N] [-cutoff_x_max X] [-bound_pts 2] [-buffer_pts 1] [-target_diam_sf 1.2] [-device 0]
+//                  [-no_projection]
 //
 // deck (host/upsp_inputs.hpp) -> video streams and the frame count (InitializeVideoStreams :392-470) -> model
 // (unstructured .tri, or structured plot3d through host/p3d_model.hpp: seams -> remap.i32, superceded nodes carry no
@@ -19,7 +20,8 @@
 // (adjust_projection_for_weights :1631-1641) -> paint calibration, tunnel conditions, model temperature, steady-state
 // Cp (phase 2 start-up :2270-2385) -> job.txt, X / Y / Z.  `-no_projection` stops before the GPU step (host-only
 // check of everything else).  Not re-hosted: `normals` / `active_comps` files, steady-state interpolation onto an
-// unstructured grid, getTargets (projected fiducials are taken from DIR/cam<c>.targets when the deck asks for patching).
+// unstructured grid.  With target_patcher = polynomial the visible, projected and sized targets of every camera
+// (getTargets / get_target_diameters, host/targets.hpp) are written to DIR/cam<c>.targets.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +35,7 @@
 #include "p3d_model.hpp"
 #include "projection_weights.hpp"
 #include "run_inputs.hpp"
+#include "targets.hpp"
 #include "upsp_inputs.hpp"
 #include "video_readers.hpp"
 
@@ -180,6 +183,18 @@ static int run_deck(const std::map<std::string, std::string>& opt) {
     if (cam.width != W || cam.height != H)
       std::cout << "Warning: calibration imageSize " << cam.width << "x" << cam.height << " differs from the video frames " << W << "x" << H
                 << std::endl;
+    if (ifile.target_patcher == TargetPatchType::Polynomial) {
+      // InitializeImagePatches up to the clustering (psp_process.cpp:2095-2123); psp_process_b200 clusters the projected
+      // targets, thresholds the boundaries on the first frame and builds the pixel lists (host/patch_geometry.hpp)
+      const float sf = has("-target_diam_sf") ? (float)std::atof(get("-target_diam_sf").c_str()) : 1.2f;
+      const std::vector<Target> targs = visible_targets(HostCamera(cam), model.xyz.data(), model.normals.data(), msize, model.tris.data(),
+                                                        (int)(model.tris.size() / 3), ifile.targets[c], ifile.oblique_angle, sf);
+      FILE* tf = std::fopen((job_dir + "/cam" + std::to_string(c) + ".targets").c_str(), "w");
+      if (!tf) return fail("Cannot write the projected targets of camera " + std::to_string(c + 1));
+      for (const Target& t : targs) std::fprintf(tf, "%.9g %.9g %.9g\n", (double)t.u, (double)t.v, (double)t.diameter);
+      std::fclose(tf);
+      std::cout << "camera " << ifile.cam_nums[c] << ": " << targs.size() << " visible targets / fiducials" << std::endl;
+    }
     if (!project) continue;
     std::vector<int32_t> code((size_t)msize);
     std::vector<float> uv((size_t)2 * msize);
