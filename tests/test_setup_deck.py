@@ -113,3 +113,39 @@ def test_deck_mode_rejections(up, tmp_path):
     make_inputs(up, tmp_path, "tri")
     (tmp_path / "steady.f").write_bytes(b"\0" * 64)
     assert "unstructured grid" in setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f", ok=False)[0].stderr
+
+
+def test_deck_normals_override_and_active_components(up, tmp_path):
+    # structured: normals csv overrides node normals (file_readers.ipp:12-90), inactive zone -> non-data nodes
+    make_inputs(up, tmp_path, "p3d", frames=1, extra_all="\tnormals = $d/n.csv\n\tactive_comps = $d/comps.csv\n")
+    (tmp_path / "n.csv").write_text("nidx, x_norm, y_norm, z_norm\n3, 0.6, 0.0, 0.8\n40, -1, 0, 0\n")
+    (tmp_path / "comps.csv").write_text("component,active\n0,1\n1,0\n")
+    r, job = setup(up, tmp_path, "-no_projection")
+    nrm = np.fromfile(job / "normals.f32", np.float32).reshape(-1, 3)
+    assert np.array_equal(nrm[3], np.float32([0.6, 0.0, 0.8])) and np.array_equal(nrm[40], np.float32([-1, 0, 0]))
+    assert np.array_equal(nrm[4], np.float32([0, 0, 1])) and "Overwrote 2/52 model surface normals" in r.stdout
+    is_data = np.fromfile(job / "is_data.u8", np.uint8)
+    want = np.ones(52, np.uint8)
+    want[[20, 23, 26, 29, 41, 46, 51]] = 0                   # superceded nodes
+    want[20:32] = 0                                          # zone 1 switched off
+    assert np.array_equal(is_data, want)
+    (tmp_path / "comps.csv").write_text("component,active\n0,1\n1,0\n2,1\n3,1\n")
+    assert "Number of components in active component file" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+    (tmp_path / "comps.csv").write_text("component,active\n0,1\n")
+    (tmp_path / "n.csv").write_text("nidx, x_norm, y_norm\n3, 0.6, 0.0\n")
+    assert "Could not parse z_norm" in setup(up, tmp_path, "-no_projection", ok=False)[0].stderr
+
+    # unstructured: a node is switched off only when all its triangles carry the same (inactive) component;
+    # the normals csv is refused with the reference's message and the run goes on
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [2, 0, 0], [2, 1, 0]], np.float32) + np.float32([0, 0, 6])
+    tri = np.array([[0, 1, 2], [0, 2, 3], [1, 4, 5], [1, 5, 2]], np.int32)
+    make_inputs(up, tmp_path, "tri", frames=1, extra_all="\tnormals = $d/n.csv\n\tactive_comps = $d/comps.csv\n")
+    write_tri(tmp_path / "model.tri", xyz, tri, np.array([1, 1, 2, 2], np.int32))
+    (tmp_path / "comps.csv").write_text("component,active\n2,0\n")
+    (tmp_path / "n.csv").write_text("nidx, x_norm, y_norm, z_norm\n0, 1, 0, 0\n")
+    r, job = setup(up, tmp_path, "-no_projection", "-cutoff_x_max", "0.5")
+    assert "can not specify normals CSV for a TriModel_" in r.stderr
+    # nodes 4, 5 belong to component 2 only; 1, 2 touch both components; x > 0.5 removes 1, 2, 4, 5 anyway
+    assert list(np.fromfile(job / "is_data.u8", np.uint8)) == [1, 0, 0, 1, 0, 0]
+    r, job = setup(up, tmp_path, "-no_projection")
+    assert list(np.fromfile(job / "is_data.u8", np.uint8)) == [1, 1, 1, 1, 0, 0]

@@ -19,9 +19,10 @@
 // projection row) -> per camera: calibration, projection matrix on the GPU, camNN-uv -> multi-camera weights
 // (adjust_projection_for_weights :1631-1641) -> paint calibration, tunnel conditions, model temperature, steady-state
 // Cp (phase 2 start-up :2270-2385) -> job.txt, X / Y / Z.  `-no_projection` stops before the GPU step (host-only
-// check of everything else).  Not re-hosted: `normals` / `active_comps` files, steady-state interpolation onto an
-// unstructured grid.  With target_patcher = polynomial the visible, projected and sized targets of every camera
-// (getTargets / get_target_diameters, host/targets.hpp) are written to DIR/cam<c>.targets.
+// check of everything else).  Not re-hosted: steady-state interpolation onto an unstructured grid.  With
+// target_patcher = polynomial the visible, projected and sized targets of every camera (getTargets /
+// get_target_diameters, host/targets.hpp) are written to DIR/cam<c>.targets.  `@all normals` (structured grids) and
+// `@all active_comps` are applied as InitializeModel / phase1 do (psp_process.cpp:2185-2189, 1462-1486).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +55,8 @@ struct ModelArrays {
   std::vector<int32_t> tris;            // [T][3]
   std::vector<uint8_t> is_data;
   std::vector<int32_t> remap;           // structured grids only
+  std::vector<int32_t> primary_comp;    // per node: its component, or INT32_MIN when it has none (Node::has_primary_component)
+  int n_components = 0;
   bool structured = false;
   int n_nodes() const { return (int)(xyz.size() / 3); }
 };
@@ -66,6 +69,18 @@ static ModelArrays load_model(const FileInputs& ifile) {
     m.tris = g.tris;
     calc_normals(g, m.normals);
     m.is_data.assign((size_t)g.n_nodes, 1);
+    // TriModel_::Node::has_primary_component (TriModel.ipp:1530-1546): every adjacent triangle carries the same component
+    m.n_components = g.number_of_components();
+    m.primary_comp.assign((size_t)g.n_nodes, INT32_MIN);
+    if (!g.comps.empty()) {
+      std::vector<uint8_t> seen((size_t)g.n_nodes, 0);
+      for (int t = 0; t < g.n_tris; ++t)
+        for (int k = 0; k < 3; ++k) {
+          const size_t n = (size_t)g.tris[(size_t)t * 3 + k];
+          if (!seen[n]) seen[n] = 1, m.primary_comp[n] = g.comps[(size_t)t];
+          else if (seen[n] == 1 && m.primary_comp[n] != g.comps[(size_t)t]) seen[n] = 2, m.primary_comp[n] = INT32_MIN;
+        }
+    }
   } else {
     const P3DModel model(ifile.grid, 1e-3f);            // psp_process.cpp:1378
     m.structured = true;
@@ -84,6 +99,9 @@ static ModelArrays load_model(const FileInputs& ifile) {
     m.is_data.resize((size_t)N);
     for (int n = 0; n < N; ++n) m.is_data[(size_t)n] = model.is_superceded(n) ? 0 : 1;   // the node iterator skips them
     m.remap = model.overlap_src_index();
+    m.n_components = model.num_zones();                   // P3DModel.h:244, Node::get_primary_component = zone
+    m.primary_comp.resize((size_t)N);
+    for (int n = 0; n < N; ++n) m.primary_comp[(size_t)n] = model.nidx2_gidx(n).zone;
   }
   return m;
 }
@@ -105,8 +123,6 @@ static int run_deck(const std::map<std::string, std::string>& opt) {
   if (ifile.registration != RegistrationType::None && ifile.registration != RegistrationType::Pixel)
     return fail("Unsupported registration type");
   if (ifile.filter_size % 2 == 0) return fail("Filter size must be odd (currently '" + std::to_string(ifile.filter_size) + "')");
-  if (ifile.has_normals()) return fail("@all:normals (surface normal overrides) is not supported by psp_setup_b200");
-  if (!ifile.active_comps.empty()) return fail("@all:active_comps is not supported by psp_setup_b200");
   std::cout << ifile << std::endl;
   const std::string job_dir = get("-job_dir");
   const int device = has("-device") ? std::atoi(get("-device").c_str()) : 0;
@@ -138,6 +154,25 @@ static int run_deck(const std::map<std::string, std::string>& opt) {
   ModelArrays model = load_model(ifile);
   const int msize = model.n_nodes();
   std::cout << "Loaded model: " << msize << " nodes, " << model.tris.size() / 3 << " triangles" << std::endl;
+  if (ifile.has_normals()) {                             // InitializeModel, psp_process.cpp:2185-2189
+    if (!model.structured)
+      std::cerr << "[ERROR] Refusing to read '" << ifile.normals << "'; can not specify normals CSV for a TriModel_" << std::endl;
+    else
+      std::cout << "Overwrote " << set_surface_normals(ifile.normals, model.normals) << "/" << msize << " model surface normals (using '"
+                << ifile.normals << "')" << std::endl;
+  }
+  if (!ifile.active_comps.empty()) {                     // psp_process.cpp:1462-1486
+    const auto active = read_active_comp_file(ifile.active_comps);
+    if ((int)active.size() > model.n_components)
+      return fail("Error: Number of components in active component file cannot be greater than the number of components in the grid");
+    for (int n = 0; n < msize; ++n) {
+      if (!model.is_data[(size_t)n] && model.structured) continue;      // the node iterator skips superceded nodes
+      const int32_t comp = model.primary_comp[(size_t)n];
+      if (comp == INT32_MIN) continue;
+      const auto it = active.find(comp);
+      if (it != active.end() && !it->second) model.is_data[(size_t)n] = 0;
+    }
+  }
   if (has("-cutoff_x_max")) {
     const float x_max = (float)std::atof(get("-cutoff_x_max").c_str());
     for (int n = 0; n < msize; ++n)
@@ -229,6 +264,8 @@ static int run_deck(const std::map<std::string, std::string>& opt) {
   write_all(job_dir + "/steady.f32", steady);
   write_all(job_dir + "/model_temp.f32", model_temp_input);
   write_all(job_dir + "/xyz.f32", model.xyz);
+  write_all(job_dir + "/normals.f32", model.normals);
+  write_all(job_dir + "/is_data.u8", model.is_data);
   std::ofstream job(job_dir + "/job.txt");
   if (!job) return fail("Cannot write '" + job_dir + "/job.txt'");
   job << std::setprecision(9);

@@ -5,6 +5,8 @@
 //   model_temperature         cpp/exec/psp_process.cpp:2287-2310   recovery-factor wall temperature or TCAVG
 //   read_psp_target_file      cpp/utils/file_readers.ipp:206-255   *Targets / *Fiducials sections of a .tgts file
 //   read_plot3d_scalar_function_file   cpp/lib/plot3d.cpp:12-101   steady-state Cp / model temperature
+//   set_surface_normals       cpp/utils/file_readers.ipp:12-90     csv (nidx, x_norm, y_norm, z_norm) overriding node normals
+//   read_active_comp_file     cpp/utils/file_readers.cpp:12-48     csv (component, active) -> nodes of inactive components
 //   intensity_histc           cpp/lib/image_processing.ipp:10-49   first-frame histogram
 //   find_peaks, first_min_threshold    cpp/utils/clustering.ipp:9-101   -> the patch boundary threshold
 //   patch_threshold           cpp/exec/psp_process.cpp:2150-2155   edges[first_min_threshold(counts, 5)] + 5
@@ -18,6 +20,7 @@
 #include <iostream>
 #include <limits>
 #include <sstream>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -165,6 +168,57 @@ inline bool read_psp_target_file(const std::string& target_file, std::vector<Mod
     break;
   }
   return true;
+}
+
+/* ---- surface normal overrides (structured models only; psp_process refuses the file for a TriModel) ---- */
+inline int set_surface_normals(const std::string& normal_file, std::vector<float>& normals /* [N][3] */) {
+  std::ifstream ifs(normal_file);
+  if (!ifs) throw std::invalid_argument("Cannot open surface normal csv file");
+  std::string line;
+  std::getline(ifs, line);
+  const auto header = detail::split_char(detail::strip_all_space(line), ',');
+  int col[4] = {-1, -1, -1, -1};
+  const char* names[4] = {"nidx", "x_norm", "y_norm", "z_norm"};
+  for (size_t i = 0; i < header.size(); ++i)
+    for (int k = 0; k < 4; ++k)
+      if (header[i] == names[k]) col[k] = (int)i;
+  for (int k = 0; k < 4; ++k)
+    if (col[k] == -1) throw std::invalid_argument(std::string("Could not parse ") + names[k] + " in normal csv file");
+  int nset = 0;
+  while (std::getline(ifs, line)) {
+    const auto terms = detail::split_char(detail::strip_all_space(line), ',');
+    long nidx;
+    float n[3];
+    try {
+      nidx = std::stoi(terms.at((size_t)col[0]));
+      for (int k = 0; k < 3; ++k) n[k] = (float)std::stod(terms.at((size_t)col[k + 1]));
+    } catch (...) {
+      throw std::invalid_argument("Cannot parse normal csv file'" + normal_file + "'");
+    }
+    if (nidx < 0 || (size_t)nidx * 3 + 2 >= normals.size()) throw std::invalid_argument("normal csv file: node index outside the model");
+    for (int k = 0; k < 3; ++k) normals[(size_t)nidx * 3 + k] = n[k];
+    ++nset;
+  }
+  return nset;
+}
+
+/* ---- active components ---- */
+inline std::unordered_map<int, bool> read_active_comp_file(const std::string& comp_file) {
+  std::ifstream ifs(comp_file);
+  if (!ifs) throw std::invalid_argument("Cannot open active component csv file");
+  std::unordered_map<int, bool> active_comps;
+  std::string line;
+  std::getline(ifs, line);   // header
+  while (std::getline(ifs, line)) {
+    const auto terms = detail::split_char(line, ',');
+    try {
+      const int comp = std::stoi(terms.at(0));
+      active_comps[comp] = std::abs(std::stoi(terms.at(1))) != 0;
+    } catch (...) {
+      throw std::invalid_argument("Cannot parse active component csv file");
+    }
+  }
+  return active_comps;
 }
 
 /* ---- plot3d scalar function file ---- */
