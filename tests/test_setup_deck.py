@@ -112,7 +112,25 @@ def test_deck_mode_rejections(up, tmp_path):
     assert r.returncode == 1 and "Must specify -paint_cal" in r.stderr
     make_inputs(up, tmp_path, "tri")
     (tmp_path / "steady.f").write_bytes(b"\0" * 64)
-    assert "unstructured grid" in setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f", ok=False)[0].stderr
+    assert "needs -steady_grid" in setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f", ok=False)[0].stderr
+
+
+def test_deck_wind_on_unstructured(up, tmp_path):
+    """-steady_p3d + -steady_grid with a .tri model: Cp interpolated from the structured steady grid (k = 10, 1/d^2)"""
+    from test_interpolation import numpy_interpolate
+    n = make_inputs(up, tmp_path, "tri", frames=1)
+    J, K = 9, 7
+    th, z = np.meshgrid(np.linspace(0, np.pi, J), np.linspace(4.5, 7.5, K))
+    sg = np.stack([2.1 * np.cos(th), 2.1 * np.sin(th), z], -1).reshape(-1, 3).astype(np.float32)
+    write_p3d(tmp_path / "steady.grid", [(J, K, sg)])
+    vals = np.sin(np.arange(J * K, dtype=np.float32)).astype(np.float32)
+    with open(tmp_path / "steady.f", "wb") as f:
+        f.write(struct.pack("<i", 1) + struct.pack("<4i", J, K, 1, 1) + vals.tobytes())
+    r, job = setup(up, tmp_path, "-no_projection", "-steady_p3d", tmp_path / "steady.f", "-steady_grid", tmp_path / "steady.grid")
+    xyz = np.fromfile(job / "xyz.f32", np.float32).reshape(-1, 3)
+    want = numpy_interpolate(sg, np.ones(J * K, bool), vals, xyz, 10)
+    got = np.fromfile(job / "steady.f32", np.float32)
+    assert len(got) == n and np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 def test_deck_normals_override_and_active_components(up, tmp_path):

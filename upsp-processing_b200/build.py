@@ -133,7 +133,7 @@ def build_inputs_probe(force: bool = False) -> str:
     """host/inputs_probe.cpp: deck / paint calibration / wtd / targets / p3d function / histogram readers and
     the structured model's seam detection (host C++) exercised from the tests."""
     src = os.path.join(HERE, "host", "inputs_probe.cpp")
-    deps = [src] + [os.path.join(HERE, "host", h) for h in ("upsp_inputs.hpp", "run_inputs.hpp", "p3d_model.hpp", "grid_readers.hpp")]
+    deps = [src] + [os.path.join(HERE, "host", h) for h in ("upsp_inputs.hpp", "run_inputs.hpp", "p3d_model.hpp", "grid_readers.hpp", "interpolation.hpp")]
     if not force and os.path.exists(INPUTS_PROBE_BIN) and os.path.getmtime(INPUTS_PROBE_BIN) >= max(map(os.path.getmtime, deps)):
         return INPUTS_PROBE_BIN
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -153,7 +153,7 @@ def build_setup_tool(force: bool = False) -> str:
     src = os.path.join(HERE, "host", "psp_setup_b200.cpp")
     deps = [src] + [os.path.join(HERE, "host", h) for h in (
         "camera_cal.hpp", "grid_readers.hpp", "p3d_model.hpp", "projection_weights.hpp", "run_inputs.hpp", "upsp_inputs.hpp",
-        "video_readers.hpp", "targets.hpp", "patch_geometry.hpp")]
+        "video_readers.hpp", "targets.hpp", "patch_geometry.hpp", "interpolation.hpp")]
     build()
     if not force and os.path.exists(SETUP_BIN) and os.path.getmtime(SETUP_BIN) >= max([os.path.getmtime(LIB)] + list(map(os.path.getmtime, deps))):
         return SETUP_BIN

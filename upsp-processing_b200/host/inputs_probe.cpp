@@ -7,10 +7,12 @@
 //   inputs_probe p3dfun FILE [seps]       run_inputs.hpp    read_plot3d_scalar_function_file
 //   inputs_probe hist FILE.u16 DEPTH      run_inputs.hpp    intensity_histc(256 bins) + first_min_threshold(5)
 //   inputs_probe overlap GRID TOL [dump]  p3d_model.hpp     P3DModel: overlap groups, src_index, triangles, normals
+//   inputs_probe interp GRID TOL DATA.f32 XYZ.f32 K OUT.f32   interpolation.hpp   upsp::interpolate onto the points of XYZ
 #include <cstdio>
 #include <cstring>
 #include <iostream>
 
+#include "interpolation.hpp"
 #include "p3d_model.hpp"
 #include "run_inputs.hpp"
 #include "upsp_inputs.hpp"
@@ -115,6 +117,21 @@ int main(int argc, char** argv) {
         dump(p + ".nrm", model.get_n().data(), model.get_n().size() * 4);
         dump(p + ".pairs", pairs.data(), pairs.size() * 4);
       }
+    } else if (cmd == "interp") {
+      if (argc < 8) throw std::invalid_argument("interp GRID TOL DATA.f32 XYZ.f32 K OUT.f32");
+      auto read_f32 = [](const std::string& path) {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        if (!f) throw std::invalid_argument("Cannot open '" + path + "'");
+        std::vector<float> v((size_t)f.tellg() / 4);
+        f.seekg(0);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
+        return v;
+      };
+      const P3DModel model(file, (float)atof(argv[3]));
+      const auto data = read_f32(argv[4]), xyz = read_f32(argv[5]);
+      const auto out = interpolate(model, data, xyz.data(), (int)(xyz.size() / 3), (unsigned)atoi(argv[6]), 2.0f);
+      dump(argv[7], out.data(), out.size() * 4);
+      std::printf("n_out %zu\n", out.size());
     } else {
       std::cerr << "inputs_probe: unknown sub-command '" << cmd << "'\n";
       return 1;

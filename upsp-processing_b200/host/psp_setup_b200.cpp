@@ -10,7 +10,7 @@
 // Deck mode: the whole of psp_process's start-up for a run, from the reference's own command line
 // (ParseOpts, cpp/exec/psp_process.cpp:1192-1310) to a complete job directory for psp_process_b200:
 //
-//   psp_setup_b200 -input_file DECK -paint_cal FILE -job_dir DIR [-steady_p3d FILE] [-model_temp_p3d FILE]
+//   psp_setup_b200 -input_file DECK -paint_cal FILE -job_dir DIR [-steady_p3d FILE] [-model_temp_p3d FILE] [-steady_grid FILE]
 //                  [-frames N] [-cutoff_x_max X] [-bound_pts 2] [-buffer_pts 1] [-target_diam_sf 1.2] [-device 0]
 //                  [-no_projection]
 //
@@ -19,7 +19,8 @@
 // projection row) -> per camera: calibration, projection matrix on the GPU, camNN-uv -> multi-camera weights
 // (adjust_projection_for_weights :1631-1641) -> paint calibration, tunnel conditions, model temperature, steady-state
 // Cp (phase 2 start-up :2270-2385) -> job.txt, X / Y / Z.  `-no_projection` stops before the GPU step (host-only
-// check of everything else).  Not re-hosted: steady-state interpolation onto an unstructured grid.  With
+// check of everything else).  Function files on an unstructured grid are interpolated from -steady_grid
+// (host/interpolation.hpp).  With
 // target_patcher = polynomial the visible, projected and sized targets of every camera (getTargets /
 // get_target_diameters, host/targets.hpp) are written to DIR/cam<c>.targets.  `@all normals` (structured grids) and
 // `@all active_comps` are applied as InitializeModel / phase1 do (psp_process.cpp:2185-2189, 1462-1486).
@@ -33,6 +34,7 @@
 
 #include "camera_cal.hpp"
 #include "grid_readers.hpp"
+#include "interpolation.hpp"
 #include "p3d_model.hpp"
 #include "projection_weights.hpp"
 #include "run_inputs.hpp"
@@ -192,9 +194,20 @@ static int run_deck(const std::map<std::string, std::string>& opt) {
   std::vector<float> model_temp_input((size_t)msize, model_temp), steady((size_t)msize, 0.0f);
   auto read_function = [&](const char* key, const char* what, std::vector<float>& dst) -> bool {
     if (!has(key) || get(key).empty()) return true;
-    if (!model.structured) {
-      fail(std::string(what) + " on an unstructured grid needs the k-nearest interpolation of psp_process (not re-hosted)");
-      return false;
+    if (!model.structured) {   // psp_process.cpp:2338-2345, 2371-2378: k-nearest inverse-distance interpolation from the steady grid
+      if (!has("-steady_grid") || get("-steady_grid").empty()) {
+        fail(std::string(what) + " function file with an unstructured grid needs -steady_grid");
+        return false;
+      }
+      const std::vector<float> in = read_plot3d_scalar_function_file(get(key));
+      const P3DModel steady_grid(get("-steady_grid"), 1e-3f);
+      if ((int)in.size() != steady_grid.size()) {
+        fail(std::string(what) + " function file inconsistent with the steady grid (expect " + std::to_string(steady_grid.size()) +
+             " values, got " + std::to_string(in.size()) + ")");
+        return false;
+      }
+      dst = interpolate(steady_grid, in, model.xyz.data(), msize, 10, 2.0f);
+      return true;
     }
     dst = read_plot3d_scalar_function_file(get(key));
     if ((int)dst.size() != msize) {
