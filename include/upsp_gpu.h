@@ -112,7 +112,8 @@ UPSP_API int upsp_gpu_set_options(upsp_gpu_ctx* ctx, int registration, int inter
                                   int hot_pixel_fix);
 /* deck @options filter / filter_size (psp_process.cpp:1802-1807): kind 0 none, 1 gaussian
  * (cv::GaussianBlur(img, img, Size(k,k), 0)), 2 box (cv::blur(img, img, Size(k,k))); k odd.
- * Gaussian sizes 3, 5, 7 (OpenCV's fixed sigma=0 kernels) are built.  A filter makes the chain
+ * Gaussian: any odd size up to 31 on the CV_16U image (no patcher; OpenCV's fixed-point taps), 3 / 5 / 7 on the CV_32F
+ * image the patcher returns.  Size 1 is the identity.  A filter makes the chain
  * materialise the registered image (no fused register+project kernel). */
 UPSP_API int upsp_gpu_set_filter(upsp_gpu_ctx* ctx, int kind, int ksize);
 /* PatchClusters geometry of camera `cam` (patches.h:74-90: bounds_x/y, internal_x/y per

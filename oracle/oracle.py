@@ -178,8 +178,32 @@ def patch_apply(img32: np.ndarray, p: Patches) -> np.ndarray:
 
 
 # ---------------------------------------------------------------- a5 filter
+def gauss_fixed_taps(ksize: int) -> np.ndarray:
+    """OpenCV's 16.16 fixed-point taps of GaussianBlur(CV_16U, (k,k), sigma=0): the bit-exact double kernel
+    (getGaussianKernelBitExact, read through cv2.getGaussianKernel) rounded with error diffusion, the centre tap
+    takes what is left of 65536 (getGaussianKernelFixedPoint_ED in OpenCV's smooth.dispatch.cpp)."""
+    import cv2
+    kern = cv2.getGaussianKernel(ksize, 0, cv2.CV_64F).ravel()
+    half, err, total = [], 0.0, 0
+    for i in range(ksize // 2):
+        adj = kern[i] * 65536.0 + err
+        v0 = int(np.rint(adj))
+        err = adj - v0
+        half.append(v0)
+        total += v0
+    return np.array(half + [65536 - 2 * total] + half[::-1], np.int32)
+
+
+def ensure_gauss_taps(kind: int, ksize: int):
+    """sizes beyond the three built-in small kernels need their taps registered (needs cv2)"""
+    if kind == 1 and ksize > 7:
+        q = gauss_fixed_taps(ksize)
+        lib().orc_set_gauss_taps(ksize, _p(q))
+
+
 def spatial_filter(img, kind, ksize):
     """cv::GaussianBlur(img,(k,k),0) (kind 1) / cv::blur(img,(k,k)) (kind 2) on u16 or f32."""
+    ensure_gauss_taps(kind, ksize)
     h, w = img.shape
     if img.dtype == np.uint16:
         src = _c(img, np.uint16)
@@ -297,6 +321,7 @@ def phase1(frames, csr, *, first_frame=0, warp=None, interp=1, patches=None, rem
         keep += [ncl, arrs, empty_i, empty_u]
     a.n_skipped, a.skipped = skipped.size, skipped.ctypes.data
     a.filter_kind, a.filter_size = int(filter_kind), int(filter_size)
+    ensure_gauss_taps(a.filter_kind, a.filter_size)
     if remap is not None:
         remap = _c(remap, np.int32)
         a.remap = remap.ctypes.data

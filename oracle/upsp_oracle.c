@@ -433,7 +433,8 @@ ORC_API void orc_patch_apply(float* img, int width, int n_clusters, const int* b
 /* default border BORDER_REFLECT_101.  kind: 1 gaussian, 2 box.               */
 /* CV_16U gaussian = OpenCV's fixed-point path (16 fractional bits per pass,  */
 /* exact accumulation, one rounding) -- PINNED against cv2 goldens for        */
-/* k = 3,5,7 (sigma = 0 -> getGaussianKernel's fixed small kernels);          */
+/* k = 3,5,7 (sigma = 0 -> getGaussianKernel's fixed small kernels) and, with */
+/* taps from orc_set_gauss_taps, for every odd size up to 31;                 */
 /* CV_16U box = integer sum * (1/area) in double, cvRound; CV_32F gaussian =  */
 /* separable float filter in OpenCV's symmetric order (exact on 12-bit data,  */
 /* last-bit differences possible next to patched pixels: cv2 may use FMA);    */
@@ -450,10 +451,26 @@ static const double* orc_small_gauss(int k) {
   return k == 3 ? k3 : (k == 5 ? k5 : (k == 7 ? k7 : NULL));
 }
 
+/* 16.16 fixed-point taps of sizes beyond 7: supplied by the caller (oracle.py derives them from cv2's bit-exact
+ * sigma = 0 kernel with OpenCV's error-diffusion rounding, getGaussianKernelFixedPoint_ED) */
+static long long orc_gauss_q[32][31];
+static int orc_gauss_q_set[32];
+ORC_API void orc_set_gauss_taps(int ksize, const int* q) {
+  if (ksize < 1 || ksize > 31) return;
+  for (int i = 0; i < ksize; ++i) orc_gauss_q[ksize][i] = q[i];
+  orc_gauss_q_set[ksize] = 1;
+}
+
 ORC_API int orc_filter_u16(const uint16_t* src, uint16_t* dst, int W, int H, int kind, int ksize) {
   const int r = ksize / 2;
   const double* kd = orc_small_gauss(ksize);
-  if (kind == 1 && !kd) return 1;
+  long long q[31];
+  if (kind == 1) {
+    if (ksize == 1) q[0] = 65536;
+    else if (kd) for (int i = 0; i < ksize; ++i) q[i] = (long long)llrint(kd[i] * 65536.0);
+    else if (ksize >= 1 && ksize <= 31 && orc_gauss_q_set[ksize]) for (int i = 0; i < ksize; ++i) q[i] = orc_gauss_q[ksize][i];
+    else return 1;
+  }
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
       if (kind == 1) {
@@ -461,8 +478,8 @@ ORC_API int orc_filter_u16(const uint16_t* src, uint16_t* dst, int W, int H, int
         for (int j = -r; j <= r; ++j) {
           long long t = 0;
           for (int i = -r; i <= r; ++i)
-            t += (long long)llrint(kd[i + r] * 65536.0) * src[(size_t)orc_reflect101(y + j, H) * W + orc_reflect101(x + i, W)];
-          S += (long long)llrint(kd[j + r] * 65536.0) * t;
+            t += q[i + r] * src[(size_t)orc_reflect101(y + j, H) * W + orc_reflect101(x + i, W)];
+          S += q[j + r] * t;
         }
         long long v = (S + (1LL << 31)) >> 32;
         dst[(size_t)y * W + x] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
@@ -480,6 +497,10 @@ ORC_API int orc_filter_u16(const uint16_t* src, uint16_t* dst, int W, int H, int
 ORC_API int orc_filter_f32(const float* src, float* dst, int W, int H, int kind, int ksize) {
   const int r = ksize / 2;
   const double* kd = orc_small_gauss(ksize);
+  if (ksize == 1) {   /* a 1x1 window is the identity for both kinds */
+    memcpy(dst, src, sizeof(float) * (size_t)W * H);
+    return 0;
+  }
   if (kind == 1 && !kd) return 1;
   if (kind == 1) {
     float* tmp = (float*)malloc(sizeof(float) * (size_t)W * H);

@@ -20,6 +20,7 @@ Outputs (small, committed):
   video_golden.npz  what the reference's Python readers (upsp.video.CineReader / MrawReader) decode
                     from those files, their properties, and the 10->12-bit table
   ../../upsp-processing_b200/host/cine_lut.inc   the same table as a C initialiser list
+  ../../upsp-processing_b200/csrc/gauss_fixed.inc   OpenCV's 16.16 fixed-point Gaussian taps, sizes 3..31
 """
 import os
 import sys
@@ -187,7 +188,37 @@ def ecc_golden():
                         rho=np.array(rhos, np.float64), shifts=shifts)
 
 
+def gauss_fixed_taps(k):
+    """OpenCV's 16.16 fixed-point taps of GaussianBlur(CV_16U, Size(k,k), sigma=0): the bit-exact double kernel
+    (cv2.getGaussianKernel) rounded with error diffusion, centre tap = 65536 - the rest (getGaussianKernelFixedPoint_ED)."""
+    kern = cv2.getGaussianKernel(k, 0, cv2.CV_64F).ravel()
+    half, err, total = [], 0.0, 0
+    for i in range(k // 2):
+        adj = kern[i] * 65536.0 + err
+        v0 = int(np.rint(adj))                 # cvRound
+        err = adj - v0
+        half.append(v0)
+        total += v0
+    return half + [65536 - 2 * total]
+
+
+def gauss_golden():
+    lines = ["// gauss_fixed.inc -- OpenCV's 16.16 fixed-point Gaussian taps for sigma = 0 (GaussianBlur on CV_16U: getGaussianKernelBitExact +",
+             "// getGaussianKernelFixedPoint_ED, error-diffusion rounding, centre tap = 65536 - the rest), first half + centre per odd size 3..31.",
+             "// Generated by tests/golden/make_golden.py gauss (cv2.getGaussianKernel(k, 0, CV_64F) -> the rounding above); tests/test_oracle_golden.py",
+             "// holds the integer filter built from these taps bit-exact against cv2.GaussianBlur for every size.",
+             "static const int kGaussFixed[15][16] = {"]
+    for k in range(3, 33, 2):
+        lines.append("  {" + ", ".join(map(str, gauss_fixed_taps(k))) + "},   // k = %d" % k)
+    lines.append("};")
+    with open(os.path.join(HERE, "..", "..", "upsp-processing_b200", "csrc", "gauss_fixed.inc"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gauss":     # only the fixed-point Gaussian taps
+        gauss_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "video":     # only the container fixtures
         video_golden()
         sys.exit(0)
@@ -199,5 +230,6 @@ if __name__ == "__main__":
     ecc_golden()
     video_golden()
     setup_golden()
+    gauss_golden()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

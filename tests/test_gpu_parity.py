@@ -260,20 +260,28 @@ def test_frame_major_read_needs_keep_flag(up, orc, gpu):
     g.close()
 
 
-@pytest.mark.parametrize("kind,ksize", [(1, 3), (1, 5), (1, 7), (2, 3), (2, 5)])
+@pytest.mark.parametrize("kind,ksize", [(1, 3), (1, 5), (1, 7), (2, 3), (2, 5), (1, 9), (1, 15), (1, 1)])
 @pytest.mark.parametrize("patches", [False, True], ids=["u16-image", "f32-image(patched)"])
 def test_chain_spatial_filter(up, orc, gpu, kind, ksize, patches):
     """deck @options filter = gaussian | box (psp_process.cpp:1802-1807) after registration and
-    patching: CV_16U image without the patcher (OpenCV's integer paths), CV_32F with it."""
+    patching: CV_16U image without the patcher (OpenCV's integer paths; Gaussian of any odd size), CV_32F with it
+    (Gaussian 3 / 5 / 7: larger float kernels depend on OpenCV's SIMD summation order and are refused)."""
     import upsp_b200
     case = Case(upsp_b200.synth, n_frames=24, n_nodes=2500, registration=True, patches=patches, seed=29,
                 filter_kind=kind, filter_size=ksize)
+    if patches and kind == 1 and ksize > 7:
+        with pytest.raises(up.UpspGpuError, match="patched"):
+            run_gpu(up, orc, case, keep_frame_major=True)
+        return
     ref = run_oracle(orc, case)
     got = run_gpu(up, orc, case, keep_frame_major=True)
     _check_chain(case, ref, got, orc)
     with pytest.raises(up.UpspGpuError):
         g = up.PspGpu(1, 10, 4)
-        g.set_filter(1, 9)          # gaussian sizes beyond OpenCV's fixed kernels are not built
+        g.set_filter(1, 33)         # gaussian sizes beyond 31 are not built
+    with pytest.raises(up.UpspGpuError):
+        g = up.PspGpu(1, 10, 4)
+        g.set_filter(2, 4)          # even sizes: psp_process.cpp:1296
 
 
 @pytest.mark.parametrize("env", [{"UPSP_FUSED_V1": "1"}, {"UPSP_PIPELINE": "0"}, {"UPSP_PIPELINE": "0", "UPSP_DECODE_P": "1"}],

@@ -207,5 +207,36 @@ def test_spatial_filter_matches_live_cv2(orc):
     for ks in (3, 5, 7):
         a, b = orc.spatial_filter(g, 1, ks), cv2.GaussianBlur(g, (ks, ks), 0)
         assert np.abs(a - b).max() <= 2.5e-7 * np.abs(b).max()
+    # CV_16U Gaussians beyond the three small kernels: OpenCV's error-diffused fixed-point taps, any odd size
+    full = rng.integers(0, 65536, (33, 47)).astype(np.uint16)
+    for ks in (1, 9, 11, 15, 21, 31):
+        for im in (img, full):
+            assert np.array_equal(orc.spatial_filter(im, 1, ks), cv2.GaussianBlur(im, (ks, ks), 0)), ks
+    assert np.array_equal(orc.spatial_filter(f, 1, 1), f) and np.array_equal(orc.spatial_filter(f, 2, 1), f)
     with pytest.raises(ValueError):
-        orc.spatial_filter(img, 1, 9)
+        orc.spatial_filter(f, 1, 9)            # CV_32F beyond 7: depends on OpenCV's SIMD summation order, not restated
+
+
+def test_fixed_point_gaussian_taps_match_cv2():
+    """csrc/gauss_fixed.inc (the taps k_filter_u16 uses for deck filter = gaussian, any odd size 3..31): the integer
+    filter  (sum_j q_j sum_i q_i p + 2^31) >> 32  with these taps equals cv2.GaussianBlur on CV_16U bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    import re
+    from conftest import ROOT
+    text = open(os.path.join(ROOT, "upsp-processing_b200", "csrc", "gauss_fixed.inc")).read()
+    rows = [list(map(int, m.split(","))) for m in re.findall(r"^\s*\{([0-9, ]+)\},", text, re.M)]
+    assert len(rows) == 15
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 4096, (61, 83)).astype(np.uint16), rng.integers(0, 65536, (40, 37)).astype(np.uint16)]
+    for k, half in zip(range(3, 33, 2), rows):
+        assert len(half) == k // 2 + 1
+        q = np.array(half + half[-2::-1], np.int64)
+        assert q.sum() == 65536
+        for img in imgs:
+            r = k // 2
+            p = np.pad(img.astype(np.int64), r, mode="reflect")          # BORDER_REFLECT_101
+            H, W = img.shape
+            rows_ = sum(q[i] * p[:, i:i + W] for i in range(k))
+            S = sum(q[j] * rows_[j:j + H] for j in range(k))
+            got = np.clip((S + (1 << 31)) >> 32, 0, 65535).astype(np.uint16)
+            assert np.array_equal(got, cv2.GaussianBlur(img, (k, k), 0)), k

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".inc"))] + [
         os.path.join(HERE, "..", "include", "upsp_gpu.h")]
 
 

@@ -8,8 +8,10 @@
 //   * CV_16U box: integer window sum, times 1/area in double, cvRound;
 //   * CV_32F Gaussian: separable float filter (exact in any summation order on 12-bit data);
 //   * CV_32F box: window sum in double, times 1/area, narrowed to float.
-// sigma = 0 selects OpenCV's fixed small kernels, available for k = 3, 5, 7 (getGaussianKernel);
-// larger Gaussian sizes are rejected at set_filter time.
+// CV_16U Gaussian: any odd size 3..31 (taps from gauss_fixed.inc = OpenCV's error-diffusion rounding of its bit-exact
+// sigma = 0 kernel).  CV_32F Gaussian (patcher on): k = 3, 5, 7 only, whose taps are dyadic so that every product is
+// exact; for larger sizes the float result depends on OpenCV's summation order inside its SIMD row / column filters
+// (measured: no ordering of the separable sum reproduces cv2 4.13 within 1 ulp), so those are rejected.
 #pragma once
 #include "common.cuh"
 #include "kernels_ecc.cuh"   // reflect101
@@ -19,8 +21,8 @@ namespace upsp {
 struct FilterSpec {
   int kind;        // 1 gaussian, 2 box
   int ksize;       // odd
-  int kq[7];       // gaussian taps * 65536 (exactly representable for k = 3, 5, 7)
-  float kf[7];     // gaussian taps as float
+  int kq[31];      // gaussian taps in 16.16 fixed point (gauss_fixed.inc)
+  float kf[7];     // gaussian taps as float, k <= 7
 };
 
 __global__ void __launch_bounds__(256)

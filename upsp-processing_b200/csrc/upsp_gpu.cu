@@ -685,6 +685,8 @@ extern "C" int upsp_gpu_set_options(upsp_gpu_ctx* c, int registration, int inter
   return UPSP_OK;
 }
 
+#include "gauss_fixed.inc"
+
 extern "C" int upsp_gpu_set_filter(upsp_gpu_ctx* c, int kind, int ksize) {
   ENTER(c);
   NOT_FINAL(c);
@@ -692,16 +694,14 @@ extern "C" int upsp_gpu_set_filter(upsp_gpu_ctx* c, int kind, int ksize) {
   c->filter = FilterSpec{};
   if (kind == 0) return UPSP_OK;
   REQUIRE(ksize >= 1 && (ksize & 1), UPSP_ERR_INVALID, "filter_size must be odd (psp_process.cpp:1296), got %d", ksize);
-  static const double k3[] = {0.25, 0.5, 0.25}, k5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625},
-                      k7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+  if (ksize == 1) return UPSP_OK;   // a 1x1 Gaussian / box window is the identity
   if (kind == 1) {
-    const double* k = ksize == 3 ? k3 : (ksize == 5 ? k5 : (ksize == 7 ? k7 : nullptr));
-    REQUIRE(k != nullptr, UPSP_ERR_INVALID,
-            "gaussian filter_size %d is not built (3, 5, 7: OpenCV's fixed sigma=0 kernels)", ksize);
-    for (int i = 0; i < ksize; ++i) {
-      c->filter.kq[i] = (int)llrint(k[i] * 65536.0);
-      c->filter.kf[i] = (float)k[i];
-    }
+    REQUIRE(ksize >= 3 && ksize <= 31, UPSP_ERR_INVALID, "gaussian filter_size %d is not built (odd sizes 3..31)", ksize);
+    const int* half = kGaussFixed[(ksize - 3) / 2];
+    const int r = ksize / 2;
+    for (int i = 0; i <= r; ++i) c->filter.kq[i] = c->filter.kq[ksize - 1 - i] = half[i];
+    if (ksize <= 7)   // dyadic taps: the float kernel of the CV_32F path is the same numbers
+      for (int i = 0; i < ksize; ++i) c->filter.kf[i] = (float)((double)c->filter.kq[i] / 65536.0);
   } else {
     REQUIRE(ksize <= 31, UPSP_ERR_INVALID, "box filter_size %d too large", ksize);
   }
@@ -978,6 +978,8 @@ static int finalize(upsp_gpu_ctx* c) {
     }
     if (c->filter.kind) {
       if (use_patch && k.has_patches) {
+        REQUIRE(c->filter.kind != 1 || c->filter.ksize <= 7, UPSP_ERR_INVALID,
+                "gaussian filter_size %d on the patched (CV_32F) image is not built: 3, 5, 7 only", c->filter.ksize);
         TRY(dmalloc(&k.d_img32, (size_t)c->batch * k.npix));
         TRY(dmalloc(&k.d_img32b, (size_t)c->batch * k.npix));
         std::vector<int> slot_pix(std::max(k.total_internal, 1), -1);
