@@ -167,3 +167,22 @@ def test_deck_normals_override_and_active_components(up, tmp_path):
     assert list(np.fromfile(job / "is_data.u8", np.uint8)) == [1, 0, 0, 1, 0, 0]
     r, job = setup(up, tmp_path, "-no_projection")
     assert list(np.fromfile(job / "is_data.u8", np.uint8)) == [1, 1, 1, 1, 0, 0]
+
+
+def test_reference_command_line_forms(up, tmp_path):
+    """cv::CommandLineParser style -key=value (what the reference's launcher writes, python/upsp/processing/tree.py:455-465)
+    is accepted next to -key value; psp_process_b200's one-step mode checks the reference's required flags first."""
+    make_inputs(up, tmp_path, "tri")
+    job = tmp_path / "job"
+    job.mkdir()
+    r = subprocess.run([up.build.build_setup_tool(), f"-input_file={tmp_path / 'deck.inp'}", f"-paint_cal={tmp_path / 'paint.cal'}",
+                        f"-job_dir={job}", "-frames=1", "-no_projection"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert job_kv(job / "job.txt")["number_frames"] == "1"
+    exe = up.build.build_host()
+    r = subprocess.run([exe, f"-input_file={tmp_path / 'deck.inp'}", f"-paint_cal={tmp_path / 'paint.cal'}"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Must specify -h5_out" in r.stderr
+    r = subprocess.run([exe, f"-input_file={tmp_path / 'deck.inp'}", "-h5_out=x.h5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Must specify -paint_cal" in r.stderr
+    r = subprocess.run([exe, f"-input_file={tmp_path / 'nope.inp'}", "-h5_out=x.h5", "-paint_cal=p"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot be opened" in r.stderr

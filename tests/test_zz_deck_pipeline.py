@@ -41,9 +41,13 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
         f"@camera\n\tnumber = 1\n\tfilename = $d/v1.mraw\n\tcalibration = $d/cam01.json\n"
         f"@options\n\ttarget_patcher = none\n\tregistration = none\n\tfilter = none\n\tfilter_size = 1\n\toblique_angle = 70\n"
         f"\tnumber_frames = -1\n@output\n\tdir = $d/out\n\tname = run12\n")
-    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(d / "deck.inp"), "-paint_cal", str(d / "paint.cal"),
-                        "-job_dir", str(d / "job")], capture_output=True, text=True, timeout=300)
+    # one step, the reference's own command line (launcher style -key=value, python/upsp/processing/tree.py:455-465)
+    r = subprocess.run([up.build.build_host(), f"-input_file={d / 'deck.inp'}", f"-h5_out={d / 'out' / 'run12.h5'}",
+                        f"-paint_cal={d / 'paint.cal'}", f"-add_out_dir={d / 'out'}", "-frames=12", "-chunk", "8"],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert "is not written (no HDF5 library" in r.stdout
+    jobd = d / "out" / "job_b200"
 
     # the projection matrix the oracle builds from the same grid and calibration
     subprocess.run([up.build.build_grid_probe(), str(d / "model.tri"), str(d / "g")], check=True, capture_output=True)
@@ -56,13 +60,10 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
     code, uv = orc.create_projection(ocam, sc["xyz"], nrm, np.ones(N, np.uint8), sc["tri"], float(thresh))
     rowptr, col, val = orc.projection_csr(code)
     assert (code >= 0).sum() > 100
-    assert np.array_equal(np.fromfile(d / "job" / "cam0.rowptr", np.int32), rowptr)
-    assert np.array_equal(np.fromfile(d / "job" / "cam0.col", np.int32), col)
-    assert np.array_equal(np.fromfile(d / "job" / "cam0.val", np.float32), val)          # one camera: weights stay 1
-
-    r = subprocess.run([up.build.build_host(), "-job_dir", str(d / "job"), "-out_dir", str(d / "out"), "-chunk", "8"],
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(jobd / "cam0.rowptr", np.int32), rowptr)
+    assert np.array_equal(np.fromfile(jobd / "cam0.col", np.int32), col)
+    assert np.array_equal(np.fromfile(jobd / "cam0.val", np.float32), val)          # one camera: weights stay 1
+    assert np.array_equal(np.fromfile(d / "out" / "cam01-uv", np.float32).view(np.uint32), uv.ravel().view(np.uint32))
 
     case = Case.__new__(Case)
     case.C, case.N, case.F, case.H, case.W = 1, N, F, H, W
@@ -156,3 +157,78 @@ def test_deck_with_polynomial_patcher(up, orc, gpu, tmp_path):
     plain.__dict__.update(case.__dict__)
     plain.patch_lists = None
     assert not same_bits(got, run_oracle(orc, plain)["itrans"])   # the patches did touch pixels that nodes read
+
+
+@pytest.mark.gpu
+def test_deck_two_cameras_average_view(up, orc, gpu, tmp_path):
+    """two cameras on one model: per-camera projection matrices, adjust_projection_for_weights with the camera centres
+    (psp_process.cpp:1623-1641; AverageViews), the chain sums the weighted camera solutions (:1814-1820)."""
+    import cv2
+    from test_projection_weights import _angles
+    synth = up.synth
+    sc = synth.make_projection_scene(n_lat=24, n_lon=48, seed=11)
+    W, H, F = sc["width"], sc["height"], 8
+    d = tmp_path
+    write_tri(d / "model.tri", sc["xyz"], sc["tri"], np.ones(len(sc["tri"]), np.int32))
+    rvecs = [np.asarray(sc["rvec"], float), np.array([0.05, 0.33, 0.3])]
+    frames = []
+    cams_txt = ""
+    for c, rv in enumerate(rvecs):
+        _cal_json(d / f"cam{c + 1:02d}.json", cv2.Rodrigues(rv)[0], sc["tvec"], sc["K"], sc["dist"], (W, H))
+        frames.append(synth.make_frames(F, H, W, seed=7 + c)[0])
+        synth.pack_12bit(frames[c].reshape(F, -1)).tofile(d / f"v{c + 1}.mraw")
+        (d / f"v{c + 1}.cih").write_text("#Camera Information Header\r\nRecord Rate(fps) : 1000\r\nTotal Frame : %d\r\n"
+                                         "Image Width : %d\r\nImage Height : %d\r\nColor Bit : 12\r\n" % (F, W, H))
+        cams_txt += f"@camera\n\tnumber = {c + 1}\n\tfilename = {d}/v{c + 1}.mraw\n\tcalibration = {d}/cam{c + 1:02d}.json\n"
+    (d / "run.wtd").write_text(open(os.path.join(GOLDEN, "sample.wtd")).read())
+    (d / "model.tgts").write_text(open(os.path.join(GOLDEN, "sample.tgts")).read())
+    cal = np.array([0.62, -1.3e-3, 2.1e-6, 2.4e-4, 3.0e-7, -1.1e-9], np.float32)
+    (d / "paint.cal").write_text("".join("%s = %.9g\n" % (k, v) for k, v in zip("abcdef", cal)))
+    (d / "out").mkdir()
+    (d / "job").mkdir()
+    (d / "deck.inp").write_text(
+        f"@general\n\ttest = t\n\trun = 1\n\tsequence = 1\n\ttunnel = ames_unitary\n@all\n\tgrid = {d}/model.tri\n\tsds = {d}/run.wtd\n"
+        f"\ttargets = {d}/model.tgts\n{cams_txt}"
+        f"@options\n\ttarget_patcher = none\n\tregistration = none\n\tfilter = none\n\tfilter_size = 1\n\toblique_angle = 70\n"
+        f"\toverlap = average_view\n\tnumber_frames = {F}\n@output\n\tdir = {d}/out\n\tname = r\n")
+    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(d / "deck.inp"), "-paint_cal", str(d / "paint.cal"),
+                        "-job_dir", str(d / "job")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([up.build.build_host(), "-job_dir", str(d / "job"), "-out_dir", str(d / "out"), "-chunk", "8"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+
+    subprocess.run([up.build.build_grid_probe(), str(d / "model.tri"), str(d / "g")], check=True, capture_output=True)
+    nrm = np.fromfile(d / "g.nrm", np.float32).reshape(-1, 3)
+    xyz = sc["xyz"].astype(np.float32)
+    N = len(xyz)
+    thresh = float(np.float32((180.0 - 70.0) * np.pi / 180.0))
+    codes, angs = [], []
+    for c, rv in enumerate(rvecs):
+        pc = subprocess.run([up.build.build_setup_tool(), "-cal", str(d / f"cam{c + 1:02d}.json"), "-print_cal"], capture_output=True, text=True)
+        parsed = {l.split()[0]: np.array(l.split()[1:], float) for l in pc.stdout.splitlines()}
+        ocam = orc.make_camera(parsed["rvec"], parsed["tvec"], sc["K"], sc["dist"], W, H)
+        codes.append(orc.create_projection(ocam, xyz, nrm, np.ones(N, np.uint8), sc["tri"], thresh)[0])
+        angs.append(_angles(xyz, nrm, orc.cam_center(ocam)))
+    seen = np.stack([c >= 0 for c in codes])
+    both = seen[0] & seen[1]
+    assert both.sum() > 30 and (seen[0] ^ seen[1]).sum() > 30
+    total = (angs[0] + angs[1]).astype(np.float32)
+    csr = []
+    for c in range(2):
+        rowptr, col, val = orc.projection_csr(codes[c])
+        w = np.where(both, (angs[c] / total).astype(np.float32), np.float32(1))[seen[c]]
+        csr.append((rowptr, col, (val * w).astype(np.float32)))
+        assert np.array_equal(np.fromfile(d / "job" / f"cam{c}.col", np.int32), col)
+        assert np.array_equal(np.fromfile(d / "job" / f"cam{c}.val", np.float32).view(np.uint32), csr[c][2].view(np.uint32))
+    case = Case.__new__(Case)
+    case.C, case.N, case.F, case.H, case.W = 2, N, F, H, W
+    case.interp, case.degree, case.fmt, case.filter_kind, case.filter_size = 1, 6, "p12", 0, 0
+    case.frames, case.csr, case.warp, case.patch_lists, case.overlap, case.synth = frames, csr, None, None, None, synth
+    case.cal, case.qbar, case.ps = cal, np.float32(657.9153), np.float32(1332.0421)
+    case.steady, case.temp = np.zeros(N, np.float32), np.full(N, 88.125, np.float32)
+    ref = run_oracle(orc, case)
+    got = np.fromfile(d / "out" / "intensity_transpose", np.float32).reshape(N, F)
+    assert same_bits(got, ref["itrans"])
+    assert same_bits(np.fromfile(d / "out" / "coverage", np.float32), ref["coverage"])
+    assert same_bits(np.fromfile(d / "out" / "gain", np.float32), ref["gain"])

@@ -57,7 +57,7 @@ HOST_BIN = os.path.join(HERE, "psp_process_b200")
 def build_host(force: bool = False) -> str:
     """The C++ host driver (g++, links libupsp_gpu.so through its C ABI only)."""
     src = os.path.join(HERE, "host", "psp_process_b200.cpp")
-    hdrs = [os.path.join(HERE, "host", h) for h in ("upsp_b200.hpp", "patch_geometry.hpp", "run_inputs.hpp", "video_readers.hpp")]
+    hdrs = [os.path.join(HERE, "host", h) for h in os.listdir(os.path.join(HERE, "host")) if h.endswith((".hpp", ".inc"))]
     build()
     if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(
             [os.path.getmtime(src), os.path.getmtime(LIB)] + list(map(os.path.getmtime, hdrs))):
@@ -153,7 +153,7 @@ def build_setup_tool(force: bool = False) -> str:
     src = os.path.join(HERE, "host", "psp_setup_b200.cpp")
     deps = [src] + [os.path.join(HERE, "host", h) for h in (
         "camera_cal.hpp", "grid_readers.hpp", "p3d_model.hpp", "projection_weights.hpp", "run_inputs.hpp", "upsp_inputs.hpp",
-        "video_readers.hpp", "targets.hpp", "patch_geometry.hpp", "interpolation.hpp")]
+        "video_readers.hpp", "targets.hpp", "patch_geometry.hpp", "interpolation.hpp", "deck_job.hpp")]
     build()
     if not force and os.path.exists(SETUP_BIN) and os.path.getmtime(SETUP_BIN) >= max([os.path.getmtime(LIB)] + list(map(os.path.getmtime, deps))):
         return SETUP_BIN

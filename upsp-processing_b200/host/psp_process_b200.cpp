@@ -33,6 +33,14 @@
 //   steady.f32 model_temp.f32   [msize]
 //
 //   psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]
+//
+// One-step mode, the reference's own command line (ParseOpts, psp_process.cpp:1192-1310; -key=value or -key value):
+//   psp_process_b200 -input_file=DECK -h5_out=FILE -paint_cal=FILE [-steady_p3d=FILE] [-steady_grid=FILE]
+//                    [-model_temp_p3d=FILE] [-frames=N] [-add_out_dir=DIR] [-bound_pts=2] [-buffer_pts=1]
+//                    [-target_diam_sf=1.2] [-cutoff_x_max=X] [-device 0] [-chunk 256]
+// runs the start-up of host/deck_job.hpp into <add_out_dir>/job_b200 and then the frame chain; flat files go to
+// -add_out_dir (default: the deck's @output dir), as in the reference.  -h5_out is required as there, but no HDF5
+// library exists in this build: the flat files are the outputs (a notice says so).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +49,9 @@
 #include <limits>
 #include <sstream>
 
+#include <sys/stat.h>
+
+#include "deck_job.hpp"
 #include "patch_geometry.hpp"
 #include "run_inputs.hpp"
 #include "upsp_b200.hpp"
@@ -82,15 +93,39 @@ static std::map<std::string, std::string> read_job(const std::string& path) {
 int main(int argc, char** argv) {
   std::string job_dir, out_dir;
   int device = 0, chunk = 256;
-  for (int i = 1; i + 1 < argc; i += 2) {
-    const std::string k = argv[i];
-    if (k == "-job_dir") job_dir = argv[i + 1];
-    else if (k == "-out_dir") out_dir = argv[i + 1];
-    else if (k == "-device") device = atoi(argv[i + 1]);
-    else if (k == "-chunk") chunk = atoi(argv[i + 1]);
+  try {
+    auto opt = parse_command_line(argc, argv);
+    if (opt.count("-device")) device = atoi(opt["-device"].c_str());
+    if (opt.count("-chunk")) chunk = atoi(opt["-chunk"].c_str());
+    if (opt.count("-input_file")) {       // the reference's command line
+      if (!opt.count("-h5_out")) {
+        std::cerr << "[ERROR] Must specify -h5_out" << std::endl;
+        return 1;
+      }
+      FileInputs peek;
+      if (!peek.Load(opt["-input_file"])) {
+        std::cerr << "[ERROR] " << peek.error << std::endl;
+        return 1;
+      }
+      out_dir = opt.count("-add_out_dir") ? opt["-add_out_dir"] : peek.out_dir;
+      job_dir = out_dir + "/job_b200";
+      mkdir(job_dir.c_str(), 0755);
+      opt["-job_dir"] = job_dir;
+      opt["-uv_dir"] = out_dir;
+      if (run_deck(opt)) return 1;
+      std::cout << "Note: -h5_out '" << opt["-h5_out"] << "' is not written (no HDF5 library in this build); outputs are the flat files in "
+                << out_dir << std::endl;
+    } else {
+      if (opt.count("-job_dir")) job_dir = opt["-job_dir"];
+      if (opt.count("-out_dir")) out_dir = opt["-out_dir"];
+    }
+  } catch (const std::exception& e) {
+    std::cerr << "psp_process_b200: " << e.what() << std::endl;
+    return 1;
   }
   if (job_dir.empty() || out_dir.empty()) {
-    std::cerr << "usage: psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]" << std::endl;
+    std::cerr << "usage: psp_process_b200 -job_dir DIR -out_dir DIR [-device 0] [-chunk 256]\n"
+                 "       psp_process_b200 -input_file=DECK -h5_out=FILE -paint_cal=FILE [psp_process options]" << std::endl;
     return 1;
   }
   try {
