@@ -262,3 +262,15 @@ def test_first_frame_threshold(probe, tmp_path, seed):
     first_min = next((m for m in minp if maxp and m > maxp[0]), 0)
     assert [int(v) for v in d["peaks"][0].split()] == maxp
     assert int(d["first_min"][0]) == first_min and int(d["threshold"][0]) == 16 * first_min + 5
+
+
+@pytest.mark.parametrize("n, maxels", [(5, 1000), (1000, 1000), (2500, 1000), (3999, 1000), (10, 0), (12345, 7)])
+def test_regression_sample(probe, tmp_path, n, maxels):
+    """the vv-*.dat files (cpp/utils/file_writers.cpp:9-31): step = n // maxels, at most maxels values"""
+    v = np.arange(n, dtype=np.float32) * np.float32(0.5)
+    v.tofile(tmp_path / "v.f32")
+    r = run(probe, "vvdump", tmp_path / "v.f32", tmp_path / "o.dat", maxels)
+    numels = maxels if maxels > 0 else n
+    step = 1 if n < numels else n // numels
+    want = v[::step][:numels]
+    assert np.array_equal(np.fromfile(tmp_path / "o.dat", np.float32), want) and r.stdout.split() == ["written", str(len(want))]

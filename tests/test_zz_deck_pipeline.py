@@ -82,6 +82,9 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
         ratio0 = ((ref["avg"] / ref["itrans"][:, 0]).astype(np.float32).astype(np.float64) - 1.0).astype(np.float32)
     assert same_bits(rd("intensity_ratio_0"), ratio0)
     assert same_bits(rd("model_temp"), case.temp) and np.array_equal(rd("steady_state"), case.steady)
+    # regression samples (psp_process.cpp:2006-2015): N = 1284 < 2000 -> stride 1, the first 1000 values
+    assert same_bits(rd("vv-int-avg.dat"), ref["avg"][:1000]) and same_bits(rd("vv-int-sample1.dat"), ratio0[:1000])
+    assert same_bits(rd("vv-cp-rms.dat"), rd("rms")[:1000])
 
 
 @pytest.mark.gpu

@@ -7,6 +7,7 @@
 //   inputs_probe p3dfun FILE [seps]       run_inputs.hpp    read_plot3d_scalar_function_file
 //   inputs_probe hist FILE.u16 DEPTH      run_inputs.hpp    intensity_histc(256 bins) + first_min_threshold(5)
 //   inputs_probe overlap GRID TOL [dump]  p3d_model.hpp     P3DModel: overlap groups, src_index, triangles, normals
+//   inputs_probe vvdump IN.f32 OUT.dat MAXELS   run_inputs.hpp  write_regression_sample (the vv-*.dat files)
 //   inputs_probe interp GRID TOL DATA.f32 XYZ.f32 K OUT.f32   interpolation.hpp   upsp::interpolate onto the points of XYZ
 #include <cstdio>
 #include <cstring>
@@ -117,6 +118,14 @@ int main(int argc, char** argv) {
         dump(p + ".nrm", model.get_n().data(), model.get_n().size() * 4);
         dump(p + ".pairs", pairs.data(), pairs.size() * 4);
       }
+    } else if (cmd == "vvdump") {
+      if (argc < 5) throw std::invalid_argument("vvdump IN.f32 OUT.dat MAXELS");
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      if (!f) throw std::invalid_argument("Cannot open '" + file + "'");
+      std::vector<float> v((size_t)f.tellg() / 4);
+      f.seekg(0);
+      f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
+      std::printf("written %d\n", write_regression_sample(argv[3], v.data(), v.size(), atoi(argv[4])));
     } else if (cmd == "interp") {
       if (argc < 8) throw std::invalid_argument("interp GRID TOL DATA.f32 XYZ.f32 K OUT.f32");
       auto read_f32 = [](const std::string& path) {

@@ -305,6 +305,11 @@ int main(int argc, char** argv) {
       // "a sample Iref/I for frame 1" (psp_process.cpp:1946-1951): avg / sol1 in float, - 1.0 in double
       for (int i = 0; i < msize; ++i) sol1[i] = (float)((double)(sol_avg_final[i] / sol1[i]) - 1.0);
       out.write_vector("intensity_ratio_0", sol1.data(), msize);
+      // regression samples (psp_process.cpp:2006-2015)
+      write_regression_sample(out_dir + "/vv-int-rms.dat", sol_rms_final.data(), (size_t)msize, 1000);
+      write_regression_sample(out_dir + "/vv-int-avg.dat", sol_avg_final.data(), (size_t)msize, 1000);
+      write_regression_sample(out_dir + "/vv-int-coverage.dat", coverage.data(), (size_t)msize, 1000);
+      write_regression_sample(out_dir + "/vv-int-sample1.dat", sol1.data(), (size_t)msize, 1000);
     }
 
     // ---- phase 2 ----
@@ -326,6 +331,8 @@ int main(int argc, char** argv) {
     out.write_vector("rms", rms.data(), msize);
     out.write_vector("avg", avg.data(), msize);
     out.write_vector("gain", gain.data(), msize);
+    write_regression_sample(out_dir + "/vv-cp-rms.dat", rms.data(), (size_t)msize, 1000);     // psp_process.cpp:2594-2597
+    write_regression_sample(out_dir + "/vv-cp-avg.dat", avg.data(), (size_t)msize, 1000);
     for (auto& s : steady)     // psp_process.cpp:2566-2570
       if (s > 3.0f) s = std::numeric_limits<float>::quiet_NaN();
     out.write_vector("steady_state", steady.data(), msize);

@@ -16,6 +16,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <limits>
@@ -274,6 +275,21 @@ inline std::vector<float> read_plot3d_scalar_function_file(const std::string& fi
     err += "\nAssuming *no* FORTRAN record separators: " + e;
   }
   throw std::invalid_argument("Failed to parse Plot3D function file '" + filename + "':" + err + "\n");
+}
+
+/* ---- regression samples: at most `maxels` evenly strided values of a result vector (vv-*.dat) ----
+ * upsp::fwrite cpp/utils/file_writers.cpp:9-31 and the identical lambda at psp_process.cpp:1984-2005 */
+inline int write_regression_sample(const std::string& fname, const float* v, size_t n, int maxels) {
+  if (n == 0) return -1;
+  const size_t numels = maxels > 0 ? (size_t)maxels : n;
+  const size_t step = n < numels ? 1 : n / numels;
+  std::vector<float> outp;
+  for (size_t jj = 0; outp.size() < numels && jj < n; jj += step) outp.push_back(v[jj]);
+  FILE* fp = std::fopen(fname.c_str(), "wb");
+  if (!fp) return -1;
+  const int res = (int)std::fwrite(outp.data(), sizeof(float), outp.size(), fp);
+  std::fclose(fp);
+  return res;
 }
 
 /* ---- first-frame histogram -> boundary threshold of the patcher ---- */
