@@ -274,3 +274,17 @@ def test_regression_sample(probe, tmp_path, n, maxels):
     step = 1 if n < numels else n // numels
     want = v[::step][:numels]
     assert np.array_equal(np.fromfile(tmp_path / "o.dat", np.float32), want) and r.stdout.split() == ["written", str(len(want))]
+
+
+def test_deck_write_file_round_trip(probe, tmp_path):
+    """FileInputs::write_file (cpp/lib/upsp_inputs.cpp:236-341): the written deck loads back to the same fields;
+    variables are put back (longest value first) and shared targets / calibration move to @all."""
+    (tmp_path / "deck.inp").write_text(DOC_DECK)
+    first = run(probe, "deck", tmp_path / "deck.inp", "write", tmp_path / "again.inp").stdout
+    text = (tmp_path / "again.inp").read_text()
+    assert "%Version 1.2.3\n%Date_Created 1/2/2026\n" in text
+    assert "\tdir = /nobackup/upsp/test_name\n" in text and "\tgrid = $dir/inputs/test-subject.grid\n" in text
+    assert text.count("\ttargets = $dir/inputs/test-subject.tgts") == 1 and text.index("targets =") < text.index("@camera")
+    assert text.count("\tcalibration = ") == 2                     # per camera: they differ
+    again = run(probe, "deck", tmp_path / "again.inp").stdout
+    assert kv(again) == kv(first)

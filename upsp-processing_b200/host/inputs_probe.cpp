@@ -1,6 +1,6 @@
 // inputs_probe -- exercises the host-side input readers from the tests (tests/test_run_inputs.py,
 // tests/test_p3d_model.py); one sub-command per reader, plain `key value` lines on stdout.
-//   inputs_probe deck FILE [check]        upsp_inputs.hpp   FileInputs::Load (+ check_all)
+//   inputs_probe deck FILE [check | write OUT]   upsp_inputs.hpp   FileInputs::Load (+ check_all / write_file)
 //   inputs_probe paintcal FILE [T Pss]    run_inputs.hpp    PaintCalibration (+ get_gain)
 //   inputs_probe wtd FILE                 run_inputs.hpp    read_tunnel_conditions + model_temperature
 //   inputs_probe tgts FILE [LABEL]        run_inputs.hpp    read_psp_target_file
@@ -40,10 +40,11 @@ int main(int argc, char** argv) {
         std::cerr << fi.error << "\n";
         return 1;
       }
-      if (argc > 3 && !fi.check_all()) {
+      if (argc > 3 && std::string(argv[3]) == "check" && !fi.check_all()) {
         std::cerr << fi.error << "\n";
         return 1;
       }
+      if (argc > 4 && std::string(argv[3]) == "write") fi.write_file(argv[4], "1/2/2026");
       std::printf("version %s\ntest_id %s\nrun %d\nsequence %d\ntunnel %s\ncameras %u\n", fi.version.c_str(), fi.test_id.c_str(),
                   fi.run, fi.sequence, fi.tunnel.c_str(), fi.cameras);
       std::printf("sds %s\ngrid %s\ngrid_type %s\nnormals %s\ngrid_units %s\nactive_comps %s\n", fi.sds.c_str(), fi.grid.c_str(),

@@ -37,7 +37,7 @@
 // One-step mode, the reference's own command line (ParseOpts, psp_process.cpp:1192-1310; -key=value or -key value):
 //   psp_process_b200 -input_file=DECK -h5_out=FILE -paint_cal=FILE [-steady_p3d=FILE] [-steady_grid=FILE]
 //                    [-model_temp_p3d=FILE] [-frames=N] [-add_out_dir=DIR] [-bound_pts=2] [-buffer_pts=1]
-//                    [-target_diam_sf=1.2] [-cutoff_x_max=X] [-device 0] [-chunk 256]
+//                    [-target_diam_sf=1.2] [-cutoff_x_max=X] [-checkout=T] [-device 0] [-chunk 256]
 // runs the start-up of host/deck_job.hpp into <add_out_dir>/job_b200 and then the frame chain; flat files go to
 // -add_out_dir (default: the deck's @output dir), as in the reference.  -h5_out is required as there, but no HDF5
 // library exists in this build: the flat files are the outputs (a notice says so).
@@ -113,6 +113,10 @@ int main(int argc, char** argv) {
       opt["-job_dir"] = job_dir;
       opt["-uv_dir"] = out_dir;
       if (run_deck(opt)) return 1;
+      if (opt.count("-checkout") && (opt["-checkout"] == "T" || opt["-checkout"] == "true" || opt["-checkout"] == "1")) {
+        std::cout << "Checkout complete (calibration / patch start-up only, psp_process.cpp:1576-1579)" << std::endl;
+        return 0;
+      }
       std::cout << "Note: -h5_out '" << opt["-h5_out"] << "' is not written (no HDF5 library in this build); outputs are the flat files in "
                 << out_dir << std::endl;
     } else {

@@ -206,6 +206,24 @@ struct FileInputs {
     return true;
   }
 
+  /* the deck written back (upsp_inputs.cpp:236-341): values that contain a variable's value get `$name` again
+   * (the longest matching value wins), targets / calibration move to @all when every camera shares them.
+   * `date` fills %Date_Created (the reference prints today's m/d/yyyy). */
+  void write_file(const std::string& out_file, const std::string& date = "") const;
+  std::string refill_vars(std::string term) const {
+    if (vars.empty()) return term;
+    int best_match = -1;
+    size_t best_size = 0;
+    for (size_t i = 0; i < vars.size(); ++i)
+      if (term.find(vars_map[i]) != std::string::npos && vars_map[i].size() > best_size) {
+        best_match = (int)i;
+        best_size = vars_map[i].size();
+      }
+    if (best_match != -1)
+      term.replace(term.find(vars_map[(size_t)best_match]), vars_map[(size_t)best_match].length(), "$" + vars[(size_t)best_match]);
+    return term;
+  }
+
   /* $name substitution, one pass per '$' in the term (upsp_inputs.cpp:668-699) */
   bool evaluate_vars(std::string& term) const {
     if (term.empty()) return true;
@@ -268,6 +286,38 @@ inline const char* to_string(PixelInterpolationType v) { return v == PixelInterp
 inline const char* to_string(FilterType v) { return v == FilterType::Gaussian ? "gaussian" : (v == FilterType::Box ? "box" : "none"); }
 inline const char* to_string(OverlapKind v) { return v == OverlapKind::BestView ? "best_view" : "average_view"; }
 inline const char* to_string(GridType v) { return v == GridType::P3D ? "p3d" : (v == GridType::Tri ? "tri" : "none"); }
+
+inline void FileInputs::write_file(const std::string& out_file, const std::string& date) const {
+  std::ofstream ofs(out_file);
+  if (!ofs.is_open()) throw std::invalid_argument("Could not open file for writing input deck");
+  if (!version.empty()) ofs << "%Version " << version << "\n%Date_Created " << date << "\n\n";
+  ofs << "@general\n\ttest = " << test_id << "\n\trun = " << run << "\n\tsequence = " << sequence << "\n";
+  if (!tunnel.empty()) ofs << "\ttunnel = " << tunnel << "\n";
+  if (!grid_units.empty()) ofs << "\tgrid_units = " << grid_units << "\n";
+  if (!vars.empty()) {
+    ofs << "@vars\n";
+    for (size_t i = 0; i < vars.size(); ++i) ofs << "\t" << vars[i] << " = " << vars_map[i] << "\n";
+  }
+  ofs << "@all\n\tgrid = " << refill_vars(grid) << "\n\tsds = " << refill_vars(sds) << "\n";
+  if (!normals.empty()) ofs << "\tnormals = " << refill_vars(normals) << "\n";
+  if (!active_comps.empty()) ofs << "\tactive_comps = " << refill_vars(active_comps) << "\n";
+  const bool targ_all = std::all_of(targets.begin(), targets.end(), [&](const std::string& t) { return t == targets[0]; });
+  const bool cal_all = std::all_of(cals.begin(), cals.end(), [&](const std::string& t) { return t == cals[0]; });
+  if (targ_all && !targets.empty()) ofs << "\ttargets = " << refill_vars(targets[0]) << "\n";
+  if (cal_all && !cals.empty()) ofs << "\tcalibration = " << refill_vars(cals[0]) << "\n";
+  for (unsigned c = 0; c < cameras; ++c) {
+    ofs << "@camera\n\tnumber = " << cam_nums[c] << "\n\tfilename = " << refill_vars(camera_filenames[c]) << "\n";
+    if (!targ_all) ofs << "\ttargets = " << refill_vars(targets[c]) << "\n";
+    if (!cal_all) ofs << "\tcalibration = " << refill_vars(cals[c]) << "\n";
+  }
+  ofs << "@options\n\ttarget_patcher = " << (target_patcher == TargetPatchType::Polynomial ? "polynomial" : "none")
+      << "\n\tregistration = " << (registration == RegistrationType::Pixel ? "pixel" : (registration == RegistrationType::Point ? "point" : "none"))
+      << "\n\tpixel_interpolation = " << (pixel_interpolation == PixelInterpolationType::Nearest ? "nearest" : "linear")
+      << "\n\tfilter = " << (filter == FilterType::Gaussian ? "gaussian" : (filter == FilterType::Box ? "box" : "none"))
+      << "\n\toverlap = " << (overlap == OverlapKind::BestView ? "best_view" : "average_view") << "\n\tfilter_size = " << filter_size
+      << "\n\toblique_angle = " << oblique_angle << "\n\tnumber_frames = " << number_frames << "\n";
+  ofs << "@output\n\tdir = " << refill_vars(out_dir) << "\n\tname = " << out_name << "\n";
+}
 
 /* the summary psp_process prints on rank 0 (upsp_inputs.cpp:753-798) */
 inline std::ostream& operator<<(std::ostream& os, const FileInputs& fi) {
