@@ -235,3 +235,90 @@ def test_deck_two_cameras_average_view(up, orc, gpu, tmp_path):
     assert same_bits(got, ref["itrans"])
     assert same_bits(np.fromfile(d / "out" / "coverage", np.float32), ref["coverage"])
     assert same_bits(np.fromfile(d / "out" / "gain", np.float32), ref["gain"])
+
+
+def sphere_zones(radius=5.0, J=49, K=13):
+    """a sphere band about the x axis as two structured zones: the zones share the "equator" row (the circle x = 0,
+    which passes in front of the camera at z = -radius) and each zone closes on itself in longitude (j = 0 and j = J-1
+    coincide: a wrapped zone, its seam also facing the camera); the face normals e_j x e_k point outwards"""
+    lon = np.linspace(0.0, 2 * np.pi, J)
+    zones = []
+    for lat0, lat1 in ((-1.2, 0.0), (0.0, 1.2)):
+        lat = np.linspace(lat0, lat1, K)
+        la, lo = np.meshgrid(lat, lon, indexing="ij")                       # [K, J]
+        p = np.stack([radius * np.sin(la), radius * np.cos(la) * np.sin(lo), -radius * np.cos(la) * np.cos(lo)], -1).astype(np.float32)
+        p[:, J - 1] = p[:, 0]
+        zones.append((J, K, p.reshape(-1, 3)))
+    zones[1][2][:J] = zones[0][2][-J:]                                      # shared equator row, bit-identical
+    return zones
+
+
+@pytest.mark.gpu
+def test_deck_structured_grid_with_seams(up, orc, gpu, tmp_path):
+    """SURVEY 8d config-4 style: a multi-zone plot3d model whose seam nodes overlap (zone-to-zone and wrapped zones).
+    Superceded nodes get no projection row; every frame's solution is copied onto them from the lowest node of their
+    group (P3DModel::adjust_solution -> remap.i32 -> upsp_gpu_set_overlap_remap)."""
+    import cv2
+    from oracle import p3d_overlap
+    from test_p3d_model import write_p3d
+    synth = up.synth
+    sc = synth.make_projection_scene(n_lat=8, n_lon=16, seed=11)            # camera only
+    W, H, F = sc["width"], sc["height"], 8
+    d = tmp_path
+    zones = sphere_zones()
+    write_p3d(d / "model.grid", zones)
+    xyz = np.concatenate([z[2] for z in zones]).astype(np.float32)
+    sizes = [(z[0], z[1]) for z in zones]
+    N = len(xyz)
+    _cal_json(d / "cam01.json", cv2.Rodrigues(np.asarray(sc["rvec"], float))[0], sc["tvec"], sc["K"], sc["dist"], (W, H))
+    frames = synth.make_frames(F, H, W, seed=9)[0]
+    synth.pack_12bit(frames.reshape(F, -1)).tofile(d / "v1.mraw")
+    (d / "v1.cih").write_text("#Camera Information Header\r\nRecord Rate(fps) : 1000\r\nTotal Frame : %d\r\n"
+                              "Image Width : %d\r\nImage Height : %d\r\nColor Bit : 12\r\n" % (F, W, H))
+    (d / "run.wtd").write_text(open(os.path.join(GOLDEN, "sample.wtd")).read())
+    (d / "model.tgts").write_text(open(os.path.join(GOLDEN, "sample.tgts")).read())
+    cal = np.array([0.62, -1.3e-3, 2.1e-6, 2.4e-4, 3.0e-7, -1.1e-9], np.float32)
+    (d / "paint.cal").write_text("".join("%s = %.9g\n" % (k, v) for k, v in zip("abcdef", cal)))
+    (d / "out").mkdir()
+    (d / "job").mkdir()
+    (d / "deck.inp").write_text(
+        f"@general\n\ttest = t\n\trun = 1\n\tsequence = 1\n\ttunnel = ames_unitary\n@all\n\tgrid = {d}/model.grid\n\tsds = {d}/run.wtd\n"
+        f"\ttargets = {d}/model.tgts\n@camera\n\tnumber = 1\n\tfilename = {d}/v1.mraw\n\tcalibration = {d}/cam01.json\n"
+        f"@options\n\ttarget_patcher = none\n\tregistration = none\n\tfilter = none\n\tfilter_size = 1\n\toblique_angle = 70\n"
+        f"\tnumber_frames = {F}\n@output\n\tdir = {d}/out\n\tname = r\n")
+    r = subprocess.run([up.build.build_setup_tool(), "-input_file", str(d / "deck.inp"), "-paint_cal", str(d / "paint.cal"),
+                        "-job_dir", str(d / "job")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([up.build.build_host(), "-job_dir", str(d / "job"), "-out_dir", str(d / "out"), "-chunk", "8"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+
+    overlap, _, _ = p3d_overlap.identify_overlap(xyz, sizes, 1e-3)
+    remap = orc.overlap_remap(N, overlap)
+    assert np.array_equal(np.fromfile(d / "job" / "remap.i32", np.int32), remap) and (remap != np.arange(N)).sum() >= 49 + 2 * 12
+    subprocess.run([up.build.build_inputs_probe(), "overlap", str(d / "model.grid"), "0.001", str(d / "g")], check=True, capture_output=True)
+    nrm = np.fromfile(d / "g.nrm", np.float32).reshape(-1, 3)
+    tri = np.fromfile(d / "g.trinodes", np.int32).reshape(-1, 3)
+    assert np.array_equal(tri.ravel(), p3d_overlap.extract_tri_nodes(sizes))
+    pc = subprocess.run([up.build.build_setup_tool(), "-cal", str(d / "cam01.json"), "-print_cal"], capture_output=True, text=True)
+    parsed = {l.split()[0]: np.array(l.split()[1:], float) for l in pc.stdout.splitlines()}
+    ocam = orc.make_camera(parsed["rvec"], parsed["tvec"], sc["K"], sc["dist"], W, H)
+    is_data = (remap == np.arange(N)).astype(np.uint8)
+    code, _ = orc.create_projection(ocam, xyz, nrm, is_data, tri, float(np.float32((180.0 - 70.0) * np.pi / 180.0)))
+    rowptr, col, val = orc.projection_csr(code)
+    assert (code >= 0).sum() > 100 and not np.any(code[is_data == 0] >= 0)
+    assert np.array_equal(np.fromfile(d / "job" / "cam0.rowptr", np.int32), rowptr)
+    assert np.array_equal(np.fromfile(d / "job" / "cam0.col", np.int32), col)
+    case = Case.__new__(Case)
+    case.C, case.N, case.F, case.H, case.W = 1, N, F, H, W
+    case.interp, case.degree, case.fmt, case.filter_kind, case.filter_size = 1, 6, "p12", 0, 0
+    case.frames, case.csr, case.warp, case.patch_lists, case.overlap, case.synth = [frames], [(rowptr, col, val)], None, None, overlap, synth
+    case.cal, case.qbar, case.ps = cal, np.float32(657.9153), np.float32(1332.0421)
+    case.steady, case.temp = np.zeros(N, np.float32), np.full(N, 88.125, np.float32)
+    ref = run_oracle(orc, case)
+    got = np.fromfile(d / "out" / "intensity_transpose", np.float32).reshape(N, F)
+    assert same_bits(got, ref["itrans"])
+    seam = np.nonzero((remap != np.arange(N)) & np.isfinite(got[:, 0]))[0]
+    assert len(seam) > 5 and np.array_equal(got[seam], got[remap[seam]])      # seam nodes carry their group's values
+    assert same_bits(np.fromfile(d / "out" / "intensity_avg", np.float32), ref["avg"])
+    assert same_bits(np.fromfile(d / "out" / "coverage", np.float32), ref["coverage"])
