@@ -28,6 +28,15 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_ref(ref_root: str = "/root/reference"):
+    """Compile the reference's dependency-free post-processing tools from the reference tree into oracle/_ref/ (only where
+    that tree exists, i.e. in the build container; the built files travel to the GPU box).  Returns the directory or None."""
+    out = os.path.join(_HERE, "_ref")
+    if os.path.isdir(os.path.join(ref_root, "cpp", "exec")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REF=" + ref_root])
+    return out if os.path.exists(os.path.join(out, "xyz_scalar_to_tbl")) else None
+
+
 _lib = None
 
 

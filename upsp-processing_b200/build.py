@@ -145,6 +145,22 @@ def build_inputs_probe(force: bool = False) -> str:
     return INPUTS_PROBE_BIN
 
 
+TBL_BIN = os.path.join(HERE, "xyz_scalar_to_tbl_b200")
+
+
+def build_tbl_tool(force: bool = False) -> str:
+    """host/xyz_scalar_to_tbl_b200.cpp: flat files -> Tecplot table (the reference's xyz_scalar_to_tbl / _delta tools)."""
+    src = os.path.join(HERE, "host", "xyz_scalar_to_tbl_b200.cpp")
+    if not force and os.path.exists(TBL_BIN) and os.path.getmtime(TBL_BIN) >= os.path.getmtime(src):
+        return TBL_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", TBL_BIN, src], capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building xyz_scalar_to_tbl_b200")
+    return TBL_BIN
+
+
 SETUP_BIN = os.path.join(HERE, "psp_setup_b200")
 
 
@@ -212,3 +228,4 @@ if __name__ == "__main__":
     print(build_setup_tool(force="--force" in sys.argv))
     print(build_weights_probe(force="--force" in sys.argv))
     print(build_inputs_probe(force="--force" in sys.argv))
+    print(build_tbl_tool(force="--force" in sys.argv))
