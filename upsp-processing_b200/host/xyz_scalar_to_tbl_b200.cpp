@@ -1,7 +1,7 @@
 // xyz_scalar_to_tbl_b200 -- the flat-file outputs of the frame chain as a Tecplot point table, per zone of the
 // structured grid.  Same arguments, messages, exit codes and bytes as the reference's two post-processing tools
-// (cpp/exec/xyz_scalar_to_tbl.cpp, cpp/exec/xyz_scalar_to_tbl_delta.cpp); tests hold the output byte for byte against
-// those tools compiled from the reference tree (oracle/_ref, `make -C oracle ref`).
+// (cpp/exec/xyz_scalar_to_tbl.cpp, cpp/exec/xyz_scalar_to_tbl_delta.cpp); tests/test_tbl_tool.py holds the output byte
+// for byte against those tools compiled from the reference tree.
 //   xyz_scalar_to_tbl_b200 grid.p3d X Y Z scalar output
 //   xyz_scalar_to_tbl_b200 -delta grid.p3d X Y Z scalar1 scalar2     -> ./xyz_scalar_delta.tecplot (scalar1 - scalar2)
 // grid.p3d: multi-zone unformatted plot3d, little endian (only its header is read); X / Y / Z / scalar: raw f32 [N]
