@@ -66,3 +66,28 @@ def test_error_behaviour_matches_reference_tool(tools, tmp_path):
         r2 = subprocess.run([mine] + args, capture_output=True, text=True, cwd=tmp_path)
         assert r1.returncode == r2.returncode == 1
         assert r1.stdout == r2.stdout, c
+
+
+@pytest.mark.parametrize("flag, msize, nframes", [(0, 1237, 301), (1, 1237, 301), (0, 100, 100), (1, 7, 2500)])
+def test_reference_transpose_tool_pins_the_restatement(tools, orc, tmp_path, flag, msize, nframes):
+    """The reference's own local_transpose / global_transpose (cpp/exec/upsp_matrix_transpose.cpp:86-212, the code of
+    psp_process.cpp:647-771) compiled from the reference tree against a single-rank loop-back MPI header
+    (oracle/mpi_stub/mpi.h) and run here: its `pressure_transpose` / `pressure` file is what the CPU restatement
+    (oracle.global_transpose) and numpy's transpose give, bit for bit.  The GPU tool is held against the same arrays in
+    tests/test_host_driver.py::test_transpose_tool_matches_numpy."""
+    _, ref = tools
+    exe = os.path.join(ref, "upsp_matrix_transpose")
+    if not os.path.exists(exe):
+        pytest.skip("reference transpose tool not built")
+    rng = np.random.default_rng(msize + flag)
+    a = rng.standard_normal((nframes, msize) if flag == 0 else (msize, nframes)).astype(np.float32)
+    a[0, 0] = np.nan
+    a.tofile(tmp_path / "in")
+    r = subprocess.run([exe, str(msize), str(nframes), str(flag), str(tmp_path / "in"), str(tmp_path)], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(tmp_path / ("pressure_transpose" if flag == 0 else "pressure"), np.float32).reshape(a.T.shape)
+    assert np.array_equal(out.view(np.uint32), np.ascontiguousarray(a.T).view(np.uint32))
+    if flag == 0:
+        mine = np.concatenate(orc.global_transpose([a], msize, nframes), 0)
+        assert np.array_equal(mine.view(np.uint32), out.view(np.uint32))
