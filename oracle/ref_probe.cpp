@@ -1,0 +1,95 @@
+// ref_probe -- TEST INFRASTRUCTURE ONLY.  A small main() linked against the reference's OWN sources that compile without
+// third-party libraries (cpp/lib/upsp_inputs.cpp, non_cv_upsp.cpp, plot3d.cpp, logging.cpp, cpp/utils/general_utils.cpp,
+// file_writers.cpp; `make -C oracle ref`, built only where /root/reference exists, output oracle/_ref/ref_probe).  It calls
+// the reference's readers and prints what they parsed in the line format of the product's host/inputs_probe, so that
+// tests/test_ref_probe.py can hold the product's restatements against the reference itself.  No reference source is
+// copied: this file only calls upsp::FileInputs::Load, upsp::PaintCalibration, upsp::read_tunnel_conditions,
+// upsp::read_plot3d_scalar_function_file, upsp::read_plot3d_grid_file / write_plot3d_grid_file and upsp::fwrite.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "grids.h"
+#include "non_cv_upsp.h"
+#include "plot3d.h"
+#include "upsp_inputs.h"
+#include "utils/file_writers.h"
+
+template <typename E>
+static std::string str(const E& e) {
+  std::ostringstream os;
+  os << e;
+  return os.str();
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const std::string cmd = argv[1], file = argv[2];
+  try {
+    if (cmd == "deck") {
+      upsp::FileInputs fi;
+      if (!fi.Load(file)) return 1;
+      if (argc > 3 && std::string(argv[3]) == "check" && !fi.check_all()) return 1;
+      if (argc > 4 && std::string(argv[3]) == "write") fi.write_file(argv[4]);
+      std::printf("test_id %s\nrun %u\nsequence %u\ntunnel %s\ncameras %u\n", fi.test_id.c_str(), fi.run, fi.sequence, fi.tunnel.c_str(),
+                  fi.cameras);
+      const char* gt = fi.grid_type == upsp::GridType::P3D ? "p3d" : (fi.grid_type == upsp::GridType::Tri ? "tri" : "none");
+      std::printf("sds %s\ngrid %s\ngrid_type %s\nnormals %s\ngrid_units %s\nactive_comps %s\n", fi.sds.c_str(), fi.grid.c_str(), gt,
+                  fi.normals.c_str(), fi.grid_units.c_str(), fi.active_comps.c_str());
+      for (unsigned c = 0; c < fi.cameras; ++c)
+        std::printf("camera %u %s %s %s\n", fi.cam_nums[c], fi.camera_filenames[c].c_str(), fi.targets[c].c_str(), fi.cals[c].c_str());
+      std::printf("target_patcher %s\nregistration %s\npixel_interpolation %s\nfilter %s\noverlap %s\n", str(fi.target_patcher).c_str(),
+                  str(fi.registration).c_str(), str(fi.pixel_interpolation).c_str(), str(fi.filter).c_str(), str(fi.overlap).c_str());
+      std::printf("filter_size %d\noblique_angle %.9g\nnumber_frames %d\nout_dir %s\nout_name %s\n", (int)fi.filter_size,
+                  (double)fi.oblique_angle, fi.number_frames, fi.out_dir.c_str(), fi.out_name.c_str());
+    } else if (cmd == "paintcal") {
+      upsp::PaintCalibration pc(file);
+      std::printf("a %.9g\nb %.9g\nc %.9g\nd %.9g\ne %.9g\nf %.9g\n", (double)pc.a, (double)pc.b, (double)pc.c, (double)pc.d, (double)pc.e,
+                  (double)pc.f);
+      if (argc > 4) std::printf("gain %.9g\n", (double)pc.get_gain((float)atof(argv[3]), (float)atof(argv[4])));
+    } else if (cmd == "wtd") {
+      const upsp::TunnelConditions tc = upsp::read_tunnel_conditions(file);
+      std::fflush(stdout);
+      std::printf("alpha %.9g\nbeta %.9g\nphi %.9g\nmach %.9g\nrey %.9g\nptot %.9g\nqbar %.9g\nttot %.9g\nps %.9g\ntcavg %.9g\n",
+                  (double)tc.alpha, (double)tc.beta, (double)tc.phi, (double)tc.mach, (double)tc.rey, (double)tc.ptot, (double)tc.qbar,
+                  (double)tc.ttot, (double)tc.ps, (double)tc.tcavg);
+    } else if (cmd == "p3dfun") {
+      const std::vector<float> sol = upsp::read_plot3d_scalar_function_file(file, argc > 3 ? atoi(argv[3]) : -1);
+      std::printf("count %zu\n", sol.size());
+      for (float v : sol) std::printf("%.9g\n", (double)v);
+    } else if (cmd == "vvdump") {
+      if (argc < 5) return 2;
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      std::vector<float> v((size_t)f.tellg() / 4);
+      f.seekg(0);
+      f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
+      std::printf("written %d\n", upsp::fwrite(argv[3], v, atoi(argv[4])));
+    } else if (cmd == "p3dgrid") {   // FILE sp|dp [OUT]: sizes as host/grid_probe prints them, optional re-write
+      const bool dp = argc > 3 && std::string(argv[3]) == "dp";
+      auto report = [](const auto& g) {
+        std::printf("n_zones %u\nn_points %zu\n", g.num_zones(), (size_t)g.x.size());
+        for (unsigned z = 0; z < g.num_zones(); ++z) std::printf("zone %u %u %u %u\n", z, g.grid_size[z][0], g.grid_size[z][1], g.grid_size[z][2]);
+      };
+      if (dp) {
+        upsp::StructuredGrid<double> g;
+        upsp::read_plot3d_grid_file(file, g);
+        report(g);
+        if (argc > 4) upsp::write_plot3d_grid_file(argv[4], g);
+      } else {
+        upsp::StructuredGrid<float> g;
+        upsp::read_plot3d_grid_file(file, g);
+        report(g);
+        if (argc > 4) upsp::write_plot3d_grid_file(argv[4], g);
+      }
+    } else {
+      return 2;
+    }
+  } catch (const std::exception& e) {
+    std::cerr << "ref_probe: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}

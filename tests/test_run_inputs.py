@@ -105,7 +105,7 @@ def test_deck_launcher_layout_and_defaults(probe, tmp_path):
     d = kv(run(probe, "deck", tmp_path / "d.inp").stdout)
     assert d["grid_type"] == ["tri"] and d["normals"] == [""] and d["sequence"] == ["7"] and d["number_frames"] == ["-1"]
     assert d["camera"] == ["1 /g/41210701.cine /g/model.tgts /c/cam01.json"]
-    assert d["overlap"] == ["average_view"] and d["registration"] == ["none"] and d["filter"] == ["none"]
+    assert d["overlap"] == ["average_views"] and d["registration"] == ["none"] and d["filter"] == ["none"]
 
 
 @pytest.mark.parametrize("line, msg", [

@@ -51,8 +51,8 @@ int main(int argc, char** argv) {
                   to_string(fi.grid_type), fi.normals.c_str(), fi.grid_units.c_str(), fi.active_comps.c_str());
       for (unsigned c = 0; c < fi.cameras; ++c)
         std::printf("camera %u %s %s %s\n", fi.cam_nums[c], fi.camera_filenames[c].c_str(), fi.targets[c].c_str(), fi.cals[c].c_str());
-      std::printf("target_patcher %s\nregistration %s\npixel_interpolation %s\nfilter %s\noverlap %s\n", to_string(fi.target_patcher),
-                  to_string(fi.registration), to_string(fi.pixel_interpolation), to_string(fi.filter), to_string(fi.overlap));
+      std::printf("target_patcher %s\nregistration %s\npixel_interpolation %s\nfilter %s\noverlap %s\n", display_name(fi.target_patcher),
+                  display_name(fi.registration), display_name(fi.pixel_interpolation), display_name(fi.filter), display_name(fi.overlap));
       std::printf("filter_size %d\noblique_angle %.9g\nnumber_frames %d\nout_dir %s\nout_name %s\n", fi.filter_size,
                   (double)fi.oblique_angle, fi.number_frames, fi.out_dir.c_str(), fi.out_name.c_str());
     } else if (cmd == "paintcal") {

@@ -285,6 +285,14 @@ inline const char* to_string(RegistrationType v) {
 inline const char* to_string(PixelInterpolationType v) { return v == PixelInterpolationType::Nearest ? "nearest" : "linear"; }
 inline const char* to_string(FilterType v) { return v == FilterType::Gaussian ? "gaussian" : (v == FilterType::Box ? "box" : "none"); }
 inline const char* to_string(OverlapKind v) { return v == OverlapKind::BestView ? "best_view" : "average_view"; }
+/* to_string: the deck keywords (what Load accepts).  display_name: what the reference's stream operators print
+ * (upsp_inputs.cpp:802-882), which differ in two places: a box filter prints as "undefined filter type" (no case for it)
+ * and the averaging overlap as "average_views" (the keyword is "average_view"); its write_file inherits both. */
+inline const char* display_name(TargetPatchType v) { return to_string(v); }
+inline const char* display_name(RegistrationType v) { return to_string(v); }
+inline const char* display_name(PixelInterpolationType v) { return to_string(v); }
+inline const char* display_name(FilterType v) { return v == FilterType::Box ? "undefined filter type" : to_string(v); }
+inline const char* display_name(OverlapKind v) { return v == OverlapKind::BestView ? "best_view" : "average_views"; }
 inline const char* to_string(GridType v) { return v == GridType::P3D ? "p3d" : (v == GridType::Tri ? "tri" : "none"); }
 
 inline void FileInputs::write_file(const std::string& out_file, const std::string& date) const {
@@ -310,12 +318,10 @@ inline void FileInputs::write_file(const std::string& out_file, const std::strin
     if (!targ_all) ofs << "\ttargets = " << refill_vars(targets[c]) << "\n";
     if (!cal_all) ofs << "\tcalibration = " << refill_vars(cals[c]) << "\n";
   }
-  ofs << "@options\n\ttarget_patcher = " << (target_patcher == TargetPatchType::Polynomial ? "polynomial" : "none")
-      << "\n\tregistration = " << (registration == RegistrationType::Pixel ? "pixel" : (registration == RegistrationType::Point ? "point" : "none"))
-      << "\n\tpixel_interpolation = " << (pixel_interpolation == PixelInterpolationType::Nearest ? "nearest" : "linear")
-      << "\n\tfilter = " << (filter == FilterType::Gaussian ? "gaussian" : (filter == FilterType::Box ? "box" : "none"))
-      << "\n\toverlap = " << (overlap == OverlapKind::BestView ? "best_view" : "average_view") << "\n\tfilter_size = " << filter_size
-      << "\n\toblique_angle = " << oblique_angle << "\n\tnumber_frames = " << number_frames << "\n";
+  ofs << "@options\n\ttarget_patcher = " << display_name(target_patcher) << "\n\tregistration = " << display_name(registration)
+      << "\n\tpixel_interpolation = " << display_name(pixel_interpolation) << "\n\tfilter = " << display_name(filter)
+      << "\n\toverlap = " << display_name(overlap) << "\n\tfilter_size = " << filter_size << "\n\toblique_angle = " << oblique_angle
+      << "\n\tnumber_frames = " << number_frames << "\n";
   ofs << "@output\n\tdir = " << refill_vars(out_dir) << "\n\tname = " << out_name << "\n";
 }
 
@@ -330,9 +336,9 @@ inline std::ostream& operator<<(std::ostream& os, const FileInputs& fi) {
     os << " camera " << fi.cam_nums[c] << "\n           filename    = " << fi.camera_filenames[c] << "\n           targets     = "
        << fi.targets[c] << "\n           calibration = " << fi.cals[c] << "\n";
   os << "\noutput dir  = " << fi.out_dir << "\noutput name = " << fi.out_name << "\n\nOptions:\n";
-  os << "  Target Patcher   = " << to_string(fi.target_patcher) << "\n  Registration     = " << to_string(fi.registration)
-     << "\n  Pixel Interp     = " << to_string(fi.pixel_interpolation) << "\n  Filter           = " << to_string(fi.filter) << " ("
-     << fi.filter_size << "x" << fi.filter_size << ")\n  Overlap          = " << to_string(fi.overlap)
+  os << "  Target Patcher   = " << display_name(fi.target_patcher) << "\n  Registration     = " << display_name(fi.registration)
+     << "\n  Pixel Interp     = " << display_name(fi.pixel_interpolation) << "\n  Filter           = " << display_name(fi.filter) << " ("
+     << fi.filter_size << "x" << fi.filter_size << ")\n  Overlap          = " << display_name(fi.overlap)
      << "\n  Oblique Angle    = " << fi.oblique_angle << "\n  Number of Frames = " << fi.number_frames << "\n";
   return os;
 }
