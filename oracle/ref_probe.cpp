@@ -4,18 +4,25 @@
 // the reference's readers and prints what they parsed in the line format of the product's host/inputs_probe, so that
 // tests/test_ref_probe.py can hold the product's restatements against the reference itself.  No reference source is
 // copied: this file only calls upsp::FileInputs::Load, upsp::PaintCalibration, upsp::read_tunnel_conditions,
-// upsp::read_plot3d_scalar_function_file, upsp::read_plot3d_grid_file / write_plot3d_grid_file and upsp::fwrite.
+// upsp::read_plot3d_scalar_function_file, upsp::read_plot3d_grid_file / write_plot3d_grid_file, upsp::fwrite and the header
+// templates upsp::find_peaks / first_min_threshold (cpp/include/utils/clustering.h, with boost_stub/ for its one Boost include),
+// and upsp::MrawReader / PSPVideo / unpack_12bit / unpack_10bit (cpp/lib/MrawReader.cpp, PSPVideo.cpp, with cv_stub/ for the
+// zero-filled CV_16U cv::Mat they fill).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
+#include "MrawReader.h"
+#include "PSPVideo.h"
 #include "grids.h"
 #include "non_cv_upsp.h"
 #include "plot3d.h"
 #include "upsp_inputs.h"
+#include "utils/clustering.h"
 #include "utils/file_writers.h"
 
 template <typename E>
@@ -67,6 +74,49 @@ int main(int argc, char** argv) {
       f.seekg(0);
       f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
       std::printf("written %d\n", upsp::fwrite(argv[3], v, atoi(argv[4])));
+    } else if (cmd == "mraw") {      // FILE.mraw [first=1] [count=all] [dump.u16]: upsp::MrawReader + PSPVideo, decoded frames
+      upsp::PSPVideo video(std::unique_ptr<upsp::VideoReader>(new upsp::MrawReader(file)));
+      const unsigned first = argc > 3 ? (unsigned)atoi(argv[3]) : 1;
+      const unsigned count = argc > 4 ? (unsigned)atoi(argv[4]) : video.get_number_frames() - first + 1;
+      std::printf("width %u\nheight %u\nbit_depth %u\nnum_frames %u\nframe_rate %u\n", video.get_width(), video.get_height(),
+                  video.get_bit_depth(), video.get_number_frames(), video.get_frame_rate());
+      FILE* dump = argc > 5 ? std::fopen(argv[5], "wb") : nullptr;
+      for (unsigned n = first; n < first + count; ++n) {
+        cv::Mat fr = video.get_frame(n);
+        if (dump) std::fwrite(fr.data, 2, (size_t)fr.rows * fr.cols, dump);
+      }
+      if (dump) std::fclose(dump);
+    } else if (cmd == "unpack") {    // IN.bin BITS N_PIXELS OUT.u16: upsp::unpack_12bit / unpack_10bit on raw packed bytes
+      if (argc < 6) return 2;
+      const int bits = atoi(argv[3]);
+      const size_t npix = (size_t)atol(argv[4]), nbytes = npix * (size_t)bits / 8;
+      std::ifstream f(file, std::ios::binary);
+      std::vector<uint8_t> packed(nbytes);
+      f.read(reinterpret_cast<char*>(packed.data()), (std::streamsize)nbytes);
+      cv::Mat out = cv::Mat::zeros(1, (int)npix, CV_16U);
+      if (bits == 12) upsp::unpack_12bit(packed.data(), out, nbytes);
+      else upsp::unpack_10bit(packed.data(), out, nbytes);
+      FILE* o = std::fopen(argv[5], "wb");
+      std::fwrite(out.data, 2, npix, o);
+      std::fclose(o);
+      std::printf("pixels %zu\n", npix);
+    } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
+      if (argc < 4) return 2;
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      std::vector<int> counts((size_t)f.tellg() / 4);
+      f.seekg(0);
+      f.read(reinterpret_cast<char*>(counts.data()), (std::streamsize)(counts.size() * 4));
+      const unsigned sep = (unsigned)atoi(argv[3]);
+      std::vector<unsigned int> maxp, minp;
+      upsp::find_peaks(counts, maxp, sep);
+      std::vector<double> inv(counts.size());
+      for (size_t i = 0; i < counts.size(); ++i) inv[i] = 1.0 / counts[i];
+      upsp::find_peaks(inv, minp, sep);
+      std::printf("max_peaks");
+      for (unsigned p : maxp) std::printf(" %u", p);
+      std::printf("\nmin_peaks");
+      for (unsigned p : minp) std::printf(" %u", p);
+      std::printf("\nfirst_min %u\n", upsp::first_min_threshold(counts, sep));
     } else if (cmd == "p3dgrid") {   // FILE sp|dp [OUT]: sizes as host/grid_probe prints them, optional re-write
       const bool dp = argc > 3 && std::string(argv[3]) == "dp";
       auto report = [](const auto& g) {

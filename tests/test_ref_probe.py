@@ -145,3 +145,68 @@ def test_plot3d_grid_reader_writer_equal_reference(up, probes, tmp_path):
             r2 = subprocess.run([probes[1], "p3dgrid", base + name, prec, str(tmp_path / "ref.x")], capture_output=True, text=True)
             assert r1.returncode == r2.returncode == 0, (name, r1.stderr, r2.stderr)
             assert r1.stdout == r2.stdout and (tmp_path / "mine.x").read_bytes() == (tmp_path / "ref.x").read_bytes(), (name, prec)
+
+
+def test_peak_finding_equals_reference(probes, tmp_path):
+    """upsp::find_peaks / first_min_threshold (cpp/utils/clustering.ipp:9-101) compiled from the reference tree: histograms
+    with plateaus, empty bins (1/0 = inf in the inverse), peaks closer than the separation (the scan's early `break`),
+    short and flat inputs."""
+    rng = np.random.default_rng(11)
+    cases = [np.array(c, np.int32) for c in ([], [3], [1, 2], [1, 5, 2], [5, 5, 5, 5], [0, 0, 0, 0, 0], [1, 3, 3, 3, 1, 0, 0, 4, 4, 2, 9, 1],
+                                             [0, 7, 0, 7, 0, 7, 0], [9, 1, 1, 1, 9, 1, 9], [1, 2, 3, 4, 5, 6], [6, 5, 4, 3, 2, 1])]
+    for _ in range(40):
+        n = int(rng.integers(3, 260))
+        base = rng.integers(0, 6, n) * rng.integers(0, 2, n)                 # many zeros and ties
+        bumps = (200 * np.exp(-((np.arange(n) - rng.uniform(0, n)) / rng.uniform(2, 20)) ** 2)).astype(int)
+        cases.append((base + bumps + (50 * np.exp(-((np.arange(n) - rng.uniform(0, n)) / 6.0) ** 2)).astype(int)).astype(np.int32))
+    for k, counts in enumerate(cases):
+        counts.tofile(tmp_path / "c.i32")
+        for sep in (0, 1, 5, 12):
+            mine, ref = both(probes, "peaks", tmp_path / "c.i32", sep)
+            assert not ref[0] and mine == ref, (k, sep, counts.tolist())
+
+
+def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
+    """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
+    tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
+    rng = np.random.default_rng(21)
+    for bits, group in ((12, 3), (10, 5)):
+        npix = 4096 * 3
+        packed = rng.integers(0, 256, npix * bits // 8, dtype=np.uint8)
+        packed[: group * 4] = [0xFF] * (group * 2) + [0x00] * (group * 2)
+        packed.tofile(tmp_path / "p.bin")
+        r = subprocess.run([probes[1], "unpack", str(tmp_path / "p.bin"), str(bits), str(npix), str(tmp_path / "o.u16")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        ref = np.fromfile(tmp_path / "o.u16", np.uint16)
+        mine = orc.unpack_12bit(packed) if bits == 12 else orc.unpack_10bit(packed)
+        assert np.array_equal(mine.ravel(), ref)
+
+
+def test_mraw_reader_equals_reference_code(up, probes, orc, tmp_path):
+    """the reference's own MrawReader + PSPVideo (cpp/lib/MrawReader.cpp:62-146) on the committed .mraw/.cih pair, on a
+    generated one and on the reference's 12bitMRAW fixture: same properties as host/video_readers.hpp reports, and its decoded
+    frames == unpack(the stored bytes the product hands to the GPU)."""
+    video_probe = up.build.build_probe()
+    files = [os.path.join(GOLDEN, "tiny12.mraw")]
+    rng = np.random.default_rng(4)
+    W, H, F = 48, 20, 5
+    fr = rng.integers(0, 4096, (F, H * W)).astype(np.uint16)
+    up.synth.pack_12bit(fr).tofile(tmp_path / "gen.mraw")
+    (tmp_path / "gen.cih").write_text("#Camera Information Header\r\nRecord Rate(fps) : 2500\r\nTotal Frame : %d\r\n"
+                                      "Image Width : %d\r\nImage Height : %d\r\nColor Bit : 12\r\n" % (F, W, H))
+    files.append(str(tmp_path / "gen.mraw"))
+    if os.path.exists("/root/reference/cpp/test/mraw/12bitMRAW.mraw"):
+        files.append("/root/reference/cpp/test/mraw/12bitMRAW.mraw")
+    for path in files:
+        r = subprocess.run([probes[1], "mraw", path, "1", "2", str(tmp_path / "ref.u16")], capture_output=True, text=True)
+        m = subprocess.run([video_probe, path, "1", "2", str(tmp_path / "mine.bin")], capture_output=True, text=True)
+        assert r.returncode == 0 and m.returncode == 0, (r.stderr, m.stderr)
+        rk = dict(l.split() for l in r.stdout.splitlines())
+        mk = dict(l.split()[:2] for l in m.stdout.splitlines() if not l.startswith("crc"))
+        for k in ("width", "height", "bit_depth", "num_frames"):
+            assert rk[k] == mk[k], (path, k)
+        assert float(rk["frame_rate"]) == float(mk["frame_rate"])
+        decoded = np.fromfile(tmp_path / "ref.u16", np.uint16)
+        stored = np.fromfile(tmp_path / "mine.bin", np.uint8)
+        assert np.array_equal(orc.unpack_12bit(stored).ravel(), decoded), path
+    assert np.array_equal(np.fromfile(tmp_path / "ref.u16", np.uint16).size, 2 * int(rk["width"]) * int(rk["height"]))

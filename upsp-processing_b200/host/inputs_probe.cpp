@@ -119,6 +119,24 @@ int main(int argc, char** argv) {
         dump(p + ".nrm", model.get_n().data(), model.get_n().size() * 4);
         dump(p + ".pairs", pairs.data(), pairs.size() * 4);
       }
+    } else if (cmd == "peaks") {     // FILE.i32 SEPARATION
+      if (argc < 4) throw std::invalid_argument("peaks FILE.i32 SEPARATION");
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      if (!f) throw std::invalid_argument("Cannot open '" + file + "'");
+      std::vector<int> counts((size_t)f.tellg() / 4);
+      f.seekg(0);
+      f.read(reinterpret_cast<char*>(counts.data()), (std::streamsize)(counts.size() * 4));
+      const unsigned sep = (unsigned)atoi(argv[3]);
+      std::vector<unsigned> maxp, minp;
+      find_peaks(counts, maxp, sep);
+      std::vector<double> inv(counts.size());
+      for (size_t i = 0; i < counts.size(); ++i) inv[i] = 1.0 / counts[i];
+      find_peaks(inv, minp, sep);
+      std::printf("max_peaks");
+      for (unsigned p : maxp) std::printf(" %u", p);
+      std::printf("\nmin_peaks");
+      for (unsigned p : minp) std::printf(" %u", p);
+      std::printf("\nfirst_min %u\n", first_min_threshold(counts, sep));
     } else if (cmd == "vvdump") {
       if (argc < 5) throw std::invalid_argument("vvdump IN.f32 OUT.dat MAXELS");
       std::ifstream f(file, std::ios::binary | std::ios::ate);
