@@ -7,6 +7,7 @@
 #define UPSP_ORACLE_CV_CORE_STUB
 #include <cstdint>
 #include <cstdlib>
+#include <iostream>
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -14,7 +15,10 @@
 #define CV_16U 2
 #define CV_32F 5
 #define CV_Assert(expr) do { if (!(expr)) throw std::runtime_error("CV_Assert failed: " #expr); } while (0)
+typedef unsigned char uchar;
 namespace cv {
+struct Scalar;
+template <typename T> struct Rect_;
 struct Size {
   int width = 0, height = 0;
   Size() = default;
@@ -37,10 +41,26 @@ class Mat {
   template <typename T> T* begin() { return reinterpret_cast<T*>(data); }
   template <typename T> T* end() { return reinterpret_cast<T*>(data) + (size_t)rows * cols; }
   template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
+  /* declared for the compiler only (see opencv.hpp here): never defined, never called */
+  Mat(Size, int, const Scalar&);
+  Mat(Size, int);
+  void convertTo(Mat&, int, double = 1, double = 0) const;
+  void copyTo(Mat) const;
+  Mat clone() const;
+  Mat operator()(const Rect_<int>&) const;
+  int depth() const;
+  int channels() const;
+  operator int() const;
  private:
   static size_t elem(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : 4); }
   int type_ = 0;
   std::shared_ptr<std::vector<unsigned char>> buf_;
 };
+Mat operator-(const Mat&, double);
+Mat operator*(double, const Mat&);
+Mat operator*(const Mat&, double);
+Mat operator/(const Mat&, double);
+Mat operator+(const Mat&, const Mat&);
+Mat& operator+=(Mat&, const Mat&);
 }  // namespace cv
 #endif

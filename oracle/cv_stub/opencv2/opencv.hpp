@@ -1,0 +1,84 @@
+/* TEST INFRASTRUCTURE ONLY: declarations (no behaviour) of the OpenCV names that cpp/utils/cv_extras.{h,ipp,cpp} mention, so
+ * that this one reference file can be COMPILED from the reference tree and its upsp::fix_hot_pixels -- which only walks a
+ * CV_16U cv::Mat with begin<>() / at<>() (see core.hpp here) -- can be run as a checker (oracle/_ref/ref_probe).  Everything
+ * else in that file (text layout, colour maps, sub-matrices) is declared but not defined and never called; the link step
+ * leaves those symbols unresolved on purpose (-Wl,--unresolved-symbols=ignore-all). */
+#ifndef UPSP_ORACLE_CV_ALL_STUB
+#define UPSP_ORACLE_CV_ALL_STUB
+#include <cmath>
+#include <string>
+#include "core.hpp"
+#define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_16UC1 2
+#define CV_32FC1 5
+#define CV_64F 6
+#define CV_8S 1
+#define CV_16S 3
+#define CV_32S 4
+#define CV_MAT_DEPTH_MASK 7
+#define CV_CN_SHIFT 3
+#define CV_MAT_DEPTH(flags) ((flags) & CV_MAT_DEPTH_MASK)
+namespace cv {
+template <typename T> struct Point_ {
+  T x, y;
+  Point_() : x(0), y(0) {}
+  Point_(T a, T b) : x(a), y(b) {}
+};
+typedef Point_<int> Point;
+typedef Point_<int> Point2i;
+typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
+template <typename T> struct Point3_ {
+  T x, y, z;
+  Point3_() : x(0), y(0), z(0) {}
+  Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
+  T dot(const Point3_& o) const;
+  Point3_ cross(const Point3_& o) const;
+};
+template <typename T> Point3_<T> operator+(const Point3_<T>&, const Point3_<T>&);
+template <typename T> Point3_<T> operator-(const Point3_<T>&, const Point3_<T>&);
+template <typename T> Point3_<T> operator-(const Point3_<T>&);
+template <typename T, typename S> Point3_<T> operator*(const Point3_<T>&, S);
+template <typename T, typename S> Point3_<T> operator*(S, const Point3_<T>&);
+template <typename T, typename S> Point3_<T> operator/(const Point3_<T>&, S);
+template <typename T> double norm(const Point3_<T>&);
+template <typename T> double norm(const Point_<T>&);
+template <typename T> struct Rect_ {
+  T x, y, width, height;
+  Rect_() : x(0), y(0), width(0), height(0) {}
+  Rect_(T a, T b, T c, T d) : x(a), y(b), width(c), height(d) {}
+  Size size() const { return Size((int)width, (int)height); }
+};
+typedef Rect_<int> Rect;
+struct Scalar {
+  double val[4];
+  Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
+  double& operator[](int i) { return val[i]; }
+};
+template <typename T, int N> struct Vec {
+  T val[N];
+  Vec() {}
+  Vec(T a, T b, T c) { val[0] = a; val[1] = b; val[2] = c; }
+  operator Scalar() const;
+  T& operator[](int i) { return val[i]; }
+  const T& operator[](int i) const { return val[i]; }
+};
+typedef Vec<unsigned char, 3> Vec3b;
+template <typename T> class Mat_ : public Mat {
+ public:
+  Mat_() {}
+  Mat_(int r, int c);
+  Mat_(const Mat&);
+  T& operator()(int r, int c);
+};
+enum { FONT_HERSHEY_DUPLEX = 2, FILLED = -1, COLORMAP_JET = 2 };
+Size getTextSize(const std::string&, int, double, int, int*);
+void rectangle(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0);
+void putText(Mat&, const std::string&, Point, int, double, Scalar, int = 1, int = 8, bool = false);
+void minMaxLoc(const Mat&, double*, double* = 0, Point* = 0, Point* = 0);
+Scalar mean(const Mat&);
+void applyColorMap(const Mat&, Mat&, int);
+void Rodrigues(const Mat&, Mat&);
+}  // namespace cv
+#endif

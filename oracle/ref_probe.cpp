@@ -7,7 +7,8 @@
 // upsp::read_plot3d_scalar_function_file, upsp::read_plot3d_grid_file / write_plot3d_grid_file, upsp::fwrite and the header
 // templates upsp::find_peaks / first_min_threshold (cpp/include/utils/clustering.h, with boost_stub/ for its one Boost include),
 // and upsp::MrawReader / PSPVideo / unpack_12bit / unpack_10bit (cpp/lib/MrawReader.cpp, PSPVideo.cpp, with cv_stub/ for the
-// zero-filled CV_16U cv::Mat they fill).
+// zero-filled CV_16U cv::Mat they fill), and upsp::fix_hot_pixels (cpp/utils/cv_extras.cpp; the rest of that file is compiled against
+// declarations only, cv_stub/opencv2/opencv.hpp, and left unresolved at link time: it is never called).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -23,6 +24,7 @@
 #include "plot3d.h"
 #include "upsp_inputs.h"
 #include "utils/clustering.h"
+#include "utils/cv_extras.h"
 #include "utils/file_writers.h"
 
 template <typename E>
@@ -100,6 +102,19 @@ int main(int argc, char** argv) {
       std::fwrite(out.data, 2, npix, o);
       std::fclose(o);
       std::printf("pixels %zu\n", npix);
+    } else if (cmd == "hotpix") {    // IN.u16 ROWS COLS OUT.u16 [N_FRAMES]: upsp::fix_hot_pixels, defaults 4064 / 512 / 5
+      if (argc < 6) return 2;
+      const int rows = atoi(argv[3]), cols = atoi(argv[4]), nf = argc > 6 ? atoi(argv[6]) : 1;
+      std::ifstream f(file, std::ios::binary);
+      FILE* o = std::fopen(argv[5], "wb");
+      for (int k = 0; k < nf; ++k) {
+        cv::Mat img = cv::Mat::zeros(rows, cols, CV_16U);
+        f.read(reinterpret_cast<char*>(img.data), (std::streamsize)((size_t)rows * cols * 2));
+        upsp::fix_hot_pixels(img);
+        std::fwrite(img.data, 2, (size_t)rows * cols, o);
+      }
+      std::fclose(o);
+      std::printf("frames %d\n", nf);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

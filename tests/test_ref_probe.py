@@ -210,3 +210,42 @@ def test_mraw_reader_equals_reference_code(up, probes, orc, tmp_path):
         stored = np.fromfile(tmp_path / "mine.bin", np.uint8)
         assert np.array_equal(orc.unpack_12bit(stored).ravel(), decoded), path
     assert np.array_equal(np.fromfile(tmp_path / "ref.u16", np.uint16).size, 2 * int(rk["width"]) * int(rk["height"]))
+
+
+def test_hot_pixel_restatement_equals_reference_code(probes, orc, tmp_path):
+    """a2: the reference's own upsp::fix_hot_pixels (cpp/utils/cv_extras.cpp:230-272, compiled from the reference tree)
+    against the CPU restatement the GPU path is held to: 0 / 1 / 5 / 6 hot pixels, neighbours that are hot themselves,
+    corners and borders, the >= 4064 and > 512 boundaries, fixes that feed later fixes (raster order), random frames."""
+    rng = np.random.default_rng(31)
+    H, W = 24, 40
+    frames = []
+
+    def frame(base=1500):
+        return rng.integers(base - 200, base + 200, (H, W)).astype(np.uint16)
+    frames.append(frame())                                            # no hot pixel
+    f = frame(); f[5, 7] = 4095; frames.append(f)                     # one
+    f = frame(); f[[0, 0, H - 1, H - 1, 9], [0, W - 1, 0, W - 1, 0]] = 4095; frames.append(f)    # five: corners + border
+    f = frame(); f[3, 3:9] = 4095; frames.append(f)                   # six in a row: too many, untouched
+    f = frame(); f[8, 8] = 4095; f[8, 9] = 4080; f[9, 8] = 4064; frames.append(f)       # hot neighbours, raster order
+    f = frame(); f[4, 4] = 4063; f[6, 6] = 4064; frames.append(f)     # threshold boundary
+    f = np.full((H, W), 3552, np.uint16); f[10, 10] = 4064; frames.append(f)            # old - new == 512: kept
+    f = np.full((H, W), 3551, np.uint16); f[10, 10] = 4064; frames.append(f)            # old - new == 513: replaced
+    f = frame(3900); f[2, 2] = 4070; f[2, 3] = 4069; frames.append(f)                   # change too small
+    f = frame(); f[0, 5] = 4095; f[1, 5] = 4095; f[H - 1, 20] = 4095; f[12, W - 1] = 4095; frames.append(f)   # 2/3-neighbour medians
+    for _ in range(30):
+        f = frame(int(rng.integers(500, 3800)))
+        n = int(rng.integers(0, 8))
+        f[rng.integers(0, H, n), rng.integers(0, W, n)] = rng.integers(4000, 4096, n)
+        frames.append(f)
+    stack = np.stack(frames)
+    stack.tofile(tmp_path / "in.u16")
+    r = subprocess.run([probes[1], "hotpix", str(tmp_path / "in.u16"), str(H), str(W), str(tmp_path / "out.u16"), str(len(frames))],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = np.fromfile(tmp_path / "out.u16", np.uint16).reshape(stack.shape)
+    changed = 0
+    for k, f in enumerate(frames):
+        mine, _ = orc.fix_hot_pixels(f)
+        assert np.array_equal(mine, ref[k]), k
+        changed += int((ref[k] != f).sum())
+    assert changed >= 12 and np.array_equal(ref[3], frames[3]) and ref[6][10, 10] == 4064 and ref[7][10, 10] == 3551
