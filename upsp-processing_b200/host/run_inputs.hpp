@@ -251,6 +251,14 @@ inline std::string read_p3d_function(const std::string& filename, std::vector<fl
   long total = 0;
   for (int z = 0; z < number_zones; ++z) total += (long)sizes[z * 4] * sizes[z * 4 + 1] * sizes[z * 4 + 2];
   if (total < 0) return "Failed to parse zone sizes";
+  {   // a header that promises more scalars than the file holds fails here instead of in the allocator
+    const std::streampos here = ifs.tellg();
+    ifs.seekg(0, std::ios::end);
+    const std::streamoff left = ifs.tellg() - here;
+    ifs.seekg(here);
+    if ((std::streamoff)total * 4 > left)
+      return "failed to read scalars (expected " + std::to_string(number_zones) + " zones, " + std::to_string(total) + " scalars)";
+  }
   sol.resize((size_t)total);
   // plot3d.cpp:68 calls the separator-less overload for the data record whatever `seps` is: with FORTRAN
   // record markers the first value read is the leading marker and every scalar sits one slot late.  Kept.
