@@ -1,0 +1,1 @@
+/* TEST INFRASTRUCTURE ONLY: named by pspRT.h, nothing of it is used. */

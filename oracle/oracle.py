@@ -451,6 +451,15 @@ def project_points(cam: Camera, xyz: np.ndarray) -> np.ndarray:
     return uv
 
 
+def cast_rays(verts, tri, rays):
+    """nearest hit of rays [n,6] (origin, direction) over triangles tri [T,3] of verts [V,3]: (hit, t, prim)"""
+    verts, tri, rays = _c(verts, np.float32), _c(tri, np.int32), _c(rays, np.float32)
+    n = len(rays)
+    hit, t, prim = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    lib().orc_cast_rays(_p(verts), _p(tri), len(tri), _p(rays), n, _p(hit), _p(t), _p(prim))
+    return hit, t, prim
+
+
 def cam_center(cam: Camera) -> np.ndarray:
     c = np.empty(3, np.float32)
     lib().orc_cam_center(C.byref(cam), _p(c))

@@ -8,7 +8,9 @@
 // templates upsp::find_peaks / first_min_threshold (cpp/include/utils/clustering.h, with boost_stub/ for its one Boost include),
 // and upsp::MrawReader / PSPVideo / unpack_12bit / unpack_10bit (cpp/lib/MrawReader.cpp, PSPVideo.cpp, with cv_stub/ for the
 // zero-filled CV_16U cv::Mat they fill), and upsp::fix_hot_pixels (cpp/utils/cv_extras.cpp; the rest of that file is compiled against
-// declarations only, cv_stub/opencv2/opencv.hpp, and left unresolved at link time: it is never called).
+// declarations only, cv_stub/opencv2/opencv.hpp, and left unresolved at link time: it is never called), and the ray caster
+// rt::BVH / rt::Triangle::intersect (cpp/raycast/pspRT.cpp, pspRTmem.cpp, with imath_stub/ for the 3-float vector, box and line
+// it is written in; the box-line pruning test of Imath is replaced by "visit every node").
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -25,6 +27,7 @@
 #include "upsp_inputs.h"
 #include "utils/clustering.h"
 #include "utils/cv_extras.h"
+#include "utils/pspRT.h"
 #include "utils/file_writers.h"
 
 template <typename E>
@@ -102,6 +105,32 @@ int main(int argc, char** argv) {
       std::fwrite(out.data, 2, npix, o);
       std::fclose(o);
       std::printf("pixels %zu\n", npix);
+    } else if (cmd == "raycast") {   // TRIS.f32 [T][9]  RAYS.f32 [n][6]  OUT.bin: rt::BVH(CreateTriangleMesh(tris), 4).intersect per ray
+      if (argc < 5) return 2;
+      auto read_f32 = [](const char* path) {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        std::vector<float> v((size_t)f.tellg() / 4);
+        f.seekg(0);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
+        return v;
+      };
+      const std::vector<float> tris = read_f32(argv[2]), rays = read_f32(argv[3]);
+      std::vector<std::shared_ptr<rt::Primitive>> prims = rt::CreateTriangleMesh(tris, 3);      // as createBVH, psp_process.cpp:45-53
+      rt::BVH scene(prims, 4);
+      FILE* o = std::fopen(argv[4], "wb");
+      for (size_t i = 0; i < rays.size() / 6; ++i) {
+        const Imath::V3f orig(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), dir(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        rt::Ray ray(orig, dir);
+        rt::Hit hitrec;
+        const int32_t hit = scene.intersect(ray, &hitrec) ? 1 : 0;
+        const int32_t prim = hit ? hitrec.primID : -1;
+        const float t = hitrec.t;
+        std::fwrite(&hit, 4, 1, o);
+        std::fwrite(&t, 4, 1, o);
+        std::fwrite(&prim, 4, 1, o);
+      }
+      std::fclose(o);
+      std::printf("rays %zu\ntriangles %zu\n", rays.size() / 6, tris.size() / 9);
     } else if (cmd == "hotpix") {    // IN.u16 ROWS COLS OUT.u16 [N_FRAMES]: upsp::fix_hot_pixels, defaults 4064 / 512 / 5
       if (argc < 6) return 2;
       const int rows = atoi(argv[3]), cols = atoi(argv[4]), nf = argc > 6 ? atoi(argv[6]) : 1;

@@ -154,6 +154,27 @@ static int nearest_hit(const orc_ray* ray, const float* verts, const int32_t* tr
   return any ? prim : -2;      /* -2: no hit at all; -1 cannot happen unless every hit had t >= FLT_MAX */
 }
 
+/* test hook: nearest hit of n rays (o[3], d[3] each) over a triangle soup; hit[i] = 0/1, t[i], prim[i] (lowest id on ties) */
+ORC_API void orc_cast_rays(const float* verts, const int32_t* tri, int n_tri, const float* rays, int n, int32_t* hit, float* t_out,
+                           int32_t* prim_out) {
+  for (int i = 0; i < n; ++i) {
+    orc_ray ray;
+    ray_init(&ray, rays + 6 * i, rays + 6 * i + 3);
+    float best = FLT_MAX;
+    int prim = -1, any = 0;
+    for (int k = 0; k < n_tri; ++k) {
+      float t;
+      if (tri_intersect(&ray, verts + 3 * tri[3 * k], verts + 3 * tri[3 * k + 1], verts + 3 * tri[3 * k + 2], &t)) {
+        any = 1;
+        if (t < best) best = t, prim = k;
+      }
+    }
+    hit[i] = any;
+    t_out[i] = best;
+    prim_out[i] = prim;
+  }
+}
+
 static void v3_normalize(float v[3]) {      /* Imath::Vec3<float>::normalize */
   const float len2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
   float l = sqrtf(len2);
