@@ -10,6 +10,7 @@
                                                   stand-alone transpose tool (mpi_stub/), and -- behind a small main() -- its deck,
                                                   paint-calibration, tunnel-condition and plot3d readers / writers, regression-sample
                                                   writer, peak finding (boost_stub/), unpack_12bit / unpack_10bit / MrawReader and
-                                                  fix_hot_pixels (cv_stub/).  The stub headers carry no algorithm of the path.
+                                                  fix_hot_pixels (cv_stub/), its ray caster (BVH + watertight triangle test,
+                                                  imath_stub/) and its kd-tree.  The stub headers carry no algorithm of the path.
 How each restatement is pinned: DESIGN.md section 4.
 """

@@ -12,6 +12,8 @@
 // rt::BVH / rt::Triangle::intersect (cpp/raycast/pspRT.cpp, pspRTmem.cpp, with imath_stub/ for the 3-float vector, box and line
 // it is written in; the box-line pruning test of Imath is replaced by "visit every node").
 #include <cstdio>
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -28,6 +30,9 @@
 #include "utils/clustering.h"
 #include "utils/cv_extras.h"
 #include "utils/pspRT.h"
+extern "C" {
+#include "utils/pspKdtree.h"
+}
 #include "utils/file_writers.h"
 
 template <typename E>
@@ -131,6 +136,48 @@ int main(int argc, char** argv) {
       }
       std::fclose(o);
       std::printf("rays %zu\ntriangles %zu\n", rays.size() / 6, tris.size() / 9);
+    } else if (cmd == "kdtree") {    // PTS.f32 [n][3]  TOL  QUERY.f32 [m][3]  OUT.txt: the reference's kd-tree (pspKdtree.c) as the models use it
+      if (argc < 6) return 2;        // line i < n:  "range i: sorted ids within TOL of point i";  line n + q: "nearest q: id"
+      auto read_f32 = [](const char* path) {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        std::vector<float> v((size_t)f.tellg() / 4);
+        f.seekg(0);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * 4));
+        return v;
+      };
+      const std::vector<float> pts = read_f32(argv[2]), qs = read_f32(argv[4]);
+      const float tol = (float)atof(argv[3]);
+      union { void* ptr; uint64_t val; } ud;
+      kdtree* root = kd_create(3);
+      for (size_t i = 0; i < pts.size() / 3; ++i) {                 // P3DModel.ipp:954-967: float coordinates widened by the call
+        ud.val = (uint64_t)i;
+        kd_insert3(root, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], ud.ptr);
+      }
+      FILE* o = std::fopen(argv[5], "w");
+      for (size_t i = 0; i < pts.size() / 3; ++i) {
+        kdres* res = kd_nearest_range3(root, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], tol);     // :1003
+        std::vector<uint64_t> ids;
+        while (!kd_res_end(res)) {
+          ud.ptr = kd_res_item_data(res);
+          ids.push_back(ud.val);
+          kd_res_next(res);
+        }
+        kd_res_free(res);
+        std::sort(ids.begin(), ids.end());
+        std::fprintf(o, "range %zu:", i);
+        for (uint64_t v : ids) std::fprintf(o, " %llu", (unsigned long long)v);
+        std::fprintf(o, "\n");
+      }
+      for (size_t q = 0; q < qs.size() / 3; ++q) {
+        const double pos[3] = {qs[3 * q], qs[3 * q + 1], qs[3 * q + 2]};                             // psp_process.cpp:92-98
+        kdres* res = kd_nearest(root, pos);
+        ud.ptr = kd_res_item_data(res);
+        kd_res_free(res);
+        std::fprintf(o, "nearest %zu: %llu\n", q, (unsigned long long)ud.val);
+      }
+      std::fclose(o);
+      kd_free(root);
+      std::printf("points %zu\nqueries %zu\n", pts.size() / 3, qs.size() / 3);
     } else if (cmd == "hotpix") {    // IN.u16 ROWS COLS OUT.u16 [N_FRAMES]: upsp::fix_hot_pixels, defaults 4064 / 512 / 5
       if (argc < 6) return 2;
       const int rows = atoi(argv[3]), cols = atoi(argv[4]), nf = argc > 6 ? atoi(argv[6]) : 1;

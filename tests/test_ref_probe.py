@@ -298,3 +298,52 @@ def test_ray_cast_restatement_equals_reference_code(up, probes, orc, tmp_path):
             assert t_other[0] == t[i]
     assert same.mean() > 0.9
     print("rays %d, hits %d, same triangle %d, tie-different triangle %d" % (len(rays), h.sum(), same.sum(), (~same).sum()))
+
+
+def _kdtree(probes, tmp_path, pts, tol, queries):
+    pts.astype(np.float32).tofile(tmp_path / "pts.f32")
+    queries.astype(np.float32).tofile(tmp_path / "q.f32")
+    r = subprocess.run([probes[1], "kdtree", str(tmp_path / "pts.f32"), repr(float(tol)), str(tmp_path / "q.f32"), str(tmp_path / "kd.txt")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    ranges, nearest = [], []
+    for line in open(tmp_path / "kd.txt"):
+        head, _, rest = line.partition(":")
+        (ranges if head.startswith("range") else nearest).append([int(v) for v in rest.split()])
+    return ranges, [n[0] for n in nearest]
+
+
+def test_kdtree_queries_equal_reference_code(probes, tmp_path):
+    """The reference's kd-tree (cpp/raycast/pspKdtree.c, compiled as C from the reference tree) as the models use it:
+    kd_nearest_range3 around every zone-edge node (P3DModel_::identifyOverlap, P3DModel.ipp:954-1003) returns exactly the nodes
+    whose squared distance in double is <= tol^2 -- the predicate host/p3d_model.hpp sweeps with -- including the reference's
+    own tolerance cases (offset 0.1 against tol 0.09 / 0.100001, test_p3dmodel.cpp:205-236); kd_nearest (getTargets,
+    get_target_diameters) returns the closest node, one of the closest on exact ties."""
+    from test_p3d_model import reference_fixture, seam_grid
+    rng = np.random.default_rng(3)
+    cases = [(np.concatenate([z[2] for z in reference_fixture(0.1)]), 0.09), (np.concatenate([z[2] for z in reference_fixture(0.1)]), 0.100001),
+             (np.concatenate([z[2] for z in reference_fixture(0.0)]), 1e-10), (np.concatenate([z[2] for z in seam_grid(1)]), 1e-3)]
+    path = "/root/reference/test/data/fml_tc3_volume.grid"
+    if os.path.exists(path):
+        raw = open(path, "rb").read()
+        nz = struct.unpack_from("<i", raw, 4)[0]
+        dims = np.frombuffer(raw, "<i4", 3 * nz, 16).reshape(nz, 3)
+        off, edge = 16 + 12 * nz + 4, []
+        for j, k, l in dims:
+            n = int(j * k * l)
+            p = np.frombuffer(raw, "<f4", 3 * n, off + 4).reshape(3, int(k), int(j)).transpose(1, 2, 0)
+            edge += [p[0], p[-1], p[:, 0], p[:, -1]]
+            off += 12 * n + 8
+        cases.append((np.concatenate(edge)[::3], 1e-3))                  # a third of the zone-edge nodes of the 14-zone grid
+    for pts, tol in cases:
+        pts = np.ascontiguousarray(pts, np.float32)
+        q = np.concatenate([pts[rng.choice(len(pts), 40)] + rng.normal(0, 0.3, (40, 3)), pts[:5]]).astype(np.float32)
+        ranges, nearest = _kdtree(probes, tmp_path, pts, tol, q)
+        t = float(np.float32(tol))
+        P = pts.astype(np.float64)
+        for i in range(0, len(pts), max(1, len(pts) // 1500)):           # every node for the small cases, a sample otherwise
+            want = np.flatnonzero(((P - P[i]) ** 2).sum(1) <= t * t)
+            assert ranges[i] == want.tolist(), (tol, i)
+        for k, qq in enumerate(q.astype(np.float64)):
+            d2 = ((P - qq) ** 2).sum(1)
+            assert d2[nearest[k]] == d2.min()
