@@ -11,6 +11,7 @@
                                                   paint-calibration, tunnel-condition and plot3d readers / writers, regression-sample
                                                   writer, peak finding (boost_stub/), unpack_12bit / unpack_10bit / MrawReader and
                                                   fix_hot_pixels (cv_stub/), its ray caster (BVH + watertight triangle test,
-                                                  imath_stub/) and its kd-tree.  The stub headers carry no algorithm of the path.
+                                                  imath_stub/), its kd-tree and its patch geometry templates (eigen_stub/: an int mask matrix).
+                                                  The stub headers carry no algorithm of the path.
 How each restatement is pinned: DESIGN.md section 4.
 """

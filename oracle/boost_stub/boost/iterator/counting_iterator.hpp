@@ -18,6 +18,7 @@ class counting_iterator {
   reference operator*() const { return v_; }
   counting_iterator& operator++() { ++v_; return *this; }
   counting_iterator operator++(int) { counting_iterator t(*this); ++v_; return t; }
+  counting_iterator operator+(std::ptrdiff_t n) const { return counting_iterator((T)(v_ + n)); }
   bool operator==(const counting_iterator& o) const { return v_ == o.v_; }
   bool operator!=(const counting_iterator& o) const { return v_ != o.v_; }
  private:

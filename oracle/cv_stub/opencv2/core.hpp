@@ -31,7 +31,8 @@ class Mat {
   int rows = 0, cols = 0;
   unsigned char* data = nullptr;
   Mat() = default;
-  Mat(int r, int c, int type) : rows(r), cols(c), type_(type), buf_(std::make_shared<std::vector<unsigned char>>((size_t)r * c * elem(type), 0)) {
+  Mat(int r, int c, int type) : rows(r), cols(c), type_(type), stride_((size_t)c),
+                                buf_(std::make_shared<std::vector<unsigned char>>((size_t)r * c * elem(type), 0)) {
     data = buf_->data();
   }
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
@@ -40,20 +41,30 @@ class Mat {
   Size size() const { return Size(cols, rows); }
   template <typename T> T* begin() { return reinterpret_cast<T*>(data); }
   template <typename T> T* end() { return reinterpret_cast<T*>(data) + (size_t)rows * cols; }
-  template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * cols + c]; }
+  template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data)[(size_t)r * stride_ + c]; }
+  template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data)[(size_t)r * stride_ + c]; }
+  /* a view of the rectangle (x, y, width, height) sharing this matrix's pixels, as cv::Mat::operator()(Rect) */
+  template <typename R> Mat roi(const R& r) const {
+    Mat v(*this);
+    v.rows = r.height;
+    v.cols = r.width;
+    v.data = data + ((size_t)r.y * stride_ + (size_t)r.x) * elem(type_);
+    return v;
+  }
   /* declared for the compiler only (see opencv.hpp here): never defined, never called */
   Mat(Size, int, const Scalar&);
   Mat(Size, int);
   void convertTo(Mat&, int, double = 1, double = 0) const;
   void copyTo(Mat) const;
   Mat clone() const;
-  Mat operator()(const Rect_<int>&) const;
+  Mat operator()(const Rect_<int>& r) const;   /* defined in opencv.hpp here, where Rect_ is complete */
   int depth() const;
   int channels() const;
   operator int() const;
- private:
+ public:
   static size_t elem(int type) { return type == CV_8U ? 1 : (type == CV_16U ? 2 : 4); }
   int type_ = 0;
+  size_t stride_ = 0;
   std::shared_ptr<std::vector<unsigned char>> buf_;
 };
 Mat operator-(const Mat&, double);

@@ -1,4 +1,6 @@
-/* TEST INFRASTRUCTURE ONLY: declarations (no behaviour) of the OpenCV names that cpp/utils/cv_extras.{h,ipp,cpp} mention, so
+/* TEST INFRASTRUCTURE ONLY: declarations of the OpenCV names that cpp/utils/cv_extras.{h,ipp,cpp} and cpp/lib/patches.ipp mention
+ * (with behaviour only for what the checkers run: 2-D point +/-, the Euclidean norm of a 2-D point, a rectangular view of a
+ * matrix and its minimum), so
  * that this one reference file can be COMPILED from the reference tree and its upsp::fix_hot_pixels -- which only walks a
  * CV_16U cv::Mat with begin<>() / at<>() (see core.hpp here) -- can be run as a checker (oracle/_ref/ref_probe).  Everything
  * else in that file (text layout, colour maps, sub-matrices) is declared but not defined and never called; the link step
@@ -24,11 +26,19 @@ template <typename T> struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}
   Point_(T a, T b) : x(a), y(b) {}
+  Point_& operator+=(const Point_& o) { x += o.x; y += o.y; return *this; }
+  Point_& operator-=(const Point_& o) { x -= o.x; y -= o.y; return *this; }
 };
+template <typename T> Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <typename T> Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
 typedef Point_<int> Point;
 typedef Point_<int> Point2i;
 typedef Point_<float> Point2f;
 typedef Point_<double> Point2d;
+template <typename T> struct Point3_;
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
+typedef Point3_<int> Point3i;
 template <typename T> struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
@@ -43,7 +53,7 @@ template <typename T, typename S> Point3_<T> operator*(const Point3_<T>&, S);
 template <typename T, typename S> Point3_<T> operator*(S, const Point3_<T>&);
 template <typename T, typename S> Point3_<T> operator/(const Point3_<T>&, S);
 template <typename T> double norm(const Point3_<T>&);
-template <typename T> double norm(const Point_<T>&);
+template <typename T> double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }   /* as OpenCV */
 template <typename T> struct Rect_ {
   T x, y, width, height;
   Rect_() : x(0), y(0), width(0), height(0) {}
@@ -68,15 +78,30 @@ typedef Vec<unsigned char, 3> Vec3b;
 template <typename T> class Mat_ : public Mat {
  public:
   Mat_() {}
-  Mat_(int r, int c);
-  Mat_(const Mat&);
-  T& operator()(int r, int c);
+  Mat_(int r, int c) : Mat(r, c, sizeof(T) == 1 ? CV_8U : (sizeof(T) == 2 ? CV_16U : CV_32F)) {}
+  Mat_(const Mat& m) : Mat(m) {}
+  T& operator()(int r, int c) { return this->template at<T>(r, c); }
+  Mat_ operator()(const Rect_<int>& r) const { return Mat_(this->roi(r)); }
 };
+inline Mat Mat::operator()(const Rect_<int>& r) const { return roi(r); }
 enum { FONT_HERSHEY_DUPLEX = 2, FILLED = -1, COLORMAP_JET = 2 };
 Size getTextSize(const std::string&, int, double, int, int*);
 void rectangle(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0);
 void putText(Mat&, const std::string&, Point, int, double, Scalar, int = 1, int = 8, bool = false);
-void minMaxLoc(const Mat&, double*, double* = 0, Point* = 0, Point* = 0);
+/* minimum (and maximum) over a CV_8U / CV_16U / CV_32F matrix or view; the locations are not computed */
+inline void minMaxLoc(const Mat& m, double* mn, double* mx = 0, Point* = 0, Point* = 0) {
+  double lo = 0, hi = 0;
+  bool first = true;
+  for (int r = 0; r < m.rows; ++r)
+    for (int c = 0; c < m.cols; ++c) {
+      const double v = m.type() == CV_8U ? (double)m.at<unsigned char>(r, c) : (m.type() == CV_16U ? (double)m.at<unsigned short>(r, c) : (double)m.at<float>(r, c));
+      if (first || v < lo) lo = v;
+      if (first || v > hi) hi = v;
+      first = false;
+    }
+  if (mn) *mn = lo;
+  if (mx) *mx = hi;
+}
 Scalar mean(const Mat&);
 void applyColorMap(const Mat&, Mat&, int);
 void Rodrigues(const Mat&, Mat&);

@@ -10,7 +10,9 @@
 // zero-filled CV_16U cv::Mat they fill), and upsp::fix_hot_pixels (cpp/utils/cv_extras.cpp; the rest of that file is compiled against
 // declarations only, cv_stub/opencv2/opencv.hpp, and left unresolved at link time: it is never called), and the ray caster
 // rt::BVH / rt::Triangle::intersect (cpp/raycast/pspRT.cpp, pspRTmem.cpp, with imath_stub/ for the 3-float vector, box and line
-// it is written in; the box-line pruning test of Imath is replaced by "visit every node").
+// it is written in; the box-line pruning test of Imath is replaced by "visit every node"), and the patch geometry templates
+// upsp::cluster_points / PatchClusters constructor / threshold_bounds (cpp/lib/patches.ipp, with eigen_stub/ for the int mask
+// matrix they mark pixels in and ref_decls.h for the one name they take from projection.h).
 #include <cstdio>
 #include <algorithm>
 #include <cstdint>
@@ -21,10 +23,12 @@
 #include <string>
 #include <vector>
 
+#include "ref_decls.h"
 #include "MrawReader.h"
 #include "PSPVideo.h"
 #include "grids.h"
 #include "non_cv_upsp.h"
+#include "patches.h"
 #include "plot3d.h"
 #include "upsp_inputs.h"
 #include "utils/clustering.h"
@@ -136,6 +140,28 @@ int main(int argc, char** argv) {
       }
       std::fclose(o);
       std::printf("rays %zu\ntriangles %zu\n", rays.size() / 6, tris.size() / 9);
+    } else if (cmd == "patches") {   // targets.txt W H boundary buffer [ref.u16 thresh offset]: InitializeImagePatches' geometry
+      if (argc < 7) return 2;        // (psp_process.cpp:2125-2163) with the reference's cluster_points / PatchClusters; output as
+      std::ifstream f(file);         // host/patch_geometry_probe prints it
+      std::vector<upsp::Target> targs;
+      upsp::Target t;
+      while (f >> t.uv.x >> t.uv.y >> t.diameter) targs.push_back(t);
+      const int W = atoi(argv[3]), H = atoi(argv[4]);
+      const unsigned bt = (unsigned)atoi(argv[5]), bf = (unsigned)atoi(argv[6]);
+      std::vector<std::vector<upsp::Target>> clusters;
+      upsp::cluster_points(targs, clusters, (int)(bt + bf));
+      upsp::PatchClusters<float> pc(clusters, cv::Size(W, H), bt, bf);
+      if (argc >= 10) {
+        cv::Mat_<uint16_t> ref(H, W);
+        std::ifstream r(argv[7], std::ios::binary);
+        r.read(reinterpret_cast<char*>(ref.data), (std::streamsize)((size_t)W * H * 2));
+        pc.threshold_bounds(ref, (unsigned)atoi(argv[8]), (unsigned)atoi(argv[9]));
+      }
+      for (size_t i = 0; i < clusters.size(); ++i) {
+        std::printf("cluster %zu %zu\n", i, clusters[i].size());
+        for (size_t j = 0; j < pc.bounds_x[i].size(); ++j) std::printf("b %u %u\n", pc.bounds_x[i][j], pc.bounds_y[i][j]);
+        for (size_t j = 0; j < pc.internal_x[i].size(); ++j) std::printf("i %u %u\n", pc.internal_x[i][j], pc.internal_y[i][j]);
+      }
     } else if (cmd == "kdtree") {    // PTS.f32 [n][3]  TOL  QUERY.f32 [m][3]  OUT.txt: the reference's kd-tree (pspKdtree.c) as the models use it
       if (argc < 6) return 2;        // line i < n:  "range i: sorted ids within TOL of point i";  line n + q: "nearest q: id"
       auto read_f32 = [](const char* path) {

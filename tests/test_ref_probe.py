@@ -347,3 +347,40 @@ def test_kdtree_queries_equal_reference_code(probes, tmp_path):
         for k, qq in enumerate(q.astype(np.float64)):
             d2 = ((P - qq) ** 2).sum(1)
             assert d2[nearest[k]] == d2.min()
+
+
+def test_patch_geometry_equals_reference_code(up, probes, tmp_path):
+    """Which pixels get patched: the reference's own cluster_points / get_target_boundary / get_cluster_boundary /
+    PatchClusters constructor / threshold_bounds (cpp/lib/patches.ipp:15-94, 240-487, header templates compiled from the
+    reference tree) against host/patch_geometry.hpp, through the two probes' identical text output: single targets, touching
+    and chained targets (multi-target clusters), targets at and beyond the frame border, several thickness settings, with and
+    without the first-frame threshold."""
+    mine = up.build.build_patch_probe()
+    rng = np.random.default_rng(17)
+    W, H = 160, 120
+    ref = rng.integers(800, 3000, (H, W)).astype(np.uint16)
+    for _ in range(60):                                                   # dark blobs: boundary pixels near them are dropped
+        y, x = int(rng.integers(0, H)), int(rng.integers(0, W))
+        ref[max(0, y - 1):y + 2, max(0, x - 1):x + 2] = rng.integers(0, 300)
+    ref.tofile(tmp_path / "ref.u16")
+    sets = []
+    for k in range(12):
+        n = int(rng.integers(1, 14))
+        t = np.stack([rng.uniform(-3, W + 3, n), rng.uniform(-3, H + 3, n), rng.uniform(2.0, 9.0, n)], 1)
+        if k % 3 == 0:                                                    # a chain of touching targets and a tight pair
+            t = np.concatenate([t, [[40 + 7 * i, 60 + 2 * i, 6.0] for i in range(5)], [[100.5, 20.25, 4.0], [103.0, 22.5, 5.5]]])
+        if k % 4 == 1:
+            t = np.concatenate([t, [[0.0, 0.0, 5.0], [W - 1.0, H - 1.0, 7.0], [W / 2, 0.4, 3.0], [-6.0, 50.0, 4.0]]])
+        sets.append(t.astype(np.float32))
+    n_multi = 0
+    for k, t in enumerate(sets):
+        (tmp_path / "t.txt").write_text("".join("%.9g %.9g %.9g\n" % tuple(float(v) for v in row) for row in t))
+        for bt, bf in ((2, 1), (2, 0), (1, 2), (3, 1)):
+            for thr in ((), (str(tmp_path / "ref.u16"), "400", "2"), (str(tmp_path / "ref.u16"), "1200", "1")):
+                args = [str(tmp_path / "t.txt"), str(W), str(H), str(bt), str(bf)] + list(thr)
+                a = subprocess.run([mine] + args, capture_output=True, text=True)
+                b = subprocess.run([probes[1], "patches"] + args, capture_output=True, text=True)
+                assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+                assert a.stdout == b.stdout, (k, bt, bf, thr)
+        n_multi += sum(1 for l in b.stdout.splitlines() if l.startswith("cluster") and int(l.split()[2]) > 1)
+    assert n_multi >= 4
