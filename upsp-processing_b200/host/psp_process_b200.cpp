@@ -279,6 +279,7 @@ int main(int argc, char** argv) {
     std::vector<float> sol_avg_final(msize), sol_rms_final(msize), coverage(msize);
     chain.read_phase1_stats(sol_avg_final.data(), sol_rms_final.data(), coverage.data());
     FlatFiles out(out_dir, true);
+    out.write_vector("intensity", nullptr, 0);   // created and left empty, as the reference does (its write-behind is disabled, :988)
     out.write_vector("intensity_rms", sol_rms_final.data(), msize);
     out.write_vector("intensity_avg", sol_avg_final.data(), msize);
     out.write_vector("coverage", coverage.data(), msize);
