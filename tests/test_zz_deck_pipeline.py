@@ -136,7 +136,7 @@ def test_deck_with_polynomial_patcher(up, orc, gpu, tmp_path):
     assert r.returncode == 0, r.stderr
     assert f"Sorted {len(targs)} targets into" in r.stdout
 
-    first = orc.fix_hot_pixels(frames[0])[0]
+    first = frames[0]              # cams[c]->get_frame(1) as InitializeImagePatches takes it: no hot-pixel fix (psp_process.cpp:2091)
     first.astype("<u2").tofile(d / "first.u16")
     hp = subprocess.run([up.build.build_inputs_probe(), "hist", str(d / "first.u16"), "12"], capture_output=True, text=True)
     thresh = int([l for l in hp.stdout.splitlines() if l.startswith("threshold")][0].split()[1])

@@ -160,8 +160,10 @@ int main(int argc, char** argv) {
     if (!any_video && !job.count("format")) throw std::invalid_argument("job.txt: neither format nor video<c> given");
     const size_t frame_bytes = p12 ? (size_t)W * H * 3 / 2 : (size_t)W * H * 2;
 
-    // first_frames_raw of the reference (psp_process.cpp:877-884): frame `first_frame`, decoded, hot pixels fixed
-    auto first_frame_of = [&](int c) {
+    // frame `first_frame` of camera c, decoded.  fix_hot = true: first_frames_raw of the reference (psp_process.cpp:877-884,
+    // hot pixels fixed: the registration reference); fix_hot = false: cams[c]->get_frame(1) as InitializeImagePatches takes it
+    // for the histogram threshold and threshold_bounds (:2091, 2145-2155), i.e. without the hot-pixel fix
+    auto first_frame_of = [&](int c, bool fix_hot) {
       const std::string b = job_dir + "/cam" + std::to_string(c);
       if (!readers[c]) {
         auto first = read_all<uint16_t>(b + ".first");
@@ -174,7 +176,7 @@ int main(int argc, char** argv) {
       if (upsp_op_unpack(device, packed.data(), readers[c]->pixel_format(), first.size(), readers[c]->unpack_lut(), first.data()) != UPSP_OK)
         throw std::runtime_error(upsp_gpu_last_error());
       int n_hot = 0;
-      if (upsp_op_fix_hot_pixels(device, first.data(), 1, H, W, &n_hot) != UPSP_OK) throw std::runtime_error(upsp_gpu_last_error());
+      if (fix_hot && upsp_op_fix_hot_pixels(device, first.data(), 1, H, W, &n_hot) != UPSP_OK) throw std::runtime_error(upsp_gpu_last_error());
       return first;
     };
 
@@ -208,7 +210,7 @@ int main(int argc, char** argv) {
         cluster_points(targs, clusters, (int)(bt + bf));
         PatchClusters pc(clusters, W, H, bt, bf);
         if (job.count("patch_thresh") || (job.count("auto_patch_thresh") && geti("auto_patch_thresh"))) {
-          const auto first = first_frame_of(c);
+          const auto first = first_frame_of(c, false);
           const unsigned bit_depth = readers[c] ? readers[c]->properties().bit_depth : 12u;
           const unsigned thresh = job.count("patch_thresh") ? (unsigned)geti("patch_thresh")
                                                             : patch_threshold(first.data(), first.size(), bit_depth);
@@ -226,7 +228,7 @@ int main(int argc, char** argv) {
         chain.set_patches(c, (int)boff.size() - 1, boff.data(), bx.data(), by.data(), ioff.data(),
                           ix.data(), iy.data());
       }
-      if (reg == "pixel") chain.set_reference_frame(c, first_frame_of(c).data());
+      if (reg == "pixel") chain.set_reference_frame(c, first_frame_of(c, true).data());
     }
     auto remap = read_all<int32_t>(job_dir + "/remap.i32", false);
     if (!remap.empty()) chain.set_overlap_remap(remap.data());
