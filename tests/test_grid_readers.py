@@ -190,3 +190,88 @@ def test_plot3d_reader_errors(up, tmp_path):
     (tmp_path / "cut.x").write_bytes(raw[:-20])
     r = subprocess.run([probe, str(tmp_path / "cut.x"), "sp"], capture_output=True, text=True)
     assert r.returncode == 1 and "truncated zone data" in r.stderr
+
+
+def numpy_intersect(xyz, tri, comps):
+    """TriModel_::intersect_grid (cpp/lib/TriModel.ipp:941-1118) restated: lowest index of every group of identical nodes,
+    collapsed triangles dropped, orphans between consecutive removed nodes removed, nodes renumbered in order"""
+    n = len(xyz)
+    groups = {}
+    for i, p in enumerate(xyz):
+        groups.setdefault(tuple(float(v) + 0.0 for v in p), []).append(i)           # + 0.0: -0.0 == 0.0
+    rep = np.arange(n)
+    for g in groups.values():
+        rep[g] = g[0]
+    removed = np.flatnonzero(rep != np.arange(n))
+    if len(removed) == 0:
+        return xyz, tri, comps, 0
+    t = rep[tri]
+    keep = (t[:, 0] != t[:, 1]) & (t[:, 0] != t[:, 2]) & (t[:, 1] != t[:, 2])
+    t, comps = t[keep], comps[keep]
+    used = np.zeros(n, bool)
+    used[t.ravel()] = True
+    gone = np.zeros(n, bool)
+    gone[removed] = True
+    orphans = 0
+    for i, r in enumerate(removed):
+        end = removed[i + 1] if i + 1 < len(removed) else len(removed)
+        for k in range(r + 1, end):
+            if not used[k] and not gone[k]:
+                gone[k] = True
+                orphans += 1
+    new = np.cumsum(~gone) - 1
+    return xyz[~gone], new[t].astype(np.int32), comps, sum(len(g) > 1 for g in groups.values()) + orphans
+
+
+def test_intersect_grid_reproduces_reference_fixtures(up, tmp_path):
+    """psp_process loads a .tri grid with intersect = true: the reference's un-intersected sphere fixtures must become its own
+    intersected ones (*.i.tri) node for node and triangle for triangle (known answers of cpp/test/test_trimodel.cpp:62-79:
+    594 -> 514 nodes, 1024 faces, 1 / 6 components; intersecting an intersected grid changes nothing)."""
+    base = "/root/reference/cpp/test/inputs/sphere_unf_"
+    if not os.path.exists(base + "single.tri"):
+        pytest.skip("reference fixtures not present on this machine")
+    probe = up.build.build_grid_probe()
+    for kind, ncomp in (("single", 1), ("multi", 6)):
+        r = subprocess.run([probe, base + kind + ".tri", str(tmp_path / "a"), "intersect"], capture_output=True, text=True)
+        info = {l.split()[0]: int(l.split()[1]) for l in r.stdout.splitlines()}
+        assert info["n_nodes"] == 514 and info["n_tris"] == 1024 and info["n_comps"] == ncomp and info["non_unique"] == 80
+        r = subprocess.run([probe, base + kind + ".i.tri", str(tmp_path / "b"), "intersect"], capture_output=True, text=True)
+        info = {l.split()[0]: int(l.split()[1]) for l in r.stdout.splitlines()}
+        assert info["n_nodes"] == 514 and info["n_tris"] == 1024 and info["non_unique"] == 0
+        for ext, dt in ((".xyz", np.float32), (".tri", np.int32), (".comp", np.int32)):
+            assert np.array_equal(np.fromfile(str(tmp_path / "a") + ext, dt), np.fromfile(str(tmp_path / "b") + ext, dt)), (kind, ext)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_intersect_grid_matches_restatement(up, tmp_path, seed):
+    probe = up.build.build_grid_probe()
+    rng = np.random.default_rng(seed)
+    xyz, _, tri = up.synth.make_sphere_mesh(8, 12, 2.0, (0, 0, 0), seed=seed)
+    xyz = xyz.astype(np.float32)
+    n0 = len(xyz)
+    dup_of = rng.choice(n0, 25, replace=False)                              # 25 duplicated nodes, some twice, spread over the list
+    extra = np.concatenate([xyz[dup_of], xyz[dup_of[:6]]])
+    pos = np.sort(rng.choice(n0, len(extra), replace=False))
+    xyz2 = np.insert(xyz, pos, extra, axis=0)
+    shift = np.arange(n0) + np.searchsorted(pos, np.arange(n0), side="right")   # new index of every original node
+    tri2 = shift[tri].astype(np.int32)
+    new_ids = pos + np.arange(len(pos))
+    for k in range(0, len(new_ids), 2):                                     # half of the copies take over a triangle corner
+        orig = shift[np.concatenate([dup_of, dup_of[:6]])[k]]
+        hits = np.argwhere(tri2 == orig)
+        if len(hits):
+            tri2[tuple(hits[0])] = new_ids[k]
+    a, b = shift[dup_of[0]], new_ids[0]
+    tri2 = np.concatenate([tri2, [[a, b, shift[tri[0, 0]]]]]).astype(np.int32)  # a triangle that collapses (two identical corners)
+    xyz2 = np.concatenate([xyz2, [[9, 9, 9]]]).astype(np.float32)           # an orphan after the last removed node: stays
+    xyz2[3] = np.where(xyz2[3] == 0, -0.0, xyz2[3])
+    comps = (np.arange(len(tri2)) % 4 + 1).astype(np.int32)
+    write_tri(tmp_path / "g.tri", xyz2, tri2, comps)
+    r = subprocess.run([probe, str(tmp_path / "g.tri"), str(tmp_path / "d"), "intersect"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = {l.split()[0]: int(l.split()[1]) for l in r.stdout.splitlines()}
+    wx, wt, wc, overlap = numpy_intersect(xyz2, tri2, comps)
+    assert info["non_unique"] == len(xyz2) - len(wx) >= 25 and info["unique_overlapping"] == overlap
+    assert np.array_equal(np.fromfile(tmp_path / "d.xyz", np.float32).reshape(-1, 3), wx)
+    assert np.array_equal(np.fromfile(tmp_path / "d.tri", np.int32).reshape(-1, 3), wt) and len(wt) < len(tri2)
+    assert np.array_equal(np.fromfile(tmp_path / "d.comp", np.int32), wc)

@@ -186,3 +186,25 @@ def test_reference_command_line_forms(up, tmp_path):
     assert r.returncode == 1 and "Must specify -paint_cal" in r.stderr
     r = subprocess.run([exe, f"-input_file={tmp_path / 'nope.inp'}", "-h5_out=x.h5", "-paint_cal=p"], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot be opened" in r.stderr
+
+
+def test_deck_tri_grid_is_intersected(up, tmp_path):
+    """psp_process loads the unstructured model with TriModel_(file, intersect = true) (psp_process.cpp:1384): duplicate nodes
+    collapse before anything is sized, so msize and every per-node output follow the intersected numbering"""
+    from test_grid_readers import numpy_intersect
+    make_inputs(up, tmp_path, "tri", frames=1)
+    xyz, _, tri = up.synth.make_sphere_mesh(8, 16, 2.0, (0, 0, 6.0), seed=3)
+    xyz = xyz.astype(np.float32)
+    dup = np.array([5, 17, 40])
+    xyz2 = np.concatenate([xyz, xyz[dup]]).astype(np.float32)               # three nodes stored twice ...
+    tri2 = tri.copy().astype(np.int32)
+    for k, n in enumerate(dup):                                              # ... and used by one triangle each
+        hit = np.argwhere(tri2 == n)[0]
+        tri2[tuple(hit)] = len(xyz) + k
+    comps = np.ones(len(tri2), np.int32)
+    write_tri(tmp_path / "model.tri", xyz2, tri2, comps)
+    r, job = setup(up, tmp_path, "-no_projection")
+    wx, wt, _, _ = numpy_intersect(xyz2, tri2, comps)
+    assert len(wx) == len(xyz) and "Found 3 non-unique points" in r.stdout
+    assert job_kv(job / "job.txt")["msize"] == str(len(xyz))
+    assert np.array_equal(np.fromfile(job / "xyz.f32", np.float32).reshape(-1, 3), wx)

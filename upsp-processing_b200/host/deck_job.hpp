@@ -61,7 +61,14 @@ struct ModelArrays {
 inline ModelArrays load_model(const FileInputs& ifile) {
   ModelArrays m;
   if (ifile.grid_type == GridType::Tri) {
-    const TriGrid g = read_tri_grid(ifile.grid);
+    TriGrid g = read_tri_grid(ifile.grid);
+    std::cout << "Read " << g.n_nodes << " nodes and " << g.n_tris << " faces" << std::endl;
+    {   // TriModel_(file, intersect = true), psp_process.cpp:1384 / TriModel.ipp:245-255
+      std::cout << "Finding overlapping points..." << std::endl;
+      const int initial_size = g.n_nodes;
+      const int overlap = intersect_grid(g);
+      std::cout << "Found " << (initial_size - g.n_nodes) << " non-unique points\nFound " << overlap << " unique overlapping points\n" << std::endl;
+    }
     m.xyz = g.xyz;
     m.tris = g.tris;
     calc_normals(g, m.normals);

@@ -1,7 +1,7 @@
 // grid_probe -- reads a .tri grid with host/grid_readers.hpp, prints its sizes and dumps
 // xyz | normals | tris (0-based) as raw little-endian arrays for tests/test_grid_readers.py; or reads
 // an unformatted plot3d grid and re-writes it in single or double precision.
-//   grid_probe FILE.tri [dump_prefix]
+//   grid_probe FILE.tri [dump_prefix [intersect]]
 //   grid_probe FILE.x sp|dp [OUT.x]
 #include <cstdio>
 #include <iostream>
@@ -35,7 +35,12 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
-    const auto g = upsp_b200::read_tri_grid(argv[1]);
+    auto g = upsp_b200::read_tri_grid(argv[1]);
+    if (argc > 3 && std::string(argv[3]) == "intersect") {      // as psp_process loads it: TriModel_(file, intersect = true)
+      const int n0 = g.n_nodes;
+      const int overlap = upsp_b200::intersect_grid(g);
+      std::printf("non_unique %d\nunique_overlapping %d\n", n0 - g.n_nodes, overlap);
+    }
     std::vector<float> nrm;
     upsp_b200::calc_normals(g, nrm);
     std::printf("n_nodes %d\nn_tris %d\nn_comps %d\nhas_comps %d\n", g.n_nodes, g.n_tris, g.number_of_components(),

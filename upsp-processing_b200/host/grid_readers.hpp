@@ -30,6 +30,80 @@ struct TriGrid {
   }
 };
 
+/* TriModel_::intersect_grid (cpp/lib/TriModel.ipp:941-1118), which psp_process runs on every .tri grid it loads
+ * (TriModel_(file, intersect = true), psp_process.cpp:1384): nodes with bit-identical coordinates collapse onto the lowest
+ * index of their group, triangles that collapse are dropped, nodes left without a triangle BETWEEN two removed nodes are
+ * removed as well (the reference's own range logic, kept: an orphan before the first or after the last removed node stays),
+ * and the remaining nodes are renumbered in order.  Returns the reference's "unique overlapping points" count; the number
+ * of removed nodes is the change of n_nodes. */
+inline int intersect_grid(TriGrid& g) {
+  const int N = g.n_nodes;
+  auto coord = [&](int n, int d) { return g.xyz[(size_t)n * 3 + d]; };
+  std::vector<int> order((size_t)N);
+  for (int n = 0; n < N; ++n) order[(size_t)n] = n;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    for (int d = 0; d < 3; ++d) {
+      if (coord(a, d) < coord(b, d)) return true;
+      if (coord(b, d) < coord(a, d)) return false;
+    }
+    return a < b;
+  });
+  std::vector<int> rep((size_t)N);
+  int n_groups = 0;
+  for (size_t i = 0; i < order.size();) {
+    size_t j = i + 1;
+    while (j < order.size() && coord(order[j], 0) == coord(order[i], 0) && coord(order[j], 1) == coord(order[i], 1) &&
+           coord(order[j], 2) == coord(order[i], 2))
+      ++j;
+    for (size_t k = i; k < j; ++k) rep[(size_t)order[k]] = order[i];     // lowest index of the group (ties sorted by index)
+    if (j - i > 1) ++n_groups;
+    i = j;
+  }
+  std::vector<int> removed_sorted;                                         // the `second` of every duplicate pair that is kept
+  for (int n = 0; n < N; ++n)
+    if (rep[(size_t)n] != n) removed_sorted.push_back(n);
+  if (removed_sorted.empty()) return 0;
+
+  // move the triangles onto the representatives, drop the ones that collapse
+  std::vector<int32_t> tris, comps;
+  std::vector<int> n_faces((size_t)N, 0);
+  for (int t = 0; t < g.n_tris; ++t) {
+    const int32_t a = rep[(size_t)g.tris[(size_t)t * 3]], b = rep[(size_t)g.tris[(size_t)t * 3 + 1]], c = rep[(size_t)g.tris[(size_t)t * 3 + 2]];
+    if (a == b || a == c || b == c) continue;
+    tris.insert(tris.end(), {a, b, c});
+    if (!g.comps.empty()) comps.push_back(g.comps[(size_t)t]);
+    ++n_faces[(size_t)a];
+    ++n_faces[(size_t)b];
+    ++n_faces[(size_t)c];
+  }
+  // orphans between consecutive removed nodes (after the last one the reference's range ends at the NUMBER of duplicates)
+  std::vector<char> removed((size_t)N, 0);
+  for (int n : removed_sorted) removed[(size_t)n] = 1;
+  int n_orphans = 0;
+  for (size_t i = 0; i < removed_sorted.size(); ++i) {
+    const int start = removed_sorted[i] + 1;
+    const int end = i + 1 < removed_sorted.size() ? removed_sorted[i + 1] : (int)removed_sorted.size();
+    for (int n = start; n < end; ++n)
+      if (n_faces[(size_t)n] == 0 && !removed[(size_t)n]) removed[(size_t)n] = 1, ++n_orphans;
+  }
+  // renumber
+  std::vector<int32_t> new_index((size_t)N, -1);
+  std::vector<float> xyz;
+  int next = 0;
+  for (int n = 0; n < N; ++n)
+    if (!removed[(size_t)n]) {
+      new_index[(size_t)n] = next++;
+      xyz.insert(xyz.end(), {coord(n, 0), coord(n, 1), coord(n, 2)});
+    }
+  for (int32_t& v : tris) v = new_index[(size_t)v];
+  g.xyz.swap(xyz);
+  g.tris.swap(tris);
+  g.comps.swap(comps);
+  g.n_nodes = next;
+  g.n_tris = (int)(g.tris.size() / 3);
+  return n_groups + n_orphans;
+}
+
 inline TriGrid read_tri_grid(const std::string& model_file) {
   std::ifstream ifs(model_file, std::ios::in | std::ios::binary);
   if (!ifs) throw std::invalid_argument("Cannot open tri grid file '" + model_file + "'");

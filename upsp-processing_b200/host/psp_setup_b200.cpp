@@ -82,8 +82,13 @@ int main(int argc, char** argv) {
     for (double d : cam.dist) std::cout << " " << d;
     std::cout << "\nimageSize " << cam.width << " " << cam.height << std::endl;
     if (print_cal) return 0;
-    const TriGrid grid = read_tri_grid(grid_file);
+    TriGrid grid = read_tri_grid(grid_file);
     std::cout << "Read " << grid.n_nodes << " nodes and " << grid.n_tris << " faces" << std::endl;
+    {   // psp_process loads the grid as TriModel_(file, intersect = true): duplicate nodes collapse (TriModel.ipp:245-255)
+      const int initial_size = grid.n_nodes;
+      const int overlap = intersect_grid(grid);
+      std::cout << "Found " << (initial_size - grid.n_nodes) << " non-unique points\nFound " << overlap << " unique overlapping points" << std::endl;
+    }
     std::vector<float> normals;
     calc_normals(grid, normals);
     std::vector<uint8_t> is_data((size_t)grid.n_nodes, 1);
