@@ -43,13 +43,14 @@ def perpendicular(n):
     return out / np.linalg.norm(out)
 
 
-def visible_targets(cv2, targets, xyz, normals, tris, rvec, tvec, K, dist, width, height, oblique_angle, diam_sf):
+def visible_targets(cv2, targets, xyz, normals, tris, rvec, tvec, K, dist, width, height, oblique_angle, diam_sf, node_normals=None):
     """targets: [(x, y, z, diameter)] float32.  Returns [(index, u, v, diameter_px, margin)]; margin = how far the
     closest decision (frame edge in px, occlusion distance, obliqueness in rad) is from flipping."""
     R = cv2.Rodrigues(np.asarray(rvec, float))[0]
     center = (-R.T @ np.asarray(tvec, float)).astype(np.float32).astype(np.float64)
     verts = np.asarray(xyz, np.float32).astype(np.float64)
-    nrm = np.asarray(normals, np.float32).astype(np.float64)
+    nrm = np.asarray(normals, np.float32).astype(np.float64)                 # Model::get_n(): the obliqueness test of getTargets
+    nrm_d = nrm if node_normals is None else np.asarray(node_normals, np.float32).astype(np.float64)   # Node::get_normal(): diameters
     thresh = np.deg2rad(180.0 - min(oblique_angle + 5.0, 90.0))
     out = []
     for i, (x, y, z, diam) in enumerate(targets):
@@ -68,7 +69,7 @@ def visible_targets(cv2, targets, xyz, normals, tris, rvec, tvec, K, dist, width
         ang = np.arccos(np.clip(nrm[nn] @ d, -1, 1))
         if not ang > thresh:
             continue
-        n_t = nrm[int(np.argmin(((verts - pos) ** 2).sum(1)))]
+        n_t = nrm_d[int(np.argmin(((verts - pos) ** 2).sum(1)))]
         a = perpendicular(n_t)
         b = np.cross(a, n_t)
         total = 0.0

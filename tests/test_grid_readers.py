@@ -275,3 +275,52 @@ def test_intersect_grid_matches_restatement(up, tmp_path, seed):
     assert np.array_equal(np.fromfile(tmp_path / "d.xyz", np.float32).reshape(-1, 3), wx)
     assert np.array_equal(np.fromfile(tmp_path / "d.tri", np.int32).reshape(-1, 3), wt) and len(wt) < len(tri2)
     assert np.array_equal(np.fromfile(tmp_path / "d.comp", np.int32), wc)
+
+
+def numpy_area_weighted_normals(xyz, tri):
+    """TriModel_::Node::get_normal (TriModel.ipp:1570-1590) with upsp::normal / upsp::area (models.ipp:137-182), float32
+    arithmetic in the reference's order, faces accumulated in ascending index"""
+    f32, f64 = np.float32, np.float64
+    xyz = xyz.astype(f32)
+    acc = np.zeros_like(xyz)
+    nd = lambda v: np.sqrt((v.astype(f64) ** 2).sum())
+    for t in tri:
+        p0, p1, p2 = xyz[t[0]], xyz[t[1]], xyz[t[2]]
+        a, b = (p2 - p1).astype(f32), (p0 - p1).astype(f32)
+        n = np.array([f32(f32(a[1] * b[2]) - f32(a[2] * b[1])), f32(f32(a[2] * b[0]) - f32(a[0] * b[2])), f32(f32(a[0] * b[1]) - f32(a[1] * b[0]))], f32)
+        nn = nd(n)
+        if f32(nn) != 0:
+            n = (n.astype(f64) / nn).astype(f32)
+        ea, eb, ec = f32(nd((p1 - p0).astype(f32))), f32(nd((p2 - p1).astype(f32))), f32(nd((p2 - p0).astype(f32)))
+        if eb > ea:
+            ea, eb = eb, ea
+        if ec > ea:
+            ea, eb, ec = ec, ea, eb
+        elif ec > eb:
+            eb, ec = ec, eb
+        pos_neg = f32(abs(f32(ec - f32(ea - eb))))
+        prod = f32(f32(f32(f32(ea + f32(eb + ec)) * pos_neg) * f32(ec + f32(ea - eb))) * f32(ea + f32(eb - ec)))
+        area = f32(0.25 * float(np.sqrt(prod, dtype=f32)))
+        for k in t:
+            acc[k] = (acc[k] + (n * area).astype(f32)).astype(f32)
+    out = acc.copy()
+    for i, v in enumerate(acc):
+        m = nd(v)
+        if m != 0:
+            out[i] = (v.astype(f64) / m).astype(f32)
+    return out
+
+
+def test_area_weighted_node_normals(up, tmp_path):
+    """what the reference's camera weights and target diameters take as the node normal of an unstructured model"""
+    probe = up.build.build_grid_probe()
+    xyz, _, tri = up.synth.make_sphere_mesh(9, 14, 3.0, (0.5, -1.0, 2.0), bump=0.15, seed=8)
+    xyz = np.concatenate([xyz, [[7.0, 7.0, 7.0]]]).astype(np.float32)        # a node without triangles: zero normal
+    write_tri(tmp_path / "g.tri", xyz, tri, np.ones(len(tri), np.int32))
+    run_probe(probe, tmp_path / "g.tri", tmp_path / "d")
+    got = np.fromfile(tmp_path / "d.nrmw", np.float32).reshape(-1, 3)
+    want = numpy_area_weighted_normals(xyz, tri)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert not np.any(got[-1]) and np.allclose(np.linalg.norm(got[:-1], axis=1), 1, atol=1e-6)
+    plain = np.fromfile(tmp_path / "d.nrm", np.float32).reshape(-1, 3)
+    assert not np.array_equal(got, plain) and np.abs(got - plain).max() < 0.3      # close to, but not, the unweighted normals

@@ -39,10 +39,11 @@ def test_visible_targets_from_deck(up, tmp_path):
     got = np.loadtxt(job / "cam0.targets", dtype=np.float32).reshape(-1, 3)
 
     subprocess.run([up.build.build_grid_probe(), str(tmp_path / "model.tri"), str(tmp_path / "g")], check=True, capture_output=True)
-    nrm = np.fromfile(tmp_path / "g.nrm", np.float32).reshape(-1, 3)
+    nrm = np.fromfile(tmp_path / "g.nrm", np.float32).reshape(-1, 3)          # Model::get_n(): visibility of getTargets
+    nrm_w = np.fromfile(tmp_path / "g.nrmw", np.float32).reshape(-1, 3)       # Node::get_normal(): get_target_diameters
     pc = subprocess.run([up.build.build_setup_tool(), "-cal", str(tmp_path / "cam01.json"), "-print_cal"], capture_output=True, text=True)
     rvec = np.array(pc.stdout.splitlines()[0].split()[1:], float)
-    want = otargets.visible_targets(cv2, targets, sc["xyz"], nrm, sc["tri"], rvec, sc["tvec"], K, sc["dist"], W, H, 70.0, 1.2)
+    want = otargets.visible_targets(cv2, targets, sc["xyz"], nrm, sc["tri"], rvec, sc["tvec"], K, sc["dist"], W, H, 70.0, 1.2, node_normals=nrm_w)
     assert 3 <= len(want) < len(dirs) - 3                      # some of each kind were rejected
     assert all(w[4] > 0.02 for w in want), "a target sits on a decision boundary; move it"
     assert f"{len(want)} visible targets" in r.stdout and len(got) == len(want)

@@ -203,6 +203,7 @@ def test_deck_two_cameras_average_view(up, orc, gpu, tmp_path):
 
     subprocess.run([up.build.build_grid_probe(), str(d / "model.tri"), str(d / "g")], check=True, capture_output=True)
     nrm = np.fromfile(d / "g.nrm", np.float32).reshape(-1, 3)
+    nrm_w = np.fromfile(d / "g.nrmw", np.float32).reshape(-1, 3)       # Node::get_normal(): what the camera weights take (projection.ipp:990)
     xyz = sc["xyz"].astype(np.float32)
     N = len(xyz)
     thresh = float(np.float32((180.0 - 70.0) * np.pi / 180.0))
@@ -212,7 +213,7 @@ def test_deck_two_cameras_average_view(up, orc, gpu, tmp_path):
         parsed = {l.split()[0]: np.array(l.split()[1:], float) for l in pc.stdout.splitlines()}
         ocam = orc.make_camera(parsed["rvec"], parsed["tvec"], sc["K"], sc["dist"], W, H)
         codes.append(orc.create_projection(ocam, xyz, nrm, np.ones(N, np.uint8), sc["tri"], thresh)[0])
-        angs.append(_angles(xyz, nrm, orc.cam_center(ocam)))
+        angs.append(_angles(xyz, nrm_w, orc.cam_center(ocam)))
     seen = np.stack([c >= 0 for c in codes])
     both = seen[0] & seen[1]
     assert both.sum() > 30 and (seen[0] ^ seen[1]).sum() > 30

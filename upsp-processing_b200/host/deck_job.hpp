@@ -48,7 +48,9 @@ inline void write_all(const std::string& path, const std::vector<T>& v) {
 }
 
 struct ModelArrays {
-  std::vector<float> xyz, normals;      // [N][3]
+  std::vector<float> xyz, normals;      // [N][3]; normals = Model::get_n() (create_projection_mat, getTargets)
+  std::vector<float> node_normals;      // [N][3]  Node::get_normal() (camera weights, target diameters): the same array for a
+                                        // structured model, the area-weighted one for an unstructured model
   std::vector<int32_t> tris;            // [T][3]
   std::vector<uint8_t> is_data;
   std::vector<int32_t> remap;           // structured grids only
@@ -72,6 +74,7 @@ inline ModelArrays load_model(const FileInputs& ifile) {
     m.xyz = g.xyz;
     m.tris = g.tris;
     calc_normals(g, m.normals);
+    node_normals_area_weighted(g, m.node_normals);
     m.is_data.assign((size_t)g.n_nodes, 1);
     // TriModel_::Node::has_primary_component (TriModel.ipp:1530-1546): every adjacent triangle carries the same component
     m.n_components = g.number_of_components();
@@ -96,6 +99,7 @@ inline ModelArrays load_model(const FileInputs& ifile) {
       m.xyz[(size_t)n * 3 + 2] = model.get_z()[(size_t)n];
     }
     m.normals = model.get_n();
+    m.node_normals = m.normals;           // P3DModel_::Node::get_normal returns the stored normal (P3DModel.ipp:1685-1687)
     std::vector<float> unused;
     std::vector<int> tn;
     model.extract_tris(unused, tn);
@@ -237,7 +241,7 @@ inline int run_deck(const std::map<std::string, std::string>& opt) {
       // InitializeImagePatches up to the clustering (psp_process.cpp:2095-2123); psp_process_b200 clusters the projected
       // targets, thresholds the boundaries on the first frame and builds the pixel lists (host/patch_geometry.hpp)
       const float sf = has("-target_diam_sf") ? (float)std::atof(get("-target_diam_sf").c_str()) : 1.2f;
-      const std::vector<Target> targs = visible_targets(HostCamera(cam), model.xyz.data(), model.normals.data(), msize, model.tris.data(),
+      const std::vector<Target> targs = visible_targets(HostCamera(cam), model.xyz.data(), model.normals.data(), model.node_normals.data(), msize, model.tris.data(),
                                                         (int)(model.tris.size() / 3), ifile.targets[c], ifile.oblique_angle, sf);
       FILE* tf = std::fopen((job_dir + "/cam" + std::to_string(c) + ".targets").c_str(), "w");
       if (!tf) return fail("Cannot write the projected targets of camera " + std::to_string(c + 1));
@@ -264,7 +268,7 @@ inline int run_deck(const std::map<std::string, std::string>& opt) {
     std::cout << "camera " << ifile.cam_nums[c] << ": projected " << msize << " model nodes, accepted " << m.col.size() << std::endl;
   }
   if (project) {
-    adjust_projection_for_weights(model.xyz.data(), model.normals.data(), centers, projs,
+    adjust_projection_for_weights(model.xyz.data(), model.node_normals.data(), centers, projs,
                                   ifile.overlap == OverlapKind::BestView ? OverlapType::BestView : OverlapType::AverageViews);
     for (unsigned c = 0; c < ifile.cameras; ++c) {
       const std::string b = job_dir + "/cam" + std::to_string(c);
@@ -280,6 +284,7 @@ inline int run_deck(const std::map<std::string, std::string>& opt) {
   write_all(job_dir + "/model_temp.f32", model_temp_input);
   write_all(job_dir + "/xyz.f32", model.xyz);
   write_all(job_dir + "/normals.f32", model.normals);
+  write_all(job_dir + "/node_normals.f32", model.node_normals);
   write_all(job_dir + "/is_data.u8", model.is_data);
   std::ofstream job(job_dir + "/job.txt");
   if (!job) return fail("Cannot write '" + job_dir + "/job.txt'");

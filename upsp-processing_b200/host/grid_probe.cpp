@@ -43,6 +43,8 @@ int main(int argc, char** argv) {
     }
     std::vector<float> nrm;
     upsp_b200::calc_normals(g, nrm);
+    std::vector<float> nrm_w;
+    upsp_b200::node_normals_area_weighted(g, nrm_w);
     std::printf("n_nodes %d\nn_tris %d\nn_comps %d\nhas_comps %d\n", g.n_nodes, g.n_tris, g.number_of_components(),
                 g.comps.empty() ? 0 : 1);
     if (argc > 2) {
@@ -55,6 +57,7 @@ int main(int argc, char** argv) {
       };
       dump(".xyz", g.xyz.data(), g.xyz.size() * 4);
       dump(".nrm", nrm.data(), nrm.size() * 4);
+      dump(".nrmw", nrm_w.data(), nrm_w.size() * 4);     // area-weighted (Node::get_normal): weights, target diameters
       dump(".tri", g.tris.data(), g.tris.size() * 4);
       dump(".comp", g.comps.data(), g.comps.size() * 4);
     }

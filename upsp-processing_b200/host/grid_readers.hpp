@@ -174,6 +174,51 @@ inline void calc_normals(const TriGrid& g, std::vector<float>& normals) {
   }
 }
 
+/* TriModel_::Node::get_normal (cpp/lib/TriModel.ipp:1570-1590): the AREA-weighted node normal, sum over the node's faces
+ * (ascending face index) of upsp::normal(tri) * upsp::area(tri) (cpp/lib/models.ipp:137-182: cross product normalised with a
+ * double norm; Heron's formula on the sorted float edge lengths), normalised.  This, not calc_normals, is what the reference's
+ * camera weights (projection.ipp:990) and target diameters (psp_process.cpp:145) take for an unstructured model. */
+inline void node_normals_area_weighted(const TriGrid& g, std::vector<float>& normals) {
+  normals.assign((size_t)3 * g.n_nodes, 0.f);
+  auto norm_d = [](float x, float y, float z) { return std::sqrt((double)x * x + (double)y * y + (double)z * z); };   // cv::norm
+  for (int t = 0; t < g.n_tris; ++t) {
+    const int32_t id[3] = {g.tris[3 * t], g.tris[3 * t + 1], g.tris[3 * t + 2]};
+    const float* p0 = &g.xyz[3 * (size_t)id[0]];
+    const float* p1 = &g.xyz[3 * (size_t)id[1]];
+    const float* p2 = &g.xyz[3 * (size_t)id[2]];
+    // upsp::normal: (p2 - p1) x (p0 - p1)
+    const float ax = p2[0] - p1[0], ay = p2[1] - p1[1], az = p2[2] - p1[2];
+    const float bx = p0[0] - p1[0], by = p0[1] - p1[1], bz = p0[2] - p1[2];
+    float n[3] = {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx};
+    const double nn = norm_d(n[0], n[1], n[2]);
+    if ((float)nn != 0.f)
+      for (float& c : n) c = (float)((double)c / nn);              // Point3f / double
+    // upsp::area: Heron, edges sorted a >= b >= c
+    float a = (float)norm_d(p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]);
+    float b = (float)norm_d(p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]);
+    float c = (float)norm_d(p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]);
+    if (b > a) std::swap(a, b);
+    if (c > a) {
+      const float tmp = a;
+      a = c;
+      c = b;
+      b = tmp;
+    } else if (c > b) {
+      std::swap(b, c);
+    }
+    const float pos_neg = std::fabs(c - (a - b));
+    const float area = (float)(0.25 * std::sqrt((a + (b + c)) * pos_neg * (c + (a - b)) * (a + (b - c))));
+    for (int32_t node : id)
+      for (int d = 0; d < 3; ++d) normals[3 * (size_t)node + d] += n[d] * area;
+  }
+  for (int node = 0; node < g.n_nodes; ++node) {
+    float* v = &normals[3 * (size_t)node];
+    const double m = norm_d(v[0], v[1], v[2]);
+    if (m != 0.0)
+      for (int d = 0; d < 3; ++d) v[d] = (float)((double)v[d] / m);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Structured grids: unformatted plot3d (cpp/include/plot3d.h:30-110, read_plot3d_grid_file /
 // write_plot3d_grid_file): Fortran records; single zone = {IDIM,JDIM,KDIM} then one x|y|z record;

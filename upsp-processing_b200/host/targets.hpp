@@ -218,7 +218,8 @@ inline std::vector<float> get_target_diameters(const HostCamera& cam, const floa
 }
 
 /* InitializeImagePatches up to the clustering: *Targets + *Fiducials of the file -> visible, projected, sized */
-inline std::vector<Target> visible_targets(const HostCamera& cam, const float* xyz, const float* normals, int n_nodes,
+/* normals: Model::get_n() (getTargets); node_normals: Node::get_normal() (get_target_diameters) */
+inline std::vector<Target> visible_targets(const HostCamera& cam, const float* xyz, const float* normals, const float* node_normals, int n_nodes,
                                            const int32_t* tris, int n_tris, const std::string& target_file, float oblique_angle,
                                            float target_diam_sf) {
   std::vector<ModelTarget> orig, fiducials;
@@ -238,7 +239,7 @@ inline std::vector<Target> visible_targets(const HostCamera& cam, const float* x
   const float thresh = (float)((180. - std::min(oblique_angle + 5.0, 90.0)) * 3.141592653589793 / 180.0);
   std::vector<ImageTarget> vis = get_targets(cam, xyz, normals, n_nodes, tris, n_tris, all, thresh);
   for (ImageTarget& t : vis) cam.map_point_to_image(t.xyz, t.u, t.v);
-  const std::vector<float> diams = get_target_diameters(cam, xyz, normals, n_nodes, vis);
+  const std::vector<float> diams = get_target_diameters(cam, xyz, node_normals, n_nodes, vis);
   std::vector<Target> out;
   for (size_t i = 0; i < vis.size(); ++i) {
     Target t;
