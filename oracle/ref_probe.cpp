@@ -39,6 +39,9 @@ extern "C" {
 }
 #include "utils/file_writers.h"
 
+/* psp_process.cpp:611-624 == upsp_matrix_transpose.cpp:70-93: linked from the latter (compiled with -Dmain=... into _ref) */
+void apportion(unsigned long int value, unsigned long int nBins, int* start, int* extent);
+
 template <typename E>
 static std::string str(const E& e) {
   std::ostringstream os;
@@ -49,6 +52,7 @@ static std::string str(const E& e) {
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   const std::string cmd = argv[1], file = argv[2];
+  if (cmd == "apportion" && argc < 4) return 2;
   try {
     if (cmd == "deck") {
       upsp::FileInputs fi;
@@ -140,6 +144,15 @@ int main(int argc, char** argv) {
       }
       std::fclose(o);
       std::printf("rays %zu\ntriangles %zu\n", rays.size() / 6, tris.size() / 9);
+    } else if (cmd == "apportion") { // VALUE NBINS: the reference's work split of frames / nodes over ranks
+      const unsigned long value = std::stoul(argv[2]), nbins = std::stoul(argv[3]);
+      std::vector<int> start(nbins), extent(nbins);
+      apportion(value, nbins, start.data(), extent.data());
+      std::printf("start");
+      for (int v : start) std::printf(" %d", v);
+      std::printf("\nextent");
+      for (int v : extent) std::printf(" %d", v);
+      std::printf("\n");
     } else if (cmd == "patches") {   // targets.txt W H boundary buffer [ref.u16 thresh offset]: InitializeImagePatches' geometry
       if (argc < 7) return 2;        // (psp_process.cpp:2125-2163) with the reference's cluster_points / PatchClusters; output as
       std::ifstream f(file);         // host/patch_geometry_probe prints it

@@ -384,3 +384,15 @@ def test_patch_geometry_equals_reference_code(up, probes, tmp_path):
                 assert a.stdout == b.stdout, (k, bt, bf, thr)
         n_multi += sum(1 for l in b.stdout.splitlines() if l.startswith("cluster") and int(l.split()[2]) > 1)
     assert n_multi >= 4
+
+
+def test_apportion_equals_reference_code(probes, orc, up):
+    """the work split of frames and nodes over ranks (apportion, psp_process.cpp:611-624; the identical function of the
+    stand-alone transpose tool is what is linked here): the restatement and the CUDA library's slices follow it."""
+    cases = [(20000, 1), (20000, 8), (50000, 8), (1000000, 8), (500000, 3), (7, 8), (8, 8), (9, 8), (0, 4), (1, 1), (12345, 7), (100, 16)]
+    for value, nbins in cases:
+        r = subprocess.run([probes[1], "apportion", str(value), str(nbins)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        ref = {l.split()[0]: [int(v) for v in l.split()[1:]] for l in r.stdout.splitlines()}
+        start, extent = orc.apportion(value, nbins)
+        assert list(map(int, start)) == ref["start"] and list(map(int, extent)) == ref["extent"], (value, nbins)
