@@ -49,6 +49,11 @@ DECKS = {
     "at-sign-in-value": "@general\n test = me@host\n run = 4\n@all\n grid = g.p3d\n",
     "no-trailing-newline-empty-blocks": "@general\n@vars\n@all\n@camera\n@options\n@output",
     "grid-types": "@all\n grid = a.b.grid\n@all\n sds = s\n",
+    # the fill of per-camera targets / calibration is decided by the LAST @all block alone (upsp_inputs.cpp:76 assigns)
+    "all-twice-last-decides": "@all\n grid = g.tri\n targets = all.tgts\n calibration = all.json\n@all\n sds = s.wtd\n"
+                              "@camera\n number = 1\n filename = c1.mraw\n",
+    "all-twice-last-fills": "@all\n grid = g.tri\n@all\n targets = all.tgts\n@camera\n number = 1\n filename = c1.mraw\n"
+                            " calibration = one.json\n@camera\n number = 2\n filename = c2.mraw\n",
 }
 BROKEN = {
     "bad-registration": "@options\n registration = fancy\n",

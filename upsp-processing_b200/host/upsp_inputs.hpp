@@ -85,6 +85,7 @@ struct FileInputs {
           vars_map.push_back(v);
         });
       } else if (buf.find("@all") != std::string::npos) {
+        fill_extras = false;   // the reference assigns load_all's result: only the LAST @all block decides
         block([&](const std::string& k, const std::string& v) {
           if (k == "sds") sds = v;
           else if (k == "grid") {
