@@ -81,9 +81,12 @@ template <typename T> class Mat_ : public Mat {
   Mat_(int r, int c) : Mat(r, c, sizeof(T) == 1 ? CV_8U : (sizeof(T) == 2 ? CV_16U : CV_32F)) {}
   Mat_(const Mat& m) : Mat(m) {}
   T& operator()(int r, int c) { return this->template at<T>(r, c); }
+  const T* begin() const { return reinterpret_cast<const T*>(this->data); }   /* continuous matrices only (what the probes make) */
+  const T* end() const { return reinterpret_cast<const T*>(this->data) + (size_t)this->rows * this->cols; }
   Mat_ operator()(const Rect_<int>& r) const { return Mat_(this->roi(r)); }
 };
 inline Mat Mat::operator()(const Rect_<int>& r) const { return roi(r); }
+inline int Mat::depth() const { return CV_MAT_DEPTH(type_); }   /* single-channel matrices only: type == depth */
 enum { FONT_HERSHEY_DUPLEX = 2, FILLED = -1, COLORMAP_JET = 2 };
 Size getTextSize(const std::string&, int, double, int, int*);
 void rectangle(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0);

@@ -12,7 +12,8 @@
 // rt::BVH / rt::Triangle::intersect (cpp/raycast/pspRT.cpp, pspRTmem.cpp, with imath_stub/ for the 3-float vector, box and line
 // it is written in; the box-line pruning test of Imath is replaced by "visit every node"), and the patch geometry templates
 // upsp::cluster_points / PatchClusters constructor / threshold_bounds (cpp/lib/patches.ipp, with eigen_stub/ for the int mask
-// matrix they mark pixels in and ref_decls.h for the one name they take from projection.h).
+// matrix they mark pixels in and ref_decls.h for the one name they take from projection.h), and upsp::intensity_histc
+// (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile).
 #include <cstdio>
 #include <algorithm>
 #include <cstdint>
@@ -41,6 +42,11 @@ extern "C" {
 
 /* psp_process.cpp:611-624 == upsp_matrix_transpose.cpp:70-93: linked from the latter (compiled with -Dmain=... into _ref) */
 void apportion(unsigned long int value, unsigned long int nBins, int* start, int* extent);
+/* cpp/lib/image_processing.ipp:10-49, instantiated for 16-bit frames in _ref/histc.o (see the Makefile) */
+namespace upsp {
+template <typename T>
+void intensity_histc(const cv::Mat_<T>& img, std::vector<int>& edges, std::vector<int>& counts, unsigned int depth, int bins);
+}
 
 template <typename E>
 static std::string str(const E& e) {
@@ -230,6 +236,21 @@ int main(int argc, char** argv) {
       }
       std::fclose(o);
       std::printf("frames %d\n", nf);
+    } else if (cmd == "hist") {      // FILE.u16 DEPTH [BINS=256]: upsp::intensity_histc as psp_process.cpp:2157 calls it, then first_min_threshold(5)
+      if (argc < 4) return 2;
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      const size_t n = (size_t)f.tellg() / 2;
+      f.seekg(0);
+      cv::Mat_<uint16_t> img(1, (int)n);
+      f.read(reinterpret_cast<char*>(img.data), (std::streamsize)(n * 2));
+      std::vector<int> edges, counts;
+      upsp::intensity_histc(img, edges, counts, (unsigned)atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 256);
+      const unsigned fm = upsp::first_min_threshold(counts, 5);
+      std::printf("bin_sz %d\nfirst_min %u\nthreshold %u\nedges", edges[1], fm, (unsigned)(edges[fm] + 5));
+      for (int e : edges) std::printf(" %d", e);
+      std::printf("\ncounts");
+      for (int c : counts) std::printf(" %d", c);
+      std::printf("\n");
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

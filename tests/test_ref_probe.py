@@ -171,6 +171,29 @@ def test_peak_finding_equals_reference(probes, tmp_path):
             assert not ref[0] and mine == ref, (k, sep, counts.tolist())
 
 
+def test_first_frame_histogram_equals_reference_code(probes, tmp_path):
+    """upsp::intensity_histc (cpp/lib/image_processing.ipp:10-50) compiled from the reference tree and called as
+    psp_process.cpp:2157 does (bit depth of the camera, 256 bins), followed by first_min_threshold(5): counts, edges, bin size and
+    the patcher's threshold equal, for 8- to 16-bit depths (a depth above 16 clamps), pixels at and above the range, bins = -1
+    (one bin per value) and other bin counts that divide the range."""
+    rng = np.random.default_rng(5)
+    imgs = [np.zeros(0, np.uint16), np.zeros(100, np.uint16), np.full(50, 65535, np.uint16), np.arange(65536, dtype=np.uint16),
+            np.array([4095, 4096, 4097, 1023, 1024, 255, 256, 0, 15, 16], np.uint16)]
+    for seed in range(6):
+        lo, hi = rng.uniform(40, 500), rng.uniform(900, 3500)
+        imgs.append(np.concatenate([rng.normal(lo, lo / 6, 4000), rng.normal(hi, hi / 8, 50000), rng.normal(30, 8, 300),
+                                    rng.integers(0, 65536, 200).astype(float)]).clip(0, 65535).astype(np.uint16))
+    n = 0
+    for img in imgs:
+        img.tofile(tmp_path / "f.u16")
+        for depth, bins in [(12, 256), (10, 256), (8, 256), (16, 256), (20, 256), (12, -1), (8, -1), (12, 64), (12, 4096), (10, 1)]:
+            mine, ref = both(probes, "hist", tmp_path / "f.u16", depth, bins)
+            mine = (mine[0], [l for l in mine[1] if not l.startswith("peaks")])     # the product's probe also lists the maxima
+            assert mine == ref and not ref[0], (len(img), depth, bins)
+            n += 1
+    assert n == 110
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""

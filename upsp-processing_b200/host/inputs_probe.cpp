@@ -87,12 +87,14 @@ int main(int argc, char** argv) {
       f.seekg(0);
       f.read(reinterpret_cast<char*>(img.data()), (std::streamsize)(img.size() * 2));
       std::vector<int> edges, counts;
-      intensity_histc(img.data(), img.size(), edges, counts, (unsigned)atoi(argv[3]), 256);
+      intensity_histc(img.data(), img.size(), edges, counts, (unsigned)atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 256);
       std::vector<unsigned> peaks;
       find_peaks(counts, peaks, 5);
-      std::printf("bin_sz %d\nfirst_min %u\nthreshold %u\npeaks", edges[1], first_min_threshold(counts, 5),
-                  patch_threshold(img.data(), img.size(), (unsigned)atoi(argv[3])));
+      const unsigned fm = first_min_threshold(counts, 5);
+      std::printf("bin_sz %d\nfirst_min %u\nthreshold %u\npeaks", edges[1], fm, (unsigned)(edges[fm] + 5));
       for (unsigned p : peaks) std::printf(" %u", p);
+      std::printf("\nedges");
+      for (int e : edges) std::printf(" %d", e);
       std::printf("\ncounts");
       for (int c : counts) std::printf(" %d", c);
       std::printf("\n");
