@@ -39,20 +39,24 @@ template <typename T> struct Point3_;
 typedef Point3_<float> Point3f;
 typedef Point3_<double> Point3d;
 typedef Point3_<int> Point3i;
+/* 3-D point arithmetic as OpenCV's types.hpp defines it (element-wise in T; division by a double is carried out in double and
+ * narrowed per element, saturate_cast<T>; the norm accumulates in double): upsp::normal / upsp::area of cpp/lib/models.ipp and
+ * the node-normal loop of ref_probe run on these */
 template <typename T> struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
   Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
-  T dot(const Point3_& o) const;
-  Point3_ cross(const Point3_& o) const;
+  T dot(const Point3_& o) const { return x * o.x + y * o.y + z * o.z; }
+  Point3_ cross(const Point3_& o) const { return Point3_(y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x); }
+  Point3_& operator+=(const Point3_& o) { x += o.x; y += o.y; z += o.z; return *this; }
 };
-template <typename T> Point3_<T> operator+(const Point3_<T>&, const Point3_<T>&);
-template <typename T> Point3_<T> operator-(const Point3_<T>&, const Point3_<T>&);
-template <typename T> Point3_<T> operator-(const Point3_<T>&);
-template <typename T, typename S> Point3_<T> operator*(const Point3_<T>&, S);
-template <typename T, typename S> Point3_<T> operator*(S, const Point3_<T>&);
-template <typename T, typename S> Point3_<T> operator/(const Point3_<T>&, S);
-template <typename T> double norm(const Point3_<T>&);
+template <typename T> Point3_<T> operator+(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> Point3_<T> operator-(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> Point3_<T> operator-(const Point3_<T>& a) { return Point3_<T>(-a.x, -a.y, -a.z); }
+template <typename T, typename S> Point3_<T> operator*(const Point3_<T>& a, S b) { return Point3_<T>((T)(a.x * b), (T)(a.y * b), (T)(a.z * b)); }
+template <typename T, typename S> Point3_<T> operator*(S b, const Point3_<T>& a) { return Point3_<T>((T)(b * a.x), (T)(b * a.y), (T)(b * a.z)); }
+template <typename T, typename S> Point3_<T> operator/(const Point3_<T>& a, S b) { return Point3_<T>((T)(a.x / b), (T)(a.y / b), (T)(a.z / b)); }
+template <typename T> double norm(const Point3_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z); }
 template <typename T> double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }   /* as OpenCV */
 template <typename T> struct Rect_ {
   T x, y, width, height;

@@ -13,9 +13,11 @@
 // it is written in; the box-line pruning test of Imath is replaced by "visit every node"), and the patch geometry templates
 // upsp::cluster_points / PatchClusters constructor / threshold_bounds (cpp/lib/patches.ipp, with eigen_stub/ for the int mask
 // matrix they mark pixels in and ref_decls.h for the one name they take from projection.h), and upsp::intensity_histc
-// (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile).
+// (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile), and upsp::normal / upsp::area of a
+// triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way).
 #include <cstdio>
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <cstdlib>
 #include <fstream>
@@ -46,6 +48,9 @@ void apportion(unsigned long int value, unsigned long int nBins, int* start, int
 namespace upsp {
 template <typename T>
 void intensity_histc(const cv::Mat_<T>& img, std::vector<int>& edges, std::vector<int>& counts, unsigned int depth, int bins);
+/* cpp/lib/models.ipp:135-184, instantiated for float in _ref/trigeom.o (upsp::Triangle: the reference's data_structs.h) */
+template <typename FP> cv::Point3_<FP> normal(const Triangle<FP>& tri);
+template <typename FP> FP area(const Triangle<FP>& tri);
 }
 
 template <typename E>
@@ -251,6 +256,40 @@ int main(int argc, char** argv) {
       std::printf("\ncounts");
       for (int c : counts) std::printf(" %d", c);
       std::printf("\n");
+    } else if (cmd == "trigeom") {   // XYZ.f32 [n][3]  TRIS.i32 [t][3]  OUT.f32: per triangle upsp::normal | upsp::area [t][4], then the node
+                                     // normals [n][3] summed as TriModel_::Node::get_normal does (TriModel.ipp:1571-1590: adjacent faces
+                                     // in ascending index, normal * area, divided by the double norm unless it is 0)
+      if (argc < 5) return 2;
+      auto rd = [](const char* p, size_t elem) {
+        std::ifstream f(p, std::ios::binary | std::ios::ate);
+        std::vector<char> b((size_t)f.tellg() / elem * elem);
+        f.seekg(0);
+        f.read(b.data(), (std::streamsize)b.size());
+        return b;
+      };
+      const std::vector<char> xb = rd(argv[2], 12), tb = rd(argv[3], 12);
+      const float* xyz = reinterpret_cast<const float*>(xb.data());
+      const int32_t* tris = reinterpret_cast<const int32_t*>(tb.data());
+      const size_t n = xb.size() / 12, nt = tb.size() / 12;
+      auto P = [&](int32_t i) { return cv::Point3f(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]); };
+      std::vector<float> out(4 * nt + 3 * n);
+      std::vector<cv::Point3f> acc(n);
+      for (size_t t = 0; t < nt; ++t) {
+        const upsp::Triangle<float> tri(P(tris[3 * t]), P(tris[3 * t + 1]), P(tris[3 * t + 2]));
+        const cv::Point3f nr = upsp::normal(tri);
+        const float ar = upsp::area(tri);
+        out[4 * t] = nr.x, out[4 * t + 1] = nr.y, out[4 * t + 2] = nr.z, out[4 * t + 3] = ar;
+        for (int k = 0; k < 3; ++k) acc[(size_t)tris[3 * t + k]] += nr * ar;
+      }
+      for (size_t i = 0; i < n; ++i) {
+        cv::Point3f v = acc[i];
+        if (cv::norm(v) != 0.0) v = v / cv::norm(v);
+        out[4 * nt + 3 * i] = v.x, out[4 * nt + 3 * i + 1] = v.y, out[4 * nt + 3 * i + 2] = v.z;
+      }
+      FILE* o = std::fopen(argv[4], "wb");
+      std::fwrite(out.data(), 4, out.size(), o);
+      std::fclose(o);
+      std::printf("tris %zu nodes %zu\n", nt, n);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

@@ -194,6 +194,43 @@ def test_first_frame_histogram_equals_reference_code(probes, tmp_path):
     assert n == 110
 
 
+def test_area_weighted_node_normals_equal_reference_code(up, probes, tmp_path):
+    """upsp::normal / upsp::area of a triangle (cpp/lib/models.ipp:135-184, compiled from the reference tree against the reference's
+    own data_structs.h) summed per node as TriModel_::Node::get_normal does (TriModel.ipp:1571-1590): what the camera weights and
+    target diameters take as the node normal of an unstructured model == host/grid_readers.hpp, bit for bit, and both == the numpy
+    restatement per triangle.  Bumpy spheres, an orphan node, needle / collinear / repeated-corner triangles (Heron's guarded
+    term), large offsets, and the reference's own sphere fixtures."""
+    from test_grid_readers import numpy_area_weighted_normals, run_probe, write_tri
+    rng = np.random.default_rng(3)
+    grids = []
+    for seed, (nlat, nlon, off) in enumerate([(9, 14, (0.5, -1.0, 2.0)), (6, 9, (1e3, -2e3, 5e2)), (14, 30, (0, 0, 0))]):
+        xyz, _, tri = up.synth.make_sphere_mesh(nlat, nlon, 3.0, off, bump=0.15, seed=seed)
+        grids.append((np.concatenate([xyz, [[7.0, 7.0, 7.0]]]).astype(np.float32), tri.astype(np.int32)))
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1e-7, 0], [5, 5, 5], [5, 5, 5.000001], [1e4, 0, 0], [0, 3, 4], [1, 1, 1]], np.float32)
+    tri = np.array([[0, 1, 2], [0, 1, 3], [4, 5, 8], [0, 6, 3], [0, 7, 1], [2, 2, 7], [1, 7, 8], [8, 7, 1], [3, 0, 6]], np.int32)
+    grids.append((xyz, tri))
+    xyz = (rng.normal(0, 1, (60, 3)) * rng.choice([1e-3, 1.0, 1e3], (60, 1))).astype(np.float32)
+    grids.append((xyz, rng.integers(0, 60, (200, 3)).astype(np.int32)))
+    base = "/root/reference/cpp/test/inputs/sphere_unf_"
+    files = [base + k for k in ("single.tri", "multi.i.tri")] if os.path.exists(base + "single.tri") else []
+    for k, (xyz, tri) in enumerate(grids):
+        write_tri(tmp_path / f"g{k}.tri", xyz, tri, np.ones(len(tri), np.int32))
+        files.append(str(tmp_path / f"g{k}.tri"))
+    for k, f in enumerate(files):
+        run_probe(up.build.build_grid_probe(), f, tmp_path / "d")
+        r = subprocess.run([probes[1], "trigeom", tmp_path / "d.xyz", tmp_path / "d.tri", tmp_path / "ref.f32"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        mine = np.fromfile(tmp_path / "d.nrmw", np.float32).reshape(-1, 3)
+        nt = os.path.getsize(tmp_path / "d.tri") // 12
+        ref = np.fromfile(tmp_path / "ref.f32", np.float32)
+        assert np.array_equal(mine.view(np.uint32), ref[4 * nt:].reshape(-1, 3).view(np.uint32)), f
+        xyz = np.fromfile(tmp_path / "d.xyz", np.float32).reshape(-1, 3)
+        tri = np.fromfile(tmp_path / "d.tri", np.int32).reshape(-1, 3)
+        assert np.array_equal(numpy_area_weighted_normals(xyz, tri).view(np.uint32), mine.view(np.uint32)), f
+        assert np.all(np.isfinite(ref)) and np.all(ref[3:4 * nt:4] >= 0)
+    assert len(files) >= 5
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
