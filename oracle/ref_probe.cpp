@@ -14,7 +14,8 @@
 // upsp::cluster_points / PatchClusters constructor / threshold_bounds (cpp/lib/patches.ipp, with eigen_stub/ for the int mask
 // matrix they mark pixels in and ref_decls.h for the one name they take from projection.h), and upsp::intensity_histc
 // (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile), and upsp::normal / upsp::area of a
-// triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way).
+// triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way), and upsp::angle_between (cpp/utils/cv_extras.ipp:67-73) with the
+// camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way).
 #include <cstdio>
 #include <algorithm>
 #include <array>
@@ -49,6 +50,9 @@ namespace upsp {
 template <typename T>
 void intensity_histc(const cv::Mat_<T>& img, std::vector<int>& edges, std::vector<int>& counts, unsigned int depth, int bins);
 /* cpp/lib/models.ipp:135-184, instantiated for float in _ref/trigeom.o (upsp::Triangle: the reference's data_structs.h) */
+/* cpp/lib/projection.ipp:222-268, instantiated for float in _ref/weighter.o (declared as oracle/weighter_prelude.h does) */
+template <typename T> struct BestView { std::vector<T> operator()(const std::vector<T>& angles) const; };
+template <typename T> struct AverageViews { std::vector<T> operator()(const std::vector<T>& angles) const; };
 template <typename FP> cv::Point3_<FP> normal(const Triangle<FP>& tri);
 template <typename FP> FP area(const Triangle<FP>& tri);
 }
@@ -290,6 +294,52 @@ int main(int argc, char** argv) {
       std::fwrite(out.data(), 4, out.size(), o);
       std::fclose(o);
       std::printf("tris %zu nodes %zu\n", nt, n);
+    } else if (cmd == "weights") {   // DIR N_CAMS N_NODES average|best: the files of host/projection_weights_probe; per node seen by >= 2
+                                     // cameras: upsp::angle_between(position - centre, normal) (cv_extras.ipp:67-73, narrowed to float
+                                     // as ProjWeights::get_angle returns it, projection.ipp:984-991) for the cameras in ascending order,
+                                     // the reference's weighter on those angles, every value of the row scaled -> DIR/cam<c>.val.ref
+      if (argc < 6) return 2;
+      const std::string dir = argv[2];
+      const int n_cams = atoi(argv[3]), n = atoi(argv[4]);
+      const bool best = std::string(argv[5]) == "best";
+      auto rd = [&](const std::string& name) {
+        std::ifstream f(dir + "/" + name, std::ios::binary | std::ios::ate);
+        std::vector<char> b((size_t)f.tellg());
+        f.seekg(0);
+        f.read(b.data(), (std::streamsize)b.size());
+        return b;
+      };
+      const std::vector<char> xb = rd("xyz.f32"), nb = rd("nrm.f32"), cb = rd("centers.f64");
+      const float* xyz = reinterpret_cast<const float*>(xb.data());
+      const float* nrm = reinterpret_cast<const float*>(nb.data());
+      const double* cen = reinterpret_cast<const double*>(cb.data());
+      std::vector<std::vector<char>> rp(n_cams), vals(n_cams);
+      for (int c = 0; c < n_cams; ++c) rp[c] = rd("cam" + std::to_string(c) + ".rowptr"), vals[c] = rd("cam" + std::to_string(c) + ".val");
+      for (int i = 0; i < n; ++i) {
+        std::vector<int> cs;
+        std::vector<float> angs;
+        const cv::Point3f pos(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), nn(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+        for (int c = 0; c < n_cams; ++c) {
+          const int32_t* r = reinterpret_cast<const int32_t*>(rp[c].data());
+          if (r[i + 1] == r[i]) continue;
+          cs.push_back(c);
+          const cv::Point3f dir3 = pos - cv::Point3f((float)cen[3 * c], (float)cen[3 * c + 1], (float)cen[3 * c + 2]);
+          angs.push_back((float)upsp::angle_between(dir3, nn));
+        }
+        if (cs.size() < 2) continue;
+        const std::vector<float> w = best ? upsp::BestView<float>()(angs) : upsp::AverageViews<float>()(angs);
+        for (size_t k = 0; k < cs.size(); ++k) {
+          const int32_t* r = reinterpret_cast<const int32_t*>(rp[cs[k]].data());
+          float* v = reinterpret_cast<float*>(vals[cs[k]].data());
+          for (int e = r[i]; e < r[i + 1]; ++e) v[e] *= w[k];
+        }
+      }
+      for (int c = 0; c < n_cams; ++c) {
+        FILE* o = std::fopen((dir + "/cam" + std::to_string(c) + ".val.ref").c_str(), "wb");
+        std::fwrite(vals[c].data(), 1, vals[c].size(), o);
+        std::fclose(o);
+      }
+      std::printf("cameras %d nodes %d\n", n_cams, n);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

@@ -231,6 +231,30 @@ def test_area_weighted_node_normals_equal_reference_code(up, probes, tmp_path):
     assert len(files) >= 5
 
 
+@pytest.mark.parametrize("n_cams,mode", [(2, "average"), (2, "best"), (3, "best"), (3, "average"), (4, "average")])
+def test_camera_weights_equal_reference_code(up, probes, tmp_path, n_cams, mode):
+    """the arithmetic of adjust_projection_for_weights from the reference tree: upsp::angle_between (cpp/utils/cv_extras.ipp:67-73)
+    and BestView / AverageViews::operator() (cpp/lib/projection.ipp:222-268) applied per multiply-seen node to the cameras in
+    ascending order == host/projection_weights.hpp (which visits them in the order the reference's priority queue pops equal rows:
+    same container, comparator and push sequence): bit for bit with two cameras and for BestView without exact ties; with >= 3
+    averaged cameras the float sum of the angles depends on that order in its last bits (2 ulp allowed, as in
+    tests/test_projection_weights.py)."""
+    from test_projection_weights import _run, _scene
+    xyz, nrm, centers, cams = _scene(up, n_cams, seed=10 + n_cams)
+    got, _ = _run(up, tmp_path, xyz, nrm, centers, cams, mode)
+    r = subprocess.run([probes[1], "weights", str(tmp_path), str(n_cams), str(len(xyz)), mode], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    changed = 0
+    for c in range(n_cams):
+        ref = np.fromfile(tmp_path / f"cam{c}.val.ref", np.float32)
+        if n_cams == 2 or mode == "best":
+            assert np.array_equal(got[c].view(np.uint32), ref.view(np.uint32)), c
+        else:
+            assert np.all(np.abs(got[c] - ref) <= 2 * np.spacing(np.abs(ref))), c
+        changed += int((ref != 1).sum())
+    assert changed > 100
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
