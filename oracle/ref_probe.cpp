@@ -15,7 +15,8 @@
 // matrix they mark pixels in and ref_decls.h for the one name they take from projection.h), and upsp::intensity_histc
 // (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile), and upsp::normal / upsp::area of a
 // triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way), and upsp::angle_between (cpp/utils/cv_extras.ipp:67-73) with the
-// camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way).
+// camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way), and the model-temperature
+// lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way).
 #include <cstdio>
 #include <algorithm>
 #include <array>
@@ -45,6 +46,8 @@ extern "C" {
 
 /* psp_process.cpp:611-624 == upsp_matrix_transpose.cpp:70-93: linked from the latter (compiled with -Dmain=... into _ref) */
 void apportion(unsigned long int value, unsigned long int nBins, int* start, int* extent);
+/* psp_process.cpp:2287-2310 with the constants of :1096-1098, compiled into _ref/modeltemp.o (see the Makefile) */
+void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float* model_out);
 /* cpp/lib/image_processing.ipp:10-49, instantiated for 16-bit frames in _ref/histc.o (see the Makefile) */
 namespace upsp {
 template <typename T>
@@ -93,9 +96,13 @@ int main(int argc, char** argv) {
     } else if (cmd == "wtd") {
       const upsp::TunnelConditions tc = upsp::read_tunnel_conditions(file);
       std::fflush(stdout);
+      float wall = 0.f, mt = 0.f;
+      upsp::TunnelConditions work = tc;    // the reference's lines leave ttot + 459.67 - 459.67 (float) behind; the values as read are printed
+      ref_model_temperature(work, &wall, &mt);
       std::printf("alpha %.9g\nbeta %.9g\nphi %.9g\nmach %.9g\nrey %.9g\nptot %.9g\nqbar %.9g\nttot %.9g\nps %.9g\ntcavg %.9g\n",
                   (double)tc.alpha, (double)tc.beta, (double)tc.phi, (double)tc.mach, (double)tc.rey, (double)tc.ptot, (double)tc.qbar,
                   (double)tc.ttot, (double)tc.ps, (double)tc.tcavg);
+      std::printf("wall_temp %.9g\nmodel_temp %.9g\n", (double)wall, (double)mt);
     } else if (cmd == "p3dfun") {
       const std::vector<float> sol = upsp::read_plot3d_scalar_function_file(file, argc > 3 ? atoi(argv[3]) : -1);
       std::printf("count %zu\n", sol.size());

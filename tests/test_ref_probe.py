@@ -25,7 +25,7 @@ def both(probes, *args):
     out = []
     for exe in probes:
         r = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True)
-        lines = [l for l in r.stdout.splitlines() if not l.startswith(("version ", "Warning", "wall_temp", "model_temp", "check 1"))]
+        lines = [l for l in r.stdout.splitlines() if not l.startswith(("version ", "Warning", "check 1"))]
         out.append((r.returncode != 0, lines))
     return out
 
@@ -108,7 +108,7 @@ def test_paint_calibration_and_tunnel_conditions_equal_reference(probes, tmp_pat
     mine, ref = both(probes, "paintcal", tmp_path / "pc.txt", 71.3, 11.82)
     assert not ref[0] and mine == ref
     mine, ref = both(probes, "wtd", os.path.join(GOLDEN, "sample.wtd"))
-    assert not ref[0] and mine == ref and len(ref[1]) == 10
+    assert not ref[0] and mine == ref and len(ref[1]) == 12 and ref[1][-2:] == ["wall_temp 90.2649002", "model_temp 88.125"]
     (tmp_path / "partial.wtd").write_text("RUN 1\n#  MACH Q\tPS   JUNK\n0.5 100.25\t2000  7\n")
     mine, ref = both(probes, "wtd", tmp_path / "partial.wtd")
     assert not ref[0] and mine == ref and "alpha nan" in ref[1]
@@ -116,6 +116,27 @@ def test_paint_calibration_and_tunnel_conditions_equal_reference(probes, tmp_pat
     if os.path.exists(path):
         mine, ref = both(probes, "wtd", path)
         assert not ref[0] and mine == ref
+
+
+def test_model_temperature_equals_reference_code(probes, tmp_path):
+    """the model temperature of phase 2 -- recovery-factor wall temperature unless the thermocouple average was read -- from the
+    reference's own lines (cpp/exec/psp_process.cpp:2287-2310 with the constants of :1096-1098, compiled from the reference
+    tree into ref_probe): subsonic to hypersonic Mach numbers, cold and hot total temperatures, with / without TCAVG, missing
+    MACH or TTF (NaN runs through both)."""
+    rng = np.random.default_rng(2)
+    cases = [(0.0, 70.0, None), (0.84, 97.43, 88.125), (0.84, 97.43, None), (2.5, 150.0, None), (7.0, 900.0, None), (0.3, -40.0, None),
+             (1.0, -459.67, None), (None, 97.0, None), (0.6, None, None), (None, None, 75.5)]
+    cases += [(float(rng.uniform(0.05, 3.0)), float(rng.uniform(-20, 200)), None if k % 3 else float(rng.uniform(40, 120))) for k in range(50)]
+    walls = set()
+    for mach, ttf, tc in cases:
+        cols = [(n, v) for n, v in (("MACH", mach), ("TTF", ttf), ("TCAVG", tc), ("Q", 650.0), ("PS", 1300.0)) if v is not None]
+        (tmp_path / "c.wtd").write_text("RUN 1 1\n#  " + "\t".join(n for n, _ in cols) + "\n" + "\t".join(repr(v) for _, v in cols) + "\n")
+        mine, ref = both(probes, "wtd", tmp_path / "c.wtd")
+        assert not ref[0] and mine == ref, (mach, ttf, tc)
+        d = dict(l.split() for l in ref[1])
+        assert d["model_temp"] == (d["tcavg"] if tc is not None else d["wall_temp"])
+        walls.add(d["wall_temp"])
+    assert len(walls) > 50
 
 
 def test_plot3d_function_file_and_regression_sample_equal_reference(probes, tmp_path):
