@@ -16,7 +16,8 @@
 // (cpp/lib/image_processing.ipp:10-50, compiled on its own into _ref/histc.o by a pipe from the reference tree, see the Makefile), and upsp::normal / upsp::area of a
 // triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way), and upsp::angle_between (cpp/utils/cv_extras.ipp:67-73) with the
 // camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way), and the model-temperature
-// lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way).
+// lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way), and the per-node loop of its
+// phase 2 (:2460-2498, _ref/phase2.o, same way; the Eigen solve inside the detrend fit is the oracle's, loaded with dlopen).
 #include <cstdio>
 #include <algorithm>
 #include <array>
@@ -48,6 +49,9 @@ extern "C" {
 void apportion(unsigned long int value, unsigned long int nBins, int* start, int* extent);
 /* psp_process.cpp:2287-2310 with the constants of :1096-1098, compiled into _ref/modeltemp.o (see the Makefile) */
 void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float* model_out);
+/* psp_process.cpp:2460-2498 compiled into _ref/phase2.o; the fitter it calls is declared in phase2_prelude.h */
+#include <dlfcn.h>
+#include "phase2_prelude.h"
 /* cpp/lib/image_processing.ipp:10-49, instantiated for 16-bit frames in _ref/histc.o (see the Makefile) */
 namespace upsp {
 template <typename T>
@@ -347,6 +351,44 @@ int main(int argc, char** argv) {
         std::fclose(o);
       }
       std::printf("cameras %d nodes %d\n", n_cams, n);
+    } else if (cmd == "phase2") {    // DIR N F DEGREE ORACLE.so: the reference's per-node loop of phase 2 on DIR/{itrans,avg_final,coverage,steady,
+                                     // model_temp}.f32, DIR/paint.cal, DIR/run.wtd -> DIR/ref_{ptrans.f32,rms.f64,avg.f64,gain.f64}
+      if (argc < 7) return 2;
+      const std::string dir = argv[2];
+      const unsigned n = (unsigned)atoi(argv[3]), F = (unsigned)atoi(argv[4]), degree = (unsigned)atoi(argv[5]);
+      void* so = dlopen(argv[6], RTLD_NOW);
+      if (!so) throw std::runtime_error(dlerror());
+      OracleFitter fitter;
+      fitter.eval = reinterpret_cast<decltype(fitter.eval)>(dlsym(so, "orc_transpoly_eval_fit"));
+      auto build = reinterpret_cast<void (*)(unsigned, unsigned, float*)>(dlsym(so, "orc_transpoly_build"));
+      if (!fitter.eval || !build) throw std::runtime_error("oracle symbols missing");
+      fitter.n_frames = F, fitter.ncoef = degree + 1;
+      fitter.A.resize((size_t)F * (degree + 1));
+      build(F, degree, fitter.A.data());
+      auto rdf = [&](const std::string& name, size_t count) {
+        std::vector<float> v(count);
+        std::ifstream f(dir + "/" + name, std::ios::binary);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(count * 4));
+        if (!f) throw std::runtime_error("short file " + name);
+        return v;
+      };
+      const std::vector<float> itrans = rdf("itrans.f32", (size_t)n * F), avgf = rdf("avg_final.f32", n), cov = rdf("coverage.f32", n),
+                               steady = rdf("steady.f32", n), temp = rdf("model_temp.f32", n);
+      upsp::PaintCalibration pcal(dir + "/paint.cal");
+      upsp::TunnelConditions tcond = upsp::read_tunnel_conditions(dir + "/run.wtd");
+      std::vector<double> rms(n, 0.), avg(n, 0.), gain(n, 0.);
+      std::vector<float> ptrans((size_t)n * F, 0.f);
+      ref_phase2_nodes(n, 0, F, cov, fitter, rms, avg, gain, tcond, steady, pcal, temp, avgf, itrans.data(), ptrans.data());
+      auto wr = [&](const std::string& name, const void* d, size_t bytes) {
+        FILE* o = std::fopen((dir + "/" + name).c_str(), "wb");
+        std::fwrite(d, 1, bytes, o);
+        std::fclose(o);
+      };
+      wr("ref_ptrans.f32", ptrans.data(), ptrans.size() * 4);
+      wr("ref_rms.f64", rms.data(), n * 8);
+      wr("ref_avg.f64", avg.data(), n * 8);
+      wr("ref_gain.f64", gain.data(), n * 8);
+      std::printf("nodes %u frames %u qbar %.9g ps %.9g\n", n, F, (double)tcond.qbar, (double)tcond.ps);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

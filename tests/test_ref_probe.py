@@ -276,6 +276,46 @@ def test_camera_weights_equal_reference_code(up, probes, tmp_path, n_cams, mode)
     assert changed > 100
 
 
+@pytest.mark.parametrize("n, F, degree", [(150, 64, 6), (40, 301, 6), (60, 33, 2)])
+def test_phase2_node_loop_equals_reference_code(probes, orc, tmp_path, n, F, degree):
+    """the per-node loop of the reference's phase 2 -- steady-state pressure -> PaintCalibration::get_gain, Iref / I, detrend,
+    delta pressure, delta Cp = p * 144 / qbar, the double rms / avg partial sums, NaN for nodes without coverage -- compiled from
+    the reference's own lines (cpp/exec/psp_process.cpp:2460-2498) and linked with its paint calibration and tunnel-condition
+    readers; only the least-squares solve inside TransPolyFitter::eval_fit (Eigen) is the oracle's.  orc_phase2, which the GPU
+    phase 2 is held against, must give the same bits: delta-Cp histories, rms, avg, gain."""
+    rng = np.random.default_rng(n + F)
+    t = np.arange(F) / F
+    itrans = (900 + 600 * rng.random((n, 1))) * (1 + 0.05 * t[None, :] ** 2 + 0.01 * rng.normal(size=(n, F)))
+    itrans = itrans.astype(np.float32)
+    itrans[3, 5] = 0.0                                      # a pixel warped in from outside the frame: inf -> NaN history
+    avg_final = itrans.astype(np.float64).mean(1).astype(np.float32)
+    coverage = (rng.random(n) > 0.1).astype(np.float32) * rng.integers(1, 3, n).astype(np.float32)
+    coverage[:4] = [0, 1, 2, 1]
+    steady = rng.normal(-0.2, 0.4, n).astype(np.float32)
+    temp = rng.uniform(60, 110, n).astype(np.float32)
+    cal = np.array([0.62, -1.3e-3, 2.1e-6, 2.4e-4, 3.0e-7, -1.1e-9], np.float32)
+    qbar, ps = np.float32(657.9153), np.float32(1332.0421)
+    for name, a in (("itrans", itrans), ("avg_final", avg_final), ("coverage", coverage), ("steady", steady), ("model_temp", temp)):
+        a.tofile(tmp_path / f"{name}.f32")
+    (tmp_path / "paint.cal").write_text("".join("%s = %.9g\n" % (k, v) for k, v in zip("abcdef", cal)))
+    (tmp_path / "run.wtd").write_text("RUN 1 1\n#  MACH\tQ\tPS\n0.84\t%.9g\t%.9g\n" % (qbar, ps))
+    r = subprocess.run([probes[1], "phase2", str(tmp_path), str(n), str(F), str(degree), orc.build()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split()[-4:] == ["qbar", "%.9g" % qbar, "ps", "%.9g" % ps]
+    pt, rms, avg, gain = orc.phase2(itrans, avg_final, coverage, steady, temp, cal, qbar, ps, degree=degree)
+    ref_pt = np.fromfile(tmp_path / "ref_ptrans.f32", np.float32).reshape(n, F)
+    with np.errstate(invalid="ignore"):
+        ref_rms = np.sqrt(np.fromfile(tmp_path / "ref_rms.f64") / F).astype(np.float32)          # finals, psp_process.cpp:2540-2547
+        ref_avg = (np.fromfile(tmp_path / "ref_avg.f64") / F).astype(np.float32)
+    ref_gain = np.fromfile(tmp_path / "ref_gain.f64").astype(np.float32)
+    same = lambda a, b: np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
+    assert same(pt, ref_pt) and same(rms, ref_rms) and same(avg, ref_avg) and same(gain, ref_gain)
+    covered = coverage > 0
+    assert np.isnan(gain[~covered]).all() and not ref_pt[~covered].any() and np.isnan(ref_pt[3]).all()
+    ok = covered & ~np.isnan(ref_pt).any(1)
+    assert ok.sum() > n // 2 and np.all(np.abs(ref_pt[ok]) > 0) and np.all(ref_rms[ok] > 0)
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
