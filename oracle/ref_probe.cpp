@@ -17,6 +17,7 @@
 // triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way), and upsp::angle_between (cpp/utils/cv_extras.ipp:67-73) with the
 // camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way), and the model-temperature
 // lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way), and the per-node loop of its
+// detrend design matrix (cpp/lib/filtering.ipp:20-24, _ref/polymat.o, same way) and the per-node loop of its
 // phase 2 (:2460-2498, _ref/phase2.o, same way; the Eigen solve inside the detrend fit is the oracle's, loaded with dlopen).
 #include <cstdio>
 #include <algorithm>
@@ -52,6 +53,8 @@ void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float
 /* psp_process.cpp:2460-2498 compiled into _ref/phase2.o; the fitter it calls is declared in phase2_prelude.h */
 #include <dlfcn.h>
 #include "phase2_prelude.h"
+/* cpp/lib/filtering.ipp:20-24 compiled into _ref/polymat.o (see the Makefile) */
+void ref_transpoly_fill(unsigned int n_frames_, unsigned int coeffs_, float* out);
 /* cpp/lib/image_processing.ipp:10-49, instantiated for 16-bit frames in _ref/histc.o (see the Makefile) */
 namespace upsp {
 template <typename T>
@@ -389,6 +392,15 @@ int main(int argc, char** argv) {
       wr("ref_avg.f64", avg.data(), n * 8);
       wr("ref_gain.f64", gain.data(), n * 8);
       std::printf("nodes %u frames %u qbar %.9g ps %.9g\n", n, F, (double)tcond.qbar, (double)tcond.ps);
+    } else if (cmd == "polymat") {   // OUT.f32 N_FRAMES DEGREE: the design matrix TransPolyFitter's constructor fills, column-major [degree+1][F]
+      if (argc < 5) return 2;
+      const unsigned F = (unsigned)atoi(argv[3]), nc = (unsigned)atoi(argv[4]) + 1;
+      std::vector<float> A((size_t)F * nc, -1.f);
+      ref_transpoly_fill(F, nc, A.data());
+      FILE* o = std::fopen(argv[2], "wb");
+      std::fwrite(A.data(), 4, A.size(), o);
+      std::fclose(o);
+      std::printf("frames %u coeffs %u\n", F, nc);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

@@ -316,6 +316,21 @@ def test_phase2_node_loop_equals_reference_code(probes, orc, tmp_path, n, F, deg
     assert ok.sum() > n // 2 and np.all(np.abs(ref_pt[ok]) > 0) and np.all(ref_rms[ok] > 0)
 
 
+def test_detrend_design_matrix_equals_reference_code(probes, orc, tmp_path):
+    """the matrix of the detrend fit, (f / n_frames)^c in the reference's mixed float / double arithmetic: the fill loop of
+    TransPolyFitter's constructor (cpp/lib/filtering.ipp:20-24) compiled from the reference tree == orc_transpoly_build, which
+    the oracle's phase 2 and the GPU's closed-form detrend are derived from"""
+    import ctypes as C
+    for F, degree in [(1, 0), (2, 1), (7, 6), (64, 6), (1000, 6), (4097, 6), (20000, 6), (333, 10)]:
+        r = subprocess.run([probes[1], "polymat", str(tmp_path / "A.f32"), str(F), str(degree)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.split() == ["frames", str(F), "coeffs", str(degree + 1)]
+        ref = np.fromfile(tmp_path / "A.f32", np.float32)
+        A = np.zeros(F * (degree + 1), np.float32)
+        orc.lib().orc_transpoly_build(C.c_uint(F), C.c_uint(degree), A.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(A.view(np.uint32), ref.view(np.uint32)), (F, degree)
+        assert np.all(ref[:F] == 1) and (F < 2 or ref[F + 1] == np.float32(1) / np.float32(F))
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
