@@ -17,7 +17,8 @@
 // triangle (cpp/lib/models.ipp:135-184, _ref/trigeom.o, same way), and upsp::angle_between (cpp/utils/cv_extras.ipp:67-73) with the
 // camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way), and the model-temperature
 // lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way), and the per-node loop of its
-// detrend design matrix (cpp/lib/filtering.ipp:20-24, _ref/polymat.o, same way) and the per-node loop of its
+// detrend design matrix (cpp/lib/filtering.ipp:20-24, _ref/polymat.o, same way), the double -> float finals of both phases and the
+// frame-1 ratio sample (psp_process.cpp:1933-1936, :1947-1949, :2543-2547, _ref/finals.o, same way) and the per-node loop of its
 // phase 2 (:2460-2498, _ref/phase2.o, same way; the Eigen solve inside the detrend fit is the oracle's, loaded with dlopen).
 #include <cstdio>
 #include <algorithm>
@@ -55,6 +56,13 @@ void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float
 #include "phase2_prelude.h"
 /* cpp/lib/filtering.ipp:20-24 compiled into _ref/polymat.o (see the Makefile) */
 void ref_transpoly_fill(unsigned int n_frames_, unsigned int coeffs_, float* out);
+/* psp_process.cpp:1933-1936, :1947-1949, :2543-2547 compiled into _ref/finals.o (see the Makefile) */
+void ref_phase1_finals(unsigned int msize, unsigned long int number_frames, const std::vector<double>& sol_avg_partial,
+                       const std::vector<double>& sol_rms_partial, std::vector<float>& sol_avg_final, std::vector<float>& sol_rms_final);
+void ref_ratio0(std::vector<float>& sol1, const std::vector<float>& sol_avg_final);
+void ref_phase2_finals(unsigned int msize, unsigned long int number_frames, const std::vector<double>& avg, const std::vector<double>& rms,
+                       const std::vector<double>& gain, std::vector<float>& avg_final, std::vector<float>& rms_final,
+                       std::vector<float>& gain_final);
 /* cpp/lib/image_processing.ipp:10-49, instantiated for 16-bit frames in _ref/histc.o (see the Makefile) */
 namespace upsp {
 template <typename T>
@@ -401,6 +409,33 @@ int main(int argc, char** argv) {
       std::fwrite(A.data(), 4, A.size(), o);
       std::fclose(o);
       std::printf("frames %u coeffs %u\n", F, nc);
+    } else if (cmd == "finals") {    // DIR N F: DIR/{sum,sumsq}.f64 + DIR/first.f32 -> phase-1 avg | rms | frame-1 ratio; the same two double
+                                     // arrays + DIR/gain.f64 as phase-2 sums -> avg | rms | gain; six float arrays [N] in DIR/ref_finals.f32
+      if (argc < 5) return 2;
+      const std::string dir = argv[2];
+      const unsigned n = (unsigned)atoi(argv[3]);
+      const unsigned long F = (unsigned long)atol(argv[4]);
+      auto rdd = [&](const std::string& name) {
+        std::vector<double> v(n);
+        std::ifstream f(dir + "/" + name, std::ios::binary);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * 8));
+        if (!f) throw std::runtime_error("short file " + name);
+        return v;
+      };
+      const std::vector<double> sum = rdd("sum.f64"), sumsq = rdd("sumsq.f64"), gain = rdd("gain.f64");
+      std::vector<float> sol1(n);
+      {
+        std::ifstream f(dir + "/first.f32", std::ios::binary);
+        f.read(reinterpret_cast<char*>(sol1.data()), (std::streamsize)(n * 4));
+      }
+      std::vector<float> a1(n, 0.f), r1(n, 0.f), a2(n, 0.f), r2(n, 0.f), g2(n, 0.f);
+      ref_phase1_finals(n, F, sum, sumsq, a1, r1);
+      ref_ratio0(sol1, a1);
+      ref_phase2_finals(n, F, sum, sumsq, gain, a2, r2, g2);
+      FILE* o = std::fopen((dir + "/ref_finals.f32").c_str(), "wb");
+      for (const std::vector<float>* v : {&a1, &r1, &sol1, &a2, &r2, &g2}) std::fwrite(v->data(), 4, n, o);
+      std::fclose(o);
+      std::printf("nodes %u frames %lu\n", n, F);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

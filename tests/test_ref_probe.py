@@ -331,6 +331,36 @@ def test_detrend_design_matrix_equals_reference_code(probes, orc, tmp_path):
         assert np.all(ref[:F] == 1) and (F < 2 or ref[F + 1] == np.float32(1) / np.float32(F))
 
 
+def test_finals_equal_reference_code(probes, orc, tmp_path):
+    """double partial sums -> the float avg / rms the reference writes, for both phases, and its frame-1 Iref / I - 1 sample
+    (cpp/exec/psp_process.cpp:1933-1936, 1947-1949, 2543-2547 compiled from the reference tree) == orc_phase1_finals /
+    orc_phase2_finals and the expression tests/test_zz_deck_pipeline.py holds `intensity_ratio_0` to; NaN and zero sums included"""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    n, F = 500, 3071
+    sum_ = rng.uniform(-2e6, 6e6, n)
+    sumsq = rng.uniform(0, 4e9, n)
+    gain = rng.normal(50, 20, n)
+    first = rng.uniform(100, 4000, n).astype(np.float32)
+    sum_[:3], sumsq[:3], gain[:3], first[:3] = [np.nan, 0.0, 1e-300], [np.nan, 0.0, 1e-300], [np.nan, 0.0, -0.0], [1000.0, 0.0, 1.0]
+    for name, a in (("sum", sum_), ("sumsq", sumsq), ("gain", gain)):
+        a.tofile(tmp_path / f"{name}.f64")
+    first.tofile(tmp_path / "first.f32")
+    r = subprocess.run([probes[1], "finals", str(tmp_path), str(n), str(F)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a1, r1, ratio, a2, r2, g2 = np.fromfile(tmp_path / "ref_finals.f32", np.float32).reshape(6, n)
+    avg, rms = orc.phase1_finals(sum_, sumsq, F)
+    same = lambda a, b: np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
+    assert same(avg, a1) and same(rms, r1)
+    with np.errstate(all="ignore"):
+        want = ((avg / first).astype(np.float32).astype(np.float64) - 1.0).astype(np.float32)
+    assert same(want, ratio) and np.isnan(ratio[0]) and np.isnan(ratio[1])            # NaN / 1000, 0 / 0
+    rf, af, gf = (np.zeros(n, np.float32) for _ in range(3))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    orc.lib().orc_phase2_finals(p(sumsq), p(sum_), p(gain), n, C.c_uint(F), p(rf), p(af), p(gf))
+    assert same(af, a2) and same(rf, r2) and same(gf, g2)
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
