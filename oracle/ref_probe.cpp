@@ -18,7 +18,8 @@
 // camera weighters BestView / AverageViews (cpp/lib/projection.ipp:222-268, _ref/weighter.o, same way), and the model-temperature
 // lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way), and the per-node loop of its
 // detrend design matrix (cpp/lib/filtering.ipp:20-24, _ref/polymat.o, same way), the double -> float finals of both phases and the
-// frame-1 ratio sample (psp_process.cpp:1933-1936, :1947-1949, :2543-2547, _ref/finals.o, same way) and the per-node loop of its
+// frame-1 ratio sample (psp_process.cpp:1933-1936, :1947-1949, :2543-2547, _ref/finals.o, same way), P3DModel_::adjust_solution
+// (cpp/lib/P3DModel.ipp:146-155, _ref/adjust.o, same way) and the per-node loop of its
 // phase 2 (:2460-2498, _ref/phase2.o, same way; the Eigen solve inside the detrend fit is the oracle's, loaded with dlopen).
 #include <cstdio>
 #include <algorithm>
@@ -27,6 +28,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -56,6 +58,8 @@ void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float
 #include "phase2_prelude.h"
 /* cpp/lib/filtering.ipp:20-24 compiled into _ref/polymat.o (see the Makefile) */
 void ref_transpoly_fill(unsigned int n_frames_, unsigned int coeffs_, float* out);
+/* cpp/lib/P3DModel.ipp:146-155 compiled into _ref/adjust.o (see the Makefile) */
+void ref_adjust_solution(const std::map<unsigned int, std::vector<unsigned int>>& overlap_pts_, std::vector<float>& sol);
 /* psp_process.cpp:1933-1936, :1947-1949, :2543-2547 compiled into _ref/finals.o (see the Makefile) */
 void ref_phase1_finals(unsigned int msize, unsigned long int number_frames, const std::vector<double>& sol_avg_partial,
                        const std::vector<double>& sol_rms_partial, std::vector<float>& sol_avg_final, std::vector<float>& sol_rms_final);
@@ -436,6 +440,23 @@ int main(int argc, char** argv) {
       for (const std::vector<float>* v : {&a1, &r1, &sol1, &a2, &r2, &g2}) std::fwrite(v->data(), 4, n, o);
       std::fclose(o);
       std::printf("nodes %u frames %lu\n", n, F);
+    } else if (cmd == "adjust") {    // PAIRS.i32 [(node, other)] N OUT.f32: P3DModel_::adjust_solution on sol[i] = i, i.e. per node the index its
+                                     // value is copied from (the remap psp_setup_b200 writes for upsp_gpu_set_overlap_remap)
+      if (argc < 5) return 2;
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      std::vector<int32_t> pairs((size_t)f.tellg() / 4);
+      f.seekg(0);
+      f.read(reinterpret_cast<char*>(pairs.data()), (std::streamsize)(pairs.size() * 4));
+      std::map<unsigned int, std::vector<unsigned int>> overlap;
+      for (size_t k = 0; k + 1 < pairs.size(); k += 2) overlap[(unsigned)pairs[k]].push_back((unsigned)pairs[k + 1]);
+      const unsigned n = (unsigned)atoi(argv[3]);
+      std::vector<float> sol(n);
+      for (unsigned i = 0; i < n; ++i) sol[i] = (float)i;
+      ref_adjust_solution(overlap, sol);
+      FILE* o = std::fopen(argv[4], "wb");
+      std::fwrite(sol.data(), 4, n, o);
+      std::fclose(o);
+      std::printf("nodes %u groups %zu\n", n, overlap.size());
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

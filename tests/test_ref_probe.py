@@ -361,6 +361,25 @@ def test_finals_equal_reference_code(probes, orc, tmp_path):
     assert same(af, a2) and same(rf, r2) and same(gf, g2)
 
 
+def test_seam_remap_equals_reference_code(probes, tmp_path):
+    """P3DModel_::adjust_solution (cpp/lib/P3DModel.ipp:146-155, compiled from the reference tree over the reference's
+    std::map<node_idx, std::vector<node_idx>>) applied to sol[i] = i == the source-index array of host/p3d_model.hpp, which
+    psp_setup_b200 writes as remap.i32 and the GPU applies after every frame (upsp_gpu_set_overlap_remap): the reference's
+    3-zone unit-test grid and a sphere of zones with seams, poles (many nodes on one point) and a wrapped zone."""
+    from test_p3d_model import reference_fixture, run_probe, write_p3d
+    from test_zz_deck_pipeline import sphere_zones
+    n_groups = 0
+    for k, (zones, tol) in enumerate([(reference_fixture(), 1e-10), (reference_fixture(0.1), 0.100001), (sphere_zones(), 1e-3)]):
+        write_p3d(tmp_path / f"g{k}.x", zones)
+        info, src, pairs, _, _ = run_probe(probes[0], tmp_path / f"g{k}.x", tol, tmp_path / f"d{k}")
+        r = subprocess.run([probes[1], "adjust", str(tmp_path / f"d{k}.pairs"), str(len(src)), str(tmp_path / "sol.f32")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        sol = np.fromfile(tmp_path / "sol.f32", np.float32)
+        assert np.array_equal(sol.astype(np.int64), src.astype(np.int64)) and (sol != np.arange(len(src))).sum() > 0, k
+        n_groups += int(r.stdout.split()[-1])
+    assert n_groups > 20
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
