@@ -19,7 +19,7 @@
 // lines of the reference's main() (cpp/exec/psp_process.cpp:2287-2310, _ref/modeltemp.o, same way), and the per-node loop of its
 // detrend design matrix (cpp/lib/filtering.ipp:20-24, _ref/polymat.o, same way), the double -> float finals of both phases and the
 // frame-1 ratio sample (psp_process.cpp:1933-1936, :1947-1949, :2543-2547, _ref/finals.o, same way), P3DModel_::adjust_solution
-// (cpp/lib/P3DModel.ipp:146-155, _ref/adjust.o, same way) and the per-node loop of its
+// (cpp/lib/P3DModel.ipp:146-155, _ref/adjust.o, same way), the per-frame tail of phase 1 (psp_process.cpp:1823-1831, _ref/accum.o, same way) and the per-node loop of its
 // phase 2 (:2460-2498, _ref/phase2.o, same way; the Eigen solve inside the detrend fit is the oracle's, loaded with dlopen).
 #include <cstdio>
 #include <algorithm>
@@ -58,6 +58,9 @@ void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float
 #include "phase2_prelude.h"
 /* cpp/lib/filtering.ipp:20-24 compiled into _ref/polymat.o (see the Makefile) */
 void ref_transpoly_fill(unsigned int n_frames_, unsigned int coeffs_, float* out);
+/* psp_process.cpp:1823-1831 compiled into _ref/accum.o (see the Makefile) */
+void ref_phase1_accumulate(unsigned int msize, std::vector<float>& sol, const std::vector<unsigned int>& skipped,
+                           std::vector<double>& local_sol_rms, std::vector<double>& local_sol_avg);
 /* cpp/lib/P3DModel.ipp:146-155 compiled into _ref/adjust.o (see the Makefile) */
 void ref_adjust_solution(const std::map<unsigned int, std::vector<unsigned int>>& overlap_pts_, std::vector<float>& sol);
 /* psp_process.cpp:1933-1936, :1947-1949, :2543-2547 compiled into _ref/finals.o (see the Makefile) */
@@ -457,6 +460,32 @@ int main(int argc, char** argv) {
       std::fwrite(sol.data(), 4, n, o);
       std::fclose(o);
       std::printf("nodes %u groups %zu\n", n, overlap.size());
+    } else if (cmd == "accum") {     // SOLS.f32 [F][N] N SKIPPED.u32 OUT.f64: the per-frame tail of phase 1 over the blended camera solutions of F
+                                     // frames in order -> sum of squares [N] | sum [N] (double); the NaN-marked rows are written back to SOLS
+      if (argc < 6) return 2;
+      const unsigned n = (unsigned)atoi(argv[3]);
+      std::ifstream f(file, std::ios::binary | std::ios::ate);
+      const size_t F = (size_t)f.tellg() / 4 / n;
+      f.seekg(0);
+      std::ifstream sf(argv[4], std::ios::binary | std::ios::ate);
+      std::vector<unsigned int> skipped((size_t)sf.tellg() / 4);
+      sf.seekg(0);
+      sf.read(reinterpret_cast<char*>(skipped.data()), (std::streamsize)(skipped.size() * 4));
+      std::vector<double> rms(n, 0.0), avg(n, 0.0);
+      std::vector<float> sol(n), marked;
+      for (size_t k = 0; k < F; ++k) {
+        f.read(reinterpret_cast<char*>(sol.data()), (std::streamsize)(n * 4));
+        ref_phase1_accumulate(n, sol, skipped, rms, avg);
+        marked.insert(marked.end(), sol.begin(), sol.end());
+      }
+      FILE* o = std::fopen(argv[5], "wb");
+      std::fwrite(rms.data(), 8, n, o);
+      std::fwrite(avg.data(), 8, n, o);
+      std::fclose(o);
+      o = std::fopen((std::string(argv[5]) + ".sol").c_str(), "wb");
+      std::fwrite(marked.data(), 4, marked.size(), o);
+      std::fclose(o);
+      std::printf("frames %zu nodes %u skipped %zu\n", F, n, skipped.size());
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

@@ -380,6 +380,31 @@ def test_seam_remap_equals_reference_code(probes, tmp_path):
     assert n_groups > 20
 
 
+def test_phase1_accumulation_equals_reference_code(up, probes, orc, tmp_path):
+    """the per-frame tail of the reference's phase 1 -- NaN for the nodes no camera sees, then the double partial sums of sol^2
+    (float product) and sol -- compiled from its own lines (cpp/exec/psp_process.cpp:1823-1831) and run over the projected
+    frames of an oracle case with the NaN marks removed: the marks come back on the same nodes and orc_phase1's sums, which the
+    GPU's avg / rms are held against, have the same bits"""
+    from chain import Case
+    case = Case(up.synth, n_nodes=1500, n_frames=40, height=64, width=96, seed=4)
+    inten, s, q = orc.phase1(case.frames, case.csr, first_frame=0, interp=case.interp)
+    skipped = np.flatnonzero(np.isnan(inten[0])).astype(np.uint32)
+    assert 0 < len(skipped) < case.N // 10 and np.isnan(inten[:, skipped]).all()
+    plain = inten.copy()
+    plain[:, skipped] = 123.0                       # what project_frame leaves there does not matter: the reference overwrites it
+    plain.tofile(tmp_path / "sols.f32")
+    skipped.tofile(tmp_path / "skipped.u32")
+    r = subprocess.run([probes[1], "accum", str(tmp_path / "sols.f32"), str(case.N), str(tmp_path / "skipped.u32"), str(tmp_path / "o.f64")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["frames", str(case.F), "nodes", str(case.N), "skipped", str(len(skipped))], r.stderr
+    ref_q, ref_s = np.fromfile(tmp_path / "o.f64").reshape(2, case.N)
+    keep = ~np.isnan(s)
+    assert np.array_equal(np.isnan(ref_s), ~keep) and np.array_equal(np.isnan(ref_q), ~keep) and np.array_equal(np.flatnonzero(~keep), skipped)
+    assert np.array_equal(ref_s[keep].view(np.uint64), s[keep].view(np.uint64)) and np.array_equal(ref_q[keep].view(np.uint64), q[keep].view(np.uint64))
+    marked = np.fromfile(str(tmp_path / "o.f64") + ".sol", np.float32).reshape(case.F, case.N)
+    assert np.array_equal(np.isnan(marked), np.isnan(inten)) and np.array_equal(marked[:, keep], inten[:, keep])
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
