@@ -58,7 +58,8 @@ void ref_model_temperature(upsp::TunnelConditions& tcond, float* wall_out, float
 #include "phase2_prelude.h"
 /* cpp/lib/filtering.ipp:20-24 compiled into _ref/polymat.o (see the Makefile) */
 void ref_transpoly_fill(unsigned int n_frames_, unsigned int coeffs_, float* out);
-/* psp_process.cpp:1823-1831 compiled into _ref/accum.o (see the Makefile) */
+/* psp_process.cpp:1813-1819 and :1823-1831 compiled into _ref/accum.o (see the Makefile) */
+void ref_blend_cameras(unsigned int c, std::vector<float>& sol, const std::vector<float>& c_sols);
 void ref_phase1_accumulate(unsigned int msize, std::vector<float>& sol, const std::vector<unsigned int>& skipped,
                            std::vector<double>& local_sol_rms, std::vector<double>& local_sol_avg);
 /* cpp/lib/P3DModel.ipp:146-155 compiled into _ref/adjust.o (see the Makefile) */
@@ -486,6 +487,36 @@ int main(int argc, char** argv) {
       std::fwrite(marked.data(), 4, marked.size(), o);
       std::fclose(o);
       std::printf("frames %zu nodes %u skipped %zu\n", F, n, skipped.size());
+    } else if (cmd == "blend") {     // DIR N N_CAMS SKIPPED.u32 OUT.f32: DIR/cam<c>.sols.f32 [F][N] (each camera's project_frame result) summed per
+                                     // frame in camera order, then the NaN marks -> the intensity rows [F][N]
+      if (argc < 7) return 2;
+      const std::string dir = argv[2];
+      const unsigned n = (unsigned)atoi(argv[3]), n_cams = (unsigned)atoi(argv[4]);
+      std::ifstream sf(argv[5], std::ios::binary | std::ios::ate);
+      std::vector<unsigned int> skipped((size_t)sf.tellg() / 4);
+      sf.seekg(0);
+      sf.read(reinterpret_cast<char*>(skipped.data()), (std::streamsize)(skipped.size() * 4));
+      std::vector<std::vector<float>> cams(n_cams);
+      for (unsigned c = 0; c < n_cams; ++c) {
+        std::ifstream f(dir + "/cam" + std::to_string(c) + ".sols.f32", std::ios::binary | std::ios::ate);
+        cams[c].resize((size_t)f.tellg() / 4);
+        f.seekg(0);
+        f.read(reinterpret_cast<char*>(cams[c].data()), (std::streamsize)(cams[c].size() * 4));
+      }
+      const size_t F = cams[0].size() / n;
+      std::vector<double> rms(n, 0.0), avg(n, 0.0);
+      FILE* o = std::fopen(argv[6], "wb");
+      for (size_t k = 0; k < F; ++k) {
+        std::vector<float> sol;
+        for (unsigned c = 0; c < n_cams; ++c) {
+          const std::vector<float> c_sols(cams[c].begin() + (std::ptrdiff_t)(k * n), cams[c].begin() + (std::ptrdiff_t)((k + 1) * n));
+          ref_blend_cameras(c, sol, c_sols);
+        }
+        ref_phase1_accumulate(n, sol, skipped, rms, avg);
+        std::fwrite(sol.data(), 4, n, o);
+      }
+      std::fclose(o);
+      std::printf("frames %zu nodes %u cameras %u\n", F, n, n_cams);
     } else if (cmd == "peaks") {     // FILE.i32 SEPARATION: upsp::find_peaks on the counts and on 1/counts, first_min_threshold
       if (argc < 4) return 2;
       std::ifstream f(file, std::ios::binary | std::ios::ate);

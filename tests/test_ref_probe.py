@@ -405,6 +405,29 @@ def test_phase1_accumulation_equals_reference_code(up, probes, orc, tmp_path):
     assert np.array_equal(np.isnan(marked), np.isnan(inten)) and np.array_equal(marked[:, keep], inten[:, keep])
 
 
+def test_camera_blend_equals_reference_code(up, probes, orc, tmp_path):
+    """two weighted cameras on one grid: the reference's own lines that sum the camera solutions of a frame (float, camera
+    order; cpp/exec/psp_process.cpp:1813-1819) and mark unseen nodes, fed with each camera's projection alone (the oracle run
+    per camera, 0 where that camera sees nothing, as project_frame leaves it) == the oracle's two-camera intensity rows"""
+    from chain import Case
+    case = Case(up.synth, n_cams=2, n_nodes=1200, n_frames=12, height=64, width=96, seed=7)
+    both_, _, _ = orc.phase1(case.frames, case.csr, first_frame=0, interp=case.interp)
+    for c in range(2):
+        one, _, _ = orc.phase1([case.frames[c]], [case.csr[c]], first_frame=0, interp=case.interp)
+        np.nan_to_num(one, nan=0.0).astype(np.float32).tofile(tmp_path / f"cam{c}.sols.f32")
+    skipped = np.flatnonzero(np.isnan(both_[0])).astype(np.uint32)
+    skipped.tofile(tmp_path / "skipped.u32")
+    r = subprocess.run([probes[1], "blend", str(tmp_path), str(case.N), "2", str(tmp_path / "skipped.u32"), str(tmp_path / "o.f32")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = np.fromfile(tmp_path / "o.f32", np.float32).reshape(case.F, case.N)
+    seen = ~np.isnan(both_[0])
+    assert 0 < len(skipped) < case.N and np.array_equal(np.isnan(ref), np.isnan(both_))
+    assert np.array_equal(ref[:, seen].view(np.uint32), both_[:, seen].view(np.uint32))
+    a, b = (np.fromfile(tmp_path / f"cam{c}.sols.f32", np.float32).reshape(case.F, case.N) for c in range(2))
+    assert ((a != 0) & (b != 0)).any(0).sum() > 50                       # nodes both cameras contribute to
+
+
 def test_unpack_restatement_equals_reference_code(probes, orc, tmp_path):
     """a1: the reference's own upsp::unpack_12bit / unpack_10bit (cpp/lib/PSPVideo.cpp:111-150, compiled from the reference
     tree) against the CPU restatement the GPU decoder is held to, on random packed bytes (every bit pattern class)."""
