@@ -18,6 +18,10 @@ def probes(up, orc):
     ref = orc.build_ref()
     if ref is None or not os.path.exists(os.path.join(ref, "ref_probe")):
         pytest.skip("oracle/_ref/ref_probe not built and the reference tree is not present on this machine")
+    # the probe is linked with --unresolved-symbols=ignore-all (the unused drawing code of cv_extras.cpp): make sure none of the
+    # entry points compiled from reference lines (oracle/Makefile, ref_*) was left unresolved by a stale object
+    nm = subprocess.run(["nm", "-C", os.path.join(ref, "ref_probe")], capture_output=True, text=True).stdout
+    assert not [l for l in nm.splitlines() if " U ref_" in l or " U upsp::intensity_histc" in l or " U upsp::normal" in l or " U upsp::area" in l]
     return up.build.build_inputs_probe(), os.path.join(ref, "ref_probe")
 
 
