@@ -209,6 +209,17 @@ UPSP_API int upsp_gpu_kernel_ms(upsp_gpu_ctx* ctx, int kernel_class, float* mean
 UPSP_API int upsp_gpu_reset_run(upsp_gpu_ctx* ctx);
 /* number of kernels this context has launched since create */
 UPSP_API int upsp_gpu_launch_count(const upsp_gpu_ctx* ctx, long long* n);
+/* which projection kernel family the context settled on at its first batch (-1 before it):
+ * 0 = gather kernels (k_project_fused4 / k_project_fused / k_project_ell1 / k_project_csr),
+ * 1 = TMA-staged boxes cut from the decoded u16 frames (k_project_tma<0>),
+ * 2 = TMA-staged boxes cut from the packed 12-bit frames, no decode pass (k_project_tma<1> + k_hot_scan12).
+ * Same results bit for bit; bench.py labels its per-kernel figures with it. */
+UPSP_API int upsp_gpu_projection_mode(const upsp_gpu_ctx* ctx, int* mode);
+/* Debug timeline: with `on` != 0 every kernel of the following batches is bracketed with CUDA events on its
+ * own stream WITHOUT taking the batch out of the two-stream pipeline; upsp_gpu_timeline_read returns up to
+ * `max_records` records {kernel_class, start_ms, end_ms} (ms since the first recorded event) and the count. */
+UPSP_API int upsp_gpu_timeline(upsp_gpu_ctx* ctx, int on);
+UPSP_API int upsp_gpu_timeline_read(upsp_gpu_ctx* ctx, float* records3, int max_records, int* n_records);
 
 /* ---- multi-GPU wiring (one process per GPU; bytes are exchanged by the host, e.g. with
  *      torch.distributed / MPI_Allgather) ------------------------------------------------ */

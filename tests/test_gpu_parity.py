@@ -363,3 +363,58 @@ def test_error_behaviour(up, gpu):
     with pytest.raises(up.UpspGpuError):
         g.phase2([0] * 6, 1.0, 1.0, np.zeros(10), np.zeros(10))
     g.close()
+
+
+def _tma_case(synth, n_frames=150, seed=11):
+    """Hot configuration in miniature (one camera, packed 12-bit frames, bilinear registration, patches,
+    seam remap) with frames that leave the staged-box fast path: a rotation / a scale too large for the
+    box (every tap through global memory), shifts that push most of the box outside the image (zero
+    fill = BORDER_CONSTANT), a shift by several pixels (the box follows the frame's own origin)."""
+    case = Case(synth, n_frames=n_frames, n_nodes=9000, height=96, width=128, registration=True,
+                patches=True, overlap=True, seed=seed, fmt="p12")
+    w = case.warp[0].reshape(-1, 2, 3)
+    c, s = np.float32(np.cos(0.2)), np.float32(np.sin(0.2))
+    w[5] = [[c, -s, 9.0], [s, c, -14.0]]
+    w[17, :, 2] = (40.0, -30.0)
+    w[18] = [[1.3, 0.0, -11.0], [0.0, 1.3, -9.0]]
+    w[33, :, 2] = (-3.7, 2.2)
+    w[34, :, 2] = (-130.0, 5.0)          # everything outside
+    if n_frames > 70:
+        w[66, :, 2] = (0.4, 97.0)
+    return case
+
+
+@pytest.mark.parametrize("mode", ["v4", "tma16", "tma12"])
+@pytest.mark.parametrize("batch,capacity", [(0, 0), (8, 0), (12, 24)], ids=["one-batch", "batch8", "ring24"])
+def test_tma_projection_modes(up, orc, gpu, monkeypatch, mode, batch, capacity):
+    """k_project_tma (boxes staged by TMA from the decoded frames / from the packed frames) against the
+    oracle, bit for bit, and the mode that actually ran.  150 frames in one batch = table stages of
+    64 + 64 + 22 frames (a 2-frame tail group); batch 8 exercises both buffer sets; ring24 streams the
+    frames through a 24-slot input ring (the packed-source boxes are cut from the ring itself)."""
+    import upsp_b200
+    from chain import push_all, setup_ctx
+    monkeypatch.setenv("UPSP_PROJ", mode)
+    case = _tma_case(upsp_b200.synth)
+    ref = run_oracle(orc, case)
+    g, sl = setup_ctx(up, orc, case, batch_frames=batch, frame_capacity=capacity)
+    push_all(up, orc, g, case, sl, chunk=capacity if capacity else None)
+    assert g.projection_mode() == {"v4": 0, "tma16": 1, "tma12": 2}[mode]
+    g.finish_phase1()
+    avg, rms, cov = g.read_phase1_stats()
+    g.transpose()
+    it = g.read_intensity_transpose()
+    g.close()
+    assert same_bits(it, ref["itrans"])
+    assert same_bits(avg, ref["avg"]) and same_bits(rms, ref["rms"])
+
+
+def test_tma_projection_weighted_values(up, orc, gpu, monkeypatch):
+    """Projection values other than 1.0 (a weighted single camera) take the float-statistics variant."""
+    import upsp_b200
+    for mode in ("tma16", "tma12"):
+        monkeypatch.setenv("UPSP_PROJ", mode)
+        case = Case(upsp_b200.synth, n_frames=40, n_nodes=5000, height=96, width=128, registration=True,
+                    weights=True, seed=12, fmt="p12")
+        ref = run_oracle(orc, case)
+        got = run_gpu(up, orc, case)
+        assert same_bits(got["itrans"], ref["itrans"]) and same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])

@@ -265,6 +265,20 @@ class PspGpu:
     def reset_run(self):
         _chk(lib().upsp_gpu_reset_run(self._h))
 
+    def projection_mode(self) -> int:
+        m = C.c_int(-1)
+        _chk(lib().upsp_gpu_projection_mode(self._h, C.byref(m)))
+        return int(m.value)
+
+    def timeline(self, on=True):
+        _chk(lib().upsp_gpu_timeline(self._h, int(bool(on))))
+
+    def timeline_read(self, max_records=4096):
+        rec = np.zeros((max_records, 3), np.float32)
+        n = C.c_int(0)
+        _chk(lib().upsp_gpu_timeline_read(self._h, _p(rec), int(max_records), C.byref(n)))
+        return rec[:n.value].copy()
+
     def launch_count(self) -> int:
         n = C.c_longlong()
         _chk(lib().upsp_gpu_launch_count(self._h, C.byref(n)))

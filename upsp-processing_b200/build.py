@@ -18,12 +18,15 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xptxas=-v",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-O2",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+# translation units of the library (each compiled to its own object, in parallel)
+UNITS = ["upsp_gpu.cu", "proj_tma.cu"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".inc"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".inc", ".h"))] + [
         os.path.join(HERE, "..", "include", "upsp_gpu.h")]
 
 
@@ -34,20 +37,43 @@ def stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+def _deps(unit: str):
+    """Headers a translation unit depends on (coarse: every header of csrc/ + the public one)."""
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".inc", ".h"))]
+    return [os.path.join(CSRC, unit), os.path.join(HERE, "..", "include", "upsp_gpu.h")] + hdrs
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "upsp_gpu.cu")]
-    env = dict(os.environ)
-    # nvcc's host compiler must be the system gcc (the image's $CC wrapper lacks libgomp specs)
-    cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []   # the image's $CC wrapper lacks libgomp specs
+    procs, objs, log = [], [], []
+    for u in UNITS:
+        obj = os.path.join(OBJ_DIR, u.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(map(os.path.getmtime, _deps(u))):
+            continue
+        cmd = [NVCC] + NVCC_FLAGS + ccbin + ["-c", "-o", obj, os.path.join(CSRC, u)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        log.append(" ".join(cmd) + "\n" + out)
+        if verbose or pr.returncode:
+            sys.stderr.write(out)
+        failed = failed or pr.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libupsp_gpu.so")
+    cmd = [NVCC] + LINK_FLAGS + ccbin + ["-o", LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
-        raise RuntimeError("nvcc failed building libupsp_gpu.so")
+        raise RuntimeError("nvcc failed linking libupsp_gpu.so")
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        f.write("\n".join(log))
     return LIB
 
 

@@ -2,6 +2,7 @@
 // affine warp (K3a), fiducial patch (K3b).
 #pragma once
 #include "common.cuh"
+#include "pixel_ops.cuh"
 
 namespace upsp {
 
@@ -13,13 +14,6 @@ namespace upsp {
 // Layout: in = [frames][frame_bytes] packed, out = [frames][npix] u16.  One thread decodes
 // 8 pixels (12 packed bytes -> one 16-byte store).  grid = (ceil(npix/8/256), frames).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void note_hot(uint32_t v, size_t pix, int thresh, int* cnt, int* pos) {
-  if ((int)v >= thresh) {
-    int s = atomicAdd(cnt, 1);
-    if (s < UPSP_HOT_STORE) pos[s] = (int)pix;
-  }
-}
-
 __device__ __forceinline__ void fix_hot_frame(uint16_t* __restrict__ img, int rows, int cols,
                                               int n, int* __restrict__ pos, int min_change) {
   int loc[UPSP_HOT_STORE];
@@ -139,17 +133,6 @@ __device__ __noinline__ void note_hot_item(const uint16_t* px, size_t pix0, int 
 // owns the contiguous item range [b*chunk, (b+1)*chunk) of the batch (item = 32 pixels).
 // Hot-pixel hand-over: `done[f]` counts finished items of frame f; the block that completes a
 // frame applies its fixes.  Requires npix % 32 == 0, 16-byte aligned frames (host-checked).
-__device__ __forceinline__ void unpack12_x8(uint32_t w0, uint32_t w1, uint32_t w2, uint4& o) {
-  const uint32_t v0 = __byte_perm(w0, w1, 0x1201);
-  const uint32_t v1 = __byte_perm(w0, w1, 0x4534);
-  const uint32_t v2 = __byte_perm(w1, w2, 0x3423);
-  const uint32_t v3 = __byte_perm(w2, w2, 0x2312);
-  o.x = ((v0 >> 4) & 0x00000FFFu) | (v0 & 0x0FFF0000u);
-  o.y = ((v1 >> 4) & 0x00000FFFu) | (v1 & 0x0FFF0000u);
-  o.z = ((v2 >> 4) & 0x00000FFFu) | (v2 & 0x0FFF0000u);
-  o.w = ((v3 >> 4) & 0x00000FFFu) | (v3 & 0x0FFF0000u);
-}
-
 __global__ void __launch_bounds__(256, 6)
 k_unpack12_scan_p(const uint8_t* __restrict__ in, size_t in_stride, uint16_t* __restrict__ out,
                   size_t npix, int nframes, int thresh, int* __restrict__ hot_cnt,
@@ -308,29 +291,6 @@ __global__ void k_warp_tables(const float* __restrict__ m6, int nframes, int W, 
   }
 }
 
-template <typename LoadT>
-__device__ __forceinline__ float warp_sample_linear(const LoadT* __restrict__ src, int W, int H,
-                                                    int X, int Y) {
-  X >>= 5;
-  Y >>= 5;
-  const int sx = X >> 5, sy = Y >> 5;
-  const float fx = frac32_exact(X & 31), fy = frac32_exact(Y & 31);
-  if (sx >= W || sx + 1 < 0 || sy >= H || sy + 1 < 0) return 0.0f;
-  const float w0 = __fmul_rn(1.0f - fy, 1.0f - fx), w1 = __fmul_rn(1.0f - fy, fx);
-  const float w2 = __fmul_rn(fy, 1.0f - fx), w3 = __fmul_rn(fy, fx);
-  const bool x0 = sx >= 0, x1 = sx + 1 < W, y0 = sy >= 0, y1 = sy + 1 < H;
-  const LoadT* r0 = src + (size_t)(y0 ? sy : 0) * W;
-  const LoadT* r1 = src + (size_t)(y1 ? sy + 1 : 0) * W;
-  float v0 = (x0 && y0) ? u2f_exact(__ldg(r0 + sx)) : 0.0f;
-  float v1 = (x1 && y0) ? u2f_exact(__ldg(r0 + sx + 1)) : 0.0f;
-  float v2 = (x0 && y1) ? u2f_exact(__ldg(r1 + sx)) : 0.0f;
-  float v3 = (x1 && y1) ? u2f_exact(__ldg(r1 + sx + 1)) : 0.0f;
-  float s = __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
-  s = __fadd_rn(s, __fmul_rn(v2, w2));
-  s = __fadd_rn(s, __fmul_rn(v3, w3));
-  return s;
-}
-
 __device__ __forceinline__ uint32_t sat_u16_rn(float v) {   // v in [0, 65536): taps are u16, weights sum to 1
   int iv = f2i_rn_small(v);
   return (uint32_t)min(max(iv, 0), 65535);
@@ -366,6 +326,32 @@ __device__ __forceinline__ float warp_px_u16(const uint16_t* __restrict__ s, int
   }
   const float r = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);   // rint, half to even
   return fminf(fmaxf(r, 0.0f), 65535.0f);
+}
+
+// the same pixel from a PACKED 12-bit frame (+ its hot-pixel fix list): the decoded frame is never materialised
+__device__ __forceinline__ float warp_px_p12(const uint8_t* __restrict__ fr, const HotFix* __restrict__ h, int W, int H,
+                                             const int* __restrict__ tab, int x, int y, int interp) {
+  const int2 xa = __ldg(reinterpret_cast<const int2*>(tab) + x);
+  const int2 ya = __ldg(reinterpret_cast<const int2*>(tab + 2 * W) + y);
+  const int X = ya.x + xa.x, Y = ya.y + xa.y;
+  if (interp == 0) {
+    const int sx = X >> 10, sy = Y >> 10;
+    return ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H)
+               ? u2f_exact(px_packed12_fixed(fr, (unsigned)(sy * W + sx), h)) : 0.0f;
+  }
+  const int Xs = X >> 5, Ys = Y >> 5;
+  const int sx = Xs >> 5, sy = Ys >> 5;
+  const unsigned fxi = Xs & 31, fyi = Ys & 31;
+  uint32_t t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xx = sx + (k & 1), yy = sy + (k >> 1);
+    t[k] = ((unsigned)xx < (unsigned)W && (unsigned)yy < (unsigned)H) ? px_packed12_fixed(fr, (unsigned)(yy * W + xx), h) : 0u;
+  }
+  // 12-bit taps, weights k/1024: every product and partial sum of OpenCV's float sequence is exact, so the
+  // value is S/1024 rounded half to even (the same identity k_project_fused4 uses)
+  const unsigned S = (t[0] * (32u - fxi) + t[1] * fxi) * (32u - fyi) + (t[2] * (32u - fxi) + t[3] * fxi) * fyi;
+  return __fadd_rn(__fmaf_rn(__uint_as_float(S + 0x4B000000u), 0.0009765625f, 12574720.0f), -12582912.0f);
 }
 
 // 8 output pixels per thread (one 16-byte store).  Near-identity maps (the registration case:
@@ -514,7 +500,8 @@ constexpr int PATCH_WARPS = 4;
 __global__ void __launch_bounds__(32 * PATCH_WARPS)
 k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict__ frames,
         size_t npix, int W, int H, const int* __restrict__ tab, int interp, int skip_frame,
-        int nframes, int bstride, float* __restrict__ pv) {
+        int nframes, int bstride, float* __restrict__ pv, const uint8_t* __restrict__ packed = nullptr,
+        size_t frame_bytes = 0, const HotFix* __restrict__ hot = nullptr) {
   extern __shared__ float psh[];
   const int cl = cl_list[blockIdx.x];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -539,6 +526,11 @@ k_patch(PatchGeom g, const int* __restrict__ cl_list, const uint16_t* __restrict
     const int s = __ldg(g.bsrc + off + i);
     float v;
     if (s < 0) v = pv[(size_t)(-1 - s) * bstride + b];
+    else if (packed != nullptr) {      // packed 12-bit source (TMA projection mode): pixels + the frame's fix list
+      const uint8_t* fr = packed + (size_t)b * frame_bytes;
+      const HotFix* h = hot ? hot + b : nullptr;
+      v = t ? warp_px_p12(fr, h, W, H, t, s % W, s / W, interp) : u2f_exact(px_packed12_fixed(fr, (unsigned)s, h));
+    }
     else if (t) v = warp_px_u16(img, W, H, t, s % W, s / W, interp);
     else v = u2f_exact(__ldg(img + s));
     c[i] = v;

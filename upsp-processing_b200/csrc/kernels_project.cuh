@@ -4,6 +4,8 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "pixel_ops.cuh"
+#include "project_args.cuh"
 
 namespace upsp {
 
@@ -19,23 +21,6 @@ namespace upsp {
 // Pixel codes: >= 0 pixel index into the camera's u16 frame; <= -2 patched-pixel slot
 // (-2 - slot) into the f32 patch-value table (patched pixels are f32 in the reference,
 // patches.ipp:104-108,159); -1 (ELL-1 table only) "no entry for this camera".
-struct ProjCam {
-  const uint16_t* frames;  // [batch][npix] registered u16 frames of this batch
-  const float* frames32;   // or (filter after patching) the f32 image of the batch; overrides `frames`
-  size_t npix;
-  const float* pv;         // [slots][bstride] patch values of this batch (or nullptr)
-  const int* code;         // ELL-1: [N]; CSR: [nnz]
-  const float* val;
-  const int* rowptr;       // CSR only: [N+1]
-};
-struct ProjArgs {
-  int n_cams, n_nodes, nframes, bstride;
-  ProjCam cam[UPSP_MAX_CAMS];
-  float* out;      // first row of this batch in the frame-major intensity buffer [F][N]
-  double* sum;     // [N]  += over the batch
-  double* sumsq;   // [N]
-};
-
 __device__ __forceinline__ float fetch_px(const ProjCam& c, int code, int b, int bstride) {
   if (code >= 0)
     return c.frames32 ? __ldg(c.frames32 + (size_t)b * c.npix + code)
@@ -156,55 +141,6 @@ k_project_csr(const ProjArgs a) {
 //     belongs to another GPU).  The frame-major intensity buffer and the separate transpose
 //     pass (8N bytes per frame) disappear; the exchange overlaps phase-1 compute.
 // Reference: psp_process.cpp:1790-1842 + local_transpose/global_transpose :647-771.
-struct FusedCam {
-  const uint16_t* frames;  // [batch][npix] decoded, hot-pixel-fixed frames (NOT registered)
-  size_t npix;
-  int W, H;
-  const int* tab;          // [batch][2W+2H] warp tables, or nullptr (registration = none)
-  const float* m6;         // [batch][6] the 2x3 maps the tables were built from (k_project_fused3)
-  const float* pv;         // [slots][bstride] patch values
-  const int* code;         // [N]
-  const float* val;        // [N]
-};
-struct FusedArgs {
-  int n_cams, n_nodes, nframes, bstride, interp, skip_frame;
-  FusedCam cam[UPSP_MAX_CAMS];
-  double* sum;
-  double* sumsq;
-  const int* perm;                     // [N] processing order: nodes sorted by pixel index (raster),
-                                       // so a warp gathers from one or two image rows
-  int n_ranks, f_total, col0;          // col0 = global frame index of the batch's first frame
-  float* dst[UPSP_MAX_RANKS];          // node-major [N_s][F] buffer of every rank
-  int node_start[UPSP_MAX_RANKS + 1];
-  // staged exchange (n_ranks > 1, pipelined): rows of nodes owned by the ranks in `stage_mask` are
-  // written to a local [N][stage_stride] staging block (column = frame inside the batch) and shipped
-  // to their owners by copy engines afterwards; the other ranks' rows go straight into the
-  // peer-mapped buffers.  Copy engines and SM stores then drive NVLink side by side.
-  float* stage;
-  int stage_stride, rank;
-  unsigned stage_mask;                 // bit r set: rank r's rows go through the staging block
-};
-
-// where a block writes node n's row segment of this batch (frame b of the batch at [b])
-__device__ __forceinline__ float* fused_row_ptr(const FusedArgs& a, int n) {
-  int r = 0;
-  while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-  if (a.stage != nullptr && ((a.stage_mask >> r) & 1u)) return a.stage + (size_t)n * a.stage_stride;
-  return a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
-}
-
-// border / nearest-neighbour pixels: rare, kept out of the hot loop's code
-__device__ __noinline__ float warp_px_slow(const uint16_t* __restrict__ s, int W, int H, int X, int Y,
-                                           int interp) {
-  if (interp == 0) {
-    const int sx = X >> 10, sy = Y >> 10;
-    return ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H) ? (float)s[(size_t)sy * W + sx] : 0.0f;
-  }
-  const float v = warp_sample_linear<uint16_t>(s, W, H, X, Y);
-  const float r = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);
-  return fminf(fmaxf(r, 0.0f), 65535.0f);
-}
-
 // ---- building blocks of the fused kernel: U consecutive frames of one camera for one node.
 // Every global load of a group is issued before any result is consumed (2U table loads, then
 // 4U tap loads in flight per thread); with one camera the table loads of group g+1 are issued

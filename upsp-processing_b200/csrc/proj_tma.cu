@@ -1,0 +1,60 @@
+// proj_tma.cu -- translation unit of the TMA-staged projection kernels (kernels_project_tma.cuh).
+#include "proj_tma.h"
+
+#include <cstdlib>
+
+#include "kernels_project_tma.cuh"
+
+namespace upsp {
+
+TmaGeom tma_geom() {
+  TmaGeom g;
+  g.nodes_per_block = TMA_NB;
+  g.strip_rows = TMA_TH;
+  g.tile_cols = TMA_TW;
+  g.box_rows = TMA_BH;
+  g.box_px16 = TMA_BW16;
+  g.box_words12 = TMA_BWB12 / 4;
+  return g;
+}
+
+template <int SRC, int CH, bool VAL1, int VAR = 0>
+static cudaError_t launch1(const CUtensorMap& map, const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
+  constexpr int smem = TmaSmem<SRC, CH, VAR == 1 ? 6 : TMA_NG>::total;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  k_project_tma<SRC, CH, VAL1, VAR><<<nblocks, TMA_NB, smem, st>>>(map, a, ex);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map, const FusedArgs& a,
+                               const TmaExtra& ex, int nblocks, cudaStream_t st) {
+  if (nblocks <= 0) return cudaSuccess;
+  static const int var = getenv("UPSP_TMA_VAR") ? atoi(getenv("UPSP_TMA_VAR")) : 0;
+  if (var == 1 && src == 0 && !seg128 && val1) return launch1<0, 16, true, 1>(map, a, ex, nblocks, st);
+  if (var == 2 && src == 0 && !seg128 && val1) return launch1<0, 16, true, 2>(map, a, ex, nblocks, st);
+#define UPSP_TMA_CASE(S, C)                                                  \
+  return val1 ? launch1<S, C, true>(map, a, ex, nblocks, st) : launch1<S, C, false>(map, a, ex, nblocks, st)
+  if (src == 0) {
+    if (seg128) UPSP_TMA_CASE(0, 32);
+    UPSP_TMA_CASE(0, 16);
+  }
+  if (seg128) UPSP_TMA_CASE(1, 32);
+  UPSP_TMA_CASE(1, 16);
+#undef UPSP_TMA_CASE
+}
+
+cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
+                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st) {
+  k_hot_scan12<<<grid, 256, 0, st>>>(in, in_stride, npix, nframes, thresh, hot_cnt, hot_pos, done, rows, cols,
+                                     reinterpret_cast<HotFix*>(fixes));
+  return cudaGetLastError();
+}
+
+size_t hot_fix_bytes() { return sizeof(HotFix); }
+
+}  // namespace upsp

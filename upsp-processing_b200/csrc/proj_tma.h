@@ -1,0 +1,46 @@
+// proj_tma.h -- host interface of the TMA-staged projection kernels (proj_tma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "project_args.cuh"
+
+namespace upsp {
+
+// geometry of the staged boxes (the host builds the block partition and the tensor maps from these)
+struct TmaGeom {
+  int nodes_per_block;   // TMA_NB
+  int strip_rows;        // TMA_TH
+  int tile_cols;         // TMA_TW: widest column span of a block's node pixels
+  int box_rows;          // TMA_BH
+  int box_px16;          // SRC 0: box width in u16 pixels
+  int box_words12;       // SRC 1: box width in 32-bit words of packed bytes
+};
+TmaGeom tma_geom();
+
+struct TmaBlock {        // nodes [node0, node0+count) of the processing order, all with a plain pixel
+  int node0, count;
+  int xmin, xmax;        // column range of the block's node pixels (xmax - xmin <= tile_cols)
+  int ymin, ymax;        // row range (ymax - ymin < strip_rows)
+  int pad0, pad1;
+};
+
+struct HotFix;           // pixel_ops.cuh
+
+struct TmaExtra {
+  const TmaBlock* blk;
+  const uint8_t* packed;        // SRC 1: packed frames of the batch (slow path), stride frame_bytes
+  size_t frame_bytes;
+  int frame0;                   // slot of the batch's first frame in the tensor map (third TMA coordinate)
+  const HotFix* hot;            // SRC 1: [batch] fix lists (nullptr: hot-pixel fix off)
+};
+
+// src 0: decoded u16 frames, 1: packed 12-bit frames.  seg128: 128-byte row segments (peer stores).
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map, const FusedArgs& a,
+                               const TmaExtra& ex, int nblocks, cudaStream_t st);
+// hot-pixel scan of packed 12-bit frames -> fix lists (read only)
+cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
+                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st);
+size_t hot_fix_bytes();
+
+}  // namespace upsp

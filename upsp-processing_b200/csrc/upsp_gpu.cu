@@ -30,6 +30,7 @@
 #include "kernels_project.cuh"
 #include "kernels_setup.cuh"
 #include "kernels_transpose.cuh"
+#include "proj_tma.h"
 
 using namespace upsp;
 
@@ -94,6 +95,9 @@ struct DriverApi {
   CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
   CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
   CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
   bool ok = false;
 };
 
@@ -118,6 +122,12 @@ static DriverApi& drv() {
     get("cuMemImportFromShareableHandle", (void**)&d.MemImportFromShareableHandle);
     get("cuMemGetAllocationGranularity", (void**)&d.MemGetAllocationGranularity);
     d.ok = ok;
+    {   // TMA descriptors (projection kernels); absence only disables those kernels
+      cudaDriverEntryPointQueryResult q;
+      void* fn = nullptr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr)
+        d.TensorMapEncodeTiled = reinterpret_cast<decltype(d.TensorMapEncodeTiled)>(fn);
+    }
   }
   return d;
 }
@@ -245,6 +255,12 @@ struct Camera {
   int* d_code = nullptr;
   float* d_val = nullptr;
   int* d_rowptr = nullptr;
+  std::vector<int> h_code;     // ELL-1 table as uploaded (block partition of the TMA projection)
+  std::vector<float> h_val;
+  // TMA projection: descriptors of the two decoded work buffers / of the packed input store; fix lists per buffer set
+  CUtensorMap tmap16[2];
+  CUtensorMap tmap12;
+  void* d_fix[2] = {nullptr, nullptr};
 };
 
 struct upsp_gpu_ctx {
@@ -262,6 +278,13 @@ struct upsp_gpu_ctx {
   uint16_t* d_lut = nullptr;
   int lut_max = 0;        // largest entry of the 10->12-bit table (0 = no table)
   int* d_perm = nullptr;  // fused mode: node processing order (Morton order of the nodes' pixels)
+  // TMA-staged projection (kernels_project_tma.cuh): 0 = off (gather kernels), 1 = boxes from the decoded u16 frames,
+  // 2 = boxes from the packed 12-bit frames (no decode pass).  Decided at the first batch (needs the pixel format).
+  int proj_mode = -1;
+  int* d_perm_tma = nullptr;      // plain-pixel nodes in block order, then the others
+  TmaBlock* d_tma_blk = nullptr;
+  int n_tma_blocks = 0, n_tma_plain = 0;
+  bool tma_val1 = false;
 
   cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
   // front-end stream (decode + hot pixels + patch of batch i+1 while the fused projection of batch i
@@ -289,6 +312,7 @@ struct upsp_gpu_ctx {
   std::vector<ProcRec> proc_recs;                // recent process_frames calls (input-ring reuse)
   size_t proc_next = 0;
   // sampled per-kernel timing
+  bool timeline = false;          // bracket every kernel, keep the pipeline overlapped (upsp_gpu_timeline)
   int sample_every = 0;
   long batch_counter = 0;
   std::vector<cudaEvent_t> kev;   // event pairs
@@ -542,6 +566,8 @@ static void free_camera(Camera& cam) {
   cudaFree(cam.d_filt16);
   cudaFree(cam.d_slot_pix);
   cudaFree(cam.d_code);
+  cudaFree(cam.d_fix[0]);
+  cudaFree(cam.d_fix[1]);
   cudaFree(cam.d_val);
   cudaFree(cam.d_rowptr);
 }
@@ -559,6 +585,8 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   for (auto& cam : c->cams) free_camera(cam);
   cudaFree(c->d_lut);
   cudaFree(c->d_perm);
+  cudaFree(c->d_perm_tma);
+  cudaFree(c->d_tma_blk);
   cudaFree(c->d_intensity);
   if (c->shared_vmm.handle) vmm_free(c->shared_vmm); else cudaFree(c->d_shared);
   if (c->ptrans_owned) cudaFree(c->d_ptrans);
@@ -929,6 +957,10 @@ static int finalize(upsp_gpu_ctx* c) {
     }
     TRY(upload(&k.d_code, code.data(), code.size()));
     TRY(upload(&k.d_val, val.data(), val.size()));
+    if (c->ell1) {
+      k.h_code = code;
+      k.h_val = val;
+    }
     // coverage = sum_c project(ones) (psp_process.cpp:1953-1966), then adjust_solution (:1974)
     for (int n = 0; n < N; ++n) {
       const int s = c->remap.empty() ? n : c->remap[n];
@@ -1049,6 +1081,123 @@ static int finalize(upsp_gpu_ctx* c) {
     }
   }
   c->finalized = true;
+  return UPSP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged projection: block partition + tensor maps (kernels_project_tma.cuh)
+// ------------------------------------------------------------------------------------------
+static int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2 = 1) {
+  DriverApi& d = drv();
+  REQUIRE(d.TensorMapEncodeTiled != nullptr, UPSP_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {b0, b1, b2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = d.TensorMapEncodeTiled(m, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, UPSP_ERR_CUDA, "cuTensorMapEncodeTiled -> %d", (int)r);
+  return UPSP_OK;
+}
+
+// Decide the projection mode of a fused single-camera context and build what the TMA kernels need:
+//   * processing order: nodes with a plain pixel, cut into blocks of <= 128 nodes whose pixels lie in one
+//     strip of `strip_rows` image rows and span <= `tile_cols` columns (so that the box a block stages per
+//     frame has a fixed size), raster order inside a block; then the nodes without a plain pixel
+//     (patched / unseen), which k_project_fused4 handles;
+//   * tensor maps over the decoded work buffers (mode 1) or the packed input store (mode 2).
+// UPSP_PROJ = v4 | tma16 | tma12 overrides the choice (A/B measurements and the parity test that pins the
+// three to identical bits).
+static int ensure_proj_mode(upsp_gpu_ctx* c) {
+  if (c->proj_mode >= 0) return UPSP_OK;
+  c->proj_mode = 0;
+  if (!c->fused || c->cams.size() != 1 || c->registration == UPSP_REG_NONE || c->interp != UPSP_INTERP_LINEAR) return UPSP_OK;
+  Camera& k = c->cams[0];
+  const bool pix13 = k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 8192);
+  if (!pix13 || (size_t)c->batch * k.npix >= ((size_t)1 << 31) || (size_t)c->batch * (size_t)(k.W + k.H) >= ((size_t)1 << 31))
+    return UPSP_OK;
+  if (drv().TensorMapEncodeTiled == nullptr) return UPSP_OK;
+  const bool ok16 = k.W % 8 == 0;
+  const bool ok12 = k.format == UPSP_PIX_PACKED12 && k.W % 32 == 0 && k.npix % 32 == 0 && k.frame_bytes % 16 == 0 &&
+                    c->registration == UPSP_REG_GIVEN && c->pipelined;
+  int want = ok12 ? 2 : (ok16 ? 1 : 0);
+  if (getenv("UPSP_FUSED_V1") && atoi(getenv("UPSP_FUSED_V1"))) want = 0;
+  if (const char* e = getenv("UPSP_PROJ")) {
+    if (!strcmp(e, "v4")) want = 0;
+    else if (!strcmp(e, "tma16")) want = ok16 ? 1 : 0;
+    else if (!strcmp(e, "tma12")) want = ok12 ? 2 : (ok16 ? 1 : 0);
+  }
+  if (want == 0) return UPSP_OK;
+  const TmaGeom g = tma_geom();
+  const int N = c->N, W = k.W;
+  std::vector<int> plain, other;
+  for (int n = 0; n < N; ++n) (k.h_code[n] >= 0 ? plain : other).push_back(n);
+  std::vector<std::pair<uint64_t, int>> keyed(plain.size());
+  for (size_t i = 0; i < plain.size(); ++i) {
+    const int code = k.h_code[plain[i]], y = code / W, x = code % W;
+    keyed[i] = {((uint64_t)(y / g.strip_rows) << 42) | ((uint64_t)x << 21) | (uint64_t)y, plain[i]};
+  }
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<TmaBlock> blocks;
+  std::vector<int> perm;
+  perm.reserve(N);
+  bool val1 = true;
+  size_t i = 0;
+  while (i < keyed.size()) {
+    const int code0 = k.h_code[keyed[i].second];
+    const int strip = (code0 / W) / g.strip_rows, x0 = code0 % W;
+    size_t j = i;
+    int ymin = 1 << 30, ymax = -1, xmax = x0;
+    while (j < keyed.size() && (int)(j - i) < g.nodes_per_block) {
+      const int code = k.h_code[keyed[j].second], y = code / W, x = code % W;
+      if (y / g.strip_rows != strip || x - x0 > g.tile_cols) break;
+      ymin = std::min(ymin, y);
+      ymax = std::max(ymax, y);
+      xmax = std::max(xmax, x);
+      ++j;
+    }
+    std::vector<std::pair<int, int>> blk;      // (pixel, node): raster order inside the block
+    for (size_t q = i; q < j; ++q) blk.push_back({k.h_code[keyed[q].second], keyed[q].second});
+    std::sort(blk.begin(), blk.end());
+    TmaBlock b{};
+    b.node0 = (int)perm.size();
+    b.count = (int)blk.size();
+    b.xmin = x0;
+    b.xmax = xmax;
+    b.ymin = ymin;
+    b.ymax = ymax;
+    blocks.push_back(b);
+    for (auto& e : blk) {
+      perm.push_back(e.second);
+      val1 = val1 && k.h_val[e.second] == 1.0f;
+    }
+    i = j;
+  }
+  c->n_tma_plain = (int)perm.size();
+  c->n_tma_blocks = (int)blocks.size();
+  c->tma_val1 = val1;
+  perm.insert(perm.end(), other.begin(), other.end());
+  TRY(upload(&c->d_perm_tma, perm.data(), perm.size()));
+  TRY(upload(&c->d_tma_blk, blocks.data(), blocks.size()));
+  if (want == 1) {
+    uint16_t* bufs[2] = {k.d_work, k.d_work2 ? k.d_work2 : k.d_work};
+    for (int b = 0; b < 2; ++b)
+      TRY(encode_tmap(&k.tmap16[b], CU_TENSOR_MAP_DATA_TYPE_UINT16, bufs[b], (uint64_t)k.W, (uint64_t)k.H, (uint64_t)c->batch,
+                      (uint64_t)k.W * 2, (uint64_t)k.npix * 2, (uint32_t)g.box_px16, (uint32_t)g.box_rows,
+                      (getenv("UPSP_TMA_VAR") && atoi(getenv("UPSP_TMA_VAR")) == 2) ? 4 : 1));
+  } else {
+    const uint64_t row_bytes = (uint64_t)k.W * 3 / 2;
+    TRY(encode_tmap(&k.tmap12, CU_TENSOR_MAP_DATA_TYPE_UINT32, k.d_in, row_bytes / 4, (uint64_t)k.H, (uint64_t)c->capacity,
+                    row_bytes, (uint64_t)k.frame_bytes, (uint32_t)g.box_words12, (uint32_t)g.box_rows));
+    for (int b = 0; b < 2; ++b) {
+      CU(cudaMalloc(&k.d_fix[b], (size_t)c->batch * hot_fix_bytes()));
+      CU(cudaMemset(k.d_fix[b], 0, (size_t)c->batch * hot_fix_bytes()));
+    }
+  }
+  c->proj_mode = want;
   return UPSP_OK;
 }
 
@@ -1178,18 +1327,22 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   pa.sumsq = c->d_sumsq;
   const int slot = off % c->capacity;
   REQUIRE(slot + nb <= c->capacity, UPSP_ERR_STATE, "batch wraps the input ring");
-  const bool prof = c->sample_every > 0 && (c->batch_counter++ % c->sample_every) == 0;
+  for (size_t ci = 0; ci < c->cams.size(); ++ci)
+    REQUIRE(c->cams[ci].format >= 0, UPSP_ERR_STATE, "camera %zu has no frames pushed", ci);
+  TRY(ensure_proj_mode(c));
+  const bool serial = c->sample_every > 0 && !c->timeline && (c->batch_counter++ % c->sample_every) == 0;
+  const bool prof = serial || c->timeline;
   // pipeline: buffer set `bs`, front end on stream SB; it may start once the fused kernel that last
   // read this buffer set (two batches ago) is done
   // A batch whose kernels are being timed (upsp_gpu_set_kernel_sampling) runs un-overlapped: its
   // front end goes on the main stream, and the next batch's front end waits for its projection, so the
   // CUDA-event durations are those of the kernels alone (they are what the roofline figures use).
   const int bs = c->pipelined ? (int)(c->pipe_batches & 1) : 0;
-  cudaStream_t SB = (c->pipelined && !prof) ? c->stream_b : c->stream;
+  cudaStream_t SB = (c->pipelined && !serial) ? c->stream_b : c->stream;
   if (c->pipelined) {
     CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
     if (c->last_sampled) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
-    c->last_sampled = prof;
+    c->last_sampled = serial;
   }
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
     Camera& k = c->cams[ci];
@@ -1202,7 +1355,15 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     CU(cudaMemsetAsync(w_hot_cnt, 0, (size_t)2 * c->batch * sizeof(int), SB));
     int* done = c->hot_fix ? w_hot_cnt + c->batch : nullptr;
     const uint8_t* in = k.d_in + (size_t)slot * k.frame_bytes;
+    const bool src12 = c->proj_mode == 2;       // the projection reads the packed frames itself: scan only
     KBEGIN_ON(0, SB);
+    if (src12) {
+      if (c->hot_fix) {
+        CU(launch_hot_scan12(in, k.frame_bytes, k.npix, nb, thresh, w_hot_cnt, w_hot_pos, w_hot_cnt + c->batch, k.H, k.W,
+                             k.d_fix[bs], c->n_sm * 2, SB));
+        KCHECK(c);
+      }
+    } else {
     static const int decode_p = getenv("UPSP_DECODE_P") ? atoi(getenv("UPSP_DECODE_P")) : -1;
     const bool persistent = (decode_p < 0 ? c->pipelined : decode_p != 0) && k.format == UPSP_PIX_PACKED12 &&
                             k.npix % 32 == 0 && k.frame_bytes % 16 == 0 && (k.npix / 32) * (size_t)nb < ((size_t)1 << 31);
@@ -1221,6 +1382,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
           (const uint16_t*)in, k.npix, w_work, k.npix, thresh, w_hot_cnt, w_hot_pos, done, k.H, k.W);
     }
     KCHECK(c);
+    }
     KEND_ON(SB);
     const bool reg = c->registration != UPSP_REG_NONE;
     if (c->registration == UPSP_REG_PIXEL) {
@@ -1253,7 +1415,8 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         if (!ncl) continue;
         k_patch<<<dim3(ncl, cdiv(nb, PATCH_WARPS)), 32 * PATCH_WARPS, sm, SB>>>(
             k.geom, k.d_cl_list + k.level_off[l], cur, k.npix, k.W, k.H,
-            (reg && c->fused) ? tabs : nullptr, c->interp, skip_frame, nb, c->batch, w_pv);
+            (reg && c->fused) ? tabs : nullptr, c->interp, skip_frame, nb, c->batch, w_pv, src12 ? in : nullptr,
+            k.frame_bytes, (src12 && c->hot_fix) ? reinterpret_cast<const HotFix*>(k.d_fix[bs]) : nullptr);
         KCHECK(c);
       }
       KEND_ON(SB);
@@ -1353,6 +1516,35 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
       pix13 = pix13 && (k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 8192));
       max_elems = std::max(max_elems, (size_t)c->batch * k.npix);
       max_elems = std::max(max_elems, (size_t)c->batch * (size_t)(k.W + k.H));
+    }
+    if (c->proj_mode > 0) {
+      // TMA-staged boxes for the nodes with a plain pixel, k_project_fused4 for the rest (patched / unseen nodes)
+      Camera& k = c->cams[0];
+      const bool seg128 = c->R > 1 && c->staged_peers < c->R - 1;
+      fa.perm = c->d_perm_tma;
+      TmaExtra ex{};
+      ex.blk = c->d_tma_blk;
+      if (c->proj_mode == 2) {
+        ex.packed = k.d_in + (size_t)slot * k.frame_bytes;
+        ex.frame_bytes = k.frame_bytes;
+        ex.frame0 = slot;
+        ex.hot = c->hot_fix ? reinterpret_cast<const HotFix*>(k.d_fix[bs]) : nullptr;
+        fa.cam[0].frames = nullptr;
+      }
+      CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex,
+                            c->n_tma_blocks, c->stream));
+      c->launches++;
+      const int n_other = c->N - c->n_tma_plain;
+      if (n_other > 0) {
+        FusedArgs fb = fa;
+        fb.perm = c->d_perm_tma + c->n_tma_plain;
+        fb.n_nodes = n_other;
+        if (seg128) k_project_fused4<1, 128, 32><<<cdiv(n_other, 128), 128, 0, c->stream>>>(fb);
+        else k_project_fused4<1, 128, 16><<<cdiv(n_other, 128), 128, 0, c->stream>>>(fb);
+        KCHECK(c);
+      }
+      KEND();
+      return UPSP_OK;
     }
     if (!fused_v1 && regk && pix13 && c->interp == UPSP_INTERP_LINEAR && max_elems < ((size_t)1 << 31)) {
       const unsigned g2 = cdiv(c->N, 128);
@@ -1992,6 +2184,37 @@ extern "C" int upsp_gpu_kernel_ms(upsp_gpu_ctx* c, int cls, float* mean_ms, int*
   }
   *mean_ms = n ? (float)(tot / n) : 0.0f;
   *n_sampled = n;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_projection_mode(const upsp_gpu_ctx* c, int* mode) {
+  REQUIRE(c && mode, UPSP_ERR_INVALID, "null argument");
+  *mode = c->proj_mode;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_timeline(upsp_gpu_ctx* c, int on) {
+  ENTER(c);
+  CU(cudaDeviceSynchronize());
+  c->timeline = on != 0;
+  c->kn = 0;
+  return UPSP_OK;
+}
+
+extern "C" int upsp_gpu_timeline_read(upsp_gpu_ctx* c, float* rec, int max_records, int* n_records) {
+  ENTER(c);
+  REQUIRE(rec && n_records, UPSP_ERR_INVALID, "null argument");
+  CU(cudaDeviceSynchronize());
+  int n = 0;
+  for (size_t i = 0; i < c->kn && n < max_records; ++i, ++n) {
+    float a = 0.0f, b = 0.0f;
+    CU(cudaEventElapsedTime(&a, c->kev[0], c->kev[2 * i]));
+    CU(cudaEventElapsedTime(&b, c->kev[0], c->kev[2 * i + 1]));
+    rec[3 * n] = (float)c->kcls[i];
+    rec[3 * n + 1] = a;
+    rec[3 * n + 2] = b;
+  }
+  *n_records = n;
   return UPSP_OK;
 }
 
