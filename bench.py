@@ -187,6 +187,109 @@ def run_step_resident(g, wl, args, dist, trace=None):
         trace.append([round((b - a) * 1e3, 2) for a, b in zip(t[:-1], t[1:])])
 
 
+# ------------------------------------------------------------------------------------------
+def parity_check(g, wl, args, rank, world, dist, n_rows=192, frames_per_rank=24, n_rows_p2=48):
+    """--check: after the last timed step every rank compares what IT holds with the CPU oracle
+    (oracle/ = checker only), on the real multi-process path:
+      1. intensity_transpose[sampled local nodes, sampled frames of EVERY rank's frame slice] bit-exact
+         vs the oracle's phase 1 of those frames (decode, hot pixels, warp, patch, projection; the
+         columns written by the peers over NVLink are checked on the rank that received them);
+      2. avg / rms of the sampled nodes == finals of the sums of the rank's FULL rows, summed per
+         rank slice in rank order like the device (a checksum over every column of the row: with
+         unit projection values the sums are exact integers);
+      3. pressure_transpose rows of a subset == the oracle's phase 2 on the same intensity rows:
+         max_f |dCp| / max_f |Cp_ref| per node (the north-star metric) and the
+         operand-scale figure of DESIGN.md section 4.
+    Reference semantics: psp_process.cpp:707-771, 1866-1872.  Returns a dict; "ok" False fails the run."""
+    from oracle import oracle as orc
+    from upsp_b200 import synth
+    orc.build()
+    orc.set_num_threads(max(1, host_threads() // world))
+    H, W, N, D = args.height, args.width, args.nodes, args.distinct
+    F_local, F_total = args.frames, args.frames * world
+    nl, n0 = g.n_local_nodes, g.first_node
+    rng = np.random.default_rng(4242 + rank)
+    rows = np.unique(np.concatenate([[0, nl - 1], rng.integers(0, nl, n_rows)])).astype(np.int64)
+    itr = np.empty((rows.size, F_total), np.float32)
+    ptr = np.empty((rows.size, F_total), np.float32)
+    one = np.empty((1, F_total), np.float32)
+    for i, r in enumerate(rows):
+        g.read_intensity_transpose(int(r), 1, out=one)
+        itr[i] = one[0]
+        g.read_pressure_transpose(int(r), 1, out=one)
+        ptr[i] = one[0]
+    avg, rms, cov = g.read_phase1_stats()
+    rms2, avg2, gain = g.read_phase2_stats()
+    gl = rows + n0                                   # global node ids
+    res = {"rank": rank, "rows": int(rows.size)}
+
+    # ---- 1. sampled columns of every rank's slice through the oracle's phase 1
+    rowptr, col, val = wl["csr"]
+    sub_rowptr = np.zeros(rows.size + 1, np.int32)
+    cnt = (rowptr[gl + 1] - rowptr[gl]).astype(np.int32)
+    sub_rowptr[1:] = np.cumsum(cnt)
+    idx = np.concatenate([np.arange(rowptr[n], rowptr[n + 1]) for n in gl]) if cnt.sum() else np.zeros(0, np.int64)
+    sub = (sub_rowptr, col[idx].astype(np.int32), val[idx].astype(np.float32))
+    bo, bx, by, io, ix, iy = wl["patches"]
+    pobj = None
+    if args.targets:
+        pobj = orc.Patches.__new__(orc.Patches)
+        pobj.n, pobj.bounds_off, pobj.internal_off = bo.size - 1, bo, io
+        pobj.bx, pobj.by, pobj.ix, pobj.iy = bx, by, ix, iy
+    B = args.batch if args.batch > 0 else 256
+    bad_cols, n_cols = 0, 0
+    for r in range(world):
+        # frames of rank r's slice: the first / last, batch edges, random ones
+        loc = np.unique(np.concatenate([[0, 1, F_local - 1, min(B - 1, F_local - 1), min(B, F_local - 1)],
+                                        rng.integers(0, F_local, frames_per_rank)])).astype(np.int64)
+        warps = synth.make_warps(F_local, seed=5 + r) if args.registration == "given" else None
+        fr = orc.unpack_12bit_frames(wl["packed"][loc % D]).reshape(loc.size, H, W)
+        for first, sel in ((0, (loc == 0) & (r == 0)), (1, ~((loc == 0) & (r == 0)))):
+            if not sel.any():
+                continue
+            it, _, _ = orc.phase1([fr[sel]], [sub], first_frame=first,
+                                  warp=[warps[loc[sel]]] if warps is not None else None, interp=1,
+                                  patches=[pobj] if pobj else None)
+            got = itr[:, r * F_local + loc[sel]].T           # [frames, rows]
+            same = (it.view(np.uint32) == np.ascontiguousarray(got).view(np.uint32)) | (np.isnan(it) & np.isnan(got))
+            bad_cols += int((~same).sum())
+            n_cols += int(same.size)
+    res["intensity_values_checked"] = n_cols
+    res["intensity_mismatches"] = bad_cols
+
+    # ---- 2. sums of the full rows, per rank slice in rank order (the device's order)
+    s = np.zeros(rows.size)
+    q = np.zeros(rows.size)
+    for r in range(world):
+        blk = itr[:, r * F_local:(r + 1) * F_local]
+        s += np.cumsum(blk.astype(np.float64), axis=1)[:, -1]
+        q += np.cumsum((blk * blk).astype(np.float64), axis=1)[:, -1]
+    a_ref, r_ref = orc.phase1_finals(s, q, F_total)
+    a_got, r_got = avg[gl], rms[gl]
+    eq = lambda x, y: (x.view(np.uint32) == y.view(np.uint32)) | (np.isnan(x) & np.isnan(y))
+    res["avg_mismatches"] = int((~eq(a_ref, a_got)).sum())
+    res["rms_mismatches"] = int((~eq(r_ref, r_got)).sum())
+
+    # ---- 3. phase 2 of a subset of the rows through the oracle
+    k = np.linspace(0, rows.size - 1, min(n_rows_p2, rows.size)).astype(np.int64)
+    p_ref, rms2_ref, avg2_ref, gain_ref = orc.phase2(itr[k], a_got[k], cov[gl[k]], wl["steady"][gl[k]], wl["temp"][gl[k]],
+                                                     wl["cal"], wl["qbar"], wl["ps"], args.degree)
+    valid = (cov[gl[k]] != 0) & np.all(np.isfinite(itr[k]) & (itr[k] != 0), axis=1)
+    d = np.abs(ptr[k][valid] - p_ref[valid]).max(axis=1)
+    cpmax = np.abs(p_ref[valid]).max(axis=1)
+    Kn = np.abs(gain_ref[valid]).astype(np.float64) * 144.0 / float(wl["qbar"])
+    rr = np.abs(a_got[k][valid, None] / itr[k][valid]).max(axis=1)
+    res["cp_rows"] = int(valid.sum())
+    res["cp_err_rel_signal_max"] = float((d / cpmax).max()) if valid.any() else 0.0       # north-star metric
+    res["cp_err_rel_operand_max"] = float((d / (Kn * rr)).max()) if valid.any() else 0.0
+    res["gain_mismatches"] = int((~eq(gain_ref[valid], gain[rows[k]][valid])).sum())
+    nanrows_same = bool(np.array_equal(np.isnan(ptr[k][~valid & (cov[gl[k]] != 0)]).all(axis=1),
+                                       np.isnan(p_ref[~valid & (cov[gl[k]] != 0)]).all(axis=1)))
+    res["ok"] = (bad_cols == 0 and res["avg_mismatches"] == 0 and res["rms_mismatches"] == 0 and
+                 res["gain_mismatches"] == 0 and nanrows_same and res["cp_err_rel_operand_max"] <= 1e-5)
+    return res
+
+
 def bench_b200(args):
     import upsp_b200 as up
     from upsp_b200 import synth
@@ -238,6 +341,16 @@ def bench_b200(args):
     stage /= args.steps
     stage = np.array([allmax(dist, float(s)) for s in stage])
     value = F_total * args.steps / (ms_dev * 1e-3)
+    check = None
+    if args.check:
+        check = parity_check(g, wl, args, rank, world, dist)
+        log(f"[bench] rank {rank} parity check: {check}")
+        if dist is not None:
+            allc = [None] * world
+            dist.all_gather_object(allc, check)
+        else:
+            allc = [check]
+        check = {"ok": all(c["ok"] for c in allc), "ranks": allc}
     g.close()
     del g
 
@@ -289,12 +402,7 @@ def bench_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (u16 pixels, f64 accumulators)", "data": "synthetic",
-        "config": {"workload": f"configs[1]: 1 camera {args.height}x{args.width} 12-bit packed, "
-                               f"{F_local} frames/GPU onto {N}-node grid",
-                   "frames_total": F_total, "nodes": N, "registration": args.registration,
-                   "patch_clusters": args.targets + 1 if args.targets else 0, "csr": args.csr,
-                   "detrend_degree": args.degree, "batch_frames": args.batch,
-                   "l2": "inputs (31 GB packed frames, 40 GB intensity) far exceed the 126 MB L2"},
+        "config": bench_config(args, world),
         "stage_ms": {n: round(float(s), 3) for n, s in zip(names, stage)},
         "chain": {"algorithmic_bytes_per_frame": 1.5 * P + 20.0 * N, "achieved_gbs": round(chain_gbs, 1),
                   "frac_of_peak": round(chain_gbs / peak, 4),
@@ -309,9 +417,14 @@ def bench_b200(args):
         "gpu_launches": int(launches), "wall_ms_per_step": round(wall_ms / args.steps, 3),
         "clocks": clocks, "e2e": e2e,
     }
+    if check is not None:
+        out["parity_checked"] = bool(check["ok"])
+        out["parity"] = check
     if args.cpu_seconds > 0:
         out["cpu_baseline"] = cpu_baseline(args, wl, budget_s=args.cpu_seconds)
     print(json.dumps(out), flush=True)
+    if check is not None and not check["ok"]:
+        raise SystemExit("bench.py --check: parity check FAILED (see the parity object of the JSON line)")
 
 
 def bench_e2e(up, wl, args, rank, world, local, dist):
@@ -385,21 +498,30 @@ def bench_e2e(up, wl, args, rank, world, local, dist):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_job(orc, wl, args, n_frames):
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignored on purpose)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_job(orc, wl, args, n_frames, seed_rank=0):
     """The reference's algorithm (CPU oracle port, OpenMP over frames / nodes like the
-    reference) on the first n_frames frames of the same workload.  Returns seconds per stage."""
+    reference) on the first n_frames frames of the same workload, starting from the PACKED 12-bit
+    frames like the GPU arm.  Returns seconds per stage."""
     from upsp_b200 import synth
-    frames = wl["frames"]
-    idx = np.arange(n_frames) % frames.shape[0]
-    fr = frames[idx]
+    idx = np.arange(n_frames) % wl["packed"].shape[0]
+    pk = wl["packed"][idx]
     bo, bx, by, io, ix, iy = wl["patches"]
     pobj = None
     if args.targets:
         pobj = orc.Patches.__new__(orc.Patches)
         pobj.n, pobj.bounds_off, pobj.internal_off = bo.size - 1, bo, io
         pobj.bx, pobj.by, pobj.ix, pobj.iy = bx, by, ix, iy
-    warp = [synth.make_warps(n_frames, seed=5)] if args.registration == "given" else None
+    warp = [synth.make_warps(n_frames, seed=5 + seed_rank)] if args.registration == "given" else None
     t0 = time.perf_counter()
+    fr = orc.unpack_12bit_frames(pk).reshape(n_frames, args.height, args.width)
     inten, s, q = orc.phase1([fr], [wl["csr"]], warp=warp, interp=1, patches=[pobj] if pobj else None)
     avg, rms = orc.phase1_finals(s, q, n_frames)
     cov = orc.coverage([wl["csr"]])
@@ -411,17 +533,23 @@ def cpu_job(orc, wl, args, n_frames):
     return t1 - t0, t2 - t1, t3 - t2
 
 
+def workload_name(args):
+    """config.workload: the same string in both arms (the driver compares them)."""
+    return (f"configs[1]: 1 camera {args.height}x{args.width} 12-bit packed, "
+            f"{args.frames} frames/GPU onto {args.nodes}-node grid")
+
+
 def cpu_baseline(args, wl, budget_s=20.0):
     from oracle import oracle as orc
     orc.build()
-    threads = orc.num_threads()
+    threads = orc.set_num_threads(host_threads())
     # probe with a few frames, then size the sample to ~budget_s of CPU work
     p = cpu_job(orc, wl, args, 2 * threads)
     per_frame = sum(p) / (2 * threads)
     n = int(max(4 * threads, min(2048, budget_s / max(per_frame, 1e-6))))
     a, b, c = cpu_job(orc, wl, args, n)
     return {"value": round(n / (a + b + c), 2), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{n} frames of the same workload (same frame size, grid, patches, warp); "
+            "sample": f"{n} packed frames of the same workload (same frame size, grid, patches, warp); "
                       f"process-frames {a:.2f}s, transpose {b:.2f}s, phase2 {c:.2f}s",
             "note": "C port of the reference's algorithm (oracle/upsp_oracle.c), OpenMP over frames and "
                     "nodes as the reference; the reference's own C++ cannot be compiled here (DESIGN.md)"}
@@ -429,7 +557,10 @@ def cpu_baseline(args, wl, budget_s=20.0):
 
 def bench_reference(args):
     """--impl reference: the reference's CPU algorithm on the host cores (oracle port; the
-    reference itself needs OpenCV C++/Eigen/MPI/HDF5, none of which exist in this image)."""
+    reference itself needs OpenCV C++/Eigen/MPI/HDF5, none of which exist in this image).  Rank 0 only;
+    all the host's cores whatever OMP_NUM_THREADS says (torchrun sets it to 1); each step is a bounded
+    sample of the GPU arm's job: the first `--ref-frames` packed frames (default 2048), per-frame cost
+    being flat in the frame count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -438,10 +569,10 @@ def bench_reference(args):
     from oracle import oracle as orc
     orc.build()
     wl = build_workload(args, synth)
-    threads = orc.num_threads()
-    n = args.ref_frames if args.ref_frames > 0 else 8 * threads
+    threads = orc.set_num_threads(host_threads())
+    n = args.ref_frames if args.ref_frames > 0 else min(2048, args.frames)
     for _ in range(args.warmup):
-        cpu_job(orc, wl, args, max(threads, n // 4))
+        cpu_job(orc, wl, args, max(threads, n // 8))
     t0 = time.perf_counter()
     parts = np.zeros(3)
     for _ in range(args.steps):
@@ -449,7 +580,7 @@ def bench_reference(args):
     dt = time.perf_counter() - t0
     v = round(n * args.steps / dt, 2)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = (f"each step = {n} frames of configs[1] ({args.height}x{args.width}, N={args.nodes}); "
+    sample = (f"each step = the first {n} packed frames of the job ({args.height}x{args.width}, N={args.nodes}); "
               f"process-frames {parts[0] / args.steps:.2f}s transpose {parts[1] / args.steps:.2f}s "
               f"phase2 {parts[2] / args.steps:.2f}s per step")
     print(json.dumps({
@@ -457,14 +588,19 @@ def bench_reference(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (u16 pixels, f64 accumulators)", "data": "synthetic",
-        "config": {"workload": f"configs[1]: 1 camera {args.height}x{args.width} 12-bit, "
-                               f"{args.frames} frames/GPU onto {args.nodes}-node grid",
-                   "registration": args.registration, "patch_clusters": args.targets + 1 if args.targets else 0,
-                   "csr": args.csr, "detrend_degree": args.degree},
+        "config": bench_config(args, world),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def bench_config(args, world):
+    """The `config` object of the JSON line: identical in both arms."""
+    return {"workload": workload_name(args), "frames_total": args.frames * world, "nodes": args.nodes,
+            "registration": args.registration, "patch_clusters": args.targets + 1 if args.targets else 0,
+            "csr": args.csr, "detrend_degree": args.degree, "batch_frames": args.batch,
+            "l2": "inputs (31 GB packed frames, 40 GB intensity) far exceed the 126 MB L2"}
 
 
 def main():
@@ -486,6 +622,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget (0 = skip)")
     ap.add_argument("--ref-frames", type=int, default=0)
+    ap.add_argument("--check", action="store_true",
+                    help="after the last timed step compare sampled outputs of every rank with the CPU oracle; "
+                         "rc != 0 on mismatch, \"parity_checked\" in the JSON line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: fewer than 3 warm-up steps requested")

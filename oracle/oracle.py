@@ -69,6 +69,15 @@ def unpack_12bit(packed: np.ndarray) -> np.ndarray:
     return out
 
 
+def unpack_12bit_frames(packed: np.ndarray) -> np.ndarray:
+    """[F, frame_bytes] packed -> [F, npix] u16, frames decoded in parallel (one frame per thread at a time)."""
+    packed = _c(packed, np.uint8)
+    F, fb = packed.shape
+    out = np.zeros((F, fb // 3 * 2), np.uint16)
+    lib().orc_unpack_12bit_frames(_p(packed), C.c_size_t(fb), C.c_int(F), _p(out))
+    return out
+
+
 def unpack_10bit(packed: np.ndarray, lut: np.ndarray | None = None) -> np.ndarray:
     packed = _c(packed, np.uint8).ravel()
     out = np.zeros(packed.size * 4 // 5, np.uint16)
@@ -422,6 +431,12 @@ def phase2(itrans, avg_final, coverage_, steady, model_temp, cal, qbar, ps, degr
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Ask OpenMP for n threads whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
 
 
 # ---------------------------------------------------------------- phase 0: projection matrix

@@ -43,6 +43,14 @@ ORC_API void orc_unpack_12bit(const uint8_t* packed, size_t nbytes, uint16_t* ds
   }
 }
 
+/* a batch of frames, one frame per loop iteration (the reference's ranks each decode their own frames,
+ * cpp/exec/psp_process.cpp:1766-1773): used by bench.py's CPU arm so that it starts from packed bytes */
+ORC_API void orc_unpack_12bit_frames(const uint8_t* packed, size_t frame_bytes, int n_frames, uint16_t* dst) {
+  const size_t npix = frame_bytes / 3 * 2;
+#pragma omp parallel for schedule(static)
+  for (int f = 0; f < n_frames; ++f) orc_unpack_12bit(packed + (size_t)f * frame_bytes, frame_bytes, dst + (size_t)f * npix);
+}
+
 ORC_API void orc_unpack_10bit(const uint8_t* packed, size_t nbytes, uint16_t* dst,
                               const uint16_t* lut /* 1024 entries or NULL */) {
   for (size_t i = 0; i + 5 <= nbytes; i += 5, dst += 4) {
@@ -868,6 +876,15 @@ ORC_API void orc_phase2_finals(const double* rms, const double* avg, const doubl
     rms_f[i] = (float)sqrt(rms[i] / n_frames);
     gain_f[i] = (float)gain[i];
   }
+}
+
+/* bench.py: torchrun exports OMP_NUM_THREADS=1; the CPU arm asks for the host's cores explicitly */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 ORC_API int orc_num_threads(void) {

@@ -206,6 +206,28 @@ def test_chain_packed12_small_batches_and_ring(up, orc, gpu, keep_frame_major):
     _check_chain(case, ref, got, orc)
 
 
+def test_ring_lap_longer_than_the_record_ring(up, orc, gpu):
+    """One frame per push / process_frames call through a 20-slot input ring: a lap of the ring spans 20 calls,
+    more than the 16 process records the library keeps, so the push that overwrites a slot must fall back to the
+    most recent process event (the evicted record used to mean "no wait")."""
+    import upsp_b200
+    from chain import push_all, setup_ctx
+    case = Case(upsp_b200.synth, n_frames=70, n_nodes=2000, fmt="p12", registration=True, seed=5)
+    ref = run_oracle(orc, case)
+    g, sl = setup_ctx(up, orc, case, batch_frames=4, frame_capacity=20)
+    push_all(up, orc, g, case, sl, chunk=1)
+    g.finish_phase1()
+    g.transpose()
+    it = g.read_intensity_transpose()
+    g.reset_run()                                  # a second run over the same ring: records of the first are void
+    push_all(up, orc, g, case, sl, chunk=1)
+    g.finish_phase1()
+    g.transpose()
+    it2 = g.read_intensity_transpose()
+    g.close()
+    assert same_bits(it, ref["itrans"]) and same_bits(it2, ref["itrans"])
+
+
 @MODES
 def test_chain_registration_patches_overlap(up, orc, gpu, keep_frame_major):
     """warp (given matrices) + polynomial patcher (incl. dependent clusters and a clipped

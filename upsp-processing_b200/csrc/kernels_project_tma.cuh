@@ -33,16 +33,16 @@ namespace upsp {
 
 constexpr int TMA_NB = 128;          // nodes (= threads) per block
 constexpr int TMA_TH = 4;            // image rows a block's node pixels may span
-constexpr int TMA_BH = TMA_TH + 2;   // rows of the staged box (bilinear +1, rounding of the warp +1)
+constexpr int TMA_G = 4;             // frames per group (one mbarrier phase, ONE box when the frames' boxes coincide)
+constexpr int TMA_BH = TMA_TH + 4;   // rows of the staged box (bilinear +1, rounding of the warp +1, +2: frames of a group move apart)
 constexpr int TMA_BW16 = 96;         // SRC 0: box width in pixels (192 B rows)
 constexpr int TMA_BWB12 = 176;       // SRC 1: box width in bytes (117 px)
 constexpr int TMA_TW = 80;           // widest column span of a block's node pixels (both sources)
-constexpr int TMA_G = 4;             // frames per group (one mbarrier phase)
 constexpr int TMA_NG = 4;            // groups in the ring
 constexpr int TMA_LA = 2;            // groups the producer runs ahead of the consumers (<= NG - 1; NG - LA groups of slack between warps)
 constexpr int TMA_S = 64;            // frames per table stage
-constexpr int TMA_SLOT16 = TMA_BH * TMA_BW16 * 2;   // bytes per staged frame (both 1152 = 9 x 128: slots stay 128-byte aligned)
-constexpr int TMA_SLOT12 = 1152;      // 1056 used
+constexpr int TMA_SLOT16 = TMA_BH * TMA_BW16 * 2;   // bytes per staged frame = the box plane, so that a box of G frames fills G slots
+constexpr int TMA_SLOT12 = TMA_BH * TMA_BWB12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -55,16 +55,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: a waiting warp sleeps in the barrier unit instead of spinning through the issue slots
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -123,7 +124,8 @@ __device__ __forceinline__ float tma_px(const unsigned char* __restrict__ sl, in
 }
 
 // shared-memory carve-up (dynamic, 128-byte aligned base)
-static_assert(TMA_SLOT16 % 128 == 0 && TMA_SLOT12 % 128 == 0 && TMA_SLOT12 >= TMA_BH * TMA_BWB12, "staged boxes must stay 128-byte aligned");
+static_assert(TMA_SLOT16 % 128 == 0 && TMA_SLOT12 % 128 == 0, "staged boxes must stay 128-byte aligned");
+static_assert(TMA_G == 4 && TMA_S % 32 == 0, "a group's frames are four neighbouring lanes of the stage set-up");
 static_assert(TMA_BWB12 % 16 == 0 && (TMA_BW16 * 2) % 16 == 0, "box rows are multiples of 16 bytes");
 template <int SRC, int CH, int NG = TMA_NG>
 struct TmaSmem {
@@ -144,13 +146,14 @@ struct TmaSmem {
 // VAL1: every projection value is exactly 1.0 (one camera: psp_process.cpp:318-322), so a node-frame
 // value is the integer pixel value itself and the sums are taken in integer arithmetic (exact; the
 // reference's double sums of these floats are exact too, so the bits agree).
-// VAR (experiments): 0 = 4-group ring, producer 2 groups ahead; 1 = 6-group ring, 4 ahead; 2 = ONE box of 4 frames per
-// group at the first frame's origin (timing probe only: wrong taps whenever the frames of a group move differently)
-template <int SRC, int CH, bool VAL1, int VAR = 0>
-__global__ void __launch_bounds__(TMA_NB, 7)
-k_project_tma(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const TmaExtra ex) {
-  constexpr int TMA_NG = VAR == 1 ? 6 : upsp::TMA_NG;
-  constexpr int TMA_LA = VAR == 1 ? 4 : upsp::TMA_LA;
+// Boxes: the G = 4 frames of a group are fetched with ONE box [G frames x BH rows] (tmapG) when the boxes of the four
+// frames fit a common origin (camera shake of a few pixels between neighbouring frames), with one box per frame
+// (tmap1) otherwise.  The TMA unit's cost is per box far more than per byte (measured: 80 cycles per 1 KB box per SM,
+// 156 per 4.6 KB box), and with one box per frame the kernel waited on it.
+template <int SRC, int CH, bool VAL1>
+__global__ void __launch_bounds__(TMA_NB, 6)
+k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__ CUtensorMap tmap1, const FusedArgs a,
+              const TmaExtra ex) {
   using L = TmaSmem<SRC, CH, TMA_NG>;
   constexpr int SLOT = L::SLOT;
   constexpr int TS = L::TS;
@@ -192,8 +195,9 @@ k_project_tma(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const
   for (int s0 = 0; s0 < a.nframes; s0 += TMA_S) {
     const int ns = min(TMA_S, a.nframes - s0);
     __syncthreads();       // previous stage fully consumed (tables, ring); first pass: barriers initialised
-    if (tid < ns) {
-      const int f = s0 + tid;
+    if (tid < TMA_S) {      // warps 0 .. S/32 - 1, whole warps: the four frames of a group are neighbouring lanes
+      const bool valid = tid < ns;
+      const int f = s0 + min(tid, ns - 1);
       double2 cf;
       int2 ye[TMA_TH];
       if (f == a.skip_frame) {      // global frame 0 is never registered: identity map, exact taps
@@ -227,28 +231,48 @@ k_project_tma(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const
       }
       // the TMA unit wants the box to start on a 16-byte boundary of global memory (measured: any other inner
       // coordinate raises "illegal instruction"): 8 px of a u16 row, 32 px (48 bytes) of a packed row
-      const int bx0 = SRC ? (sxmin & ~31) : (sxmin & ~7);
-      const int by0 = symin;
+      constexpr int XMASK = SRC ? ~31 : ~7;
       constexpr int BWPX = SRC ? (TMA_BWB12 * 2) / 3 : TMA_BW16;
       // sane coordinates only (the shifts below must not overflow); anything else takes the slow path
-      const bool fit = (sxmax + 1 - bx0 < BWPX) && (symax + 1 - by0 < TMA_BH) && bx0 > -(1 << 20) && bx0 < (1 << 20) &&
-                       by0 > -(1 << 20) && by0 < (1 << 20);
-      unsigned char flag = fit ? 0 : 1;
-      if (SRC && fit && ex.hot != nullptr) {
+      const bool sane = sxmin > -(1 << 20) && sxmax < (1 << 20) && symin > -(1 << 20) && symax < (1 << 20);
+      int bx0 = sxmin & XMASK, by0 = symin;
+      const bool fit1 = sane && (sxmax + 1 - bx0 < BWPX) && (symax + 1 - by0 < TMA_BH);
+      // common box of the group's four frames?
+      int gxmin = sxmin, gxmax = sxmax, gymin = symin, gymax = symax;
+      bool gall = valid && sane;
+#pragma unroll
+      for (int d = 1; d < TMA_G; d <<= 1) {
+        gxmin = min(gxmin, __shfl_xor_sync(0xffffffffu, gxmin, d));
+        gxmax = max(gxmax, __shfl_xor_sync(0xffffffffu, gxmax, d));
+        gymin = min(gymin, __shfl_xor_sync(0xffffffffu, gymin, d));
+        gymax = max(gymax, __shfl_xor_sync(0xffffffffu, gymax, d));
+        gall = __shfl_xor_sync(0xffffffffu, (int)gall, d) && gall;
+      }
+      const int gbx0 = gxmin & XMASK;
+      const bool gfit = gall && (gxmax + 1 - gbx0 < BWPX) && (gymax + 1 - gymin < TMA_BH);
+      if (gfit) {
+        bx0 = gbx0;
+        by0 = gymin;
+      }
+      const bool fit = gfit || fit1;
+      unsigned char flag = (fit ? 0 : 1) | (gfit ? 4 : 0);
+      if (SRC && fit && valid && ex.hot != nullptr) {
         const HotFix* h = ex.hot + f;
         const int nh = h->n;
         for (int i = 0; i < nh; ++i) {
           const int hx = h->pos[i] % W - bx0, hy = h->pos[i] / W - by0;
-          if ((unsigned)hx < (unsigned)BWPX && (unsigned)hy < (unsigned)TMA_BH) flag = 2;
+          if ((unsigned)hx < (unsigned)BWPX && (unsigned)hy < (unsigned)TMA_BH) flag |= 2;
         }
       }
-      s_coef[tid] = cf;
+      if (valid) {
+        s_coef[tid] = cf;
 #pragma unroll
-      for (int r = 0; r < TMA_TH; ++r) s_y[tid * TMA_TH + r] = make_int2(ye[r].x - (fit ? bx0 << 10 : 0), ye[r].y - (fit ? by0 << 10 : 0));
-      s_org[tid] = make_int2(bx0, by0);
-      s_flag[tid] = flag;
-    } else if (tid < TMA_S) {
-      s_flag[tid] = 0;
+        for (int r = 0; r < TMA_TH; ++r) s_y[tid * TMA_TH + r] = make_int2(ye[r].x - (fit ? bx0 << 10 : 0), ye[r].y - (fit ? by0 << 10 : 0));
+        s_org[tid] = make_int2(fit ? bx0 : 0, fit ? by0 : 0);
+        s_flag[tid] = flag;
+      } else {
+        s_flag[tid] = 0;
+      }
     }
     __syncthreads();
     const int ngr = (ns + TMA_G - 1) / TMA_G;
@@ -257,17 +281,16 @@ k_project_tma(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const
       const unsigned slot = gi % TMA_NG, use = gi / TMA_NG;
       if (use > 0) mbar_wait(empty + slot, (use - 1) & 1);
       const int nf = min(TMA_G, ns - g * TMA_G);
-      if (VAR == 2) {
-        mbar_expect_tx(full + slot, (uint32_t)TMA_G * TMA_BH * TMA_BW16 * 2);
+      mbar_expect_tx(full + slot, (uint32_t)nf * SLOT);
+      if (s_flag[g * TMA_G] & 4) {       // one box for the group's four frames
         const int2 o = s_org[g * TMA_G];
-        tma_load_3d(ring + (slot * TMA_G) * SLOT, &tmap, full + slot, o.x, o.y, ex.frame0 + s0 + g * TMA_G);
+        tma_load_3d(ring + (slot * TMA_G) * SLOT, &tmapG, full + slot, SRC ? (o.x >> 5) * 12 : o.x, o.y, ex.frame0 + s0 + g * TMA_G);
         return;
       }
-      mbar_expect_tx(full + slot, (uint32_t)nf * (SRC ? TMA_BH * TMA_BWB12 : TMA_BH * TMA_BW16 * 2));
       for (int j = 0; j < nf; ++j) {
         const int i = g * TMA_G + j;
         const int2 o = s_org[i];
-        tma_load_3d(ring + (slot * TMA_G + j) * SLOT, &tmap, full + slot, SRC ? (o.x >> 5) * 12 : o.x, o.y, ex.frame0 + s0 + i);
+        tma_load_3d(ring + (slot * TMA_G + j) * SLOT, &tmap1, full + slot, SRC ? (o.x >> 5) * 12 : o.x, o.y, ex.frame0 + s0 + i);
       }
     };
     if (tid == 0)
@@ -459,7 +482,14 @@ static __device__ __noinline__ void hot_list_build(const uint8_t* __restrict__ f
   *out = h;
 }
 
-__global__ void __launch_bounds__(256)
+// rare path of the scan: one item (48 packed bytes = 32 pixels) holds a hot pixel; re-read it and note which
+static __device__ __noinline__ void note_hot_item12(const uint8_t* __restrict__ frame, unsigned i, int thresh, int* cnt, int* pos) {
+  for (unsigned k = 0; k < 32; ++k) note_hot(px_packed12(frame, i * 32 + k), (size_t)i * 32 + k, thresh, cnt, pos);
+}
+
+// Small on purpose (<= 32 registers, any block size): it runs on the front-end stream UNDER the projection of
+// the previous batch, in the registers / issue slots that kernel leaves free.
+__global__ void __launch_bounds__(256, 8)
 k_hot_scan12(const uint8_t* __restrict__ in, size_t in_stride, size_t npix, int nframes, int thresh,
              int* __restrict__ hot_cnt, int* __restrict__ hot_pos, int* __restrict__ done, int rows, int cols,
              HotFix* __restrict__ fixes) {
@@ -477,28 +507,19 @@ k_hot_scan12(const uint8_t* __restrict__ in, size_t in_stride, size_t npix, int 
     const uint8_t* frame = in + (size_t)f * in_stride;
     const uint4* src = reinterpret_cast<const uint4*>(frame);
     const unsigned iend = seg_end - fbeg;
-    for (unsigned i = it0 - fbeg + threadIdx.x; i < iend; i += 256) {
+    for (unsigned i = it0 - fbeg + threadIdx.x; i < iend; i += blockDim.x) {
       const uint4 b0 = ld_stream_u4(src + 3 * i), b1 = ld_stream_u4(src + 3 * i + 1), b2 = ld_stream_u4(src + 3 * i + 2);
-      const uint32_t wd[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
       uint32_t hot = 0;
-      uint4 o[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        unpack12_x8(wd[3 * k], wd[3 * k + 1], wd[3 * k + 2], o[k]);
-        hot |= (((o[k].x | 0x80008000u) - t2) | ((o[k].y | 0x80008000u) - t2) | ((o[k].z | 0x80008000u) - t2) |
-                ((o[k].w | 0x80008000u) - t2));
-      }
-      if (hot & 0x80008000u) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t pw[4] = {o[k].x, o[k].y, o[k].z, o[k].w};
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            note_hot(pw[m] & 0xFFFFu, (size_t)i * 32 + k * 8 + m * 2, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
-            note_hot(pw[m] >> 16, (size_t)i * 32 + k * 8 + m * 2 + 1, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
-          }
-        }
-      }
+      uint4 o;
+#define UPSP_SCAN_X8(W0, W1, W2)                                                                              \
+  unpack12_x8(W0, W1, W2, o);                                                                                 \
+  hot |= (((o.x | 0x80008000u) - t2) | ((o.y | 0x80008000u) - t2) | ((o.z | 0x80008000u) - t2) | ((o.w | 0x80008000u) - t2))
+      UPSP_SCAN_X8(b0.x, b0.y, b0.z);
+      UPSP_SCAN_X8(b0.w, b1.x, b1.y);
+      UPSP_SCAN_X8(b1.z, b1.w, b2.x);
+      UPSP_SCAN_X8(b2.y, b2.z, b2.w);
+#undef UPSP_SCAN_X8
+      if (hot & 0x80008000u) note_hot_item12(frame, i, thresh, hot_cnt + f, hot_pos + f * UPSP_HOT_STORE);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

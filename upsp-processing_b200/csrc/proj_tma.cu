@@ -15,30 +15,30 @@ TmaGeom tma_geom() {
   g.box_rows = TMA_BH;
   g.box_px16 = TMA_BW16;
   g.box_words12 = TMA_BWB12 / 4;
+  g.group_frames = TMA_G;
   return g;
 }
 
-template <int SRC, int CH, bool VAL1, int VAR = 0>
-static cudaError_t launch1(const CUtensorMap& map, const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
-  constexpr int smem = TmaSmem<SRC, CH, VAR == 1 ? 6 : TMA_NG>::total;
+template <int SRC, int CH, bool VAL1>
+static cudaError_t launch1(const CUtensorMap& map_group, const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex,
+                           int nblocks, cudaStream_t st) {
+  constexpr int smem = TmaSmem<SRC, CH, TMA_NG>::total;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  k_project_tma<SRC, CH, VAL1, VAR><<<nblocks, TMA_NB, smem, st>>>(map, a, ex);
+  k_project_tma<SRC, CH, VAL1><<<nblocks, TMA_NB, smem, st>>>(map_group, map_single, a, ex);
   return cudaGetLastError();
 }
 
-cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map, const FusedArgs& a,
-                               const TmaExtra& ex, int nblocks, cudaStream_t st) {
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map_group, const CUtensorMap& map_single,
+                               const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
   if (nblocks <= 0) return cudaSuccess;
-  static const int var = getenv("UPSP_TMA_VAR") ? atoi(getenv("UPSP_TMA_VAR")) : 0;
-  if (var == 1 && src == 0 && !seg128 && val1) return launch1<0, 16, true, 1>(map, a, ex, nblocks, st);
-  if (var == 2 && src == 0 && !seg128 && val1) return launch1<0, 16, true, 2>(map, a, ex, nblocks, st);
-#define UPSP_TMA_CASE(S, C)                                                  \
-  return val1 ? launch1<S, C, true>(map, a, ex, nblocks, st) : launch1<S, C, false>(map, a, ex, nblocks, st)
+#define UPSP_TMA_CASE(S, C)                                                                              \
+  return val1 ? launch1<S, C, true>(map_group, map_single, a, ex, nblocks, st)                           \
+              : launch1<S, C, false>(map_group, map_single, a, ex, nblocks, st)
   if (src == 0) {
     if (seg128) UPSP_TMA_CASE(0, 32);
     UPSP_TMA_CASE(0, 16);
@@ -50,7 +50,8 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMa
 
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
                               int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st) {
-  k_hot_scan12<<<grid, 256, 0, st>>>(in, in_stride, npix, nframes, thresh, hot_cnt, hot_pos, done, rows, cols,
+  static const int scan_threads = getenv("UPSP_SCAN_THREADS") ? atoi(getenv("UPSP_SCAN_THREADS")) : 256;   // tuning knob
+  k_hot_scan12<<<grid, scan_threads, 0, st>>>(in, in_stride, npix, nframes, thresh, hot_cnt, hot_pos, done, rows, cols,
                                      reinterpret_cast<HotFix*>(fixes));
   return cudaGetLastError();
 }

@@ -15,6 +15,7 @@ struct TmaGeom {
   int box_rows;          // TMA_BH
   int box_px16;          // SRC 0: box width in u16 pixels
   int box_words12;       // SRC 1: box width in 32-bit words of packed bytes
+  int group_frames;      // TMA_G: frames fetched by one box when their boxes coincide
 };
 TmaGeom tma_geom();
 
@@ -36,8 +37,9 @@ struct TmaExtra {
 };
 
 // src 0: decoded u16 frames, 1: packed 12-bit frames.  seg128: 128-byte row segments (peer stores).
-cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map, const FusedArgs& a,
-                               const TmaExtra& ex, int nblocks, cudaStream_t st);
+// map_group: box of group_frames frames; map_single: box of one frame (same tensor, same rows x columns).
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map_group, const CUtensorMap& map_single,
+                               const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st);
 // hot-pixel scan of packed 12-bit frames -> fix lists (read only)
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
                               int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st);

@@ -258,8 +258,8 @@ struct Camera {
   std::vector<int> h_code;     // ELL-1 table as uploaded (block partition of the TMA projection)
   std::vector<float> h_val;
   // TMA projection: descriptors of the two decoded work buffers / of the packed input store; fix lists per buffer set
-  CUtensorMap tmap16[2];
-  CUtensorMap tmap12;
+  CUtensorMap tmap16[2], tmap16g[2];     // one-frame boxes / boxes of a whole frame group (kernels_project_tma.cuh)
+  CUtensorMap tmap12, tmap12g;
   void* d_fix[2] = {nullptr, nullptr};
 };
 
@@ -311,6 +311,7 @@ struct upsp_gpu_ctx {
   struct ProcRec { int off, count; cudaEvent_t ev; };
   std::vector<ProcRec> proc_recs;                // recent process_frames calls (input-ring reuse)
   size_t proc_next = 0;
+  bool push_wait_all = false;                    // next push waits on ev_proc (set by reset_run)
   // sampled per-kernel timing
   bool timeline = false;          // bracket every kernel, keep the pipeline overlapped (upsp_gpu_timeline)
   int sample_every = 0;
@@ -1184,14 +1185,18 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
   TRY(upload(&c->d_tma_blk, blocks.data(), blocks.size()));
   if (want == 1) {
     uint16_t* bufs[2] = {k.d_work, k.d_work2 ? k.d_work2 : k.d_work};
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 2; ++b) {
       TRY(encode_tmap(&k.tmap16[b], CU_TENSOR_MAP_DATA_TYPE_UINT16, bufs[b], (uint64_t)k.W, (uint64_t)k.H, (uint64_t)c->batch,
-                      (uint64_t)k.W * 2, (uint64_t)k.npix * 2, (uint32_t)g.box_px16, (uint32_t)g.box_rows,
-                      (getenv("UPSP_TMA_VAR") && atoi(getenv("UPSP_TMA_VAR")) == 2) ? 4 : 1));
+                      (uint64_t)k.W * 2, (uint64_t)k.npix * 2, (uint32_t)g.box_px16, (uint32_t)g.box_rows, 1));
+      TRY(encode_tmap(&k.tmap16g[b], CU_TENSOR_MAP_DATA_TYPE_UINT16, bufs[b], (uint64_t)k.W, (uint64_t)k.H, (uint64_t)c->batch,
+                      (uint64_t)k.W * 2, (uint64_t)k.npix * 2, (uint32_t)g.box_px16, (uint32_t)g.box_rows, (uint32_t)g.group_frames));
+    }
   } else {
     const uint64_t row_bytes = (uint64_t)k.W * 3 / 2;
     TRY(encode_tmap(&k.tmap12, CU_TENSOR_MAP_DATA_TYPE_UINT32, k.d_in, row_bytes / 4, (uint64_t)k.H, (uint64_t)c->capacity,
-                    row_bytes, (uint64_t)k.frame_bytes, (uint32_t)g.box_words12, (uint32_t)g.box_rows));
+                    row_bytes, (uint64_t)k.frame_bytes, (uint32_t)g.box_words12, (uint32_t)g.box_rows, 1));
+    TRY(encode_tmap(&k.tmap12g, CU_TENSOR_MAP_DATA_TYPE_UINT32, k.d_in, row_bytes / 4, (uint64_t)k.H, (uint64_t)c->capacity,
+                    row_bytes, (uint64_t)k.frame_bytes, (uint32_t)g.box_words12, (uint32_t)g.box_rows, (uint32_t)g.group_frames));
     for (int b = 0; b < 2; ++b) {
       CU(cudaMalloc(&k.d_fix[b], (size_t)c->batch * hot_fix_bytes()));
       CU(cudaMemset(k.d_fix[b], 0, (size_t)c->batch * hot_fix_bytes()));
@@ -1236,12 +1241,22 @@ extern "C" int upsp_gpu_push_frames(upsp_gpu_ctx* c, int cam, const void* host, 
   REQUIRE(k.format == format, UPSP_ERR_INVALID, "camera %d was fed format %d before", cam, k.format);
   // slots being overwritten must have been consumed: wait for the process_frames calls
   // whose frames (an earlier lap of the ring) live in the slots of [off, off+count)
-  for (auto& r : c->proc_recs) {
-    if (r.count == 0) continue;
+  {
     const long lo = (long)off - c->capacity, hi = (long)off + count - c->capacity;  // previous lap
-    const bool overlap_prev = r.off < hi && r.off + r.count > lo;
-    const bool older = r.off + r.count <= lo;  // even older laps: also done by stream order, cheap to wait
-    if (overlap_prev || older) CU(cudaStreamWaitEvent(c->copy_stream, r.ev, 0));
+    long covered = 0;           // frames of the previous lap whose process_frames record is still held
+    for (auto& r : c->proc_recs) {
+      if (r.count == 0) continue;
+      const bool overlap_prev = r.off < hi && r.off + r.count > lo;
+      const bool older = r.off + r.count <= lo;  // even older laps: also done by stream order, cheap to wait
+      if (overlap_prev || older) CU(cudaStreamWaitEvent(c->copy_stream, r.ev, 0));
+      if (overlap_prev) covered += std::min<long>(hi, r.off + r.count) - std::max<long>(lo, r.off);
+    }
+    // The record ring holds the last 16 calls.  When a lap of the input ring spans more calls than that, the
+    // record of the slots being overwritten is gone: fall back to the most recent process_frames event (stream
+    // order covers every older call).  Same after upsp_gpu_reset_run, which forgets the records.
+    const long need = std::min<long>(hi, c->frames_processed) - std::max<long>(lo, 0);
+    if (c->push_wait_all || (hi > 0 && covered < need)) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_proc, 0));
+    c->push_wait_all = false;
   }
   int done = 0;
   while (done < count) {
@@ -1359,8 +1374,9 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     KBEGIN_ON(0, SB);
     if (src12) {
       if (c->hot_fix) {
+        static const int scan_bpsm = getenv("UPSP_SCAN_BPSM") ? atoi(getenv("UPSP_SCAN_BPSM")) : 2;   // tuning knob
         CU(launch_hot_scan12(in, k.frame_bytes, k.npix, nb, thresh, w_hot_cnt, w_hot_pos, w_hot_cnt + c->batch, k.H, k.W,
-                             k.d_fix[bs], c->n_sm * 2, SB));
+                             k.d_fix[bs], c->n_sm * scan_bpsm, SB));
         KCHECK(c);
       }
     } else {
@@ -1531,8 +1547,8 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         ex.hot = c->hot_fix ? reinterpret_cast<const HotFix*>(k.d_fix[bs]) : nullptr;
         fa.cam[0].frames = nullptr;
       }
-      CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex,
-                            c->n_tma_blocks, c->stream));
+      CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->proj_mode == 2 ? k.tmap12g : k.tmap16g[bs],
+                            c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex, c->n_tma_blocks, c->stream));
       c->launches++;
       const int n_other = c->N - c->n_tma_plain;
       if (n_other > 0) {
@@ -1550,9 +1566,12 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
       const unsigned g2 = cdiv(c->N, 128);
       // rows stored straight into peer memory (>= 3 ranks, or staging off): 128-byte segments
       const bool seg128 = c->R > 1 && c->staged_peers < c->R - 1;
+      // UPSP_PROJ_PAD: extra dynamic shared memory per block = a cap on the resident projection blocks per SM,
+      // which leaves registers for the co-resident front end (tuning knob)
+      static const int proj_pad = getenv("UPSP_PROJ_PAD") ? atoi(getenv("UPSP_PROJ_PAD")) : 0;
 #define FUSED4(NCAM)                                                               \
-  if (seg128) k_project_fused4<NCAM, 128, 32><<<g2, 128, 0, c->stream>>>(fa);      \
-  else k_project_fused4<NCAM, 128, 16><<<g2, 128, 0, c->stream>>>(fa)
+  if (seg128) k_project_fused4<NCAM, 128, 32><<<g2, 128, proj_pad, c->stream>>>(fa);      \
+  else k_project_fused4<NCAM, 128, 16><<<g2, 128, proj_pad, c->stream>>>(fa)
       switch (fa.n_cams) {
         case 1: FUSED4(1); break;
         case 2: FUSED4(2); break;
@@ -2159,6 +2178,8 @@ extern "C" int upsp_gpu_reset_run(upsp_gpu_ctx* c) {
   c->frames_processed = 0;
   c->kn = 0;
   c->batch_counter = 0;
+  for (auto& r : c->proc_recs) r.count = 0;     // frame offsets start over: the records of the last run mean nothing now
+  c->push_wait_all = true;                      // ... and the next push waits for whatever is still queued
   return UPSP_OK;
 }
 
