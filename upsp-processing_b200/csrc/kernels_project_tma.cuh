@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// Per-frame column coefficients (M0, M3) * 1024 of the batch (identity for the unregistered global frame 0), in
+// CONSTANT memory: every lane of a warp reads the same frame's pair, and as shared-memory loads those broadcasts
+// cost two wavefronts each of the load/store data pipe this kernel is bound by (ncu r2i: 76 % of its peak, a tenth
+// of it these loads).  Two sets: the copy for batch i+1 (front-end stream) runs under the kernel of batch i.
+constexpr int TMA_MAXB = 1024;       // largest batch the table holds (host-checked)
+__constant__ double2 c_tma_coef[2][TMA_MAXB];
+
 // cv::warpAffine at one pixel from a packed frame, any coordinates (the box of a frame did not fit)
 static __device__ __noinline__ float warp_px_slow12(const uint8_t* __restrict__ fr, const HotFix* __restrict__ h, int W, int H,
                                              int X, int Y) {
@@ -135,8 +142,7 @@ struct TmaSmem {
   static constexpr int tile_off = ring_bytes;
   static constexpr int tile_bytes = TMA_NB * TS * 4;
   static constexpr int rowp_off = tile_off + tile_bytes;
-  static constexpr int coef_off = rowp_off + TMA_NB * 8;
-  static constexpr int y_off = coef_off + TMA_S * 16;
+  static constexpr int y_off = rowp_off + TMA_NB * 8;
   static constexpr int org_off = y_off + TMA_S * TMA_TH * 8;
   static constexpr int bar_off = org_off + TMA_S * 8;
   static constexpr int flag_off = bar_off + 2 * NG * 8;
@@ -161,7 +167,7 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   unsigned char* ring = smem;
   float* tile = reinterpret_cast<float*>(smem + L::tile_off);
   float** rowp = reinterpret_cast<float**>(smem + L::rowp_off);
-  double2* s_coef = reinterpret_cast<double2*>(smem + L::coef_off);
+  const double2* __restrict__ coef = c_tma_coef[ex.coef_set];   // [batch] (constant bank)
   int2* s_y = reinterpret_cast<int2*>(smem + L::y_off);        // [S][TH]: (X0,Y0)[ymin+r] minus the box origin
   int2* s_org = reinterpret_cast<int2*>(smem + L::org_off);    // [S]: box origin (px, row) of the frame
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::bar_off);
@@ -192,21 +198,22 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   double s = 0.0, q = 0.0;
   unsigned gidx = 0;        // groups issued / consumed so far by this block (ring position)
 
-  for (int s0 = 0; s0 < a.nframes; s0 += TMA_S) {
-    const int ns = min(TMA_S, a.nframes - s0);
+  // blockIdx.y = which slice of the batch's frames (ex.split_frames each, a multiple of the table stage): twice the
+  // blocks at half the length, so that the last wave of the grid is short (3953 blocks on 148 x 6 slots were 4.45 waves)
+  const int f_begin = ex.split_frames > 0 ? (int)blockIdx.y * ex.split_frames : 0;
+  const int f_end = ex.split_frames > 0 ? min(a.nframes, f_begin + ex.split_frames) : a.nframes;
+  for (int s0 = f_begin; s0 < f_end; s0 += TMA_S) {
+    const int ns = min(TMA_S, f_end - s0);
     __syncthreads();       // previous stage fully consumed (tables, ring); first pass: barriers initialised
     if (tid < TMA_S) {      // warps 0 .. S/32 - 1, whole warps: the four frames of a group are neighbouring lanes
       const bool valid = tid < ns;
       const int f = s0 + min(tid, ns - 1);
-      double2 cf;
+      const double2 cf = coef[f];   // identity (1024, 0) for the unregistered frame
       int2 ye[TMA_TH];
       if (f == a.skip_frame) {      // global frame 0 is never registered: identity map, exact taps
-        cf = make_double2(1024.0, 0.0);
 #pragma unroll
         for (int r = 0; r < TMA_TH; ++r) ye[r] = make_int2(16, (min(bd.ymin + r, H - 1) << 10) + 16);
       } else {
-        const float* M = cam.m6 + (size_t)f * 6;
-        cf = make_double2((double)__ldg(M) * 1024.0, (double)__ldg(M + 3) * 1024.0);
         const int2* ty = reinterpret_cast<const int2*>(cam.tab) + ((size_t)f * (unsigned)(W + H) + (unsigned)W);
 #pragma unroll
         for (int r = 0; r < TMA_TH; ++r) ye[r] = __ldg(ty + min(bd.ymin + r, H - 1));
@@ -265,7 +272,6 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
         }
       }
       if (valid) {
-        s_coef[tid] = cf;
 #pragma unroll
         for (int r = 0; r < TMA_TH; ++r) s_y[tid * TMA_TH + r] = make_int2(ye[r].x - (fit ? bx0 << 10 : 0), ye[r].y - (fit ? by0 << 10 : 0));
         s_org[tid] = make_int2(fit ? bx0 : 0, fit ? by0 : 0);
@@ -339,7 +345,7 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < TMA_G; ++j) {
             const int i = c0 + u + j;
-            const double2 cf = s_coef[i];
+            const double2 cf = coef[s0 + i];
             const int2 ya = s_y[i * TMA_TH + yrel];
             const int X = ya.x + __double2int_rn(__dmul_rn(cf.x, dpx));
             const int Y = ya.y + __double2int_rn(__dmul_rn(cf.y, dpx));
@@ -356,7 +362,7 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
             ri[j] = 0u;
             if (j >= nf) continue;
             const int i = c0 + u + j;
-            const double2 cf = s_coef[i];
+            const double2 cf = coef[s0 + i];
             const int2 ya = s_y[i * TMA_TH + yrel];
             const int X = ya.x + __double2int_rn(__dmul_rn(cf.x, dpx));
             const int Y = ya.y + __double2int_rn(__dmul_rn(cf.y, dpx));
@@ -404,9 +410,12 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
       if (vec_ok && nb == CH) {
         constexpr int LPN = CH / 4;      // lanes per node row segment
         const int fq = (lane % LPN) * 4;
+        // CH = 16: the two nodes of a quarter warp are 4 tile rows apart (4 * TS = 80 words = 16 banks: their two
+        // 16-word segments tile the 32 banks; neighbouring rows, 20 banks apart, overlapped in 4 of them)
+        const int nsel = CH == 16 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LPN;
 #pragma unroll
         for (int it = 0; it < LPN; ++it) {
-          const int nl = w * 32 + it * (32 / LPN) + lane / LPN;
+          const int nl = w * 32 + it * (32 / LPN) + nsel;
           float* rp = rowp[nl];
           if (rp != nullptr) {
             const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
@@ -424,8 +433,13 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
     gidx += ngr;
   }
   if (live) {
-    a.sum[n] += s;
-    a.sumsq[n] += q;
+    if (ex.split_frames > 0) {      // several blocks per node: VAL1 only (integer sums, exact in any order)
+      atomicAdd(a.sum + n, s);
+      atomicAdd(a.sumsq + n, q);
+    } else {
+      a.sum[n] += s;
+      a.sumsq[n] += q;
+    }
   }
 }
 

@@ -29,7 +29,8 @@ static cudaError_t launch1(const CUtensorMap& map_group, const CUtensorMap& map_
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  k_project_tma<SRC, CH, VAL1><<<nblocks, TMA_NB, smem, st>>>(map_group, map_single, a, ex);
+  const unsigned ny = ex.split_frames > 0 ? (unsigned)((a.nframes + ex.split_frames - 1) / ex.split_frames) : 1u;
+  k_project_tma<SRC, CH, VAL1><<<dim3((unsigned)nblocks, ny), TMA_NB, smem, st>>>(map_group, map_single, a, ex);
   return cudaGetLastError();
 }
 
@@ -50,12 +51,19 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMa
 
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
                               int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st) {
-  static const int scan_threads = getenv("UPSP_SCAN_THREADS") ? atoi(getenv("UPSP_SCAN_THREADS")) : 256;   // tuning knob
+  static const int scan_threads = getenv("UPSP_SCAN_THREADS") ? atoi(getenv("UPSP_SCAN_THREADS")) : 128;   // tuning knob
   k_hot_scan12<<<grid, scan_threads, 0, st>>>(in, in_stride, npix, nframes, thresh, hot_cnt, hot_pos, done, rows, cols,
                                      reinterpret_cast<HotFix*>(fixes));
   return cudaGetLastError();
 }
 
 size_t hot_fix_bytes() { return sizeof(HotFix); }
+
+cudaError_t tma_set_coef(int set, const double2* dev_coef, int n, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_tma_coef, dev_coef, (size_t)n * sizeof(double2), (size_t)set * TMA_MAXB * sizeof(double2),
+                                 cudaMemcpyDeviceToDevice, st);
+}
+int tma_max_batch() { return TMA_MAXB; }
+int tma_stage_frames() { return TMA_S; }
 
 }  // namespace upsp

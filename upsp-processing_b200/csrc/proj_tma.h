@@ -34,6 +34,8 @@ struct TmaExtra {
   size_t frame_bytes;
   int frame0;                   // slot of the batch's first frame in the tensor map (third TMA coordinate)
   const HotFix* hot;            // SRC 1: [batch] fix lists (nullptr: hot-pixel fix off)
+  int split_frames;             // > 0: grid.y slices of this many frames each (integer statistics only), 0: one block per node tile
+  int coef_set;                 // which of the two constant-memory coefficient tables holds this batch (tma_set_coef)
 };
 
 // src 0: decoded u16 frames, 1: packed 12-bit frames.  seg128: 128-byte row segments (peer stores).
@@ -44,5 +46,9 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMa
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
                               int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st);
 size_t hot_fix_bytes();
+// (M0, M3) * 1024 of `n` frames (device array of double2, identity for the unregistered frame) -> constant table `set`
+cudaError_t tma_set_coef(int set, const double2* dev_coef, int n, cudaStream_t st);
+int tma_max_batch();
+int tma_stage_frames();
 
 }  // namespace upsp

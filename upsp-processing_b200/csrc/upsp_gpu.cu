@@ -9,6 +9,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -221,6 +222,7 @@ struct Camera {
   float* d_rho = nullptr;     // [F_local]
   int* d_iters = nullptr;     // [F_local]
   int* d_tab = nullptr;       // [F_local][2W+2H] warp tables of every local frame
+  double2* d_coef = nullptr;  // [F_local] (M0, M3) * 1024 of every local frame, identity for global frame 0 (TMA projection)
   uint8_t* d_skip = nullptr;  // [batch]
   uint16_t* d_ref16 = nullptr;
   // ECC (registration = pixel)
@@ -291,6 +293,7 @@ struct upsp_gpu_ctx {
   // runs on `stream`); high priority so its few long-lived blocks get SM slots as soon as they free up
   cudaStream_t stream_b = nullptr;
   cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr}, ev_tabs = nullptr;
+  cudaEvent_t ev_dec[2] = {nullptr, nullptr};    // decode / scan (+ coefficient table) of a buffer set done: the TMA kernel may start
   bool pipelined = false;
   bool last_sampled = false;   // the previous batch ran un-overlapped for kernel timing
   long pipe_batches = 0;
@@ -465,6 +468,7 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
       CU(cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, hi));
       for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_front[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_dec[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_back[i], cudaEventDisableTiming));
       }
       CU(cudaEventCreateWithFlags(&c->ev_tabs, cudaEventDisableTiming));
@@ -548,6 +552,7 @@ static void free_camera(Camera& cam) {
   cudaFree(cam.d_rho);
   cudaFree(cam.d_iters);
   cudaFree(cam.d_tab);
+  cudaFree(cam.d_coef);
   cudaFree(cam.d_skip);
   cudaFree(cam.d_ref16);
   cudaFree(cam.d_eccT);
@@ -617,6 +622,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   if (c->ev_pb) cudaEventDestroy(c->ev_pb);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_front[i]) cudaEventDestroy(c->ev_front[i]);
+    if (c->ev_dec[i]) cudaEventDestroy(c->ev_dec[i]);
     if (c->ev_back[i]) cudaEventDestroy(c->ev_back[i]);
   }
   if (c->ev_tabs) cudaEventDestroy(c->ev_tabs);
@@ -982,6 +988,7 @@ static int finalize(upsp_gpu_ctx* c) {
     if (c->registration != UPSP_REG_NONE) {
       if (!c->fused) TRY(dmalloc(&k.d_warp, (size_t)c->batch * k.npix));
       TRY(dmalloc(&k.d_tab, (size_t)std::max(c->F_local, 1) * (2 * k.W + 2 * k.H)));
+      TRY(dmalloc(&k.d_coef, (size_t)std::max(c->F_local, 1)));
       if (c->registration == UPSP_REG_GIVEN)
         REQUIRE(k.has_m6, UPSP_ERR_STATE, "registration=given but camera %zu has no warp matrices", ci);
       if (c->registration == UPSP_REG_PIXEL) {
@@ -1086,6 +1093,14 @@ static int finalize(upsp_gpu_ctx* c) {
 }
 
 
+// column coefficients of the warp maps as the TMA projection reads them from constant memory: (M0, M3) * 1024 in
+// double (k_warp_tables' own expression), identity for the frame that is never registered (psp_process.cpp:1777)
+__global__ void k_tma_coef(const float* __restrict__ m6, int n, int skip, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = i == skip ? make_double2(1024.0, 0.0) : make_double2((double)m6[(size_t)i * 6] * 1024.0, (double)m6[(size_t)i * 6 + 3] * 1024.0);
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA-staged projection: block partition + tensor maps (kernels_project_tma.cuh)
 // ------------------------------------------------------------------------------------------
@@ -1120,7 +1135,7 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
   const bool pix13 = k.format == UPSP_PIX_PACKED12 || (k.format == UPSP_PIX_PACKED10 && c->lut_max < 8192);
   if (!pix13 || (size_t)c->batch * k.npix >= ((size_t)1 << 31) || (size_t)c->batch * (size_t)(k.W + k.H) >= ((size_t)1 << 31))
     return UPSP_OK;
-  if (drv().TensorMapEncodeTiled == nullptr) return UPSP_OK;
+  if (drv().TensorMapEncodeTiled == nullptr || c->batch > tma_max_batch()) return UPSP_OK;
   const bool ok16 = k.W % 8 == 0;
   const bool ok12 = k.format == UPSP_PIX_PACKED12 && k.W % 32 == 0 && k.npix % 32 == 0 && k.frame_bytes % 16 == 0 &&
                     c->registration == UPSP_REG_GIVEN && c->pipelined;
@@ -1144,6 +1159,7 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
   std::sort(keyed.begin(), keyed.end());
   std::vector<TmaBlock> blocks;
   std::vector<int> perm;
+  const bool lane_assign = !(getenv("UPSP_TMA_LANES") && atoi(getenv("UPSP_TMA_LANES")) == 0);   // A/B knob
   perm.reserve(N);
   bool val1 = true;
   size_t i = 0;
@@ -1163,6 +1179,46 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
     std::vector<std::pair<int, int>> blk;      // (pixel, node): raster order inside the block
     for (size_t q = i; q < j; ++q) blk.push_back({k.h_code[keyed[q].second], keyed[q].second});
     std::sort(blk.begin(), blk.end());
+    if (lane_assign) {
+      // Which warp of the block takes which node: the four taps of a node-frame are shared-memory loads at
+      // (row - box row) * row stride + (column - box column), the same offset for every node of a frame up to the
+      // sub-pixel rotation, so WHICH banks the 32 lanes of a warp hit is fixed by the node pixels.  Nodes are dealt to
+      // the block's warps so that as few lanes as possible share a bank without sharing the 32-bit word (raster order
+      // put half a row and the start of the next one in a warp: 2.3 wavefronts per tap load, ncu r2i).
+      const int nw = ((int)blk.size() + 31) / 32;
+      std::vector<std::vector<std::pair<int, int>>> wn(nw);
+      std::vector<std::array<std::array<std::vector<int>, 32>, 8>> words(nw);    // [warp][box phase][bank] -> distinct words
+      const int nphase = want == 1 ? 2 : 8;      // column of the node inside the box modulo 2 px (u16) / 8 px (packed: 12 bytes)
+      auto word_of = [&](int code, int par) {
+        const int ry = code / W - ymin, rx = code % W - x0 + par;
+        return want == 1 ? ry * (g.box_px16 / 2) + (rx >> 1) : ry * g.box_words12 + ((rx + (rx >> 1)) >> 2);   // u16 pair / packed byte floor(1.5 x)
+      };
+      for (auto& e : blk) {
+        int best = -1, best_cost = 1 << 30;
+        for (int w = 0; w < nw; ++w) {
+          const int cap = std::min(32, (int)blk.size() - 32 * w);
+          if ((int)wn[w].size() >= cap) continue;
+          int cost = 0;
+          for (int par = 0; par < nphase; ++par) {
+            const int wd = word_of(e.first, par);
+            const auto& v = words[w][par][wd & 31];
+            if (!v.empty() && std::find(v.begin(), v.end(), wd) == v.end()) cost += (int)v.size();
+          }
+          if (cost < best_cost) {
+            best_cost = cost;
+            best = w;
+          }
+        }
+        wn[best].push_back(e);
+        for (int par = 0; par < nphase; ++par) {
+          const int wd = word_of(e.first, par);
+          auto& v = words[best][par][wd & 31];
+          if (std::find(v.begin(), v.end(), wd) == v.end()) v.push_back(wd);
+        }
+      }
+      blk.clear();
+      for (auto& v : wn) blk.insert(blk.end(), v.begin(), v.end());
+    }
     TmaBlock b{};
     b.node0 = (int)perm.size();
     b.count = (int)blk.size();
@@ -1356,7 +1412,10 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   cudaStream_t SB = (c->pipelined && !serial) ? c->stream_b : c->stream;
   if (c->pipelined) {
     CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
-    if (c->last_sampled) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
+    // UPSP_FRONT=serial: the front end of batch i+1 starts after the projection of batch i (no decode under the
+    // projection; the patch kernel still runs beside the TMA kernel of its own batch)
+    static const bool front_serial = getenv("UPSP_FRONT") && !strcmp(getenv("UPSP_FRONT"), "serial");
+    if (c->last_sampled || front_serial) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
     c->last_sampled = serial;
   }
   for (size_t ci = 0; ci < c->cams.size(); ++ci) {
@@ -1374,7 +1433,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     KBEGIN_ON(0, SB);
     if (src12) {
       if (c->hot_fix) {
-        static const int scan_bpsm = getenv("UPSP_SCAN_BPSM") ? atoi(getenv("UPSP_SCAN_BPSM")) : 2;   // tuning knob
+        static const int scan_bpsm = getenv("UPSP_SCAN_BPSM") ? atoi(getenv("UPSP_SCAN_BPSM")) : 1;   // one small block per SM beside the projection (measured r2g/r2l)
         CU(launch_hot_scan12(in, k.frame_bytes, k.npix, nb, thresh, w_hot_cnt, w_hot_pos, w_hot_cnt + c->batch, k.H, k.W,
                              k.d_fix[bs], c->n_sm * scan_bpsm, SB));
         KCHECK(c);
@@ -1406,6 +1465,13 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
       k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), nb), 256, 0, c->stream>>>(
           k.d_m6 + (size_t)off * 6, nb, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
       KCHECK(c);
+      k_tma_coef<<<cdiv(nb, 256), 256, 0, c->stream>>>(k.d_m6 + (size_t)off * 6, nb, (c->f0 + off == 0) ? 0 : -1, k.d_coef + off);
+      KCHECK(c);
+    }
+    if (c->proj_mode > 0)       // this batch's column coefficients -> constant table `bs`
+      CU(tma_set_coef(bs, k.d_coef + off, nb, c->registration == UPSP_REG_PIXEL ? c->stream : SB));
+    if (c->pipelined && c->proj_mode > 0) {   // the TMA kernel needs the decoded frames / fix lists, not the patch values
+      CU(cudaEventRecord(c->ev_dec[bs], SB));
     }
     const int* tabs = reg ? k.d_tab + (size_t)off * (2 * k.W + 2 * k.H) : nullptr;   // this batch's tables
     const uint16_t* cur = w_work;
@@ -1484,7 +1550,9 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   }
   if (c->pipelined) {
     CU(cudaEventRecord(c->ev_front[bs], SB));
-    CU(cudaStreamWaitEvent(c->stream, c->ev_front[bs], 0));
+    // TMA modes: the big kernel starts on the decoded frames alone, the patch kernel runs beside it on the front-end
+    // stream, and only the small kernel of the patched / unseen nodes waits for the patch values
+    CU(cudaStreamWaitEvent(c->stream, c->proj_mode > 0 ? c->ev_dec[bs] : c->ev_front[bs], 0));
   }
   if (c->fused) {
     fa.n_cams = pa.n_cams;
@@ -1540,6 +1608,15 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
       fa.perm = c->d_perm_tma;
       TmaExtra ex{};
       ex.blk = c->d_tma_blk;
+      ex.coef_set = bs;
+      {
+        // unit projection values (integer statistics): cut the batch into frame slices so that the grid's last wave is
+        // short; UPSP_TMA_SPLIT = number of slices (default 2, 1 = off)
+        static const int nsplit = getenv("UPSP_TMA_SPLIT") ? std::max(1, atoi(getenv("UPSP_TMA_SPLIT"))) : 2;
+        const int stage = tma_stage_frames();
+        const int per = ((nb + nsplit - 1) / nsplit + stage - 1) / stage * stage;
+        ex.split_frames = (c->tma_val1 && nsplit > 1 && per < nb) ? per : 0;
+      }
       if (c->proj_mode == 2) {
         ex.packed = k.d_in + (size_t)slot * k.frame_bytes;
         ex.frame_bytes = k.frame_bytes;
@@ -1551,6 +1628,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
                             c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex, c->n_tma_blocks, c->stream));
       c->launches++;
       const int n_other = c->N - c->n_tma_plain;
+      if (c->pipelined) CU(cudaStreamWaitEvent(c->stream, c->ev_front[bs], 0));
       if (n_other > 0) {
         FusedArgs fb = fa;
         fb.perm = c->d_perm_tma + c->n_tma_plain;
@@ -1660,6 +1738,9 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
     for (auto& k : c->cams) {
       k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), count), 256, 0, c->stream>>>(
           k.d_m6 + (size_t)off * 6, count, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
+      KCHECK(c);
+      const int skip = (c->f0 + off <= 0 && c->f0 + off + count > 0) ? -(c->f0 + off) : -1;
+      k_tma_coef<<<cdiv(count, 256), 256, 0, c->stream>>>(k.d_m6 + (size_t)off * 6, count, skip, k.d_coef + off);
       KCHECK(c);
     }
   }
@@ -1880,10 +1961,21 @@ static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
   return UPSP_OK;
 }
 
+template <int NC, int CL, bool PK>
+static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st);
+
+// UPSP_PHASE2_SCALAR=1 keeps the scalar kernel (A/B measurements; the two must agree to the last bit except where the
+// packed one sums a thread's Chebyshev moments in two interleaved partial sums)
 template <int NC, int CL>
 static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
+  static const bool scalar = getenv("UPSP_PHASE2_SCALAR") && atoi(getenv("UPSP_PHASE2_SCALAR"));
+  return scalar ? launch_phase2_sym_pk<NC, CL, false>(a, st) : launch_phase2_sym_pk<NC, CL, true>(a, st);
+}
+
+template <int NC, int CL, bool PK>
+static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st) {
   constexpr int NT = 512;
-  auto kern = k_phase2_sym<NC, NT, CL>;
+  auto kern = k_phase2_sym<NC, NT, CL, PK>;
   const size_t smem = (size_t)(a.F / CL) * sizeof(float);
   // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
   if (smem > 24 * 1024)
