@@ -29,27 +29,23 @@ def test_baseline_scale_parity(up, orc, gpu):
     from upsp_b200 import synth
     F = 512
     args = types.SimpleNamespace(height=1024, width=1024, nodes=500_000, frames=F, targets=32, distinct=128,
-                                 degree=6, batch=0, csr="surface", registration="given")
+                                 degree=6, batch=0, csr="surface", registration="given", cams=1, overlap_groups=0, config=1)
     wl = bench.build_workload(args, synth)
     # ---- oracle: the whole job
     orc.set_num_threads(bench.host_threads())
     idx = np.arange(F) % args.distinct
-    fr = orc.unpack_12bit_frames(wl["packed"][idx]).reshape(F, args.height, args.width)
-    bo, bx, by, io, ix, iy = wl["patches"]
-    pobj = orc.Patches.__new__(orc.Patches)
-    pobj.n, pobj.bounds_off, pobj.internal_off = bo.size - 1, bo, io
-    pobj.bx, pobj.by, pobj.ix, pobj.iy = bx, by, ix, iy
+    fr = orc.unpack_12bit_frames(wl["packed"][0][idx]).reshape(F, args.height, args.width)
     warps = synth.make_warps(F, seed=5)
-    inten, s, q = orc.phase1([fr], [wl["csr"]], warp=[warps], interp=1, patches=[pobj])
+    inten, s, q = orc.phase1([fr], wl["csr"], warp=[warps], interp=1, patches=bench.oracle_patches(orc, wl, args))
     del fr
     avg, rms = orc.phase1_finals(s, q, F)
-    cov = orc.coverage([wl["csr"]])
+    cov = orc.coverage(wl["csr"])
     itr = orc.global_transpose([inten], args.nodes, F)[0]
     del inten
     # ---- product, through the C ABI
     g = bench.configure(up, wl, args, 0, 1, 0, 0, None)
     for o in range(0, F, args.distinct):
-        g.push_frames(0, wl["packed"][:min(args.distinct, F - o)], up.PIX_PACKED12, o, min(args.distinct, F - o))
+        g.push_frames(0, wl["packed"][0][:min(args.distinct, F - o)], up.PIX_PACKED12, o, min(args.distinct, F - o))
     g.process_frames(0, F)
     g.finish_phase1()
     g.transpose()

@@ -156,10 +156,13 @@ struct TmaSmem {
 // frames fit a common origin (camera shake of a few pixels between neighbouring frames), with one box per frame
 // (tmap1) otherwise.  The TMA unit's cost is per box far more than per byte (measured: 80 cycles per 1 KB box per SM,
 // 156 per 4.6 KB box), and with one box per frame the kernel waited on it.
-template <int SRC, int CH, bool VAL1>
-__global__ void __launch_bounds__(TMA_NB, 6)
+// NG groups in the ring, the producer LA groups ahead of the consumers, MINB resident blocks per SM asked of ptxas.
+template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6>
+__global__ void __launch_bounds__(TMA_NB, MINB)
 k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__ CUtensorMap tmap1, const FusedArgs a,
               const TmaExtra ex) {
+  constexpr int TMA_NG = NG, TMA_LA = LA;      // shadow the defaults below
+  static_assert(LA >= 1 && LA < NG, "look-ahead must leave a free group");
   using L = TmaSmem<SRC, CH, TMA_NG>;
   constexpr int SLOT = L::SLOT;
   constexpr int TS = L::TS;

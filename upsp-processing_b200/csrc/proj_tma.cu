@@ -2,6 +2,7 @@
 #include "proj_tma.h"
 
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels_project_tma.cuh"
 
@@ -19,24 +20,40 @@ TmaGeom tma_geom() {
   return g;
 }
 
-template <int SRC, int CH, bool VAL1>
+template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6>
 static cudaError_t launch1(const CUtensorMap& map_group, const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex,
                            int nblocks, cudaStream_t st) {
-  constexpr int smem = TmaSmem<SRC, CH, TMA_NG>::total;
+  constexpr int smem = TmaSmem<SRC, CH, NG>::total;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1, NG, LA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const unsigned ny = ex.split_frames > 0 ? (unsigned)((a.nframes + ex.split_frames - 1) / ex.split_frames) : 1u;
-  k_project_tma<SRC, CH, VAL1><<<dim3((unsigned)nblocks, ny), TMA_NB, smem, st>>>(map_group, map_single, a, ex);
+  k_project_tma<SRC, CH, VAL1, NG, LA, MINB><<<dim3((unsigned)nblocks, ny), TMA_NB, smem, st>>>(map_group, map_single, a, ex);
   return cudaGetLastError();
 }
 
 cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map_group, const CUtensorMap& map_single,
                                const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
   if (nblocks <= 0) return cudaSuccess;
+  // UPSP_TMA_RING = "NG.LA.MINB" picks another ring depth / look-ahead / occupancy target of the hot instantiation
+  // (packed source, 64-byte segments, unit values): tuning knob
+  static const char* ring = getenv("UPSP_TMA_RING");
+  if (ring && src == 1 && !seg128 && val1) {
+#define UPSP_RING(NG, LA, MB) \
+    if (!strcmp(ring, #NG "." #LA "." #MB)) return launch1<1, 16, true, NG, LA, MB>(map_group, map_single, a, ex, nblocks, st)
+    UPSP_RING(3, 2, 7);
+    UPSP_RING(3, 1, 7);
+    UPSP_RING(3, 2, 6);
+    UPSP_RING(4, 3, 6);
+    UPSP_RING(5, 3, 5);
+    UPSP_RING(6, 4, 5);
+    UPSP_RING(4, 2, 5);
+    UPSP_RING(2, 1, 8);
+#undef UPSP_RING
+  }
 #define UPSP_TMA_CASE(S, C)                                                                              \
   return val1 ? launch1<S, C, true>(map_group, map_single, a, ex, nblocks, st)                           \
               : launch1<S, C, false>(map_group, map_single, a, ex, nblocks, st)

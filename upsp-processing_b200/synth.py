@@ -156,6 +156,17 @@ def make_overlap(n_nodes, n_groups=50, seed=4):
     return ov
 
 
+def overlap_src_index(n_nodes, overlap):
+    """The array upsp_gpu_set_overlap_remap takes: out[n] = sol[src[n]] is what P3DModel_::adjust_solution
+    (cpp/lib/P3DModel.ipp:144-157) does to a solution vector (lower node index of an overlap group wins)."""
+    idx = np.arange(n_nodes, dtype=np.int32)
+    for curr in sorted(overlap):
+        for alt in overlap[curr]:
+            if curr < alt:
+                idx[alt] = idx[curr]
+    return idx
+
+
 def make_warps(n_frames, seed=5, trans=1.0, lin=5e-4):
     """Per-frame inverse affine maps near identity: translation within +-trans px, linear part
     within +-lin of identity.  f32 [F,6] row-major 2x3."""
