@@ -71,8 +71,9 @@ def test_two_ranks_match_oracle(up, orc, gpu, keep_frame_major, same_device):
     assert np.all(e_op <= 1e-5 + noise + cond)
 
 
-@pytest.mark.parametrize("R,staged", [(3, None), (4, "1"), (8, "3"), (8, None)])
-def test_many_ranks_one_gpu(up, orc, gpu, R, staged, monkeypatch):
+@pytest.mark.parametrize("R,staged,ship", [(3, None, None), (4, "1", None), (8, "3", None), (8, None, None),
+                                           (4, "3", "sm"), (8, "7", "sm"), (3, "1", "sm")])
+def test_many_ranks_one_gpu(up, orc, gpu, R, staged, ship, monkeypatch):
     """R ranks as R contexts on one device.  >= 3 ranks store rows straight into the owners' buffers
     in 128-byte segments (default); UPSP_STAGED_PEERS=k sends the next k ranks' rows through the
     staging block + copy engines instead (mixed exchange).  Small batches so that both staging
@@ -80,6 +81,8 @@ def test_many_ranks_one_gpu(up, orc, gpu, R, staged, monkeypatch):
     import upsp_b200
     if staged is not None:
         monkeypatch.setenv("UPSP_STAGED_PEERS", staged)
+    if ship is not None:          # staged rows shipped by the SM kernel k_ship_rows instead of the copy engines
+        monkeypatch.setenv("UPSP_SHIP", ship)
     case = Case(upsp_b200.synth, n_frames=96, n_nodes=2003, registration=True, patches=True, overlap=True,
                 seed=33, fmt="p12")
     ref = run_oracle(orc, case, n_ranks=R)

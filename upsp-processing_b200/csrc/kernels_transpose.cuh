@@ -72,4 +72,39 @@ k_transpose_a2a(const XposeArgs a) {
   }
 }
 
+// ---- staged exchange, shipped by the SMs: rows of the other ranks' nodes, which the projection kernel left in the
+// local staging block [N][stride] (column = frame inside the batch), go to columns [col0, col0 + nb) of their owners'
+// node-major buffers [N_s][F].  A batch makes nb * 4 bytes (1 KB at 256 frames) of every row contiguous at the
+// destination, against 64 / 128 bytes when the projection kernel stores there itself; the kernel is small (a few warps
+// per SM) and runs beside the projection of the next batch, so neither the projection nor the copy engines (290 GB/s
+// per GPU, measured) sit on the NVLink path.  Reference: the MPI_Alltoallv of global_transpose,
+// cpp/exec/psp_process.cpp:707-771.  Peers are interleaved row by row so that every link is busy all the time.
+struct ShipArgs {
+  const float* stage;
+  int stride, nb, n_peers, max_rows;
+  float* dst[UPSP_MAX_RANKS];        // owner's buffer, already offset to column col0 of its row 0
+  int row0[UPSP_MAX_RANKS];          // first node of the owner in the staging block
+  int rows[UPSP_MAX_RANKS];
+  size_t dst_stride;                 // F (floats)
+};
+
+__global__ void __launch_bounds__(128)
+k_ship_rows(const ShipArgs a) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const bool vec = (a.nb & 3) == 0 && (a.stride & 3) == 0;
+  for (int r = w; r < a.max_rows; r += warps) {
+    for (int p = 0; p < a.n_peers; ++p) {
+      if (r >= a.rows[p]) continue;
+      const float* src = a.stage + (size_t)(a.row0[p] + r) * a.stride;
+      float* dst = a.dst[p] + (size_t)r * a.dst_stride;
+      if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        for (int i = lane * 4; i < a.nb; i += 128) st_stream_f4(dst + i, ld_stream_f4(src + i));
+      } else {
+        for (int i = lane; i < a.nb; i += 32) dst[i] = src[i];
+      }
+    }
+  }
+}
+
 }  // namespace upsp

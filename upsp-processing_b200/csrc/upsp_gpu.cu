@@ -308,6 +308,8 @@ struct upsp_gpu_ctx {
   bool staged_xchg = false;
   unsigned stage_mask = 0;         // ranks whose rows travel through the staging block
   int staged_peers = 0;
+  bool ship_sm = false;           // staged rows shipped by k_ship_rows instead of the copy engines
+  int ship_bpsm = 1;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
   cudaEvent_t ev_pa = nullptr, ev_pb = nullptr;  // process_frames timing
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user timer
@@ -747,6 +749,10 @@ extern "C" int upsp_gpu_set_filter(upsp_gpu_ctx* c, int kind, int ksize) {
 
 extern "C" int upsp_gpu_set_unpack_lut(upsp_gpu_ctx* c, const uint16_t* lut) {
   ENTER(c);
+  // one table per context, and its largest value decides which projection kernels are eligible (12-bit fast paths):
+  // it cannot change once frames have been decoded with it
+  REQUIRE(c->frames_processed == 0 && !c->finalized, UPSP_ERR_STATE,
+          "set_unpack_lut after frames were processed (the table is fixed for the run)");
   cudaFree(c->d_lut);
   c->d_lut = nullptr;
   c->lut_max = 0;
@@ -1065,6 +1071,10 @@ static int finalize(upsp_gpu_ctx* c) {
   //            4 direct 86 ms, 2 + 5: 87 ms).
   // So: `staged_peers` = 1 at 2 ranks, 0 otherwise; UPSP_STAGED_PEERS=k routes the next k ranks' rows
   // through the staging block (0: all direct).
+  // Round 2: the staged rows can also be shipped by a small SM kernel (k_ship_rows: 1 KB row pieces per batch, all
+  // peers interleaved) instead of the copy engines: UPSP_SHIP = sm | ce, UPSP_SHIP_BPSM = blocks of 128 threads per SM.
+  c->ship_sm = getenv("UPSP_SHIP") && !strcmp(getenv("UPSP_SHIP"), "sm");
+  c->ship_bpsm = getenv("UPSP_SHIP_BPSM") ? std::max(1, atoi(getenv("UPSP_SHIP_BPSM"))) : 1;
   c->staged_peers = c->R == 2 ? 1 : 0;
   if (getenv("UPSP_STAGED_PEERS")) c->staged_peers = std::min(std::max(atoi(getenv("UPSP_STAGED_PEERS")), 0), c->R - 1);
   if (!c->pipelined || c->R <= 1) c->staged_peers = 0;
@@ -1700,6 +1710,27 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
       // [f0+off, f0+off+nb) of rank s's node-major buffer, one strided copy per peer (copy engines)
       constexpr int NX = upsp_gpu_ctx::NX;
       for (int j = 0; j < NX; ++j) CU(cudaStreamWaitEvent(c->stream_x[j], c->ev_back[bs], 0));
+      if (c->ship_sm) {
+        // SM shipper (kernels_transpose.cuh): one small kernel for all staged peers, beside the next projection
+        ShipArgs sa{};
+        sa.stage = c->d_stage[bs];
+        sa.stride = c->stage_stride;
+        sa.nb = nb;
+        sa.dst_stride = (size_t)c->F;
+        for (int d = 1; d <= c->staged_peers; ++d) {
+          const int s = (c->rank + d) % c->R;
+          if (c->n_count[s] <= 0) continue;
+          sa.dst[sa.n_peers] = reinterpret_cast<float*>(c->peer_base[s]) + (size_t)(c->f0 + off);
+          sa.row0[sa.n_peers] = c->n_start[s];
+          sa.rows[sa.n_peers] = c->n_count[s];
+          sa.max_rows = std::max(sa.max_rows, c->n_count[s]);
+          sa.n_peers++;
+        }
+        if (sa.n_peers > 0) {
+          k_ship_rows<<<c->n_sm * c->ship_bpsm, 128, 0, c->stream_x[0]>>>(sa);
+          KCHECK(c);
+        }
+      } else {
       // every peer's row block is cut into `parts` pieces so that NX copies are in flight at any time
       const int parts = std::max(1, (NX + c->staged_peers - 1) / c->staged_peers);
       int q = 0;
@@ -1714,6 +1745,7 @@ static int process_batch(upsp_gpu_ctx* c, int off, int nb) {
                                (size_t)nb * sizeof(float), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice,
                                c->stream_x[q++ % NX]));
         }
+      }
       }
       for (int j = 0; j < NX; ++j) CU(cudaEventRecord(c->ev_x[bs][j], c->stream_x[j]));
     }

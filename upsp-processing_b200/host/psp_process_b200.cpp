@@ -198,6 +198,8 @@ int main(int argc, char** argv) {
       auto rowptr = read_all<int32_t>(b + ".rowptr"), col = read_all<int32_t>(b + ".col");
       auto val = read_all<float>(b + ".val");
       if ((int)rowptr.size() != msize + 1) throw std::invalid_argument("rowptr size inconsistent with msize");
+      if (rowptr.back() < 0 || col.size() != (size_t)rowptr.back() || val.size() != col.size())
+        throw std::invalid_argument("job directory: cam" + std::to_string(c) + ".col/.val do not hold rowptr[msize] entries");
       chain.set_projection(c, rowptr.data(), col.data(), val.data());
       std::ifstream targets_file(b + ".targets");
       if (patcher == "polynomial" && targets_file) {
@@ -225,6 +227,9 @@ int main(int argc, char** argv) {
         auto boff = read_all<int32_t>(b + ".patch_boff"), ioff = read_all<int32_t>(b + ".patch_ioff");
         auto bx = read_all<uint32_t>(b + ".patch_bx"), by = read_all<uint32_t>(b + ".patch_by");
         auto ix = read_all<uint32_t>(b + ".patch_ix"), iy = read_all<uint32_t>(b + ".patch_iy");
+        if (boff.empty() || boff.size() != ioff.size() || (size_t)boff.back() != bx.size() || bx.size() != by.size() ||
+            (size_t)ioff.back() != ix.size() || ix.size() != iy.size())
+          throw std::invalid_argument("job directory: patch arrays of camera " + std::to_string(c) + " do not match their offsets");
         chain.set_patches(c, (int)boff.size() - 1, boff.data(), bx.data(), by.data(), ioff.data(),
                           ix.data(), iy.data());
       }
@@ -243,6 +248,9 @@ int main(int argc, char** argv) {
     if (regmode == UPSP_REG_GIVEN)
       for (int c = 0; c < cameras; ++c) {
         auto m6 = read_all<float>(job_dir + "/cam" + std::to_string(c) + ".warp");
+        if (m6.size() != (size_t)number_frames * 6)
+          throw std::invalid_argument("job directory: cam" + std::to_string(c) + ".warp holds " + std::to_string(m6.size()) +
+                                      " floats, expected 6 per frame");
         chain.set_warp_matrices(c, 0, number_frames, m6.data());
       }
 
