@@ -157,19 +157,27 @@ struct TmaSmem {
 // (tmap1) otherwise.  The TMA unit's cost is per box far more than per byte (measured: 80 cycles per 1 KB box per SM,
 // 156 per 4.6 KB box), and with one box per frame the kernel waited on it.
 // NG groups in the ring, the producer LA groups ahead of the consumers, MINB resident blocks per SM asked of ptxas.
-template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6>
+// IT16 (with VAL1): the node-major rows are stored as 16-bit integers.  With unit projection values a node-frame value
+// IS the rounded warped pixel (an integer < 2^16, exact in either type), so the row store, the all-to-all over NVLink
+// and the read of phase 2 move half the bytes; the ABI's readers widen to float (upsp_gpu.cu).  The staging tile keeps its
+// byte geometry: a chunk is 2 CH frames of 2 bytes instead of CH frames of 4.
+template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6, bool IT16 = false>
 __global__ void __launch_bounds__(TMA_NB, MINB)
 k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__ CUtensorMap tmap1, const FusedArgs a,
               const TmaExtra ex) {
   constexpr int TMA_NG = NG, TMA_LA = LA;      // shadow the defaults below
   static_assert(LA >= 1 && LA < NG, "look-ahead must leave a free group");
+  static_assert(!IT16 || VAL1, "16-bit rows need integer node values");
+  constexpr int CHF = IT16 ? 2 * CH : CH;      // frames per chunk
+  constexpr int ESZ = IT16 ? 2 : 4;            // bytes per stored value
+  static_assert(CHF <= TMA_S && TMA_S % CHF == 0, "a table stage is a whole number of chunks");
   using L = TmaSmem<SRC, CH, TMA_NG>;
   constexpr int SLOT = L::SLOT;
   constexpr int TS = L::TS;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
-  float* tile = reinterpret_cast<float*>(smem + L::tile_off);
-  float** rowp = reinterpret_cast<float**>(smem + L::rowp_off);
+  unsigned char* tile = smem + L::tile_off;                     // [node][TS * 4 bytes]: CHF values + 16 bytes of padding
+  unsigned char** rowp = reinterpret_cast<unsigned char**>(smem + L::rowp_off);
   const double2* __restrict__ coef = c_tma_coef[ex.coef_set];   // [batch] (constant bank)
   int2* s_y = reinterpret_cast<int2*>(smem + L::y_off);        // [S][TH]: (X0,Y0)[ymin+r] minus the box origin
   int2* s_org = reinterpret_cast<int2*>(smem + L::org_off);    // [S]: box origin (px, row) of the frame
@@ -182,7 +190,17 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool live = tid < bd.count;
   const int n = live ? __ldg(a.perm + bd.node0 + tid) : -1;
-  rowp[tid] = live ? fused_row_ptr(a, n) : nullptr;
+  if (IT16) {       // 16-bit rows: same addressing as fused_row_ptr in 2-byte elements (no staging in this mode)
+    unsigned char* rp = nullptr;
+    if (live) {
+      int r = 0;
+      while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
+      rp = reinterpret_cast<unsigned char*>(a.dst[r]) + ((size_t)(n - a.node_start[r]) * a.f_total + a.col0) * 2;
+    }
+    rowp[tid] = rp;
+  } else {
+    rowp[tid] = live ? reinterpret_cast<unsigned char*>(fused_row_ptr(a, n)) : nullptr;
+  }
   if (tid == 0) {
     for (int i = 0; i < TMA_NG; ++i) {
       mbar_init(full + i, 1);
@@ -196,8 +214,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   const int px = code % W, py = code / W;
   const double dpx = (double)px;
   const int yrel = py - bd.ymin;
-  const bool vec_ok = ((a.f_total | a.col0) & 3) == 0;
-  float* trow = tile + tid * TS;
+  const bool vec_ok = ((a.f_total | a.col0) & (IT16 ? 7 : 3)) == 0;      // 16-byte aligned row segments
+  unsigned char* trow = tile + tid * (TS * 4);
   double s = 0.0, q = 0.0;
   unsigned gidx = 0;        // groups issued / consumed so far by this block (ring position)
 
@@ -305,8 +323,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
     if (tid == 0)
       for (int g = 0; g < min(TMA_LA, ngr); ++g) issue(g, gidx + g);
 
-    for (int c0 = 0; c0 < ns; c0 += CH) {
-      const int nb = min(CH, ns - c0);
+    for (int c0 = 0; c0 < ns; c0 += CHF) {
+      const int nb = min(CHF, ns - c0);
       const int b0 = s0 + c0;
       for (int u = 0; u < nb; u += TMA_G) {
         const int g = (c0 + u) / TMA_G;
@@ -384,7 +402,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
         if (nf == TMA_G) {
-          *reinterpret_cast<float4*>(trow + u) = make_float4(sol[0], sol[1], sol[2], sol[3]);
+          if (IT16) *reinterpret_cast<uint2*>(trow + u * 2) = make_uint2(ri[0] | (ri[1] << 16), ri[2] | (ri[3] << 16));
+          else *reinterpret_cast<float4*>(trow + u * 4) = make_float4(sol[0], sol[1], sol[2], sol[3]);
           if (VAL1) {
             unsigned si = 0, qi = 0;      // 4 * 4095 and 4 * 4095^2 fit easily
 #pragma unroll
@@ -403,32 +422,38 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
           }
         } else {
           for (int j = 0; j < nf; ++j) {
-            trow[u + j] = sol[j];
+            if (IT16) reinterpret_cast<unsigned short*>(trow)[u + j] = (unsigned short)ri[j];
+            else reinterpret_cast<float*>(trow)[u + j] = sol[j];
             q += (double)__fmul_rn(sol[j], sol[j]);
             s += (double)sol[j];
           }
         }
       }
       __syncwarp();
-      if (vec_ok && nb == CH) {
-        constexpr int LPN = CH / 4;      // lanes per node row segment
-        const int fq = (lane % LPN) * 4;
+      if (vec_ok && nb == CHF) {
+        constexpr int LPN = CH / 4;      // lanes per node row segment (16 bytes each)
+        const int fq = (lane % LPN) * 16;      // byte offset inside the segment
         // CH = 16: the two nodes of a quarter warp are 4 tile rows apart (4 * TS = 80 words = 16 banks: their two
         // 16-word segments tile the 32 banks; neighbouring rows, 20 banks apart, overlapped in 4 of them)
         const int nsel = CH == 16 ? (lane >> 3) + 4 * ((lane >> 2) & 1) : lane / LPN;
 #pragma unroll
         for (int it = 0; it < LPN; ++it) {
           const int nl = w * 32 + it * (32 / LPN) + nsel;
-          float* rp = rowp[nl];
+          unsigned char* rp = rowp[nl];
           if (rp != nullptr) {
-            const float4 o = *reinterpret_cast<const float4*>(tile + nl * TS + fq);
-            *reinterpret_cast<float4*>(rp + b0 + fq) = o;
+            const float4 o = *reinterpret_cast<const float4*>(tile + nl * (TS * 4) + fq);
+            *reinterpret_cast<float4*>(rp + (size_t)b0 * ESZ + fq) = o;
           }
         }
-      } else if (lane < nb) {
+      } else {
         for (int j = 0; j < 32; ++j) {
-          float* rp = rowp[w * 32 + j];
-          if (rp != nullptr) rp[b0 + lane] = tile[(w * 32 + j) * TS + lane];
+          unsigned char* rp = rowp[w * 32 + j];
+          if (rp == nullptr) continue;
+          const unsigned char* tr = tile + (w * 32 + j) * (TS * 4);
+          for (int f = lane; f < nb; f += 32) {
+            if (IT16) reinterpret_cast<unsigned short*>(rp)[b0 + f] = reinterpret_cast<const unsigned short*>(tr)[f];
+            else reinterpret_cast<float*>(rp)[b0 + f] = reinterpret_cast<const float*>(tr)[f];
+          }
         }
       }
       __syncwarp();

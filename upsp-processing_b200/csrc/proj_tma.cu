@@ -20,24 +20,31 @@ TmaGeom tma_geom() {
   return g;
 }
 
-template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6>
+template <int SRC, int CH, bool VAL1, int NG = TMA_NG, int LA = TMA_LA, int MINB = 6, bool IT16 = false>
 static cudaError_t launch1(const CUtensorMap& map_group, const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex,
                            int nblocks, cudaStream_t st) {
   constexpr int smem = TmaSmem<SRC, CH, NG>::total;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1, NG, LA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_project_tma<SRC, CH, VAL1, NG, LA, MINB, IT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const unsigned ny = ex.split_frames > 0 ? (unsigned)((a.nframes + ex.split_frames - 1) / ex.split_frames) : 1u;
-  k_project_tma<SRC, CH, VAL1, NG, LA, MINB><<<dim3((unsigned)nblocks, ny), TMA_NB, smem, st>>>(map_group, map_single, a, ex);
+  k_project_tma<SRC, CH, VAL1, NG, LA, MINB, IT16><<<dim3((unsigned)nblocks, ny), TMA_NB, smem, st>>>(map_group, map_single, a, ex);
   return cudaGetLastError();
 }
 
-cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map_group, const CUtensorMap& map_single,
-                               const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, const CUtensorMap& map_group,
+                               const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st) {
   if (nblocks <= 0) return cudaSuccess;
+  if (rows16) {      // 16-bit node-major rows (unit projection values only)
+    if (!val1) return cudaErrorInvalidValue;
+    if (src == 0) return seg128 ? launch1<0, 32, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st)
+                                : launch1<0, 16, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st);
+    return seg128 ? launch1<1, 32, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st)
+                  : launch1<1, 16, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st);
+  }
   // UPSP_TMA_RING = "NG.LA.MINB" picks another ring depth / look-ahead / occupancy target of the hot instantiation
   // (packed source, 64-byte segments, unit values): tuning knob
   static const char* ring = getenv("UPSP_TMA_RING");

@@ -40,8 +40,9 @@ struct TmaExtra {
 
 // src 0: decoded u16 frames, 1: packed 12-bit frames.  seg128: 128-byte row segments (peer stores).
 // map_group: box of group_frames frames; map_single: box of one frame (same tensor, same rows x columns).
-cudaError_t launch_project_tma(int src, bool seg128, bool val1, const CUtensorMap& map_group, const CUtensorMap& map_single,
-                               const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st);
+// rows16: node-major rows stored as 16-bit integers (val1 only; dst[] are then 2-byte element buffers).
+cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, const CUtensorMap& map_group,
+                               const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st);
 // hot-pixel scan of packed 12-bit frames -> fix lists (read only)
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
                               int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st);

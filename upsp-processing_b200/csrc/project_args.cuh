@@ -49,6 +49,10 @@ struct FusedArgs {
   float* stage;
   int stage_stride, rank;
   unsigned stage_mask;                 // bit r set: rank r's rows go through the staging block
+  // 16-bit row mode: the few nodes whose values are not integers (patched pixels) or not numbers (unseen nodes) keep
+  // float rows in a side buffer of their owner; row_index[n] = row of node n in that buffer (dst[] then point at the
+  // side buffers).  nullptr: row = n - node_start[owner].
+  const int* row_index;
 };
 
 // where a block writes node n's row segment of this batch (frame b of the batch at [b])
@@ -56,7 +60,8 @@ __device__ __forceinline__ float* fused_row_ptr(const FusedArgs& a, int n) {
   int r = 0;
   while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
   if (a.stage != nullptr && ((a.stage_mask >> r) & 1u)) return a.stage + (size_t)n * a.stage_stride;
-  return a.dst[r] + (size_t)(n - a.node_start[r]) * a.f_total + a.col0;
+  const int row = a.row_index != nullptr ? __ldg(a.row_index + n) : n - a.node_start[r];
+  return a.dst[r] + (size_t)row * a.f_total + a.col0;
 }
 
 }  // namespace upsp

@@ -308,6 +308,15 @@ struct upsp_gpu_ctx {
   bool staged_xchg = false;
   unsigned stage_mask = 0;         // ranks whose rows travel through the staging block
   int staged_peers = 0;
+  // 16-bit row mode (TMA projection with unit values, decided in ensure_proj_mode): rows of plain nodes are 16-bit
+  // integers at the start of the shared block, the other (patched / unseen) nodes keep float rows in a side buffer behind them
+  bool it16 = false;
+  int* d_other_idx = nullptr;       // [N]: -1 plain node, else row in the owner's side buffer
+  int* d_other_local = nullptr;     // local indices of this rank's side-buffer nodes
+  int n_other_local = 0;
+  size_t side_off[UPSP_MAX_RANKS] = {0};   // byte offset of rank r's side buffer in its shared block
+  float* d_bounce = nullptr;        // readers: rows widened to float on their way to the host
+  size_t bounce_floats = 0;
   bool ship_sm = false;           // staged rows shipped by k_ship_rows instead of the copy engines
   int ship_bpsm = 1;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
@@ -594,6 +603,9 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaFree(c->d_lut);
   cudaFree(c->d_perm);
   cudaFree(c->d_perm_tma);
+  cudaFree(c->d_other_idx);
+  cudaFree(c->d_other_local);
+  cudaFree(c->d_bounce);
   cudaFree(c->d_tma_blk);
   cudaFree(c->d_intensity);
   if (c->shared_vmm.handle) vmm_free(c->shared_vmm); else cudaFree(c->d_shared);
@@ -631,6 +643,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   for (int i = 0; i < 2; ++i) {
     for (auto e : c->ev_x[i]) if (e) cudaEventDestroy(e);
     cudaFree(c->d_stage[i]);
+    c->d_stage[i] = nullptr;
   }
   for (auto sx : c->stream_x) if (sx) cudaStreamDestroy(sx);
   if (c->stream_b) cudaStreamDestroy(c->stream_b);
@@ -1129,6 +1142,8 @@ static int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, uint6
   return UPSP_OK;
 }
 
+static int phase2_cluster(int F);
+
 // Decide the projection mode of a fused single-camera context and build what the TMA kernels need:
 //   * processing order: nodes with a plain pixel, cut into blocks of <= 128 nodes whose pixels lie in one
 //     strip of `strip_rows` image rows and span <= `tile_cols` columns (so that the box a block stages per
@@ -1266,6 +1281,40 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
     for (int b = 0; b < 2; ++b) {
       CU(cudaMalloc(&k.d_fix[b], (size_t)c->batch * hot_fix_bytes()));
       CU(cudaMemset(k.d_fix[b], 0, (size_t)c->batch * hot_fix_bytes()));
+    }
+  }
+  // 16-bit node-major rows?  Unit projection values make every value of a plain node an integer < 2^16; the other nodes
+  // (patched: float values, unseen: NaN) keep float rows in a side buffer behind the 16-bit rows of their owner.  Needs
+  // the symmetric phase-2 kernel (the one that reads 16-bit rows) and 16-byte aligned row segments.  UPSP_ITRANS16=0: off.
+  {
+    const int cl = phase2_cluster(c->F);
+    bool ok = val1 && !(getenv("UPSP_ITRANS16") && atoi(getenv("UPSP_ITRANS16")) == 0) && cl > 0 && c->F % (8 * cl) == 0 &&
+              c->F % 8 == 0;
+    std::vector<int> oidx(N, -1), cnt(c->R, 0), local;
+    for (int r = 0; r < c->R && ok; ++r) {
+      for (int n = c->n_start[r]; n < c->n_start[r] + c->n_count[r]; ++n)
+        if (k.h_code[n] < 0) {
+          if (r == c->rank) local.push_back(n - c->n_start[r]);
+          oidx[n] = cnt[r]++;
+        }
+      auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+      c->side_off[r] = al((size_t)c->n_count[r] * c->F * sizeof(uint16_t));
+      // the side buffer must fit behind the 16-bit rows inside the block sized for float rows
+      ok = ok && c->side_off[r] + (size_t)cnt[r] * c->F * sizeof(float) <= (size_t)c->n_count[r] * c->F * sizeof(float);
+    }
+    if (ok) {
+      c->it16 = true;
+      c->n_other_local = (int)local.size();
+      TRY(upload(&c->d_other_idx, oidx.data(), oidx.size()));
+      if (!local.empty()) TRY(upload(&c->d_other_local, local.data(), local.size()));
+      // rows go straight to their owners in this mode (half the NVLink bytes of the float rows): no staging block
+      c->staged_xchg = false;
+      c->staged_peers = 0;
+      c->stage_mask = 0;
+      for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_stage[i]);
+        c->d_stage[i] = nullptr;
+      }
     }
   }
   c->proj_mode = want;
@@ -1634,7 +1683,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         ex.hot = c->hot_fix ? reinterpret_cast<const HotFix*>(k.d_fix[bs]) : nullptr;
         fa.cam[0].frames = nullptr;
       }
-      CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->proj_mode == 2 ? k.tmap12g : k.tmap16g[bs],
+      CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->it16, c->proj_mode == 2 ? k.tmap12g : k.tmap16g[bs],
                             c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex, c->n_tma_blocks, c->stream));
       c->launches++;
       const int n_other = c->N - c->n_tma_plain;
@@ -1643,6 +1692,10 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         FusedArgs fb = fa;
         fb.perm = c->d_perm_tma + c->n_tma_plain;
         fb.n_nodes = n_other;
+        if (c->it16) {      // float rows of the patched / unseen nodes: the owners' side buffers
+          fb.row_index = c->d_other_idx;
+          for (int r = 0; r < c->R; ++r) fb.dst[r] = reinterpret_cast<float*>(c->peer_base[r] + c->side_off[r]);
+        }
         if (seg128) k_project_fused4<1, 128, 32><<<cdiv(n_other, 128), 128, 0, c->stream>>>(fb);
         else k_project_fused4<1, 128, 16><<<cdiv(n_other, 128), 128, 0, c->stream>>>(fb);
         KCHECK(c);
@@ -1993,7 +2046,7 @@ static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
   return UPSP_OK;
 }
 
-template <int NC, int CL, bool PK>
+template <int NC, int CL, bool PK, bool IN16 = false>
 static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st);
 
 // UPSP_PHASE2_SCALAR=1 keeps the scalar kernel (A/B measurements; the two must agree to the last bit except where the
@@ -2001,13 +2054,14 @@ static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st);
 template <int NC, int CL>
 static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
   static const bool scalar = getenv("UPSP_PHASE2_SCALAR") && atoi(getenv("UPSP_PHASE2_SCALAR"));
+  if (a.itrans16 != nullptr) return launch_phase2_sym_pk<NC, CL, true, true>(a, st);
   return scalar ? launch_phase2_sym_pk<NC, CL, false>(a, st) : launch_phase2_sym_pk<NC, CL, true>(a, st);
 }
 
-template <int NC, int CL, bool PK>
+template <int NC, int CL, bool PK, bool IN16>
 static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st) {
   constexpr int NT = 512;
-  auto kern = k_phase2_sym<NC, NT, CL, PK>;
+  auto kern = k_phase2_sym<NC, NT, CL, PK, IN16>;
   const size_t smem = (size_t)(a.F / CL) * sizeof(float);
   // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
   if (smem > 24 * 1024)
@@ -2034,6 +2088,8 @@ static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, 
   if (a.n_local == 0) return UPSP_OK;
   const int cl = phase2_cluster(a.F);
   int rc = UPSP_OK;
+  REQUIRE(phase2_symmetric(a) || (a.itrans16 == nullptr && a.row_list == nullptr), UPSP_ERR_STATE,
+          "16-bit intensity rows need the symmetric phase-2 kernel");
   if (phase2_symmetric(a)) {
     switch (cl) {
       case 1: rc = launch_phase2_sym<NC, 1>(a, st); break;
@@ -2086,7 +2142,8 @@ static int phase2_cluster(int F) {
 static bool phase2_symmetric(const Phase2Args& a) {
   const int cl = phase2_cluster(a.F);
   return a.fit_out == nullptr && cl > 0 && a.F % (8 * cl) == 0 &&
-         (reinterpret_cast<uintptr_t>(a.itrans) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ptrans) & 15) == 0;
+         (reinterpret_cast<uintptr_t>(a.itrans) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ptrans) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.itrans16) & 15) == 0;
 }
 
 static void fill_basis(Phase2Args& a, int F, int degree) {
@@ -2143,7 +2200,23 @@ extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, con
   CU(cudaEventRecord(c->ev_a, c->stream));
   const bool prof = c->sample_every > 0;
   KBEGIN(6);
-  TRY(dispatch_phase2(c, a, c->stream, &c->launches));
+  if (c->it16) {
+    // 16-bit rows of the plain nodes, then the float rows of the side buffer (patched / unseen nodes)
+    Phase2Args b = a;
+    b.itrans16 = reinterpret_cast<const unsigned short*>(c->d_shared);
+    b.other_idx = c->d_other_idx;
+    TRY(dispatch_phase2(c, b, c->stream, &c->launches));
+    if (c->n_other_local > 0) {
+      Phase2Args o = a;
+      o.itrans = reinterpret_cast<const float*>(c->d_shared + c->side_off[c->rank]);
+      o.other_idx = c->d_other_idx;
+      o.row_list = c->d_other_local;
+      o.n_local = c->n_other_local;
+      TRY(dispatch_phase2(c, o, c->stream, &c->launches));
+    }
+  } else {
+    TRY(dispatch_phase2(c, a, c->stream, &c->launches));
+  }
   KEND();
   if (c->N_local) {
     k_phase2_finals<<<cdiv(c->N_local, 256), 256, 0, c->stream>>>(
@@ -2183,10 +2256,54 @@ extern "C" int upsp_gpu_read_intensity(upsp_gpu_ctx* c, int off, int n, float* h
   return d2h(c, host, c->d_intensity + (size_t)off * c->N, (size_t)n * c->N * sizeof(float));
 }
 
+// 16-bit row mode: rows [row0, row0 + nrows) x frames [f0, f0 + nf) of intensity_transpose as floats (the values the
+// float rows would hold: integers are exact, the side buffer's rows are copied)
+__global__ void __launch_bounds__(256)
+k_itrans_rows_f32(const uint16_t* __restrict__ it16, const float* __restrict__ side, const int* __restrict__ other_idx,
+                  int node0, int row0, int F, int f0, int nf, float* __restrict__ out, size_t out_pitch) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (f >= nf) return;
+  const int oi = __ldg(other_idx + node0 + row0 + r);
+  const size_t col = (size_t)f0 + f;
+  out[(size_t)r * out_pitch + f] = oi >= 0 ? side[(size_t)oi * F + col] : (float)it16[(size_t)(row0 + r) * F + col];
+}
+
+// widen rows [noff, noff+nn) x frames [foff, foff+nf) into the bounce buffer chunk by chunk and copy each chunk out
+static int read_itrans16(upsp_gpu_ctx* c, int noff, int nn, int foff, int nf, float* host, size_t pitch, cudaStream_t st) {
+  if (nn == 0 || nf == 0) return UPSP_OK;
+  const size_t want = std::min((size_t)nn * nf, (size_t)64 << 20);         // <= 256 MB of floats
+  if (c->bounce_floats < std::max(want, (size_t)nf)) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(c->d_bounce);
+    c->d_bounce = nullptr;
+    c->bounce_floats = std::max(want, (size_t)nf);
+    TRY(dmalloc(&c->d_bounce, c->bounce_floats));
+  }
+  const int rows_per = (int)std::max<size_t>(1, std::min<size_t>(c->bounce_floats / nf, 65535));
+  const uint16_t* it16 = reinterpret_cast<const uint16_t*>(c->d_shared);
+  const float* side = reinterpret_cast<const float*>(c->d_shared + c->side_off[c->rank]);
+  for (int r0 = 0; r0 < nn; r0 += rows_per) {
+    const int nr = std::min(rows_per, nn - r0);
+    k_itrans_rows_f32<<<dim3(cdiv(nf, 256), nr), 256, 0, st>>>(it16, side, c->d_other_idx, c->n0, noff + r0, c->F, foff, nf,
+                                                               c->d_bounce, (size_t)nf);
+    KCHECK(c);
+    CU(cudaMemcpy2DAsync(host + (size_t)r0 * pitch, pitch * sizeof(float), c->d_bounce, (size_t)nf * sizeof(float),
+                         (size_t)nf * sizeof(float), (size_t)nr, cudaMemcpyDeviceToHost, st));
+  }
+  return UPSP_OK;
+}
+
 extern "C" int upsp_gpu_read_intensity_transpose(upsp_gpu_ctx* c, int off, int n, float* host) {
   ENTER(c);
   REQUIRE(off >= 0 && n >= 0 && off + n <= c->N_local && (host || n == 0), UPSP_ERR_INVALID, "bad range");
   REQUIRE(c->transposed, UPSP_ERR_STATE, "transpose first");
+  if (c->it16) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->d2h_stream));      // the bounce buffer is shared with the streamed block reads
+    TRY(read_itrans16(c, off, n, 0, c->F, host, (size_t)c->F, c->d2h_stream));
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    return UPSP_OK;
+  }
   return d2h(c, host, c->d_itrans + (size_t)off * c->F, (size_t)n * c->F * sizeof(float));
 }
 
@@ -2205,6 +2322,7 @@ extern "C" int upsp_gpu_read_intensity_transpose_block_async(upsp_gpu_ctx* c, in
   }
   if (nn == 0 || nf == 0) return UPSP_OK;
   CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_proc, 0));
+  if (c->it16) return read_itrans16(c, noff, nn, foff, nf, host, pitch, c->d2h_stream);
   CU(cudaMemcpy2DAsync(host, pitch * sizeof(float), c->d_itrans + (size_t)noff * c->F + foff,
                        (size_t)c->F * sizeof(float), (size_t)nf * sizeof(float), (size_t)nn,
                        cudaMemcpyDeviceToHost, c->d2h_stream));
