@@ -218,7 +218,14 @@ def configure(up, wl, args, rank, world, local, capacity, dist):
             g.set_warp_matrices(c, 0, synth.make_warps(g.n_frames, seed=5 + rank + 100 * c))
         if reg == up.REG_PIXEL:
             g.set_reference_frame(c, wl["frames"][c][0])
-    if world > 1:
+    if world > 1 and args.exchange == "nccl":
+        # measured comparison: frame-major phase 1 + local transpose + grouped ncclSend / ncclRecv (no peer mappings)
+        import torch
+        g.set_exchange(up.XCHG_NCCL)
+        uid = torch.frombuffer(bytearray(up.nccl_unique_id() if rank == 0 else bytes(up.NCCL_ID_BYTES)), dtype=torch.uint8).clone()
+        dist.broadcast(uid, src=0)
+        g.nccl_init(bytes(uid.numpy().tobytes()))
+    elif world > 1:
         import torch
         h = torch.frombuffer(bytearray(g.ipc_export()), dtype=torch.uint8).clone()
         allh = [torch.empty_like(h) for _ in range(world)]
@@ -409,6 +416,7 @@ def bench_b200(args):
             kms = [g.kernel_ms(k) for k in range(7)]     # of the last timed step
     ms_dev = g.timer_stop()
     pmode = g.projection_mode()          # 0: k_project_fused4 (global taps), 1: TMA boxes of decoded frames, 2: of packed frames
+    row_b = g.row_bytes()                # 2: node-major rows stored as 16-bit integers (unit projection values), else 4
     g.sync()
     barrier(dist)
     wall_ms = (time.time() - t_wall) * 1e3
@@ -434,7 +442,7 @@ def bench_b200(args):
 
     # ---------------- end-to-end arm (host buffers through the C ABI)
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and args.exchange == "peer":      # the streamed column reads of the e2e arm need the fused exchange
         e2e = bench_e2e(up, wl, args, rank, world, local, dist)
 
     if rank != 0:
@@ -455,7 +463,8 @@ def bench_b200(args):
     knames = ["k_hot_scan12" if pmode == 2 else "k_unpack12_scan_p", "k_frame_prep", "k_warp_affine8_u16", "k_patch",
               "k_project_tma" if pmode else "k_project_fused4", "k_transpose_a2a", "k_phase2_sym"]
     kalg = [B * 1.5 * P if pmode == 2 else B * 3.5 * P, 0.0, B * 4.0 * P, 0.0,
-            B * ((1.5 if pmode == 2 else 2.0) * P * args.cams + 4.0 * N), 8.0 * N * F_local, 8.0 * (N / world) * F_total]
+            B * ((1.5 if pmode == 2 else 2.0) * P * args.cams + row_b * N), 8.0 * N * F_local,
+            (row_b + 4.0) * (N / world) * F_total]
     klaunch = [nbatch * args.cams, nbatch, nbatch, nbatch * args.cams, nbatch, 1, 1]
     kernels = {}
     for nm, (ms, ns), ab, nl in zip(knames, kms, kalg, klaunch):
@@ -485,6 +494,7 @@ def bench_b200(args):
         "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (u16 pixels, f64 accumulators)", "data": "synthetic",
         "config": bench_config(args, world),
+        "intensity_row_bytes": row_b,
         "projection_mode": {0: "global taps (k_project_fused4)", 1: "TMA boxes of decoded u16 frames",
                             2: "TMA boxes of the packed 12-bit frames"}.get(pmode, str(pmode)),
         "stage_ms": {n: round(float(s), 3) for n, s in zip(names, stage)},
@@ -686,7 +696,7 @@ def bench_config(args, world):
     return {"workload": workload_name(args), "frames_total": args.frames * world, "nodes": args.nodes,
             "cameras": args.cams, "registration": args.registration,
             "patch_clusters": args.targets + 1 if args.targets else 0, "seam_groups": args.overlap_groups,
-            "csr": args.csr, "detrend_degree": args.degree, "batch_frames": args.batch,
+            "csr": args.csr, "detrend_degree": args.degree, "batch_frames": args.batch, "exchange": args.exchange,
             "l2": "inputs (tens of GB of packed frames and of intensity rows per GPU) far exceed the 126 MB L2"}
 
 
@@ -710,12 +720,14 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--csr", default="surface", choices=["surface", "random"])
     ap.add_argument("--registration", default="given", choices=["given", "none", "pixel"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="peer: exchange fused into the projection kernel (default); nccl: the reference's structure on NCCL")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget (0 = skip)")
     ap.add_argument("--ref-frames", type=int, default=0)
-    ap.add_argument("--check", action="store_true",
-                    help="after the last timed step compare sampled outputs of every rank with the CPU oracle; "
-                         "rc != 0 on mismatch, \"parity_checked\" in the JSON line")
+    ap.add_argument("--check", action=argparse.BooleanOptionalAction, default=True,
+                    help="after the last timed step (outside the timed region) compare sampled outputs of every rank "
+                         "with the CPU oracle; rc != 0 on mismatch, \"parity_checked\" in the JSON line (--no-check: skip)")
     args = ap.parse_args()
     preset = dict(CFG, overlap_groups=0)
     preset.update({k: v for k, v in CONFIGS[args.config].items() if k != "name"})

@@ -218,6 +218,10 @@ UPSP_API int upsp_gpu_projection_mode(const upsp_gpu_ctx* ctx, int* mode);
 /* Debug timeline: with `on` != 0 every kernel of the following batches is bracketed with CUDA events on its
  * own stream WITHOUT taking the batch out of the two-stream pipeline; upsp_gpu_timeline_read returns up to
  * `max_records` records {kernel_class, start_ms, end_ms} (ms since the first recorded event) and the count. */
+/* bytes per stored value of the node-major intensity rows in device memory: 4 (float), or 2 once the context has
+ * chosen 16-bit integer rows (one camera, unit projection values; decided at the first batch).  Reporting only: the
+ * readers always deliver floats. */
+UPSP_API int upsp_gpu_row_bytes(const upsp_gpu_ctx* ctx, int* bytes);
 UPSP_API int upsp_gpu_timeline(upsp_gpu_ctx* ctx, int on);
 UPSP_API int upsp_gpu_timeline_read(upsp_gpu_ctx* ctx, float* records3, int max_records, int* n_records);
 
@@ -229,7 +233,14 @@ UPSP_API int upsp_gpu_timeline_read(upsp_gpu_ctx* ctx, float* records3, int max_
  * rank order).  After import, UPSP_XCHG_PEER transposes store directly into peer HBM. */
 UPSP_API int upsp_gpu_ipc_export(upsp_gpu_ctx* ctx, void* handle);
 UPSP_API int upsp_gpu_ipc_import(upsp_gpu_ctx* ctx, const void* handles);
-/* NCCL communicator for the sum/sum-sq all-reduce and the UPSP_XCHG_NCCL exchange */
+/* UPSP_XCHG_NCCL: the reference's own structure on NCCL (replaces MPI_Isend / MPI_Recv of global_transpose,
+ * cpp/exec/psp_process.cpp:707-771, and the MPI_Allreduce of the sums, :1866-1872): phase 1 keeps the frame-major
+ * intermediate, upsp_gpu_transpose packs node-major blocks per destination rank (chunks of 1024 frames), moves them with
+ * grouped ncclSend / ncclRecv and reassembles them; upsp_gpu_finish_phase1 uses ncclAllReduce.  No peer mappings are
+ * needed (no ipc_export / ipc_import).  libnccl.so.2 is bound at run time (UPSP_NCCL_LIB=path overrides the search).
+ * It is the measured comparison of the default UPSP_XCHG_PEER (exchange fused into the projection kernel), not the
+ * fast path: DESIGN.md section 5.  Call set_exchange before the first process_frames, nccl_init on every rank with the
+ * id that rank 0 got from nccl_unique_id. */
 UPSP_API int upsp_gpu_nccl_unique_id(void* id128);
 UPSP_API int upsp_gpu_nccl_init(upsp_gpu_ctx* ctx, const void* id128);
 UPSP_API int upsp_gpu_set_exchange(upsp_gpu_ctx* ctx, int exchange);

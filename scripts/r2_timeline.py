@@ -10,7 +10,7 @@ from upsp_b200 import synth
 up.build.build()
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 args = types.SimpleNamespace(height=1024, width=1024, nodes=500000, frames=F, targets=32, distinct=128, degree=6,
-                             batch=0, csr="surface", registration="given", cams=1, overlap_groups=0, config=1)
+                             batch=0, csr="surface", registration="given", cams=1, overlap_groups=0, config=1, exchange="peer")
 wl = bench.build_workload(args, synth)
 g = bench.configure(up, wl, args, 0, 1, 0, 0, None)
 for o in range(0, g.n_frames, 128):

@@ -430,6 +430,21 @@ def test_tma_projection_modes(up, orc, gpu, monkeypatch, mode, batch, capacity):
     assert same_bits(avg, ref["avg"]) and same_bits(rms, ref["rms"])
 
 
+@pytest.mark.parametrize("stream", ["0", "1"], ids=["rows-in-smem", "streaming-pair"])
+def test_chain_16bit_rows_and_phase2_paths(up, orc, gpu, monkeypatch, stream):
+    """Unit projection values + a frame count divisible by 8: the node-major rows are stored as 16-bit integers (float
+    side rows for the patched / unseen nodes) and phase 2 reads them either into shared memory (k_phase2_sym<IN16>) or
+    through the streaming pair k_phase2_moments / k_phase2_apply (the multi-GPU path for long rows, forced here).  The
+    whole chain against the oracle, every output through the ABI's readers (which widen the rows to float)."""
+    import upsp_b200
+    monkeypatch.setenv("UPSP_PHASE2_STREAM", stream)
+    case = Case(upsp_b200.synth, n_frames=200, n_nodes=6000, height=96, width=128, registration=True, patches=True,
+                seed=17, fmt="p12")
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case, batch_frames=64)
+    _check_chain(case, ref, got, orc)
+
+
 def test_tma_projection_weighted_values(up, orc, gpu, monkeypatch):
     """Projection values other than 1.0 (a weighted single camera) take the float-statistics variant."""
     import upsp_b200

@@ -29,7 +29,7 @@ def test_baseline_scale_parity(up, orc, gpu):
     from upsp_b200 import synth
     F = 512
     args = types.SimpleNamespace(height=1024, width=1024, nodes=500_000, frames=F, targets=32, distinct=128,
-                                 degree=6, batch=0, csr="surface", registration="given", cams=1, overlap_groups=0, config=1)
+                                 degree=6, batch=0, csr="surface", registration="given", cams=1, overlap_groups=0, config=1, exchange="peer")
     wl = bench.build_workload(args, synth)
     # ---- oracle: the whole job
     orc.set_num_threads(bench.host_threads())
@@ -91,14 +91,17 @@ def test_baseline_scale_parity(up, orc, gpu):
     assert np.array_equal(np.isnan(pt[sel][inval]), np.isnan(p_ref[inval]))
 
 
-def test_torchrun_two_processes(up, gpu, tmp_path):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_torchrun_two_processes(up, gpu, tmp_path, exchange):
+    """exchange = nccl: the reference's structure (frame-major phase 1, local transpose into send blocks, grouped
+    ncclSend / ncclRecv, reassembly; ncclAllReduce of the sums) through the same check."""
     if gpu < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
            "--frames", "1024", "--nodes", "60000", "--height", "512", "--width", "512", "--targets", "12",
-           "--e2e-steps", "0", "--cpu-seconds", "0", "--check"]
+           "--e2e-steps", "0", "--cpu-seconds", "0", "--check", "--exchange", exchange]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-4000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]

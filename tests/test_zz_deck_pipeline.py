@@ -46,7 +46,6 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
                         f"-paint_cal={d / 'paint.cal'}", f"-add_out_dir={d / 'out'}", "-frames=12", "-chunk", "8"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "is not written (no HDF5 library" in r.stdout
     jobd = d / "out" / "job_b200"
 
     # the projection matrix the oracle builds from the same grid and calibration
@@ -85,6 +84,19 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
     # regression samples (psp_process.cpp:2006-2015): N = 1284 < 2000 -> stride 1, the first 1000 values
     assert same_bits(rd("vv-int-avg.dat"), ref["avg"][:1000]) and same_bits(rd("vv-int-sample1.dat"), ratio0[:1000])
     assert same_bits(rd("vv-cp-rms.dat"), rd("rms")[:1000])
+    # the two HDF5 files (psp_process.cpp:2400-2420, 2535-2604), written by host/psp_hdf5.hpp and read by tests/h5min.py
+    import h5min
+    h5, ex = h5min.File(str(d / "out" / "run12.h5")), h5min.File(str(d / "out" / "extras.h5"))
+    for f, transposed in ((h5, 1), (ex, 0)):
+        assert f.root.attrs["psph5_version"][0] == 1 and f.root.attrs["nodal"][0] == 1 and f.root.attrs["structured"][0] == 0
+        assert f.root.attrs["transpose"][0] == transposed
+        assert np.array_equal(f.root["Grid/x"].data, xyz[:, 0]) and np.array_equal(f.root["Grid/z"].data, xyz[:, 2])
+        assert np.array_equal(f.root["Grid/triangles"].data, np.asarray(sc["tri"], np.uint32).reshape(-1, 3))
+        assert same_bits(f.root["rms"].data, rd("rms")) and same_bits(f.root["coverage"].data, ref["coverage"])
+        assert same_bits(f.root["model_temp"].data, case.temp) and f.root["rms"].attrs["units"] == ["delta Cp"]
+        assert f.root["Condition/dynamic_pressure"].data[0] == case.qbar and f.root["Condition/static_pressure"].data[0] == case.ps
+        assert f.root["Condition/frame_rate"].attrs["units"] == ["Hz"] and f.root["Condition/focal_length"].data.shape == (1,)
+    assert same_bits(ex.root["average"].data, rd("avg")) and "average" not in h5.root.children
 
 
 @pytest.mark.gpu

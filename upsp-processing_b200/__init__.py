@@ -23,6 +23,7 @@ INTERP_NEAREST, INTERP_LINEAR = 0, 1
 PATCH_NONE, PATCH_POLYNOMIAL = 0, 1
 FILTER_NONE, FILTER_GAUSSIAN, FILTER_BOX = 0, 1, 2
 XCHG_PEER, XCHG_NCCL = 0, 1
+NCCL_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
 
@@ -270,6 +271,11 @@ class PspGpu:
         _chk(lib().upsp_gpu_projection_mode(self._h, C.byref(m)))
         return int(m.value)
 
+    def row_bytes(self) -> int:
+        b = C.c_int(4)
+        _chk(lib().upsp_gpu_row_bytes(self._h, C.byref(b)))
+        return int(b.value)
+
     def timeline(self, on=True):
         _chk(lib().upsp_gpu_timeline(self._h, int(bool(on))))
 
@@ -290,8 +296,21 @@ class PspGpu:
         _chk(lib().upsp_gpu_ipc_export(self._h, buf))
         return buf.raw
 
+    def set_exchange(self, exchange):
+        _chk(lib().upsp_gpu_set_exchange(self._h, int(exchange)))
+
+    def nccl_init(self, uid: bytes):
+        buf = C.create_string_buffer(bytes(uid), NCCL_ID_BYTES)
+        _chk(lib().upsp_gpu_nccl_init(self._h, buf))
+
     def ipc_import(self, handles: bytes):
         _chk(lib().upsp_gpu_ipc_import(self._h, C.c_char_p(handles)))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    _chk(lib().upsp_gpu_nccl_unique_id(buf))
+    return buf.raw
 
 
 def connect_local(ctxs):

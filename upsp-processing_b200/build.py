@@ -117,6 +117,23 @@ def build_transpose_tool(force: bool = False) -> str:
     return XPOSE_BIN
 
 
+H5_PROBE_BIN = os.path.join(HERE, "psp_hdf5_probe")
+
+
+def build_h5_probe(force: bool = False) -> str:
+    """host/psp_hdf5_probe.cpp: writes a sample PSP HDF5 file with host/psp_hdf5.hpp (no library dependency at all)."""
+    src = os.path.join(HERE, "host", "psp_hdf5_probe.cpp")
+    hdr = os.path.join(HERE, "host", "psp_hdf5.hpp")
+    if not force and os.path.exists(H5_PROBE_BIN) and os.path.getmtime(H5_PROBE_BIN) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return H5_PROBE_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", H5_PROBE_BIN, src], capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building psp_hdf5_probe")
+    return H5_PROBE_BIN
+
+
 PATCH_PROBE_BIN = os.path.join(HERE, "patch_geometry_probe")
 
 

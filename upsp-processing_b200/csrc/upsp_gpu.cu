@@ -5,6 +5,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 
@@ -132,6 +133,60 @@ static DriverApi& drv() {
   }
   return d;
 }
+
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen of the libnccl.so.2 the process already has, e.g. torch's): the library has no
+// link-time dependency on it, and only the UPSP_XCHG_NCCL exchange needs it.  Minimal declarations of nccl.h.
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* Comm;
+  void* so = nullptr;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  static constexpr int kFloat = 7, kDouble = 8, kSum = 0;      // ncclFloat32, ncclFloat64, ncclSum
+};
+
+static NcclApi& nccl() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried) return a;
+  tried = true;
+  const char* names[] = {getenv("UPSP_NCCL_LIB"), "libnccl.so.2", "libnccl.so",
+                         "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    a.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.so) break;
+  }
+  if (!a.so) return a;
+#define UPSP_NCCL_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.so, name))
+  UPSP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  UPSP_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  UPSP_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  UPSP_NCCL_SYM(GroupStart, "ncclGroupStart");
+  UPSP_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+  UPSP_NCCL_SYM(Send, "ncclSend");
+  UPSP_NCCL_SYM(Recv, "ncclRecv");
+  UPSP_NCCL_SYM(AllReduce, "ncclAllReduce");
+  UPSP_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef UPSP_NCCL_SYM
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv && a.AllReduce;
+  return a;
+}
+#define NCCLCHK(expr)                                                                                   \
+  do {                                                                                                  \
+    int r_ = (expr);                                                                                    \
+    if (r_ != 0) return fail(UPSP_ERR_COMM, "%s -> %s", #expr, nccl().GetErrorString ? nccl().GetErrorString(r_) : "?"); \
+  } while (0)
 
 struct VmmBlock {
   CUmemGenericAllocationHandle handle = 0;
@@ -315,6 +370,9 @@ struct upsp_gpu_ctx {
   int* d_other_local = nullptr;     // local indices of this rank's side-buffer nodes
   int n_other_local = 0;
   size_t side_off[UPSP_MAX_RANKS] = {0};   // byte offset of rank r's side buffer in its shared block
+  float* d_p2coef = nullptr;        // streaming phase 2: coefficients (+ gain) per local row
+  double* d_p2parts = nullptr;      // ... and the chunks' partial sums
+  size_t p2coef_n = 0, p2parts_n = 0;
   float* d_bounce = nullptr;        // readers: rows widened to float on their way to the host
   size_t bounce_floats = 0;
   bool ship_sm = false;           // staged rows shipped by k_ship_rows instead of the copy engines
@@ -359,6 +417,9 @@ struct upsp_gpu_ctx {
   bool peer_is_ipc[UPSP_MAX_RANKS] = {false};
   bool peers_ready = false;
   int exchange = UPSP_XCHG_PEER;
+  NcclApi::Comm nccl_comm = nullptr;       // UPSP_XCHG_NCCL
+  float* d_nccl_send = nullptr;            // [N][chunk] blocks per destination rank
+  float* d_nccl_recv = nullptr;            // [R][N_local][chunk]
   bool phase1_done = false, transposed = false, phase2_done = false;
   int frames_processed = 0;
 };
@@ -606,6 +667,8 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaFree(c->d_other_idx);
   cudaFree(c->d_other_local);
   cudaFree(c->d_bounce);
+  cudaFree(c->d_p2coef);
+  cudaFree(c->d_p2parts);
   cudaFree(c->d_tma_blk);
   cudaFree(c->d_intensity);
   if (c->shared_vmm.handle) vmm_free(c->shared_vmm); else cudaFree(c->d_shared);
@@ -624,6 +687,9 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaFree(c->d_tsum);
   cudaFree(c->d_tsq);
   cudaFree(c->d_peer_ptrs);
+  cudaFree(c->d_nccl_send);
+  cudaFree(c->d_nccl_recv);
+  if (c->nccl_comm && nccl().ok) nccl().CommDestroy(c->nccl_comm);
   if (c->ev_push) cudaEventDestroy(c->ev_push);
   if (c->ev_proc) cudaEventDestroy(c->ev_proc);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -936,7 +1002,8 @@ static int finalize(upsp_gpu_ctx* c) {
   for (auto& k : c->cams)
     for (int n = 0; n < N && c->ell1; ++n)
       if (k.rowptr[n + 1] - k.rowptr[n] > 1) c->ell1 = false;
-  c->fused = c->ell1 && c->cfg.keep_frame_major == 0 && c->filter.kind == 0;
+  // the NCCL exchange needs the frame-major intermediate (local transpose into send blocks + ncclSend/ncclRecv)
+  c->fused = c->ell1 && c->cfg.keep_frame_major == 0 && c->filter.kind == 0 && c->exchange == UPSP_XCHG_PEER;
   // two-stream pipeline: front end (decode, hot pixels, patch) of batch i+1 overlaps the fused
   // projection of batch i.  Not with the device ECC solve (its blur/moment kernels want the whole
   // GPU) and not in the unfused modes.  UPSP_PIPELINE=0 turns it off.
@@ -1889,7 +1956,14 @@ extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
   }
   CU(cudaEventRecord(c->ev_a, c->stream));
   const double *sum = c->d_sum, *sq = c->d_sumsq;
-  if (c->R > 1) {
+  if (c->R > 1 && c->exchange == UPSP_XCHG_NCCL) {
+    // the reference's MPI_Allreduce(MPI_SUM) of the per-rank sums (psp_process.cpp:1866-1872)
+    REQUIRE(c->nccl_comm != nullptr, UPSP_ERR_STATE, "UPSP_XCHG_NCCL: call upsp_gpu_nccl_init first");
+    NCCLCHK(nccl().AllReduce(c->d_sum, c->d_tsum, (size_t)c->N, NcclApi::kDouble, NcclApi::kSum, c->nccl_comm, c->stream));
+    NCCLCHK(nccl().AllReduce(c->d_sumsq, c->d_tsq, (size_t)c->N, NcclApi::kDouble, NcclApi::kSum, c->nccl_comm, c->stream));
+    sum = c->d_tsum;
+    sq = c->d_tsq;
+  } else if (c->R > 1) {
     REQUIRE(c->peers_ready, UPSP_ERR_STATE,
             "multi-rank context is not wired (upsp_gpu_ipc_import / upsp_gpu_connect_local)");
     // every rank lays its shared block out as [itrans N_r x F | sum N | sumsq N]: offsets depend on N_r
@@ -1922,7 +1996,68 @@ extern "C" int upsp_gpu_finish_phase1(upsp_gpu_ctx* c) {
 extern "C" int upsp_gpu_transpose(upsp_gpu_ctx* c) {
   ENTER(c);
   REQUIRE(c->finalized, UPSP_ERR_STATE, "no frames processed");
-  REQUIRE(c->exchange == UPSP_XCHG_PEER, UPSP_ERR_STATE, "only UPSP_XCHG_PEER is built");
+  if (c->exchange == UPSP_XCHG_NCCL && c->R > 1) {
+    // The reference's own structure (local_transpose + global_transpose, psp_process.cpp:647-771) on NCCL: per chunk of
+    // this rank's frames, k_transpose_a2a packs one node-major block [N_s][chunk] per destination rank into the send
+    // buffer, one grouped ncclSend / ncclRecv round moves the blocks, and strided device copies reassemble the received
+    // blocks into columns [f0_r + c0, ...) of intensity_transpose.  Chunked so that the send / receive buffers stay small
+    // (N x chunk floats each); every rank derives every rank's chunk sizes from apportion(), so the rounds match.
+    REQUIRE(c->nccl_comm != nullptr, UPSP_ERR_STATE, "UPSP_XCHG_NCCL: call upsp_gpu_nccl_init first");
+    REQUIRE(!c->fused, UPSP_ERR_STATE, "UPSP_XCHG_NCCL needs the frame-major intermediate");
+    const int Fc = 1024;
+    int fmax = 0;
+    for (int r = 0; r < c->R; ++r) fmax = std::max(fmax, c->f_count[r]);
+    if (!c->d_nccl_send) {
+      TRY(dmalloc(&c->d_nccl_send, (size_t)c->N * Fc));
+      TRY(dmalloc(&c->d_nccl_recv, (size_t)std::max(c->N_local, 1) * Fc * c->R));
+    }
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    for (int c0 = 0; c0 < fmax; c0 += Fc) {
+      const int nc = std::max(0, std::min(Fc, c->F_local - c0));
+      if (nc > 0) {
+        XposeArgs a{};
+        a.src = c->d_intensity + (size_t)c0 * c->N;
+        a.rows = nc;
+        a.cols = c->N;
+        a.n_ranks = c->R;
+        a.f_total = nc;
+        a.col0 = 0;
+        for (int r = 0; r < c->R; ++r) {
+          a.dst[r] = c->d_nccl_send + (size_t)c->n_start[r] * nc;
+          a.node_start[r] = c->n_start[r];
+        }
+        a.node_start[c->R] = c->N;
+        k_transpose_a2a<<<dim3(cdiv(c->N, XT), cdiv(nc, XT)), 256, 0, c->stream>>>(a);
+        KCHECK(c);
+      }
+      NCCLCHK(nccl().GroupStart());
+      size_t roff = 0;
+      std::vector<size_t> roffs(c->R);
+      for (int r = 0; r < c->R; ++r) {
+        const int ncr = std::max(0, std::min(Fc, c->f_count[r] - c0));
+        roffs[r] = roff;
+        if (nc > 0 && c->n_count[r] > 0)
+          NCCLCHK(nccl().Send(c->d_nccl_send + (size_t)c->n_start[r] * nc, (size_t)c->n_count[r] * nc, NcclApi::kFloat, r,
+                              c->nccl_comm, c->stream));
+        if (ncr > 0 && c->N_local > 0)
+          NCCLCHK(nccl().Recv(c->d_nccl_recv + roff, (size_t)c->N_local * ncr, NcclApi::kFloat, r, c->nccl_comm, c->stream));
+        roff += (size_t)c->N_local * ncr;
+      }
+      NCCLCHK(nccl().GroupEnd());
+      for (int r = 0; r < c->R; ++r) {      // reassembly (psp_process.cpp:755-765)
+        const int ncr = std::max(0, std::min(Fc, c->f_count[r] - c0));
+        if (ncr > 0 && c->N_local > 0)
+          CU(cudaMemcpy2DAsync(c->d_itrans + (size_t)c->f_start[r] + c0, (size_t)c->F * sizeof(float), c->d_nccl_recv + roffs[r],
+                               (size_t)ncr * sizeof(float), (size_t)ncr * sizeof(float), (size_t)c->N_local,
+                               cudaMemcpyDeviceToDevice, c->stream));
+      }
+    }
+    CU(cudaEventRecord(c->ev_b, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->stage_ms[2], c->ev_a, c->ev_b));
+    c->transposed = true;
+    return UPSP_OK;
+  }
   if (c->fused) {  // k_project_fused already wrote node-major rows (local and peer)
     CU(cudaStreamSynchronize(c->stream));
     c->stage_ms[2] = 0.0f;
@@ -2114,7 +2249,60 @@ static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, 
   return UPSP_OK;
 }
 
+// long 16-bit rows: the streaming kernel pair (kernels_phase2.cuh)
+template <int NC>
+static int launch_phase2_stream(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
+  if (a.n_local == 0) return UPSP_OK;
+  const int nchunk = (a.F / 2 + P2S_CHUNK - 1) / P2S_CHUNK;
+  const size_t ncoef = (size_t)a.n_local * (UPSP_MAX_COEF + 1), nparts = (size_t)a.n_local * nchunk * 2;
+  if (c->p2coef_n < ncoef) {
+    cudaFree(c->d_p2coef);
+    c->d_p2coef = nullptr;
+    TRY(dmalloc(&c->d_p2coef, ncoef));
+    c->p2coef_n = ncoef;
+  }
+  if (c->p2parts_n < nparts) {
+    cudaFree(c->d_p2parts);
+    c->d_p2parts = nullptr;
+    TRY(dmalloc(&c->d_p2parts, nparts));
+    c->p2parts_n = nparts;
+  }
+  k_phase2_moments<NC, 512><<<a.n_local, 512, 0, st>>>(a, c->d_p2coef);
+  CU(cudaGetLastError());
+  k_phase2_apply<NC, 256><<<dim3(nchunk, a.n_local), 256, 0, st>>>(a, c->d_p2coef, c->d_p2parts, nchunk);
+  CU(cudaGetLastError());
+  k_phase2_parts<<<cdiv(a.n_local, 256), 256, 0, st>>>(a, c->d_p2parts, nchunk);
+  CU(cudaGetLastError());
+  *launches += 3;
+  return UPSP_OK;
+}
+
 static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
+  // UPSP_PHASE2_STREAM = 1 forces the streaming pair (16-bit rows only; off by default, kept as the measured alternative
+  // and for the parity test that pins it).  Measured (r2u, 1 GPU, 20 000-frame rows): 23.9 ms against 17.0 ms with the row in shared memory;
+  // phase 2 is bound by instruction issue, and the pair divides and converts every element twice.
+  static const int stream_env = getenv("UPSP_PHASE2_STREAM") ? atoi(getenv("UPSP_PHASE2_STREAM")) : -1;
+  if (a.itrans16 != nullptr && a.row_list == nullptr && a.F % 8 == 0 &&
+      (stream_env == 1 || (stream_env != 0 && phase2_cluster(a.F) == 0))) {
+    int rc = UPSP_OK;
+    for (int r0 = 0; r0 < a.n_local && !rc; r0 += 65535) {      // grid.y limit: rows in slabs
+      Phase2Args b = a;
+      b.n_local = std::min(65535, a.n_local - r0);
+      b.node0 = a.node0 + r0;
+      b.itrans16 = a.itrans16 + (size_t)r0 * a.F;
+      b.ptrans = a.ptrans + (size_t)r0 * a.F;
+      b.rms = a.rms + r0;
+      b.avgp = a.avgp + r0;
+      b.gain = a.gain + r0;
+      switch (a.ncoef) {
+#define UPSP_P2S(K) case K: rc = launch_phase2_stream<K>(c, b, st, launches); break;
+        UPSP_P2S(1) UPSP_P2S(2) UPSP_P2S(3) UPSP_P2S(4) UPSP_P2S(5) UPSP_P2S(6) UPSP_P2S(7) UPSP_P2S(8) UPSP_P2S(9)
+#undef UPSP_P2S
+        default: return fail(UPSP_ERR_INVALID, "detrend degree %d not in [0,%d]", a.ncoef - 1, UPSP_MAX_COEF - 1);
+      }
+    }
+    return rc;
+  }
   switch (a.ncoef) {
     case 1: return launch_phase2<1>(c, a, st, launches);
     case 2: return launch_phase2<2>(c, a, st, launches);
@@ -2456,6 +2644,12 @@ extern "C" int upsp_gpu_projection_mode(const upsp_gpu_ctx* c, int* mode) {
   return UPSP_OK;
 }
 
+extern "C" int upsp_gpu_row_bytes(const upsp_gpu_ctx* c, int* bytes) {
+  REQUIRE(c && bytes, UPSP_ERR_INVALID, "null argument");
+  *bytes = c->it16 ? 2 : 4;
+  return UPSP_OK;
+}
+
 extern "C" int upsp_gpu_timeline(upsp_gpu_ctx* c, int on) {
   ENTER(c);
   CU(cudaDeviceSynchronize());
@@ -2577,20 +2771,27 @@ extern "C" int upsp_gpu_connect_local(upsp_gpu_ctx** ctxs, int n) {
 
 extern "C" int upsp_gpu_set_exchange(upsp_gpu_ctx* c, int exchange) {
   ENTER(c);
-  REQUIRE(exchange == UPSP_XCHG_PEER, UPSP_ERR_INVALID,
-          "exchange %d: only UPSP_XCHG_PEER (fused transpose + peer stores) is built", exchange);
+  REQUIRE(exchange == UPSP_XCHG_PEER || exchange == UPSP_XCHG_NCCL, UPSP_ERR_INVALID, "exchange %d", exchange);
+  REQUIRE(!c->finalized, UPSP_ERR_STATE, "set_exchange after the first process_frames");
+  if (exchange == UPSP_XCHG_NCCL) REQUIRE(nccl().ok, UPSP_ERR_COMM, "libnccl.so.2 not found (UPSP_NCCL_LIB=path)");
   c->exchange = exchange;
   return UPSP_OK;
 }
-
 extern "C" int upsp_gpu_nccl_unique_id(void* id) {
-  (void)id;
-  return fail(UPSP_ERR_COMM, "NCCL exchange is not built in this round; use UPSP_XCHG_PEER");
+  REQUIRE(id != nullptr, UPSP_ERR_INVALID, "null id");
+  REQUIRE(nccl().ok, UPSP_ERR_COMM, "libnccl.so.2 not found (UPSP_NCCL_LIB=path)");
+  NCCLCHK(nccl().GetUniqueId(reinterpret_cast<NcclApi::UniqueId*>(id)));
+  return UPSP_OK;
 }
 extern "C" int upsp_gpu_nccl_init(upsp_gpu_ctx* c, const void* id) {
-  (void)c;
-  (void)id;
-  return fail(UPSP_ERR_COMM, "NCCL exchange is not built in this round; use UPSP_XCHG_PEER");
+  ENTER(c);
+  REQUIRE(id != nullptr, UPSP_ERR_INVALID, "null id");
+  REQUIRE(nccl().ok, UPSP_ERR_COMM, "libnccl.so.2 not found (UPSP_NCCL_LIB=path)");
+  REQUIRE(c->nccl_comm == nullptr, UPSP_ERR_STATE, "communicator already created");
+  NcclApi::UniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  NCCLCHK(nccl().CommInitRank(&c->nccl_comm, c->R, uid, c->rank));
+  return UPSP_OK;
 }
 
 // ------------------------------------------------------------------------------------------

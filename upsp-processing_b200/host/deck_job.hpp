@@ -55,6 +55,8 @@ struct ModelArrays {
   std::vector<uint8_t> is_data;
   std::vector<int32_t> remap;           // structured grids only
   std::vector<int32_t> primary_comp;    // per node: its component, or INT32_MIN when it has none (Node::has_primary_component)
+  std::vector<int32_t> tri_comps;       // [T] component of every triangle (unstructured; 0 where the file has none): /Grid/components
+  std::vector<int32_t> zone_sizes;      // [zones][3] (structured): /Grid/grid_sizes
   int n_components = 0;
   bool structured = false;
   int n_nodes() const { return (int)(xyz.size() / 3); }
@@ -73,6 +75,8 @@ inline ModelArrays load_model(const FileInputs& ifile) {
     }
     m.xyz = g.xyz;
     m.tris = g.tris;
+    m.tri_comps = g.comps;
+    m.tri_comps.resize((size_t)g.n_tris, 0);
     calc_normals(g, m.normals);
     node_normals_area_weighted(g, m.node_normals);
     m.is_data.assign((size_t)g.n_nodes, 1);
@@ -108,6 +112,11 @@ inline ModelArrays load_model(const FileInputs& ifile) {
     for (int n = 0; n < N; ++n) m.is_data[(size_t)n] = model.is_superceded(n) ? 0 : 1;   // the node iterator skips them
     m.remap = model.overlap_src_index();
     m.n_components = model.num_zones();                   // P3DModel.h:244, Node::get_primary_component = zone
+    for (int zn = 0; zn < model.num_zones(); ++zn) {        // PSPHDF5.ipp:170-176: zone_size(i, 0), (i, 1), (i, 2)
+      m.zone_sizes.push_back(model.zone_size(zn, 0));
+      m.zone_sizes.push_back(model.zone_size(zn, 1));
+      m.zone_sizes.push_back(1);
+    }
     m.primary_comp.resize((size_t)N);
     for (int n = 0; n < N; ++n) m.primary_comp[(size_t)n] = model.nidx2_gidx(n).zone;
   }
@@ -286,6 +295,10 @@ inline int run_deck(const std::map<std::string, std::string>& opt) {
   write_all(job_dir + "/normals.f32", model.normals);
   write_all(job_dir + "/node_normals.f32", model.node_normals);
   write_all(job_dir + "/is_data.u8", model.is_data);
+  // what the HDF5 outputs need beyond the flat files (host/psp_hdf5.hpp, psp_process.cpp:2400-2420)
+  write_all(job_dir + "/tris.i32", model.tris);
+  if (model.structured) write_all(job_dir + "/grid_sizes.i32", model.zone_sizes);
+  else write_all(job_dir + "/tri_comps.i32", model.tri_comps);
   std::ofstream job(job_dir + "/job.txt");
   if (!job) return fail("Cannot write '" + job_dir + "/job.txt'");
   job << std::setprecision(9);
@@ -303,6 +316,27 @@ inline int run_deck(const std::map<std::string, std::string>& opt) {
       << "\ncal_f = " << pcal.f << "\n";
   job << "test_id = " << ifile.test_id << "\nrun = " << ifile.run << "\nsequence = " << ifile.sequence << "\ngrid_units = "
       << ifile.grid_units << "\nout_dir = " << ifile.out_dir << "\nout_name = " << ifile.out_name << "\n";
+  {
+    // /Condition of the HDF5 files: tunnel conditions (.wtd) + camera settings of camera 1 (psp_process.cpp:1581-1589;
+    // get_focal_length = cameraMatrix(0,0) * pix_sz_, and the JSON calibration reader leaves pix_sz_ at -1: CameraCal.cpp:56, 240-249)
+    const auto& vp0 = cams[0]->properties();
+    job << "structured = " << (model.structured ? 1 : 0) << "\n";
+    char line[512];
+    std::snprintf(line, sizeof line, "tc_alpha = %.9g\ntc_beta = %.9g\ntc_phi = %.9g\ntc_mach = %.9g\ntc_rey = %.9g\ntc_ptot = %.9g\n"
+                  "tc_ttot = %.9g\ntc_tcavg = %.9g\n", (double)tcond.alpha, (double)tcond.beta, (double)tcond.phi, (double)tcond.mach,
+                  (double)tcond.rey, (double)tcond.ptot, (double)tcond.ttot, (double)tcond.tcavg);
+    job << line;
+    std::snprintf(line, sizeof line, "cam_frame_rate = %d\ncam_fstop = %.9g\ncam_exposure = %.9g\n", (int)vp0.frame_rate,
+                  (double)vp0.aperture, (double)vp0.exposure);
+    job << line;
+    job << "cam_focal_lengths =";
+    for (unsigned c = 0; c < ifile.cameras; ++c) {
+      const upsp_camera_model cam = read_json_camera_calibration(ifile.cals[c]);
+      std::snprintf(line, sizeof line, " %.9g", (double)(float)(cam.fx * (double)-1.0f));
+      job << line;
+    }
+    job << "\ncode_version = " << (has("-code_version") ? get("-code_version") : std::string("upsp-processing_b200")) << "\n";
+  }
   std::cout << "Wrote job directory " << job_dir << std::endl;
   return 0;
 }

@@ -39,8 +39,8 @@
 //                    [-model_temp_p3d=FILE] [-frames=N] [-add_out_dir=DIR] [-bound_pts=2] [-buffer_pts=1]
 //                    [-target_diam_sf=1.2] [-cutoff_x_max=X] [-checkout=T] [-device 0] [-chunk 256]
 // runs the start-up of host/deck_job.hpp into <add_out_dir>/job_b200 and then the frame chain; flat files go to
-// -add_out_dir (default: the deck's @output dir), as in the reference.  -h5_out is required as there, but no HDF5
-// library exists in this build: the flat files are the outputs (a notice says so).
+// -add_out_dir (default: the deck's @output dir), as in the reference.  -h5_out is required as there; it and
+// <add_out_dir>/extras.h5 are written by host/psp_hdf5.hpp (hand-written HDF5 subset: no HDF5 library in this image).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +51,7 @@
 
 #include <sys/stat.h>
 
+#include "psp_hdf5.hpp"
 #include "deck_job.hpp"
 #include "patch_geometry.hpp"
 #include "run_inputs.hpp"
@@ -93,6 +94,7 @@ static std::map<std::string, std::string> read_job(const std::string& path) {
 int main(int argc, char** argv) {
   std::string job_dir, out_dir;
   int device = 0, chunk = 256;
+  std::string h5_out;      // -h5_out of the reference's command line (empty: job-directory mode, flat files only)
   try {
     auto opt = parse_command_line(argc, argv);
     if (opt.count("-device")) device = atoi(opt["-device"].c_str());
@@ -117,11 +119,11 @@ int main(int argc, char** argv) {
         std::cout << "Checkout complete (calibration / patch start-up only, psp_process.cpp:1576-1579)" << std::endl;
         return 0;
       }
-      std::cout << "Note: -h5_out '" << opt["-h5_out"] << "' is not written (no HDF5 library in this build); outputs are the flat files in "
-                << out_dir << std::endl;
+      h5_out = opt["-h5_out"];
     } else {
       if (opt.count("-job_dir")) job_dir = opt["-job_dir"];
       if (opt.count("-out_dir")) out_dir = opt["-out_dir"];
+      if (opt.count("-h5_out")) h5_out = opt["-h5_out"];
     }
   } catch (const std::exception& e) {
     std::cerr << "psp_process_b200: " << e.what() << std::endl;
@@ -352,6 +354,61 @@ int main(int argc, char** argv) {
       if (s > 3.0f) s = std::numeric_limits<float>::quiet_NaN();
     out.write_vector("steady_state", steady.data(), msize);
     out.write_vector("model_temp", model_temp.data(), msize);
+    if (!h5_out.empty()) {
+      // the two HDF5 files of psp_process.cpp:2400-2420 / 2535-2604: -h5_out (transposed flag, rms / coverage / steady_state /
+      // model_temp) and <add_out_dir>/extras.h5 (+ average); grid, /Condition and code_version in both
+      auto xyz = read_all<float>(job_dir + "/xyz.f32", false);
+      auto tris = read_all<int32_t>(job_dir + "/tris.i32", false);
+      if (xyz.size() != (size_t)msize * 3) throw std::invalid_argument("job directory: xyz.f32 is needed for -h5_out");
+      std::vector<float> gx(msize), gy(msize), gz(msize);
+      for (int n = 0; n < msize; ++n) gx[n] = xyz[(size_t)n * 3], gy[n] = xyz[(size_t)n * 3 + 1], gz[n] = xyz[(size_t)n * 3 + 2];
+      auto gets = [&](const char* k) { return job.count(k) ? job.at(k) : std::string(); };
+      auto getd = [&](const char* k) { return job.count(k) ? (float)atof(job.at(k).c_str()) : std::numeric_limits<float>::quiet_NaN(); };
+      H5TunnelConditions tc;
+      tc.test_id = gets("test_id");
+      tc.run = job.count("run") ? geti("run") : 0;
+      tc.seq = job.count("sequence") ? geti("sequence") : 0;
+      tc.alpha = getd("tc_alpha"); tc.beta = getd("tc_beta"); tc.phi = getd("tc_phi"); tc.mach = getd("tc_mach");
+      tc.rey = getd("tc_rey"); tc.ptot = getd("tc_ptot"); tc.qbar = p.qbar; tc.ttot = getd("tc_ttot");
+      tc.tcavg = getd("tc_tcavg"); tc.ps = p.ps;
+      H5CameraSettings cs;
+      cs.framerate = job.count("cam_frame_rate") ? geti("cam_frame_rate") : 0;
+      cs.fstop = job.count("cam_fstop") ? getf("cam_fstop") : 0.0f;
+      cs.exposure = job.count("cam_exposure") ? getf("cam_exposure") : 0.0f;
+      {
+        std::istringstream fl(gets("cam_focal_lengths"));
+        for (float v; fl >> v;) cs.focal_lengths.push_back(v);
+      }
+      const bool structured = job.count("structured") && geti("structured") != 0;
+      const std::string files[2] = {h5_out, out_dir + "/extras.h5"};
+      std::cout << "Initializing output files:" << std::endl;
+      for (int k = 0; k < 2; ++k) {
+        std::cout << "    " << files[k] << std::endl;
+        PSPWriter w(files[k], (size_t)msize, /*transposed=*/k == 0);
+        if (structured) {
+          w.write_structured_grid(gx, gy, gz, read_all<int32_t>(job_dir + "/grid_sizes.i32"), gets("grid_units"));
+        } else {
+          const auto comps = read_all<int32_t>(job_dir + "/tri_comps.i32", false);
+          std::vector<unsigned> tn(tris.begin(), tris.end());
+          std::vector<int> cp(comps.begin(), comps.end());
+          cp.resize(tn.size() / 3, 0);
+          w.write_unstructured_grid(gx, gy, gz, tn, cp, gets("grid_units"));
+        }
+        w.write_tunnel_conditions(tc);
+        w.write_camera_settings(cs);
+        w.write_string_attribute("code_version", gets("code_version"));
+        if (k == 1) {
+          w.write_new_dataset("rms", rms, "delta Cp");
+          w.write_new_dataset("average", avg, "delta Cp");
+        } else {
+          w.write_new_dataset("rms", rms, "delta Cp");
+        }
+        w.write_new_dataset("coverage", coverage);
+        w.write_new_dataset("steady_state", steady, "Cp");
+        w.write_new_dataset("model_temp", model_temp, "F");
+        w.close();
+      }
+    }
     std::cout << "Write pressure transpose ..." << std::endl;
     {
       const size_t rows = std::max<size_t>(1, (256u << 20) / ((size_t)number_frames * 4));
