@@ -1,3 +1,4 @@
+# build here first (the binary travels to the GPU box, git ignores it): nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/probes/tma_bench scripts/probes/tma_bench.cu -lcuda
 P=scripts/probes/tma_bench
 {
 $P 96 6 1 6 8 2000 2 1

@@ -1,3 +1,4 @@
+# build here first (the binary travels to the GPU box, git ignores it): nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/probes/tma_probe scripts/probes/tma_probe.cu -lcuda
 P=scripts/probes/tma_probe
 {
 $P 128 96 150 80 6 0 0 0

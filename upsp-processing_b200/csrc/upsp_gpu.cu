@@ -1730,7 +1730,8 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     if (c->proj_mode > 0) {
       // TMA-staged boxes for the nodes with a plain pixel, k_project_fused4 for the rest (patched / unseen nodes)
       Camera& k = c->cams[0];
-      const bool seg128 = c->R > 1 && c->staged_peers < c->R - 1;
+      static const bool force_seg128 = getenv("UPSP_FORCE_SEG128") && atoi(getenv("UPSP_FORCE_SEG128"));   // A/B knob: the multi-rank variant on one GPU
+      const bool seg128 = (c->R > 1 && c->staged_peers < c->R - 1) || force_seg128;
       fa.perm = c->d_perm_tma;
       TmaExtra ex{};
       ex.blk = c->d_tma_blk;
