@@ -347,6 +347,21 @@ def test_phase2_mid_length_rows(up, orc, gpu):
     _check_chain(case, ref, got, orc)
 
 
+@pytest.mark.parametrize("registration,F", [(False, 32768), (True, 32768), (True, 98304)],
+                         ids=["float-rows-2cta", "16bit-rows-2cta", "16bit-rows-8cta"])
+def test_phase2_clustered_rows(up, orc, gpu, registration, F):
+    """Rows too long for one CTA's shared memory (multi-GPU weak scaling makes them N_gpus times longer): the symmetric
+    phase-2 kernel runs as a cluster of 2 / 8 CTAs per row: moments over distributed shared memory behind ONE cluster
+    barrier, partial statistics through global memory (k_phase2_cl_parts).  With registration the projection takes the
+    TMA path and the rows are 16-bit integers (+ float side rows for the unseen nodes)."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=F, n_nodes=24, registration=registration, seed=41, height=32, width=32,
+                fmt="p12" if registration else "u16")
+    ref = run_oracle(orc, case)
+    got = run_gpu(up, orc, case)
+    _check_chain(case, ref, got, orc)
+
+
 def test_streamed_column_block_reads(up, orc, gpu):
     """upsp_gpu_read_intensity_transpose_block_async: column blocks read while later frames are
     still being processed equal the final intensity_transpose."""

@@ -74,8 +74,9 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, con
 }
 
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
-                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st) {
-  static const int scan_threads = getenv("UPSP_SCAN_THREADS") ? atoi(getenv("UPSP_SCAN_THREADS")) : 128;   // tuning knob
+                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, int threads, cudaStream_t st) {
+  static const int env_threads = getenv("UPSP_SCAN_THREADS") ? atoi(getenv("UPSP_SCAN_THREADS")) : 0;   // tuning knob
+  const int scan_threads = env_threads > 0 ? env_threads : threads;
   k_hot_scan12<<<grid, scan_threads, 0, st>>>(in, in_stride, npix, nframes, thresh, hot_cnt, hot_pos, done, rows, cols,
                                      reinterpret_cast<HotFix*>(fixes));
   return cudaGetLastError();

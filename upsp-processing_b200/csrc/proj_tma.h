@@ -45,7 +45,7 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, con
                                const CUtensorMap& map_single, const FusedArgs& a, const TmaExtra& ex, int nblocks, cudaStream_t st);
 // hot-pixel scan of packed 12-bit frames -> fix lists (read only)
 cudaError_t launch_hot_scan12(const uint8_t* in, size_t in_stride, size_t npix, int nframes, int thresh, int* hot_cnt,
-                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, cudaStream_t st);
+                              int* hot_pos, int* done, int rows, int cols, void* fixes, int grid, int threads, cudaStream_t st);
 size_t hot_fix_bytes();
 // (M0, M3) * 1024 of `n` frames (device array of double2, identity for the unregistered frame) -> constant table `set`
 cudaError_t tma_set_coef(int set, const double2* dev_coef, int n, cudaStream_t st);

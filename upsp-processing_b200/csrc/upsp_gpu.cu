@@ -370,11 +370,14 @@ struct upsp_gpu_ctx {
   int* d_other_local = nullptr;     // local indices of this rank's side-buffer nodes
   int n_other_local = 0;
   size_t side_off[UPSP_MAX_RANKS] = {0};   // byte offset of rank r's side buffer in its shared block
+  double* d_cl_parts = nullptr;     // clustered phase 2: [row][CL][4] partial statistics
+  size_t cl_parts_n = 0;
   float* d_p2coef = nullptr;        // streaming phase 2: coefficients (+ gain) per local row
   double* d_p2parts = nullptr;      // ... and the chunks' partial sums
   size_t p2coef_n = 0, p2parts_n = 0;
   float* d_bounce = nullptr;        // readers: rows widened to float on their way to the host
   size_t bounce_floats = 0;
+  bool front_serial_now = false;     // this batch's front end runs after the previous projection (process_batch_impl)
   bool ship_sm = false;           // staged rows shipped by k_ship_rows instead of the copy engines
   int ship_bpsm = 1;
   cudaEvent_t ev_push = nullptr, ev_proc = nullptr, ev_a = nullptr, ev_b = nullptr;
@@ -668,6 +671,7 @@ extern "C" int upsp_gpu_destroy(upsp_gpu_ctx* c) {
   cudaFree(c->d_other_local);
   cudaFree(c->d_bounce);
   cudaFree(c->d_p2coef);
+  cudaFree(c->d_cl_parts);
   cudaFree(c->d_p2parts);
   cudaFree(c->d_tma_blk);
   cudaFree(c->d_intensity);
@@ -1511,6 +1515,13 @@ static int ecc_run_batch(upsp_gpu_ctx* c, Camera& k, int off, int nb) {
   return UPSP_OK;
 }
 
+// rows stored straight into peer memory (>= 3 ranks, or staging off, or 16-bit rows at any rank count): 128-byte segments.
+// UPSP_FORCE_SEG128=1: the same kernel variant on one GPU (A/B measurements).
+static bool seg128_variant(const upsp_gpu_ctx* c) {
+  static const bool force = getenv("UPSP_FORCE_SEG128") && atoi(getenv("UPSP_FORCE_SEG128"));
+  return (c->R > 1 && c->staged_peers < c->R - 1) || force;
+}
+
 // one batch: local frames [off, off+nb)
 static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
   ProjArgs pa{};
@@ -1540,7 +1551,12 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
     // UPSP_FRONT=serial: the front end of batch i+1 starts after the projection of batch i (no decode under the
     // projection; the patch kernel still runs beside the TMA kernel of its own batch)
-    static const bool front_serial = getenv("UPSP_FRONT") && !strcmp(getenv("UPSP_FRONT"), "serial");
+    // Default: serial when the projection is the 128-byte-segment variant (rows stored straight into peer memory): its
+    // larger tile leaves 5 blocks per SM and the scan beside it costs more than it hides (measured on one GPU with the
+    // variant forced, r2z/r2aa: 48.6 ms overlapped, 43.5 ms serial with the scan at 4 x 256 threads per SM).
+    static const char* front_env = getenv("UPSP_FRONT");
+    const bool front_serial = front_env ? !strcmp(front_env, "serial") : (c->proj_mode > 0 && seg128_variant(c));
+    c->front_serial_now = front_serial;
     if (c->last_sampled || front_serial) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
     c->last_sampled = serial;
   }
@@ -1559,9 +1575,12 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     KBEGIN_ON(0, SB);
     if (src12) {
       if (c->hot_fix) {
-        static const int scan_bpsm = getenv("UPSP_SCAN_BPSM") ? atoi(getenv("UPSP_SCAN_BPSM")) : 1;   // one small block per SM beside the projection (measured r2g/r2l)
+        // one small block per SM beside the projection (measured r2g/r2l); a full-size grid when nothing runs beside it
+        static const int scan_env = getenv("UPSP_SCAN_BPSM") ? atoi(getenv("UPSP_SCAN_BPSM")) : 0;
+        const int scan_bpsm = scan_env > 0 ? scan_env : ((c->front_serial_now || serial || !c->pipelined) ? 4 : 1);
+        const int scan_threads = (c->front_serial_now || serial || !c->pipelined) ? 256 : 128;
         CU(launch_hot_scan12(in, k.frame_bytes, k.npix, nb, thresh, w_hot_cnt, w_hot_pos, w_hot_cnt + c->batch, k.H, k.W,
-                             k.d_fix[bs], c->n_sm * scan_bpsm, SB));
+                             k.d_fix[bs], c->n_sm * scan_bpsm, scan_threads, SB));
         KCHECK(c);
       }
     } else {
@@ -1730,8 +1749,7 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     if (c->proj_mode > 0) {
       // TMA-staged boxes for the nodes with a plain pixel, k_project_fused4 for the rest (patched / unseen nodes)
       Camera& k = c->cams[0];
-      static const bool force_seg128 = getenv("UPSP_FORCE_SEG128") && atoi(getenv("UPSP_FORCE_SEG128"));   // A/B knob: the multi-rank variant on one GPU
-      const bool seg128 = (c->R > 1 && c->staged_peers < c->R - 1) || force_seg128;
+      const bool seg128 = seg128_variant(c);
       fa.perm = c->d_perm_tma;
       TmaExtra ex{};
       ex.blk = c->d_tma_blk;
@@ -1889,9 +1907,12 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
   if (c->registration == UPSP_REG_GIVEN && count > 0) {
     // OpenCV-style fixed-point warp tables of every frame of this call (one launch per camera)
     for (auto& k : c->cams) {
-      k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), count), 256, 0, c->stream>>>(
-          k.d_m6 + (size_t)off * 6, count, k.W, k.H, c->interp, k.d_tab + (size_t)off * (2 * k.W + 2 * k.H));
-      KCHECK(c);
+      for (int s0 = 0; s0 < count; s0 += 65535) {      // grid.y limit: slabs of frames
+        const int ns = std::min(65535, count - s0);
+        k_warp_tables<<<dim3(cdiv(std::max(k.W, k.H), 256), ns), 256, 0, c->stream>>>(
+            k.d_m6 + (size_t)(off + s0) * 6, ns, k.W, k.H, c->interp, k.d_tab + (size_t)(off + s0) * (2 * k.W + 2 * k.H));
+        KCHECK(c);
+      }
       const int skip = (c->f0 + off <= 0 && c->f0 + off + count > 0) ? -(c->f0 + off) : -1;
       k_tma_coef<<<cdiv(count, 256), 256, 0, c->stream>>>(k.d_m6 + (size_t)off * 6, count, skip, k.d_coef + off);
       KCHECK(c);
@@ -2227,11 +2248,26 @@ static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, 
   REQUIRE(phase2_symmetric(a) || (a.itrans16 == nullptr && a.row_list == nullptr), UPSP_ERR_STATE,
           "16-bit intensity rows need the symmetric phase-2 kernel");
   if (phase2_symmetric(a)) {
+    Phase2Args b = a;
+    if (cl > 1) {      // clustered rows leave their partial statistics in global memory (one cluster barrier per row)
+      const size_t need = ((size_t)c->N_local + 1) * 8 * 4;
+      if (c->cl_parts_n < need) {
+        cudaFree(c->d_cl_parts);
+        c->d_cl_parts = nullptr;
+        TRY(dmalloc(&c->d_cl_parts, need));
+        c->cl_parts_n = need;
+      }
+      b.cl_parts = c->d_cl_parts;
+    }
     switch (cl) {
-      case 1: rc = launch_phase2_sym<NC, 1>(a, st); break;
-      case 2: rc = launch_phase2_sym<NC, 2>(a, st); break;
-      case 4: rc = launch_phase2_sym<NC, 4>(a, st); break;
-      default: rc = launch_phase2_sym<NC, 8>(a, st); break;
+      case 1: rc = launch_phase2_sym<NC, 1>(b, st); break;
+      case 2: rc = launch_phase2_sym<NC, 2>(b, st); break;
+      case 4: rc = launch_phase2_sym<NC, 4>(b, st); break;
+      default: rc = launch_phase2_sym<NC, 8>(b, st); break;
+    }
+    if (!rc && cl > 1) {
+      k_phase2_cl_parts<<<cdiv(b.n_local, 256), 256, 0, st>>>(b, cl);
+      ++*launches;
     }
   } else if (cl > 0) {
     const size_t seg = (size_t)(((a.F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
