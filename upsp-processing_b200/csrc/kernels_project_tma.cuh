@@ -137,7 +137,11 @@ static_assert(TMA_BWB12 % 16 == 0 && (TMA_BW16 * 2) % 16 == 0, "box rows are mul
 template <int SRC, int CH, int NG = TMA_NG>
 struct TmaSmem {
   static constexpr int SLOT = SRC ? TMA_SLOT12 : TMA_SLOT16;
-  static constexpr int TS = CH + 4;
+  // tile row = CH floats (or 2 CH 16-bit values).  CH = 16: + 16 bytes of padding (80-byte rows).  CH = 32 (128-byte row
+  // segments for peer stores): no padding, the eight 16-byte chunks of a row are XOR-swizzled with the row index
+  // instead, which keeps the block at 37 KB with a 3-group ring: six blocks per SM like the 64-byte variant (with the
+  // padded 18 KB tile + 4-group ring it was five, and the scan beside it cost 9 ms per 20 000 frames, r2z)
+  static constexpr int TS = CH == 32 ? CH : CH + 4;
   static constexpr int ring_bytes = NG * TMA_G * SLOT;
   static constexpr int tile_off = ring_bytes;
   static constexpr int tile_bytes = TMA_NB * TS * 4;
@@ -216,6 +220,9 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   const int yrel = py - bd.ymin;
   const bool vec_ok = ((a.f_total | a.col0) & (IT16 ? 7 : 3)) == 0;      // 16-byte aligned row segments
   unsigned char* trow = tile + tid * (TS * 4);
+  constexpr bool SWZ = CH == 32;
+  // byte offset `off` inside this thread's tile row -> its place (16-byte chunks swizzled with the row index)
+  auto tpos = [&](int row, int off) -> int { return SWZ ? ((((off >> 4) ^ (row & 7)) << 4) | (off & 15)) : off; };
   double s = 0.0, q = 0.0;
   unsigned gidx = 0;        // groups issued / consumed so far by this block (ring position)
 
@@ -402,8 +409,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
         if (nf == TMA_G) {
-          if (IT16) *reinterpret_cast<uint2*>(trow + u * 2) = make_uint2(ri[0] | (ri[1] << 16), ri[2] | (ri[3] << 16));
-          else *reinterpret_cast<float4*>(trow + u * 4) = make_float4(sol[0], sol[1], sol[2], sol[3]);
+          if (IT16) *reinterpret_cast<uint2*>(trow + tpos(tid, u * 2)) = make_uint2(ri[0] | (ri[1] << 16), ri[2] | (ri[3] << 16));
+          else *reinterpret_cast<float4*>(trow + tpos(tid, u * 4)) = make_float4(sol[0], sol[1], sol[2], sol[3]);
           if (VAL1) {
             unsigned si = 0, qi = 0;      // 4 * 4095 and 4 * 4095^2 fit easily
 #pragma unroll
@@ -422,8 +429,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
           }
         } else {
           for (int j = 0; j < nf; ++j) {
-            if (IT16) reinterpret_cast<unsigned short*>(trow)[u + j] = (unsigned short)ri[j];
-            else reinterpret_cast<float*>(trow)[u + j] = sol[j];
+            if (IT16) *reinterpret_cast<unsigned short*>(trow + tpos(tid, (u + j) * 2)) = (unsigned short)ri[j];
+            else *reinterpret_cast<float*>(trow + tpos(tid, (u + j) * 4)) = sol[j];
             q += (double)__fmul_rn(sol[j], sol[j]);
             s += (double)sol[j];
           }
@@ -441,7 +448,7 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
           const int nl = w * 32 + it * (32 / LPN) + nsel;
           unsigned char* rp = rowp[nl];
           if (rp != nullptr) {
-            const float4 o = *reinterpret_cast<const float4*>(tile + nl * (TS * 4) + fq);
+            const float4 o = *reinterpret_cast<const float4*>(tile + nl * (TS * 4) + tpos(nl, fq));
             *reinterpret_cast<float4*>(rp + (size_t)b0 * ESZ + fq) = o;
           }
         }
@@ -451,8 +458,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
           if (rp == nullptr) continue;
           const unsigned char* tr = tile + (w * 32 + j) * (TS * 4);
           for (int f = lane; f < nb; f += 32) {
-            if (IT16) reinterpret_cast<unsigned short*>(rp)[b0 + f] = reinterpret_cast<const unsigned short*>(tr)[f];
-            else reinterpret_cast<float*>(rp)[b0 + f] = reinterpret_cast<const float*>(tr)[f];
+            if (IT16) reinterpret_cast<unsigned short*>(rp)[b0 + f] = *reinterpret_cast<const unsigned short*>(tr + tpos(w * 32 + j, f * 2));
+            else reinterpret_cast<float*>(rp)[b0 + f] = *reinterpret_cast<const float*>(tr + tpos(w * 32 + j, f * 4));
           }
         }
       }

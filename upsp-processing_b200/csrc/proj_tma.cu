@@ -40,9 +40,9 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, con
   if (nblocks <= 0) return cudaSuccess;
   if (rows16) {      // 16-bit node-major rows (unit projection values only)
     if (!val1) return cudaErrorInvalidValue;
-    if (src == 0) return seg128 ? launch1<0, 32, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st)
+    if (src == 0) return seg128 ? launch1<0, 32, true, 3, 2, 6, true>(map_group, map_single, a, ex, nblocks, st)
                                 : launch1<0, 16, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st);
-    return seg128 ? launch1<1, 32, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st)
+    return seg128 ? launch1<1, 32, true, 3, 2, 6, true>(map_group, map_single, a, ex, nblocks, st)
                   : launch1<1, 16, true, TMA_NG, TMA_LA, 6, true>(map_group, map_single, a, ex, nblocks, st);
   }
   // UPSP_TMA_RING = "NG.LA.MINB" picks another ring depth / look-ahead / occupancy target of the hot instantiation
@@ -61,9 +61,10 @@ cudaError_t launch_project_tma(int src, bool seg128, bool val1, bool rows16, con
     UPSP_RING(2, 1, 8);
 #undef UPSP_RING
   }
+  // 128-byte-segment variants (C = 32): 3-group ring, see TmaSmem
 #define UPSP_TMA_CASE(S, C)                                                                              \
-  return val1 ? launch1<S, C, true>(map_group, map_single, a, ex, nblocks, st)                           \
-              : launch1<S, C, false>(map_group, map_single, a, ex, nblocks, st)
+  return val1 ? launch1<S, C, true, (C == 32 ? 3 : TMA_NG), TMA_LA>(map_group, map_single, a, ex, nblocks, st)   \
+              : launch1<S, C, false, (C == 32 ? 3 : TMA_NG), TMA_LA>(map_group, map_single, a, ex, nblocks, st)
   if (src == 0) {
     if (seg128) UPSP_TMA_CASE(0, 32);
     UPSP_TMA_CASE(0, 16);

@@ -1519,7 +1519,8 @@ static int ecc_run_batch(upsp_gpu_ctx* c, Camera& k, int off, int nb) {
 // UPSP_FORCE_SEG128=1: the same kernel variant on one GPU (A/B measurements).
 static bool seg128_variant(const upsp_gpu_ctx* c) {
   static const bool force = getenv("UPSP_FORCE_SEG128") && atoi(getenv("UPSP_FORCE_SEG128"));
-  return (c->R > 1 && c->staged_peers < c->R - 1) || force;
+  static const bool force64 = getenv("UPSP_FORCE_SEG64") && atoi(getenv("UPSP_FORCE_SEG64"));      // A/B knob: 64-byte segments to peers
+  return ((c->R > 1 && c->staged_peers < c->R - 1) || force) && !force64;
 }
 
 // one batch: local frames [off, off+nb)
@@ -1551,11 +1552,12 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
     CU(cudaStreamWaitEvent(SB, c->ev_back[bs], 0));
     // UPSP_FRONT=serial: the front end of batch i+1 starts after the projection of batch i (no decode under the
     // projection; the patch kernel still runs beside the TMA kernel of its own batch)
-    // Default: serial when the projection is the 128-byte-segment variant (rows stored straight into peer memory): its
-    // larger tile leaves 5 blocks per SM and the scan beside it costs more than it hides (measured on one GPU with the
-    // variant forced, r2z/r2aa: 48.6 ms overlapped, 43.5 ms serial with the scan at 4 x 256 threads per SM).
+    // Measured with the 128-byte-segment variant of the projection (rows stored straight into peer memory; 5 blocks per
+    // SM): on ONE GPU with the variant forced, serial + a full-size scan wins (43.5 against 48.6 ms, r2z/r2aa); on 8 GPUs,
+    // where the kernel also waits on its NVLink stores, the scan beside it fills those gaps and overlapped wins (51.5
+    // against 54.7 ms, r2t/r2ac).  So overlapped stays the default everywhere.
     static const char* front_env = getenv("UPSP_FRONT");
-    const bool front_serial = front_env ? !strcmp(front_env, "serial") : (c->proj_mode > 0 && seg128_variant(c));
+    const bool front_serial = front_env ? !strcmp(front_env, "serial") : false;
     c->front_serial_now = front_serial;
     if (c->last_sampled || front_serial) CU(cudaStreamWaitEvent(SB, c->ev_back[bs ^ 1], 0));
     c->last_sampled = serial;
@@ -2180,9 +2182,21 @@ static void cheb_ginv(int F, int nc, float xa, float xb, bool sym, double* ginv)
 static int phase2_cluster(int F);
 static bool phase2_symmetric(const Phase2Args& a);
 
+template <int NC, bool ROW_SMEM, int CL, int NT>
+static int launch_phase2_cl_nt(const Phase2Args& a, size_t smem, cudaStream_t st);
+
+// Short rows (<= 8192 frames, one CTA per row): 128 threads per row instead of 512.  The per-row set-up (block
+// reductions, coefficient solve) is a quarter of the warp instructions then, and several rows share an SM.
 template <int NC, bool ROW_SMEM, int CL>
 static int launch_phase2_cl(const Phase2Args& a, size_t smem, cudaStream_t st) {
-  constexpr int NT = 512;
+  if constexpr (CL == 1 && ROW_SMEM) {
+    if (a.F <= 8192) return launch_phase2_cl_nt<NC, ROW_SMEM, CL, 128>(a, smem, st);
+  }
+  return launch_phase2_cl_nt<NC, ROW_SMEM, CL, 512>(a, smem, st);
+}
+
+template <int NC, bool ROW_SMEM, int CL, int NT>
+static int launch_phase2_cl_nt(const Phase2Args& a, size_t smem, cudaStream_t st) {
   auto kern = k_phase2<NC, ROW_SMEM, NT, CL>;
   // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
   if (smem > 24 * 1024)
@@ -2215,9 +2229,19 @@ static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
   return scalar ? launch_phase2_sym_pk<NC, CL, false>(a, st) : launch_phase2_sym_pk<NC, CL, true>(a, st);
 }
 
+template <int NC, int CL, bool PK, bool IN16, int NT>
+static int launch_phase2_sym_nt(const Phase2Args& a, cudaStream_t st);
+
 template <int NC, int CL, bool PK, bool IN16>
 static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st) {
-  constexpr int NT = 512;
+  if constexpr (CL == 1 && PK) {      // short rows: see launch_phase2_cl
+    if (a.F <= 8192) return launch_phase2_sym_nt<NC, CL, PK, IN16, 128>(a, st);
+  }
+  return launch_phase2_sym_nt<NC, CL, PK, IN16, 512>(a, st);
+}
+
+template <int NC, int CL, bool PK, bool IN16, int NT>
+static int launch_phase2_sym_nt(const Phase2Args& a, cudaStream_t st) {
   auto kern = k_phase2_sym<NC, NT, CL, PK, IN16>;
   const size_t smem = (size_t)(a.F / CL) * sizeof(float);
   // static + dynamic shared memory may exceed the 48 KB default even when the dynamic part alone does not
