@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-O=gpurun_out/r2q
+O=gpurun_out/r2q${N:-}
 N=${1:-8}
 nvidia-smi topo -m > ${O}_topo.txt 2>&1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --steps 3 --warmup 3 --e2e-steps 1 --cpu-seconds 0 --check > ${O}_bench$N.json 2> ${O}_bench$N.err

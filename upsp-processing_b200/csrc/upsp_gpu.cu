@@ -571,7 +571,9 @@ extern "C" int upsp_gpu_create(const upsp_gpu_config* cfg, upsp_gpu_ctx** out) {
     c->off_sum = al(nf * sizeof(float));
     c->off_sumsq = c->off_sum + al((size_t)c->N * sizeof(double));
     c->shared_bytes = c->off_sumsq + al((size_t)c->N * sizeof(double));
-    if (c->R > 1) {
+    // UPSP_FORCE_VMM=1: the peer-mappable (CUDA VMM) allocation on a single rank too (A/B: is the allocation kind what
+    // multi-rank phase 1 pays for?)
+    if (c->R > 1 || (getenv("UPSP_FORCE_VMM") && atoi(getenv("UPSP_FORCE_VMM")))) {
       CU(cudaFree(0));  // make sure the primary context exists before driver-API calls
       TRY(vmm_alloc(c->shared_vmm, c->shared_bytes, cfg->device));
       c->d_shared = reinterpret_cast<char*>(c->shared_vmm.ptr);
