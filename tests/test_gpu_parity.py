@@ -460,6 +460,29 @@ def test_chain_16bit_rows_and_phase2_paths(up, orc, gpu, monkeypatch, stream):
     _check_chain(case, ref, got, orc)
 
 
+def test_chain_batch_blocked_rows_single_rank(up, orc, gpu, monkeypatch):
+    """UPSP_BLOCKED=1: the batch-blocked 16-bit row layout of the multi-rank exchange on one rank (chain against the
+    oracle; frames pushed and processed in calls that are not multiples of the batch)."""
+    import upsp_b200
+    from chain import push_all, setup_ctx
+    monkeypatch.setenv("UPSP_BLOCKED", "1")
+    case = Case(upsp_b200.synth, n_frames=200, n_nodes=6000, height=96, width=128, registration=True, patches=True,
+                seed=18, fmt="p12")
+    ref = run_oracle(orc, case)
+    g, sl = setup_ctx(up, orc, case, batch_frames=64)
+    push_all(up, orc, g, case, sl, chunk=40)            # calls of 40 frames: batches are cut at the 64-frame block edges
+    g.finish_phase1()
+    got = dict(intensity=None)
+    got["avg"], got["rms"], got["coverage"] = g.read_phase1_stats()
+    g.transpose()
+    got["itrans"] = g.read_intensity_transpose()
+    g.phase2(case.cal, case.qbar, case.ps, case.steady, case.temp, case.degree)
+    got["ptrans"] = g.read_pressure_transpose()
+    got["rms2"], got["avg2"], got["gain"] = g.read_phase2_stats()
+    g.close()
+    _check_chain(case, ref, got, orc)
+
+
 def test_tma_projection_weighted_values(up, orc, gpu, monkeypatch):
     """Projection values other than 1.0 (a weighted single camera) take the float-statistics variant."""
     import upsp_b200

@@ -90,3 +90,22 @@ def test_many_ranks_one_gpu(up, orc, gpu, R, staged, ship, monkeypatch):
     assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
     assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact across ranks"
     assert same_bits(got["gain"], ref["gain"])
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_ranks_batch_blocked_rows(up, orc, gpu, R):
+    """Several ranks, every rank the same multiple-of-8 number of frames, power-of-two batch: the 16-bit rows of the plain
+    nodes live in the batch-blocked layout [source rank * batches + local batch][node][batch length] (what a projection
+    batch stores into a peer is one contiguous region), phase 2 and the readers follow it.  528 frames = 2 x 264 or
+    4 x 132: the last block of every rank is partly filled."""
+    import upsp_b200
+    case = Case(upsp_b200.synth, n_frames=528, n_nodes=2003, registration=True, patches=True, seed=35, fmt="p12")
+    ref = run_oracle(orc, case, n_ranks=R)
+    got = _run_ranks(up, orc, case, False, True, R=R, batch_frames=64)
+    assert same_bits(got["avg"], ref["avg"]) and same_bits(got["rms"], ref["rms"])
+    assert same_bits(got["itrans"], ref["itrans"]), "intensity_transpose not bit-exact across ranks"
+    assert same_bits(got["gain"], ref["gain"])
+    exact = run_oracle(orc, case, n_ranks=R, exact_fit=True)
+    e_exact, _ = cp_errors(case, exact, got)
+    cond = 8 * np.finfo(np.float32).eps * monomial_mass(orc, ref)
+    assert np.all(e_exact <= 1e-6 + cond)

@@ -199,7 +199,11 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
     if (live) {
       int r = 0;
       while (r + 1 < a.n_ranks && n >= a.node_start[r + 1]) ++r;
-      rp = reinterpret_cast<unsigned char*>(a.dst[r]) + ((size_t)(n - a.node_start[r]) * a.f_total + a.col0) * 2;
+      if (a.blk_len > 0)      // batch-blocked destination: [block][N_r][blk_len]
+        rp = reinterpret_cast<unsigned char*>(a.dst[r]) +
+             (((size_t)a.blk_index * (size_t)(a.node_start[r + 1] - a.node_start[r]) + (size_t)(n - a.node_start[r])) * a.blk_len + a.blk_j0) * 2;
+      else
+        rp = reinterpret_cast<unsigned char*>(a.dst[r]) + ((size_t)(n - a.node_start[r]) * a.f_total + a.col0) * 2;
     }
     rowp[tid] = rp;
   } else {
@@ -218,7 +222,8 @@ k_project_tma(const __grid_constant__ CUtensorMap tmapG, const __grid_constant__
   const int px = code % W, py = code / W;
   const double dpx = (double)px;
   const int yrel = py - bd.ymin;
-  const bool vec_ok = ((a.f_total | a.col0) & (IT16 ? 7 : 3)) == 0;      // 16-byte aligned row segments
+  const bool vec_ok = a.blk_len > 0 ? ((a.blk_len | a.blk_j0) & 7) == 0
+                                    : ((a.f_total | a.col0) & (IT16 ? 7 : 3)) == 0;      // 16-byte aligned row segments
   unsigned char* trow = tile + tid * (TS * 4);
   constexpr bool SWZ = CH == 32;
   // byte offset `off` inside this thread's tile row -> its place (16-byte chunks swizzled with the row index)

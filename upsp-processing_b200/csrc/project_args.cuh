@@ -53,6 +53,10 @@ struct FusedArgs {
   // float rows in a side buffer of their owner; row_index[n] = row of node n in that buffer (dst[] then point at the
   // side buffers).  nullptr: row = n - node_start[owner].
   const int* row_index;
+  // 16-bit rows, batch-blocked destination (multi-rank): rank s holds [block][N_s][blk_len] values, block = source rank *
+  // blocks per rank + local batch; this launch writes block blk_index from frame blk_j0 of the block on.  blk_len = 0:
+  // node-major rows [N_s][f_total].
+  int blk_len, blk_index, blk_j0;
 };
 
 // where a block writes node n's row segment of this batch (frame b of the batch at [b])

@@ -366,6 +366,10 @@ struct upsp_gpu_ctx {
   // 16-bit row mode (TMA projection with unit values, decided in ensure_proj_mode): rows of plain nodes are 16-bit
   // integers at the start of the shared block, the other (patched / unseen) nodes keep float rows in a side buffer behind them
   bool it16 = false;
+  // ... and in multi-rank runs those 16-bit rows live in a batch-blocked layout [source rank * blk_kb + local batch][N_local]
+  // [blk_len]: what a batch of the projection stores into a peer is then one contiguous region per peer instead of
+  // 128-byte pieces of 80-320 KB rows
+  int blk_len = 0, blk_kb = 0;
   int* d_other_idx = nullptr;       // [N]: -1 plain node, else row in the owner's side buffer
   int* d_other_local = nullptr;     // local indices of this rank's side-buffer nodes
   int n_other_local = 0;
@@ -1363,6 +1367,18 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
     const int cl = phase2_cluster(c->F);
     bool ok = val1 && !(getenv("UPSP_ITRANS16") && atoi(getenv("UPSP_ITRANS16")) == 0) && cl > 0 && c->F % (8 * cl) == 0 &&
               c->F % 8 == 0;
+    // batch-blocked layout: several ranks, every rank the same number of frames (a multiple of 8), power-of-two batch
+    int blk_len = 0, blk_kb = 0;
+    {
+      static const int blocked_env = getenv("UPSP_BLOCKED") ? atoi(getenv("UPSP_BLOCKED")) : -1;      // 0: row-major, 1: also on one rank
+      const bool pow2 = c->batch >= 64 && (c->batch & (c->batch - 1)) == 0;
+      bool equal = c->F % c->R == 0 && (c->F / c->R) % 8 == 0;
+      for (int r = 0; r < c->R; ++r) equal = equal && c->f_count[r] == c->F / c->R && c->f_start[r] == r * (c->F / c->R);
+      if (ok && pow2 && equal && blocked_env != 0 && (c->R > 1 || blocked_env == 1)) {
+        blk_len = c->batch;
+        blk_kb = (c->F / c->R + blk_len - 1) / blk_len;
+      }
+    }
     std::vector<int> oidx(N, -1), cnt(c->R, 0), local;
     for (int r = 0; r < c->R && ok; ++r) {
       for (int n = c->n_start[r]; n < c->n_start[r] + c->n_count[r]; ++n)
@@ -1371,12 +1387,15 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
           oidx[n] = cnt[r]++;
         }
       auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-      c->side_off[r] = al((size_t)c->n_count[r] * c->F * sizeof(uint16_t));
+      const size_t row_elems = blk_len > 0 ? (size_t)c->R * blk_kb * blk_len : (size_t)c->F;      // blocked: tail batches padded
+      c->side_off[r] = al((size_t)c->n_count[r] * row_elems * sizeof(uint16_t));
       // the side buffer must fit behind the 16-bit rows inside the block sized for float rows
       ok = ok && c->side_off[r] + (size_t)cnt[r] * c->F * sizeof(float) <= (size_t)c->n_count[r] * c->F * sizeof(float);
     }
     if (ok) {
       c->it16 = true;
+      c->blk_len = blk_len;
+      c->blk_kb = blk_kb;
       c->n_other_local = (int)local.size();
       TRY(upload(&c->d_other_idx, oidx.data(), oidx.size()));
       if (!local.empty()) TRY(upload(&c->d_other_local, local.data(), local.size()));
@@ -1773,6 +1792,11 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         ex.hot = c->hot_fix ? reinterpret_cast<const HotFix*>(k.d_fix[bs]) : nullptr;
         fa.cam[0].frames = nullptr;
       }
+      if (c->it16 && c->blk_len > 0) {
+        fa.blk_len = c->blk_len;
+        fa.blk_index = c->rank * c->blk_kb + off / c->blk_len;
+        fa.blk_j0 = off % c->blk_len;
+      }
       CU(launch_project_tma(c->proj_mode - 1, seg128, c->tma_val1, c->it16, c->proj_mode == 2 ? k.tmap12g : k.tmap16g[bs],
                             c->proj_mode == 2 ? k.tmap12 : k.tmap16[bs], fa, ex, c->n_tma_blocks, c->stream));
       c->launches++;
@@ -1782,7 +1806,8 @@ static int process_batch_impl(upsp_gpu_ctx* c, int off, int nb) {
         FusedArgs fb = fa;
         fb.perm = c->d_perm_tma + c->n_tma_plain;
         fb.n_nodes = n_other;
-        if (c->it16) {      // float rows of the patched / unseen nodes: the owners' side buffers
+        if (c->it16) {      // float rows of the patched / unseen nodes: the owners' side buffers (node-major)
+          fb.blk_len = 0;
           fb.row_index = c->d_other_idx;
           for (int r = 0; r < c->R; ++r) fb.dst[r] = reinterpret_cast<float*>(c->peer_base[r] + c->side_off[r]);
         }
@@ -1932,6 +1957,8 @@ extern "C" int upsp_gpu_process_frames(upsp_gpu_ctx* c, int off, int count) {
     const int o = off + done;
     int nb = std::min(c->batch, count - done);
     nb = std::min(nb, c->capacity - (o % c->capacity));
+    if (c->proj_mode < 0 && done == 0) nb = std::min(nb, c->batch - (o % c->batch));      // mode not decided yet: stay inside a block
+    if (c->blk_len > 0) nb = std::min(nb, c->blk_len - (o % c->blk_len));                 // blocked rows: a batch lives in one block
     TRY(process_batch(c, o, nb));
     done += nb;
   }
@@ -2345,7 +2372,7 @@ static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st
   // and for the parity test that pins it).  Measured (r2u, 1 GPU, 20 000-frame rows): 23.9 ms against 17.0 ms with the row in shared memory;
   // phase 2 is bound by instruction issue, and the pair divides and converts every element twice.
   static const int stream_env = getenv("UPSP_PHASE2_STREAM") ? atoi(getenv("UPSP_PHASE2_STREAM")) : -1;
-  if (a.itrans16 != nullptr && a.row_list == nullptr && a.F % 8 == 0 &&
+  if (a.itrans16 != nullptr && a.row_list == nullptr && a.F % 8 == 0 && a.blk_log2 == 0 &&
       (stream_env == 1 || (stream_env != 0 && phase2_cluster(a.F) == 0))) {
     int rc = UPSP_OK;
     for (int r0 = 0; r0 < a.n_local && !rc; r0 += 65535) {      // grid.y limit: rows in slabs
@@ -2456,6 +2483,15 @@ extern "C" int upsp_gpu_phase2(upsp_gpu_ctx* c, const upsp_phase2_params* p, con
     Phase2Args b = a;
     b.itrans16 = reinterpret_cast<const unsigned short*>(c->d_shared);
     b.other_idx = c->d_other_idx;
+    if (c->blk_len > 0) {
+      int lg = 0;
+      while ((1 << lg) < c->blk_len) ++lg;
+      b.blk_log2 = lg;
+      b.blk_kb = c->blk_kb;
+      b.blk_floc = c->F / c->R;
+      b.blk_rows = c->N_local;
+      b.blk_magic = (unsigned)((((unsigned long long)1) << 32) / (unsigned)b.blk_floc + 1);
+    }
     TRY(dispatch_phase2(c, b, c->stream, &c->launches));
     if (c->n_other_local > 0) {
       Phase2Args o = a;
@@ -2511,12 +2547,23 @@ extern "C" int upsp_gpu_read_intensity(upsp_gpu_ctx* c, int off, int n, float* h
 // float rows would hold: integers are exact, the side buffer's rows are copied)
 __global__ void __launch_bounds__(256)
 k_itrans_rows_f32(const uint16_t* __restrict__ it16, const float* __restrict__ side, const int* __restrict__ other_idx,
-                  int node0, int row0, int F, int f0, int nf, float* __restrict__ out, size_t out_pitch) {
+                  int node0, int row0, int F, int f0, int nf, float* __restrict__ out, size_t out_pitch, int blk_len,
+                  int blk_kb, int blk_floc, int blk_rows) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (f >= nf) return;
   const int oi = __ldg(other_idx + node0 + row0 + r);
   const size_t col = (size_t)f0 + f;
-  out[(size_t)r * out_pitch + f] = oi >= 0 ? side[(size_t)oi * F + col] : (float)it16[(size_t)(row0 + r) * F + col];
+  float v;
+  if (oi >= 0) {
+    v = side[(size_t)oi * F + col];
+  } else if (blk_len > 0) {      // batch-blocked rows: [source rank * blk_kb + local batch][blk_rows][blk_len]
+    const int src = (int)(col / (size_t)blk_floc), o = (int)(col - (size_t)src * blk_floc);
+    const size_t blk = (size_t)src * blk_kb + (size_t)(o / blk_len);
+    v = (float)it16[(blk * blk_rows + (size_t)(row0 + r)) * blk_len + (size_t)(o % blk_len)];
+  } else {
+    v = (float)it16[(size_t)(row0 + r) * F + col];
+  }
+  out[(size_t)r * out_pitch + f] = v;
 }
 
 // widen rows [noff, noff+nn) x frames [foff, foff+nf) into the bounce buffer chunk by chunk and copy each chunk out
@@ -2536,7 +2583,8 @@ static int read_itrans16(upsp_gpu_ctx* c, int noff, int nn, int foff, int nf, fl
   for (int r0 = 0; r0 < nn; r0 += rows_per) {
     const int nr = std::min(rows_per, nn - r0);
     k_itrans_rows_f32<<<dim3(cdiv(nf, 256), nr), 256, 0, st>>>(it16, side, c->d_other_idx, c->n0, noff + r0, c->F, foff, nf,
-                                                               c->d_bounce, (size_t)nf);
+                                                               c->d_bounce, (size_t)nf, c->blk_len, c->blk_kb,
+                                                               c->blk_len > 0 ? c->F / c->R : 0, c->N_local);
     KCHECK(c);
     CU(cudaMemcpy2DAsync(host + (size_t)r0 * pitch, pitch * sizeof(float), c->d_bounce, (size_t)nf * sizeof(float),
                          (size_t)nf * sizeof(float), (size_t)nr, cudaMemcpyDeviceToHost, st));
