@@ -397,8 +397,11 @@ def bench_b200(args):
     for _ in range(args.warmup):
         run_step_resident(g, wl, args, dist)
     g.sync()
-    barrier(dist)
+    # rank 0 forks nvidia-smi BEFORE the rendezvous: the fork of this process (tens of GB of pinned host memory mapped)
+    # takes ~20 ms, and a rank that starts its timer that much earlier only waits for rank 0 at the first in-step barrier,
+    # which the max-over-ranks device time then charges to the steps (7 ms per step at --steps 3)
     sampler = ClockSampler(local) if rank == 0 else None
+    barrier(dist)
     # per-kernel CUDA events in the LAST timed step only: every 8th batch runs un-overlapped (the
     # library serialises a sampled batch so that event durations are the kernels' own) + phase 2
     g.set_kernel_sampling(0)
