@@ -517,7 +517,7 @@ def bench_b200(args):
     if check is not None:
         out["parity_checked"] = bool(check["ok"])
         out["parity"] = check
-    if args.cpu_seconds > 0:
+    if args.cpu_seconds > 0 and world == 1:       # a reported baseline of the single-GPU line only
         out["cpu_baseline"] = cpu_baseline(args, wl, budget_s=args.cpu_seconds)
     print(json.dumps(out), flush=True)
     if check is not None and not check["ok"]:
