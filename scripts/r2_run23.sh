@@ -1,0 +1,20 @@
+mkdir -p gpurun_out
+O=gpurun_out/r2an
+run() {  # name cl nt extra-args...
+  name=$1; cl=$2; nt=$3; shift 3
+  UPSP_P2_CL=$cl UPSP_P2_NT=$nt timeout 300 python bench.py --steps 3 --warmup 2 --e2e-steps 0 --cpu-seconds 0 "$@" > ${O}_$name.json 2> ${O}_$name.err; rc=$?
+  python -c "
+import json
+try:
+    d=json.loads(open('${O}_$name.json').read().strip().splitlines()[-1])
+    print('$name cl=$cl nt=$nt rc=$rc ms/step', d['ms_per_step'], 'phase2', d['stage_ms']['phase2'], 'parity', d.get('parity_checked'))
+except Exception as e:
+    print('$name cl=$cl nt=$nt rc=$rc ERR', e)
+"
+}
+run f20k_c2n256 2 256
+run f20k_c4n128 4 128
+run f20k_c4n256 4 256
+run f40k_c2n512 2 512 --frames 40000 --nodes 250000 --no-check
+run f40k_c4n256 4 256 --frames 40000 --nodes 250000 --no-check
+run f40k_c8n256 8 256 --frames 40000 --nodes 250000 --no-check

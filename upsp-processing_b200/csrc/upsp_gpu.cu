@@ -1219,7 +1219,7 @@ static int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, void* base, uint6
   return UPSP_OK;
 }
 
-static int phase2_cluster(int F);
+static int phase2_cluster(int F, bool in16 = false);
 
 // Decide the projection mode of a fused single-camera context and build what the TMA kernels need:
 //   * processing order: nodes with a plain pixel, cut into blocks of <= 128 nodes whose pixels lie in one
@@ -1364,7 +1364,7 @@ static int ensure_proj_mode(upsp_gpu_ctx* c) {
   // (patched: float values, unseen: NaN) keep float rows in a side buffer behind the 16-bit rows of their owner.  Needs
   // the symmetric phase-2 kernel (the one that reads 16-bit rows) and 16-byte aligned row segments.  UPSP_ITRANS16=0: off.
   {
-    const int cl = phase2_cluster(c->F);
+    const int cl = phase2_cluster(c->F, true);
     bool ok = val1 && !(getenv("UPSP_ITRANS16") && atoi(getenv("UPSP_ITRANS16")) == 0) && cl > 0 && c->F % (8 * cl) == 0 &&
               c->F % 8 == 0;
     // batch-blocked layout: several ranks, every rank the same number of frames (a multiple of 8), power-of-two batch
@@ -2208,7 +2208,7 @@ static void cheb_ginv(int F, int nc, float xa, float xb, bool sym, double* ginv)
     }
 }
 
-static int phase2_cluster(int F);
+static int phase2_cluster(int F, bool in16);
 static bool phase2_symmetric(const Phase2Args& a);
 
 template <int NC, bool ROW_SMEM, int CL, int NT>
@@ -2261,10 +2261,16 @@ static int launch_phase2_sym(const Phase2Args& a, cudaStream_t st) {
 template <int NC, int CL, bool PK, bool IN16, int NT>
 static int launch_phase2_sym_nt(const Phase2Args& a, cudaStream_t st);
 
+// threads per CTA: 512; 128 for short rows (see launch_phase2_cl); 256 for clustered 16-bit rows (see phase2_cluster).
+// UPSP_P2_NT=512 keeps 512 threads for those (A/B).
 template <int NC, int CL, bool PK, bool IN16>
 static int launch_phase2_sym_pk(const Phase2Args& a, cudaStream_t st) {
-  if constexpr (CL == 1 && PK) {      // short rows: see launch_phase2_cl
+  if constexpr (CL == 1 && PK) {
     if (a.F <= 8192) return launch_phase2_sym_nt<NC, CL, PK, IN16, 128>(a, st);
+  }
+  if constexpr (PK && IN16 && CL >= 2) {
+    static const int nt_env = getenv("UPSP_P2_NT") ? atoi(getenv("UPSP_P2_NT")) : 0;
+    if (nt_env != 512) return launch_phase2_sym_nt<NC, CL, PK, IN16, 256>(a, st);
   }
   return launch_phase2_sym_nt<NC, CL, PK, IN16, 512>(a, st);
 }
@@ -2296,7 +2302,7 @@ template <int NC>
 static int launch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st, long long* launches) {
   (void)c;
   if (a.n_local == 0) return UPSP_OK;
-  const int cl = phase2_cluster(a.F);
+  const int cl = phase2_cluster(a.F, a.itrans16 != nullptr);
   int rc = UPSP_OK;
   REQUIRE(phase2_symmetric(a) || (a.itrans16 == nullptr && a.row_list == nullptr), UPSP_ERR_STATE,
           "16-bit intensity rows need the symmetric phase-2 kernel");
@@ -2373,7 +2379,7 @@ static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st
   // phase 2 is bound by instruction issue, and the pair divides and converts every element twice.
   static const int stream_env = getenv("UPSP_PHASE2_STREAM") ? atoi(getenv("UPSP_PHASE2_STREAM")) : -1;
   if (a.itrans16 != nullptr && a.row_list == nullptr && a.F % 8 == 0 && a.blk_log2 == 0 &&
-      (stream_env == 1 || (stream_env != 0 && phase2_cluster(a.F) == 0))) {
+      (stream_env == 1 || (stream_env != 0 && phase2_cluster(a.F, true) == 0))) {
     int rc = UPSP_OK;
     for (int r0 = 0; r0 < a.n_local && !rc; r0 += 65535) {      // grid.y limit: rows in slabs
       Phase2Args b = a;
@@ -2408,17 +2414,29 @@ static int dispatch_phase2(upsp_gpu_ctx* c, const Phase2Args& a, cudaStream_t st
 }
 
 // cluster size for a row of F frames: smallest CL in {1,2,4,8} whose per-CTA segment leaves room
-// for 2 CTAs per SM (<= 90 KB + 18.6 KB static each); 0 = does not fit even with 8 (two HBM passes)
-static int phase2_cluster(int F) {
+// for 2 CTAs per SM (<= 90 KB + 18.6 KB static each); 0 = does not fit even with 8 (two HBM passes).
+// 16-bit rows that need a cluster anyway take twice that many CTAs of 256 threads (<= 45 KB each, four CTAs per SM:
+// four rows' barrier phases overlap instead of two).  Measured on one GPU, phase 2 of 10^10 node-frames (gpurun_out/r2an,
+// r2ao): 40 000-frame rows 19.5 ms as 2 x 512 threads, 18.4 as 4 x 256; 80 000: 20.6 as 4 x 512, 18.8 as 8 x 256;
+// 160 000: 21.9 as 8 x 512, 21.4 as 8 x 256.  Rows that fit one CTA stay there: 20 000 frames 16.4 ms as 1 x 512, 17.4 as
+// 2 x 256, 19.9 as 4 x 128.  UPSP_P2_CL / UPSP_P2_NT force a shape.
+static int phase2_cluster(int F, bool in16) {
+  static const int forced = getenv("UPSP_P2_CL") ? atoi(getenv("UPSP_P2_CL")) : 0;
+  if ((forced == 1 || forced == 2 || forced == 4 || forced == 8) && F % (8 * forced) == 0 &&
+      (size_t)(F / forced) * sizeof(float) <= 200 * 1024)
+    return forced;
   const size_t seg_budget = 90 * 1024, seg_max = 200 * 1024;
   for (int cl = 1; cl <= 8; cl *= 2) {
     const size_t seg = (size_t)(((F + cl * 4 - 1) / (cl * 4)) * 4) * sizeof(float);
-    if (seg <= seg_budget || (cl == 8 && seg <= seg_max)) return cl;
+    if (seg <= seg_budget || (cl == 8 && seg <= seg_max)) {
+      if (in16 && (cl == 2 || cl == 4) && F % (16 * cl) == 0) return 2 * cl;
+      return cl;
+    }
   }
   return 0;
 }
 static bool phase2_symmetric(const Phase2Args& a) {
-  const int cl = phase2_cluster(a.F);
+  const int cl = phase2_cluster(a.F, a.itrans16 != nullptr);
   return a.fit_out == nullptr && cl > 0 && a.F % (8 * cl) == 0 &&
          (reinterpret_cast<uintptr_t>(a.itrans) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ptrans) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(a.itrans16) & 15) == 0;
