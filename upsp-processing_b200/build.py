@@ -134,6 +134,24 @@ def build_h5_probe(force: bool = False) -> str:
     return H5_PROBE_BIN
 
 
+ADD_FIELD_BIN = os.path.join(HERE, "add_field_b200")
+
+
+def build_add_field_tool(force: bool = False) -> str:
+    """host/add_field_b200.cpp: the reference's `add_field` (flat [rows x extent] float file -> chunked HDF5 dataset) on
+    host/h5_append.hpp, no HDF5 library."""
+    src = os.path.join(HERE, "host", "add_field_b200.cpp")
+    deps = [src, os.path.join(HERE, "host", "h5_append.hpp")]
+    if not force and os.path.exists(ADD_FIELD_BIN) and os.path.getmtime(ADD_FIELD_BIN) >= max(map(os.path.getmtime, deps)):
+        return ADD_FIELD_BIN
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", ADD_FIELD_BIN, src], capture_output=True, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building add_field_b200")
+    return ADD_FIELD_BIN
+
+
 PATCH_PROBE_BIN = os.path.join(HERE, "patch_geometry_probe")
 
 
