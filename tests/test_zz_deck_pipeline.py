@@ -97,6 +97,13 @@ def test_deck_to_flat_files(up, orc, gpu, tmp_path):
         assert f.root["Condition/dynamic_pressure"].data[0] == case.qbar and f.root["Condition/static_pressure"].data[0] == case.ps
         assert f.root["Condition/frame_rate"].attrs["units"] == ["Hz"] and f.root["Condition/focal_length"].data.shape == (1,)
     assert same_bits(ex.root["average"].data, rd("avg")) and "average" not in h5.root.children
+    # the documented last step of a run (docs/sphinx/quick-start.rst:125-160): add_field <h5> frames <pressure_transpose> <frames>
+    r = subprocess.run([up.build.build_add_field_tool(), str(d / "out" / "run12.h5"), "frames", str(d / "out" / "pressure_transpose"),
+                        str(F)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    h5b = h5min.File(str(d / "out" / "run12.h5"))
+    assert h5b.root["frames"].shape == (N, F) and same_bits(h5b.root["frames"].data, rd("pressure_transpose", (N, F)))
+    assert same_bits(h5b.root["rms"].data, rd("rms")) and np.array_equal(h5b.root["Grid/x"].data, xyz[:, 0])
 
 
 @pytest.mark.gpu
