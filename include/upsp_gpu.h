@@ -136,6 +136,10 @@ UPSP_API int upsp_gpu_set_warp_matrices(upsp_gpu_ctx* ctx, int cam, int local_of
  * async H2D of `count` frames of camera `cam` starting at local frame `local_offset`. */
 UPSP_API int upsp_gpu_push_frames(upsp_gpu_ctx* ctx, int cam, const void* host_frames, int format,
                                   int local_offset, int count);
+/* Blocks until every push_frames issued so far has read its host buffer (the reader may refill it: the hand-over of
+ * input_frames slots between __async_read_ahead and the frame loop, psp_process.cpp:897-908).  Does not wait for
+ * process_frames; with an input ring smaller than the local slice it waits for the slots being overwritten to be consumed. */
+UPSP_API int upsp_gpu_wait_pushes(upsp_gpu_ctx* ctx);
 /* replaces the OpenMP frame loop psp_process.cpp:1753-1843 for local frames
  * [local_offset, local_offset+count): hot-pixel fix, register, patch, project, camera
  * sum, NaN fill, sum / sum-of-squares, overlap remap, row store.  Asynchronous. */

@@ -224,6 +224,10 @@ class PspGpu:
     def wait_reads(self):
         _chk(lib().upsp_gpu_wait_reads(self._h))
 
+    def wait_pushes(self):
+        """Every push_frames issued so far has read its host buffer (processing may still be running)."""
+        _chk(lib().upsp_gpu_wait_pushes(self._h))
+
     def read_phase1_stats(self):
         avg, rms, cov = (np.empty(self.n_nodes, np.float32) for _ in range(3))
         _chk(lib().upsp_gpu_read_phase1_stats(self._h, _p(avg), _p(rms), _p(cov)))

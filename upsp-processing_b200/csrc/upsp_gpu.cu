@@ -2646,6 +2646,12 @@ extern "C" int upsp_gpu_read_intensity_transpose_block_async(upsp_gpu_ctx* c, in
   return UPSP_OK;
 }
 
+extern "C" int upsp_gpu_wait_pushes(upsp_gpu_ctx* c) {
+  ENTER(c);
+  CU(cudaStreamSynchronize(c->copy_stream));
+  return UPSP_OK;
+}
+
 extern "C" int upsp_gpu_wait_reads(upsp_gpu_ctx* c) {
   ENTER(c);
   CU(cudaStreamSynchronize(c->d2h_stream));

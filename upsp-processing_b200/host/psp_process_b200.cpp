@@ -282,7 +282,7 @@ int main(int argc, char** argv) {
           if (!vids[c]) throw std::invalid_argument("frame file of camera " + std::to_string(c) + " is too short");
           chain.push_frames(c, buf.data(), p12 ? UPSP_PIX_PACKED12 : UPSP_PIX_U16, off, n);
         }
-        chain.sync();   // buf is reused for the next camera / chunk
+        chain.wait_pushes();   // buf is reused for the next camera / chunk; the previous chunk's processing keeps running
       }
       chain.process_frames(off, n);
     }

@@ -141,6 +141,7 @@ class FrameChain {
   void push_frames(int cam, const void* frames, int format, int local_offset, int count) {
     check(upsp_gpu_push_frames(ctx_, cam, frames, format, local_offset, count));
   }
+  void wait_pushes() { check(upsp_gpu_wait_pushes(ctx_)); }     // the pushed host buffers may be refilled; processing goes on
   void process_frames(int local_offset, int count) { check(upsp_gpu_process_frames(ctx_, local_offset, count)); }
   void finish_phase1() { check(upsp_gpu_finish_phase1(ctx_)); }
   void global_transpose() { check(upsp_gpu_transpose(ctx_)); }
