@@ -96,12 +96,40 @@ int main(int argc, char** argv) {
   int device = 0, chunk = 256;
   std::string h5_out;      // -h5_out of the reference's command line (empty: job-directory mode, flat files only)
   try {
-    auto opt = parse_command_line(argc, argv);
+    auto opt = parse_command_line(argc, argv, {"-no_projection", "-help", "-h", "-usage", "-?", "--help"});
+    if (opt.count("-help") || opt.count("-h") || opt.count("-usage") || opt.count("-?") || opt.count("--help")) {
+      // ParseOpts prints the parser's message and main() ends with status 1 (psp_process.cpp:1225-1228, 1362-1367)
+      std::cout << "Process Unsteady Pressure-Sensitive Paint (uPSP) video files into pressure-time history on model surface grid\n"
+                   "Usage: psp_process_b200 [params]\n"
+                   "\t-input_file       full input deck\n"
+                   "\t-frames           override input_file number of frames\n"
+                   "\t-code_version     version of the repo (deprecated) [XYZ]\n"
+                   "\t-trans_nodes      number of nodes per chunk in transposed solution (unused, kept for compatibility) [250]\n"
+                   "\t-add_out_dir      output directory for any additional debugging files (default=input deck-specified output directory)\n"
+                   "\t-checkout         perform calibration update checkout [F]\n"
+                   "\t-bound_pts        thickness of cluster boundary [2]\n"
+                   "\t-buffer_pts       thickness of buffer between targets and cluster boundary [1]\n"
+                   "\t-target_diam_sf   scale factor to apply onto target diameter [1.2]\n"
+                   "\t-cutoff_x_max     ignore nodes beyond this value in projection\n"
+                   "\t-h5_out           output hdf5 file\n"
+                   "\t-steady_p3d       steady state p3d function file (for wind-on); units of Cp\n"
+                   "\t-steady_grid      steady state p3d grid (needed for wind-on unstructured)\n"
+                   "\t-paint_cal        unsteady gain paint calibration file\n"
+                   "\t-model_temp_p3d   temperature p3d function file; units of Temperature degrees F\n"
+                   "\t-device, -chunk   GPU ordinal [0], frames per push / process call [256]\n"
+                   "or, from a job directory: psp_process_b200 -job_dir DIR -out_dir DIR [-h5_out FILE]" << std::endl;
+      std::cerr << "[ERROR] Failed to validate command line options; aborting" << std::endl;
+      return 1;
+    }
     if (opt.count("-device")) device = atoi(opt["-device"].c_str());
     if (opt.count("-chunk")) chunk = atoi(opt["-chunk"].c_str());
     if (opt.count("-input_file")) {       // the reference's command line
-      if (!opt.count("-h5_out")) {
+      if (!opt.count("-h5_out")) {       // ParseOpts' order: input_file, h5_out, paint_cal, then the deck (psp_process.cpp:1230-1249)
         std::cerr << "[ERROR] Must specify -h5_out" << std::endl;
+        return 1;
+      }
+      if (!opt.count("-paint_cal")) {
+        std::cerr << "[ERROR] Must specify -paint_cal" << std::endl;
         return 1;
       }
       FileInputs peek;
