@@ -62,3 +62,16 @@ def test_all_denominators_with_a_fixed_numerator():
         rc0 = (1.0 / b.astype(np.float64)).astype(np.float32)
         for d in (-2, 0, 2):
             assert _count_bad(a, b, (rc0.view(np.int32) + d).view(np.float32)) == 0
+
+
+def test_zero_half_test_of_the_packed_denominators_is_exact():
+    """k_phase2_sym<IN16> takes the fast division for a group of eight 16-bit intensities unless one of them is zero: the
+    unsigned minimum of the eight halves (VIMNMX.U16x2), then ((m - 0x00010001) & ~m & 0x80008000) != 0 on the two halves
+    left.  A borrow out of a zero low half can only add a second positive, so the test is exact."""
+    lo = np.arange(65536, dtype=np.uint64)
+    rng = np.random.default_rng(0)
+    his = np.unique(np.concatenate([[0, 1, 2, 0x7FFF, 0x8000, 0x8001, 0xFFFE, 0xFFFF], rng.integers(0, 65536, 200)])).astype(np.uint64)
+    for h in his:
+        m = (h << np.uint64(16)) | lo
+        t = ((m - np.uint64(0x00010001)) & np.uint64(0xFFFFFFFF)) & (~m & np.uint64(0xFFFFFFFF)) & np.uint64(0x80008000)
+        assert np.array_equal(t != 0, (lo == 0) | (h == 0))
