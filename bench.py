@@ -17,7 +17,11 @@ gain + delta-Cp.  One JSON line on stdout (rank 0).
             step, intensity_transpose + pressure_transpose D2H every step
   roofline: dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline: the CPU oracle (C port of the reference's algorithm, all host threads) on a
-            bounded sample of the same workload
+            bounded sample of the same workload (the single-GPU line only)
+  parity  : --check (default on, outside the timed region): every rank compares sampled rows of what it holds after
+            the last timed step with the CPU oracle (intensity_transpose, avg, rms, gain bit for bit; delta-Cp by the
+            criterion of DESIGN.md section 4); "parity_checked" false and exit status != 0 on a mismatch
+  --config {1,2,3} selects BASELINE.json's configs[1..3]; --exchange nccl the NCCL arm; --registration pixel the ECC line
 """
 from __future__ import annotations
 
